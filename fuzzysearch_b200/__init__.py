@@ -1,0 +1,57 @@
+"""fuzzysearch_b200 -- B200-native (sm_100a CUDA) drop-in for fuzzysearch's near-match search.
+
+Same public API as the reference (fuzzysearch/__init__.py:35-83):
+
+>>> find_near_matches(b'PATTERN', b'---PATERN---', max_l_dist=1)
+[Match(start=3, end=9, dist=1, matched=b'PATERN')]
+
+Every search runs as hand-written CUDA kernels behind the C-ABI of libfuzzb200.so
+(include/fuzzb200.h); there is no CPU fallback -- without the library or a GPU the calls raise.
+"""
+__version__ = "0.1.0"
+
+__all__ = ["find_near_matches", "find_near_matches_in_file", "Match", "LevenshteinSearchParams",
+           "DeviceSequence", "ExactSearch", "SubstitutionsOnlySearch", "LevenshteinSearch",
+           "GenericSearch", "choose_search_class"]
+
+from .common import LevenshteinSearchParams, Match
+from .search import (DeviceSequence, ExactSearch, GenericSearch, LevenshteinSearch,
+                     SubstitutionsOnlySearch)
+
+
+def find_near_matches(subsequence, sequence, max_substitutions=None, max_insertions=None,
+                      max_deletions=None, max_l_dist=None):
+    """search for near-matches of subsequence in sequence (fuzzysearch/__init__.py:35-57).
+
+    The nearly-matching parts of the sequence must meet the given limits on substitutions,
+    insertions, deletions and their total (the Levenshtein distance)."""
+    search_params = LevenshteinSearchParams(max_substitutions, max_insertions, max_deletions,
+                                            max_l_dist)
+    search_class = choose_search_class(search_params)
+    matches = search_class.search(subsequence, sequence, search_params)
+    return search_class.consolidate_matches(matches)
+
+
+def choose_search_class(search_params):
+    """fuzzysearch/__init__.py:60-83."""
+    max_substitutions, max_insertions, max_deletions, max_l_dist = search_params.unpacked
+    if max_l_dist == 0:
+        return ExactSearch
+    elif max_insertions == 0 and max_deletions == 0:
+        return SubstitutionsOnlySearch
+    elif max_l_dist <= min(
+            (max_substitutions if max_substitutions is not None else (1 << 29)),
+            (max_insertions if max_insertions is not None else (1 << 29)),
+            (max_deletions if max_deletions is not None else (1 << 29)),
+    ):
+        return LevenshteinSearch
+    else:
+        return GenericSearch
+
+
+def find_near_matches_in_file(subsequence, sequence_file, max_substitutions=None, max_insertions=None,
+                              max_deletions=None, max_l_dist=None, _chunk_size=2 ** 20):
+    """search for near-matches of subsequence in a file (fuzzysearch/__init__.py:86-200)."""
+    from .file_search import find_near_matches_in_file as impl
+    return impl(subsequence, sequence_file, max_substitutions, max_insertions, max_deletions,
+                max_l_dist, _chunk_size)

@@ -1,0 +1,288 @@
+"""ctypes binding of libfuzzb200.so (C-ABI declared in include/fuzzb200.h).
+
+There is no Python or CPU fallback: if the shared library is missing or no CUDA device is usable
+the calls raise (``NativeLibraryMissing`` / ``CudaError``).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfuzzb200.so")
+
+FZB_OK = 0
+FZB_E_INVALID = -1
+FZB_E_CUDA = -2
+FZB_E_UNSUPPORTED = -3
+FZB_E_NGRAM_ZERO = -4
+FZB_MAX_PATTERN = 255
+
+RAW, FINAL = 0, 1
+F_NO_FINAL, F_FORCE_DENSE, F_FORCE_LP, F_FORCE_NGRAMS = 1, 2, 4, 8
+
+ROUTE_NAMES = {0: "exact", 1: "ngrams/sampled-filter", 2: "ngrams/dense-filter", 3: "lp",
+               4: "hamming", 5: "generic-ngrams", 6: "generic-lp"}
+
+
+class NativeLibraryMissing(ImportError):
+    pass
+
+
+class CudaError(RuntimeError):
+    pass
+
+
+class UnsupportedError(NotImplementedError):
+    pass
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [("gpu_ms", ctypes.c_double), ("filter_ms", ctypes.c_double),
+                ("bytes_scanned", ctypes.c_uint64), ("n_candidates", ctypes.c_uint64),
+                ("n_launches", ctypes.c_uint32), ("route", ctypes.c_uint32)]
+
+
+# every symbol include/fuzzb200.h declares: name -> (restype, argtypes)
+_vp, _u8p = ctypes.c_void_p, ctypes.c_void_p
+_u32, _u64, _i32, _i64 = ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int, ctypes.c_int64
+_vpp = ctypes.POINTER(ctypes.c_void_p)
+SYMBOLS = {
+    "fzb_version": (_i32, []),
+    "fzb_device_count": (_i32, []),
+    "fzb_last_error": (ctypes.c_char_p, []),
+    "fzb_haystack_create": (_i32, [_u8p, _u64, _i32, _vpp]),
+    "fzb_haystack_create_shard": (_i32, [_u8p, _u64, _u64, _u64, _u64, _u64, _i32, _vpp]),
+    "fzb_haystack_adopt_device": (_i32, [_vp, _u64, _u64, _u64, _u64, _u64, _i32, _vpp]),
+    "fzb_haystack_alloc": (_i32, [_u64, _i32, _vpp, _vpp]),
+    "fzb_haystack_fill_synthetic": (_i32, [_vp, _u8p, _u32, _u64]),
+    "fzb_synth_host": (None, [_u8p, _u64, _u64, _u8p, _u32, _u64]),
+    "fzb_haystack_write": (_i32, [_vp, _u64, _u8p, _u64]),
+    "fzb_haystack_read": (_i32, [_vp, _u64, _u8p, _u64]),
+    "fzb_haystack_len": (_u64, [_vp]),
+    "fzb_haystack_destroy": (None, [_vp]),
+    "fzb_search_levenshtein": (_i32, [_vp, _u8p, _u32, _u32, _u32, _vpp]),
+    "fzb_search_hamming": (_i32, [_vp, _u8p, _u32, _u32, _u32, _vpp]),
+    "fzb_search_generic": (_i32, [_vp, _u8p, _u32, _u32, _u32, _u32, _u32, _u32, _vpp]),
+    "fzb_search_exact": (_i32, [_vp, _u8p, _u32, _u32, _vpp]),
+    "fzb_find_near_matches": (_i32, [_u8p, _u32, _u8p, _u64, _u32, _u32, _u32, _u32, _i32, _vpp]),
+    "fzb_result_count": (_u64, [_vp, _i32]),
+    "fzb_result_copy": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "fzb_result_stats": (_i32, [_vp, ctypes.POINTER(Stats)]),
+    "fzb_result_destroy": (None, [_vp]),
+    "fzb_consolidate": (_i64, [_vp, _vp, _vp, _u64, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeLibraryMissing(
+                "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C fuzzysearch_b200/csrc`). fuzzysearch_b200 has no CPU fallback."
+                % LIB_PATH)
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            f = getattr(l, name)
+            f.restype = res
+            f.argtypes = args
+        _lib = l
+    return _lib
+
+
+def device_count():
+    return int(lib().fzb_device_count())
+
+
+def last_error():
+    return lib().fzb_last_error().decode("utf-8", "replace")
+
+
+def check(rc):
+    if rc == FZB_OK:
+        return
+    msg = last_error()
+    if rc in (FZB_E_INVALID, FZB_E_NGRAM_ZERO):
+        raise ValueError(msg)
+    if rc == FZB_E_UNSUPPORTED:
+        raise UnsupportedError(msg)
+    raise CudaError(msg)
+
+
+def as_u8(buf):
+    """bytes-like -> contiguous numpy uint8 view (zero-copy where possible)."""
+    if isinstance(buf, np.ndarray):
+        if buf.dtype != np.uint8:
+            raise TypeError("numpy sequences must have dtype uint8")
+        return np.ascontiguousarray(buf).reshape(-1)
+    try:
+        mv = memoryview(buf)
+    except TypeError:
+        raise TypeError("only contiguous sequences of single-byte values are supported")
+    if mv.itemsize != 1 or not mv.contiguous:
+        raise TypeError("only contiguous sequences of single-byte values are supported")
+    return np.frombuffer(mv, dtype=np.uint8)
+
+
+def ptr(arr):
+    return ctypes.c_void_p(arr.ctypes.data if arr.size else 0)
+
+
+class Result(object):
+    """Owns an fzb_result*; exposes the raw and final lists as numpy arrays."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    def close(self):
+        if self._h:
+            lib().fzb_result_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def count(self, which=FINAL):
+        return int(lib().fzb_result_count(self._h, which))
+
+    def arrays(self, which=FINAL, anchors=False):
+        n = self.count(which)
+        start = np.empty(n, dtype=np.int64)
+        end = np.empty(n, dtype=np.int64)
+        dist = np.empty(n, dtype=np.int32)
+        if anchors:
+            ng = np.empty(n, dtype=np.int32)
+            ix = np.empty(n, dtype=np.int64)
+            check(lib().fzb_result_copy(self._h, which, ptr(start), ptr(end), ptr(dist), ptr(ng), ptr(ix)))
+            return start, end, dist, ng, ix
+        check(lib().fzb_result_copy(self._h, which, ptr(start), ptr(end), ptr(dist), None, None))
+        return start, end, dist
+
+    def triples(self, which=FINAL):
+        s, e, d = self.arrays(which)
+        return list(zip(s.tolist(), e.tolist(), d.tolist()))
+
+    def stats(self):
+        st = Stats()
+        check(lib().fzb_result_stats(self._h, ctypes.byref(st)))
+        return {"gpu_ms": st.gpu_ms, "filter_ms": st.filter_ms, "bytes_scanned": st.bytes_scanned,
+                "n_candidates": st.n_candidates, "n_launches": st.n_launches,
+                "route": ROUTE_NAMES.get(st.route, str(st.route))}
+
+
+class Haystack(object):
+    """Owns an fzb_haystack*: a device-resident sequence (or one shard of a global sequence)."""
+
+    def __init__(self, handle, dev_ptr=None):
+        self._h = handle
+        self.dev_ptr = dev_ptr
+
+    @classmethod
+    def from_host(cls, data, device=0, buf_lo=0, global_len=None, own_lo=None, own_hi=None):
+        a = as_u8(data)
+        n = a.size
+        if global_len is None:
+            global_len, own_lo, own_hi = n, 0, n
+        h = ctypes.c_void_p()
+        check(lib().fzb_haystack_create_shard(ptr(a), n, buf_lo, global_len, own_lo, own_hi, device,
+                                              ctypes.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def alloc(cls, n, device=0):
+        h = ctypes.c_void_p()
+        dp = ctypes.c_void_p()
+        check(lib().fzb_haystack_alloc(n, device, ctypes.byref(h), ctypes.byref(dp)))
+        return cls(h, dp.value)
+
+    @classmethod
+    def adopt(cls, dev_ptr, buf_len, device=0, buf_lo=0, global_len=None, own_lo=None, own_hi=None):
+        if global_len is None:
+            global_len, own_lo, own_hi = buf_len, 0, buf_len
+        h = ctypes.c_void_p()
+        check(lib().fzb_haystack_adopt_device(ctypes.c_void_p(dev_ptr), buf_len, buf_lo, global_len,
+                                              own_lo, own_hi, device, ctypes.byref(h)))
+        return cls(h, dev_ptr)
+
+    def close(self):
+        if self._h:
+            lib().fzb_haystack_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __len__(self):
+        return int(lib().fzb_haystack_len(self._h))
+
+    def fill_synthetic(self, alphabet, seed):
+        a = as_u8(alphabet)
+        check(lib().fzb_haystack_fill_synthetic(self._h, ptr(a), a.size, seed))
+
+    def write(self, offset, data):
+        a = as_u8(data)
+        check(lib().fzb_haystack_write(self._h, offset, ptr(a), a.size))
+
+    def read(self, offset, n):
+        out = np.empty(n, dtype=np.uint8)
+        check(lib().fzb_haystack_read(self._h, offset, ptr(out), n))
+        return out.tobytes()
+
+    def _pat(self, pattern):
+        p = as_u8(pattern)
+        return p, ptr(p), p.size
+
+    def search_levenshtein(self, pattern, k, flags=0):
+        p, pp, m = self._pat(pattern)
+        r = ctypes.c_void_p()
+        check(lib().fzb_search_levenshtein(self._h, pp, m, k, flags, ctypes.byref(r)))
+        return Result(r)
+
+    def search_hamming(self, pattern, k, flags=0):
+        p, pp, m = self._pat(pattern)
+        r = ctypes.c_void_p()
+        check(lib().fzb_search_hamming(self._h, pp, m, k, flags, ctypes.byref(r)))
+        return Result(r)
+
+    def search_generic(self, pattern, max_subs, max_ins, max_dels, max_l, flags=0):
+        p, pp, m = self._pat(pattern)
+        r = ctypes.c_void_p()
+        check(lib().fzb_search_generic(self._h, pp, m, max_subs, max_ins, max_dels, max_l, flags,
+                                       ctypes.byref(r)))
+        return Result(r)
+
+    def search_exact(self, pattern, flags=0):
+        p, pp, m = self._pat(pattern)
+        r = ctypes.c_void_p()
+        check(lib().fzb_search_exact(self._h, pp, m, flags, ctypes.byref(r)))
+        return Result(r)
+
+
+def synth_host(global_offset, n, alphabet, seed):
+    a = as_u8(alphabet)
+    out = np.empty(n, dtype=np.uint8)
+    lib().fzb_synth_host(ptr(out), global_offset, n, ptr(a), a.size, seed)
+    return out
+
+
+def find_near_matches_host(pattern, haystack, max_subs, max_ins, max_dels, max_l, device=0):
+    """One-shot C-ABI call with host buffers (upload + search + consolidate)."""
+    p = as_u8(pattern)
+    a = as_u8(haystack)
+    r = ctypes.c_void_p()
+    check(lib().fzb_find_near_matches(ptr(p), p.size, ptr(a), a.size, max_subs, max_ins, max_dels, max_l,
+                                      device, ctypes.byref(r)))
+    return Result(r)
+
+
+def consolidate(start, end, dist):
+    start = np.ascontiguousarray(start, dtype=np.int64)
+    end = np.ascontiguousarray(end, dtype=np.int64)
+    dist = np.ascontiguousarray(dist, dtype=np.int32)
+    n = start.size
+    os_, oe, od = np.empty(n, np.int64), np.empty(n, np.int64), np.empty(n, np.int32)
+    cnt = lib().fzb_consolidate(ptr(start), ptr(end), ptr(dist), n, ptr(os_), ptr(oe), ptr(od))
+    if cnt < 0:
+        check(int(cnt))
+    return os_[:cnt], oe[:cnt], od[:cnt]

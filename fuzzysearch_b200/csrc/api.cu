@@ -1,0 +1,795 @@
+// api.cu -- host side of libfuzzb200.so: the C-ABI declared in include/fuzzb200.h.
+//
+// No CPU search path exists in this file: every search launches the sm_100a kernels of kernels.cuh
+// and fails with FZB_E_CUDA when no device is usable.  The only host-side algorithm is the
+// O(N log N) consolidation of the (small) match list, which the reference also performs after its
+// search (common.py:185-189).
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "lp_kernels.cuh"
+
+using namespace fzb;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess)                                                            \
+            return fail(FZB_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));      \
+    } while (0)
+
+extern "C" int fzb_version(void) { return FZB_VERSION; }
+
+extern "C" int fzb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" const char *fzb_last_error(void) { return g_err.c_str(); }
+
+// ------------------------------------------------------------------------------------------------
+// handles
+// ------------------------------------------------------------------------------------------------
+struct fzb_haystack {
+    int device = 0;
+    uint8_t *d = nullptr;  // H[0] == global position buf_lo
+    bool owned = true;
+    uint64_t buf_len = 0, buf_lo = 0, global_len = 0, own_lo = 0, own_hi = 0;
+    uint64_t padded_len = 0;
+    cudaStream_t stream = nullptr;
+    uint32_t *d_bitmap = nullptr;
+    uint64_t bitmap_words = 0;
+    RawRec *d_out = nullptr;
+    uint32_t out_cap = 0;
+    uint32_t *d_counters = nullptr;
+    uint32_t *h_counters = nullptr;  // pinned
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    int sm_count = 148;
+    uint32_t *d_scratch = nullptr;  // candidate lists of the LP / generic kernels
+    uint64_t scratch_words = 0;
+};
+
+struct fzb_result {
+    std::vector<RawRec> raw;
+    std::vector<RawRec> fin;
+    bool final_is_raw = false;
+    fzb_stats stats{};
+};
+
+static uint64_t round_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+
+static int haystack_common_init(fzb_haystack *h) {
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (auto &e : h->ev) CK(cudaEventCreate(&e));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, h->device));
+    h->sm_count = prop.multiProcessorCount;
+    uint64_t granules = (h->padded_len >> kGranuleShift) + 2;
+    h->bitmap_words = round_up((granules + 31) / 32, 32);
+    CK(cudaMalloc(&h->d_bitmap, h->bitmap_words * sizeof(uint32_t)));
+    CK(cudaMalloc(&h->d_counters, CNT_COUNT * sizeof(uint32_t)));
+    CK(cudaMallocHost(&h->h_counters, CNT_COUNT * sizeof(uint32_t)));
+    h->out_cap = 1u << 16;
+    CK(cudaMalloc(&h->d_out, (size_t)h->out_cap * sizeof(RawRec)));
+    return FZB_OK;
+}
+
+static int check_shard(uint64_t buf_len, uint64_t buf_lo, uint64_t global_len, uint64_t own_lo,
+                       uint64_t own_hi) {
+    if (buf_lo + buf_len > global_len || own_lo > own_hi || own_hi > global_len ||
+        (own_lo < own_hi && (own_lo < buf_lo || own_hi > buf_lo + buf_len)))
+        return fail(FZB_E_INVALID, "inconsistent shard geometry");
+    if (buf_lo % 16 != 0) return fail(FZB_E_INVALID, "buf_lo must be a multiple of 16");
+    return FZB_OK;
+}
+
+static int alloc_buffer(fzb_haystack *h) {
+    h->padded_len = round_up(h->buf_len, 16) + 64;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMalloc(&h->d, h->padded_len));
+    CK(cudaMemset(h->d + h->buf_len, 0, h->padded_len - h->buf_len));
+    return FZB_OK;
+}
+
+extern "C" void fzb_haystack_destroy(fzb_haystack *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->owned && h->d) cudaFree(h->d);
+    if (h->d_bitmap) cudaFree(h->d_bitmap);
+    if (h->d_out) cudaFree(h->d_out);
+    if (h->d_counters) cudaFree(h->d_counters);
+    if (h->d_scratch) cudaFree(h->d_scratch);
+    if (h->h_counters) cudaFreeHost(h->h_counters);
+    for (auto &e : h->ev)
+        if (e) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" int fzb_haystack_create_shard(const uint8_t *host, uint64_t buf_len, uint64_t buf_lo,
+                                         uint64_t global_len, uint64_t own_lo, uint64_t own_hi,
+                                         int device, fzb_haystack **out) {
+    if (!out) return fail(FZB_E_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!host && buf_len) return fail(FZB_E_INVALID, "host buffer is NULL");
+    int rc = check_shard(buf_len, buf_lo, global_len, own_lo, own_hi);
+    if (rc) return rc;
+    if (fzb_device_count() <= device || device < 0)
+        return fail(FZB_E_CUDA, "CUDA device %d not available (%d devices)", device, fzb_device_count());
+    fzb_haystack *h = new (std::nothrow) fzb_haystack();
+    if (!h) return fail(FZB_E_CUDA, "out of host memory");
+    h->device = device;
+    h->buf_len = buf_len;
+    h->buf_lo = buf_lo;
+    h->global_len = global_len;
+    h->own_lo = own_lo;
+    h->own_hi = own_hi;
+    rc = alloc_buffer(h);
+    if (rc == FZB_OK) rc = haystack_common_init(h);
+    if (rc == FZB_OK && buf_len) {
+        cudaError_t e = cudaMemcpyAsync(h->d, host, buf_len, cudaMemcpyHostToDevice, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) rc = fail(FZB_E_CUDA, "H2D copy failed: %s", cudaGetErrorString(e));
+    }
+    if (rc) {
+        fzb_haystack_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return FZB_OK;
+}
+
+extern "C" int fzb_haystack_create(const uint8_t *host, uint64_t n, int device, fzb_haystack **out) {
+    return fzb_haystack_create_shard(host, n, 0, n, 0, n, device, out);
+}
+
+extern "C" int fzb_haystack_adopt_device(const void *dev_ptr, uint64_t buf_len, uint64_t buf_lo,
+                                         uint64_t global_len, uint64_t own_lo, uint64_t own_hi,
+                                         int device, fzb_haystack **out) {
+    if (!out) return fail(FZB_E_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!dev_ptr || ((uintptr_t)dev_ptr & 15)) return fail(FZB_E_INVALID, "dev_ptr must be 16-byte aligned");
+    int rc = check_shard(buf_len, buf_lo, global_len, own_lo, own_hi);
+    if (rc) return rc;
+    if (fzb_device_count() <= device || device < 0) return fail(FZB_E_CUDA, "CUDA device %d not available", device);
+    fzb_haystack *h = new (std::nothrow) fzb_haystack();
+    if (!h) return fail(FZB_E_CUDA, "out of host memory");
+    h->device = device;
+    h->owned = false;
+    h->d = (uint8_t *)dev_ptr;
+    h->buf_len = buf_len;
+    h->buf_lo = buf_lo;
+    h->global_len = global_len;
+    h->own_lo = own_lo;
+    h->own_hi = own_hi;
+    h->padded_len = round_up(buf_len, 16) + 64;
+    rc = haystack_common_init(h);
+    if (rc) {
+        fzb_haystack_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return FZB_OK;
+}
+
+extern "C" int fzb_haystack_alloc(uint64_t n, int device, fzb_haystack **out, void **dev_ptr) {
+    if (!out) return fail(FZB_E_INVALID, "out is NULL");
+    *out = nullptr;
+    if (fzb_device_count() <= device || device < 0) return fail(FZB_E_CUDA, "CUDA device %d not available", device);
+    fzb_haystack *h = new (std::nothrow) fzb_haystack();
+    if (!h) return fail(FZB_E_CUDA, "out of host memory");
+    h->device = device;
+    h->buf_len = n;
+    h->global_len = n;
+    h->own_hi = n;
+    int rc = alloc_buffer(h);
+    if (rc == FZB_OK) rc = haystack_common_init(h);
+    if (rc) {
+        fzb_haystack_destroy(h);
+        return rc;
+    }
+    if (dev_ptr) *dev_ptr = h->d;
+    *out = h;
+    return FZB_OK;
+}
+
+extern "C" void fzb_synth_host(uint8_t *dst, uint64_t global_offset, uint64_t n, const uint8_t *alphabet,
+                               uint32_t alphabet_len, uint64_t seed) {
+    uint64_t i = 0;
+    while (i < n) {
+        uint64_t g = global_offset + i;
+        uint32_t w = synth_word(seed, g / 4, alphabet, alphabet_len);
+        for (uint64_t b = g % 4; b < 4 && i < n; b++, i++) dst[i] = (uint8_t)(w >> (8 * b));
+    }
+}
+
+extern "C" int fzb_haystack_fill_synthetic(fzb_haystack *h, const uint8_t *alphabet, uint32_t alphabet_len,
+                                           uint64_t seed) {
+    if (!h || !alphabet || alphabet_len == 0 || alphabet_len > 256) return fail(FZB_E_INVALID, "bad arguments");
+    if (!h->owned) return fail(FZB_E_INVALID, "cannot fill an adopted buffer");
+    CK(cudaSetDevice(h->device));
+    uint8_t *d_alpha = nullptr;
+    CK(cudaMalloc(&d_alpha, 256));
+    CK(cudaMemcpyAsync(d_alpha, alphabet, alphabet_len, cudaMemcpyHostToDevice, h->stream));
+    int64_t nwords = (int64_t)(round_up(h->buf_len, 4) / 4);
+    k_fill_synth<<<h->sm_count * 8, 256, 0, h->stream>>>(h->d, (int64_t)h->buf_lo, nwords, seed, d_alpha,
+                                                        alphabet_len);
+    CK(cudaGetLastError());
+    // bytes past buf_len must stay zero (the last word may have spilled over)
+    if (h->buf_len % 4)
+        CK(cudaMemsetAsync(h->d + h->buf_len, 0, 4 - h->buf_len % 4, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaFree(d_alpha));
+    return FZB_OK;
+}
+
+extern "C" int fzb_haystack_write(fzb_haystack *h, uint64_t global_offset, const uint8_t *src, uint64_t n) {
+    if (!h || (!src && n)) return fail(FZB_E_INVALID, "bad arguments");
+    if (global_offset < h->buf_lo || global_offset + n > h->buf_lo + h->buf_len)
+        return fail(FZB_E_INVALID, "write outside the buffer");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(h->d + (global_offset - h->buf_lo), src, n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return FZB_OK;
+}
+
+extern "C" int fzb_haystack_read(fzb_haystack *h, uint64_t global_offset, uint8_t *dst, uint64_t n) {
+    if (!h || (!dst && n)) return fail(FZB_E_INVALID, "bad arguments");
+    if (global_offset < h->buf_lo || global_offset + n > h->buf_lo + h->buf_len)
+        return fail(FZB_E_INVALID, "read outside the buffer");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(dst, h->d + (global_offset - h->buf_lo), n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return FZB_OK;
+}
+
+extern "C" uint64_t fzb_haystack_len(const fzb_haystack *h) { return h ? h->global_len : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// consolidation (common.py:145-189).  Groups are the connected components of interval overlap
+// (SURVEY F11): sort by (start,end), sweep with the running hull end; a match joins the current
+// group iff start < hull_end (this also reproduces the reference for empty matches, which never
+// overlap anything they merely touch).  Winner = min (dist, -(end-start)), ties -> smallest
+// (start,end).  Output sorted by (start,end,dist).
+// ------------------------------------------------------------------------------------------------
+static void consolidate_recs(std::vector<RawRec> v, std::vector<RawRec> &out) {
+    out.clear();
+    if (v.empty()) return;
+    std::sort(v.begin(), v.end(), [](const RawRec &a, const RawRec &b) {
+        if (a.start != b.start) return a.start < b.start;
+        if (a.end != b.end) return a.end < b.end;
+        return a.dist < b.dist;
+    });
+    RawRec best = v[0];
+    int64_t hull_end = v[0].end;
+    auto better = [](const RawRec &a, const RawRec &b) {  // a strictly better than b
+        if (a.dist != b.dist) return a.dist < b.dist;
+        int64_t la = a.end - a.start, lb = b.end - b.start;
+        if (la != lb) return la > lb;
+        if (a.start != b.start) return a.start < b.start;
+        return a.end < b.end;
+    };
+    for (size_t i = 1; i < v.size(); i++) {
+        if (v[i].start < hull_end) {
+            if (better(v[i], best)) best = v[i];
+            hull_end = std::max(hull_end, v[i].end);
+        } else {
+            out.push_back(best);
+            best = v[i];
+            hull_end = v[i].end;
+        }
+    }
+    out.push_back(best);
+    std::sort(out.begin(), out.end(), [](const RawRec &a, const RawRec &b) {
+        if (a.start != b.start) return a.start < b.start;
+        if (a.end != b.end) return a.end < b.end;
+        return a.dist < b.dist;
+    });
+}
+
+extern "C" int64_t fzb_consolidate(const int64_t *start, const int64_t *end, const int32_t *dist, uint64_t n,
+                                   int64_t *out_start, int64_t *out_end, int32_t *out_dist) {
+    if (n && (!start || !end || !dist)) return fail(FZB_E_INVALID, "NULL input");
+    std::vector<RawRec> v(n), o;
+    for (uint64_t i = 0; i < n; i++) {
+        v[i].start = start[i];
+        v[i].end = end[i];
+        v[i].dist = dist[i];
+        v[i].idx = -1;
+        v[i].ngram = -1;
+    }
+    consolidate_recs(std::move(v), o);
+    for (size_t i = 0; i < o.size(); i++) {
+        if (out_start) out_start[i] = o[i].start;
+        if (out_end) out_end[i] = o[i].end;
+        if (out_dist) out_dist[i] = o[i].dist;
+    }
+    return (int64_t)o.size();
+}
+
+// ------------------------------------------------------------------------------------------------
+// search plumbing
+// ------------------------------------------------------------------------------------------------
+static void fill_params(const fzb_haystack *h, const uint8_t *pattern, uint32_t m, ScanParams &p) {
+    memset(&p, 0, sizeof p);
+    p.H = h->d;
+    p.buf_lo = (int64_t)h->buf_lo;
+    p.buf_len = (int64_t)h->buf_len;
+    p.N = (int64_t)h->global_len;
+    p.own_lo = (int64_t)h->own_lo;
+    p.own_hi = (int64_t)h->own_hi;
+    p.bitmap = h->d_bitmap;
+    p.m = (int)m;
+    memcpy(p.P, pattern, m);
+}
+
+static int check_halo(const fzb_haystack *h, uint64_t halo) {
+    uint64_t need_lo = h->own_lo > halo ? h->own_lo - halo : 0;
+    uint64_t need_hi = std::min(h->global_len, h->own_hi + halo);
+    if (h->own_lo == h->own_hi) return FZB_OK;
+    if (h->buf_lo > need_lo || h->buf_lo + h->buf_len < need_hi)
+        return fail(FZB_E_INVALID, "shard halo too small: need %llu bytes each side",
+                    (unsigned long long)halo);
+    return FZB_OK;
+}
+
+static int ensure_out_cap(fzb_haystack *h, uint64_t need) {
+    if (need <= h->out_cap) return FZB_OK;
+    uint64_t cap = h->out_cap;
+    while (cap < need) cap *= 2;
+    if (cap > (1ull << 31)) return fail(FZB_E_UNSUPPORTED, "more than 2^31 raw matches");
+    CK(cudaFree(h->d_out));
+    h->d_out = nullptr;
+    CK(cudaMalloc(&h->d_out, (size_t)cap * sizeof(RawRec)));
+    h->out_cap = (uint32_t)cap;
+    return FZB_OK;
+}
+
+// Runs `launch_verify` (which must enqueue the emitting kernel(s) on h->stream) until the output
+// buffer was large enough; leaves the records in res->raw.
+template <class F>
+static int run_emitting(fzb_haystack *h, fzb_result *res, F launch_verify) {
+    for (int attempt = 0; attempt < 8; attempt++) {
+        CK(cudaMemsetAsync(h->d_counters, 0, CNT_COUNT * sizeof(uint32_t), h->stream));
+        int rc = launch_verify();
+        if (rc) return rc;
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(h->ev[2], h->stream));
+        CK(cudaMemcpyAsync(h->h_counters, h->d_counters, CNT_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                           h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        uint32_t n = h->h_counters[CNT_OUT];
+        res->stats.n_candidates = h->h_counters[CNT_CAND];
+        if (n <= h->out_cap) {
+            res->raw.resize(n);
+            if (n) {
+                CK(cudaMemcpyAsync(res->raw.data(), h->d_out, (size_t)n * sizeof(RawRec), cudaMemcpyDeviceToHost,
+                                   h->stream));
+                CK(cudaStreamSynchronize(h->stream));
+            }
+            return FZB_OK;
+        }
+        rc = ensure_out_cap(h, n);
+        if (rc) return rc;
+    }
+    return fail(FZB_E_CUDA, "output buffer kept overflowing");
+}
+
+static void finish_stats(fzb_haystack *h, fzb_result *res, bool has_filter) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev[0], h->ev[2]);
+    res->stats.gpu_ms = ms;
+    if (has_filter) {
+        cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+        res->stats.filter_ms = ms;
+    }
+}
+
+static void sort_generation_order(std::vector<RawRec> &v) {
+    std::sort(v.begin(), v.end(), [](const RawRec &a, const RawRec &b) {
+        if (a.ngram != b.ngram) return a.ngram < b.ngram;
+        return a.idx < b.idx;
+    });
+}
+
+static void sort_canonical(std::vector<RawRec> &v) {
+    std::sort(v.begin(), v.end(), [](const RawRec &a, const RawRec &b) {
+        if (a.start != b.start) return a.start < b.start;
+        if (a.end != b.end) return a.end < b.end;
+        return a.dist < b.dist;
+    });
+}
+
+static int set_filter_attrs(size_t smem) {
+    // per device: the attribute belongs to the function on the current device
+    CK(cudaFuncSetAttribute(k_filter_sampled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k_filter_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return FZB_OK;
+}
+
+// n-gram Levenshtein search (also serves exact search as k == 0, L == m)
+static int search_lev_ngrams(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint32_t k, uint32_t flags,
+                             fzb_result *res) {
+    ScanParams p;
+    fill_params(h, pattern, m, p);
+    p.k = (int)k;
+    p.L = (int)(m / (k + 1));
+    if (p.L == 0) return fail(FZB_E_NGRAM_ZERO, "the subsequence length must be greater than max_l_dist");
+    p.n_ngrams = (int)m / p.L;  // range(0, m-L+1, L)
+    int rc = check_halo(h, (uint64_t)m + k);
+    if (rc) return rc;
+    const bool sampled = !(flags & FZB_F_FORCE_DENSE) && m >= 4 && ((int)m - (int)k - 3) / 4 >= (int)k + 1 &&
+                         (int)m - (int)k - 3 >= 0;
+    p.q = sampled ? 4 : std::min(p.L, 4);
+    res->stats.route = k == 0 ? 0 : (sampled ? 1 : 2);
+
+    CK(cudaSetDevice(h->device));
+    const int64_t nvec = (int64_t)(round_up(h->buf_len, 16) / 16);
+    const int64_t ntiles = (nvec + kTileVecs - 1) / kTileVecs;
+    const size_t smem = kTblSize + 256 * sizeof(uint32_t);
+    rc = set_filter_attrs(smem);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(h->d_bitmap, 0, h->bitmap_words * sizeof(uint32_t), h->stream));
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    if (ntiles > 0) {
+        int grid = (int)std::min<int64_t>(ntiles, (int64_t)h->sm_count * 4);
+        if (sampled)
+            k_filter_sampled<<<grid, kFilterThreads, smem, h->stream>>>(p, nvec, ntiles);
+        else
+            k_filter_dense<<<grid, kFilterThreads, smem, h->stream>>>(p, nvec, ntiles);
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(h->ev[1], h->stream));
+    res->stats.n_launches = 1;
+    res->stats.bytes_scanned = h->buf_len;
+    rc = run_emitting(h, res, [&]() -> int {
+        int grid = h->sm_count * 4;
+        k_verify_lev<<<grid, kVerifyThreads, 0, h->stream>>>(p, h->bitmap_words, h->d_out, h->out_cap,
+                                                             h->d_counters);
+        res->stats.n_launches++;
+        return FZB_OK;
+    });
+    if (rc) return rc;
+    finish_stats(h, res, true);
+    sort_generation_order(res->raw);
+    return FZB_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// LP / generic routes (lp_kernels.cuh)
+// ------------------------------------------------------------------------------------------------
+static int ensure_scratch(fzb_haystack *h, uint64_t words) {
+    if (words <= h->scratch_words) return FZB_OK;
+    if (h->d_scratch) CK(cudaFree(h->d_scratch));
+    h->d_scratch = nullptr;
+    h->scratch_words = 0;
+    CK(cudaMalloc(&h->d_scratch, words * sizeof(uint32_t)));
+    h->scratch_words = words;
+    return FZB_OK;
+}
+
+// Runs an LP-style kernel with growing per-thread candidate capacity until no list overflowed.
+template <class F>
+static int run_lp(fzb_haystack *h, fzb_result *res, F launch) {
+    const int grid = h->sm_count * 4;
+    const uint64_t threads = (uint64_t)grid * kLpThreads;
+    for (int cap = 256; cap <= (1 << 16); cap *= 8) {
+        int rc = ensure_scratch(h, threads * 2 * (uint64_t)cap);
+        if (rc) return rc;
+        rc = run_emitting(h, res, [&]() -> int {
+            launch(grid, cap);
+            res->stats.n_launches++;
+            return FZB_OK;
+        });
+        if (rc) return rc;
+        if (!h->h_counters[CNT_OVERFLOW]) return FZB_OK;
+    }
+    return fail(FZB_E_UNSUPPORTED, "candidate explosion: more than 65536 live candidates for one start");
+}
+
+static int search_lev_lp(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint32_t k, fzb_result *res) {
+    if (k > 0xFFFF) return fail(FZB_E_UNSUPPORTED, "max_l_dist too large");
+    ScanParams p;
+    fill_params(h, pattern, m, p);
+    p.k = (int)k;
+    int rc = check_halo(h, (uint64_t)m + k);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    CK(cudaEventRecord(h->ev[1], h->stream));
+    res->stats.route = 3;
+    res->stats.bytes_scanned = h->buf_len;
+    rc = run_lp(h, res, [&](int grid, int cap) {
+        k_lev_lp<<<grid, kLpThreads, 0, h->stream>>>(p, h->d_scratch, cap, h->d_out, h->out_cap, h->d_counters);
+    });
+    if (rc) return rc;
+    finish_stats(h, res, false);
+    res->stats.filter_ms = res->stats.gpu_ms;
+    sort_canonical(res->raw);
+    return FZB_OK;
+}
+
+static int search_generic(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint32_t max_subs, uint32_t max_ins,
+                          uint32_t max_dels, uint32_t max_l, bool ngrams, uint32_t flags, fzb_result *res) {
+    // after LevenshteinSearchParams normalisation (common.py:100-116) every limit is <= max_l or
+    // max_l <= their sum; the packed candidate keeps 6 bits per counter
+    const uint32_t lim = 63;
+    if (max_l > lim) return fail(FZB_E_UNSUPPORTED, "max_l_dist > 63 is not supported by the generic search");
+    // counters can never exceed max_l (each op costs >= 1 except dels inside ins+del pairs, <= max_l too)
+    max_subs = std::min(max_subs, max_l);
+    max_ins = std::min(max_ins, max_l);
+    max_dels = std::min(max_dels, max_l);
+    ScanParams p;
+    fill_params(h, pattern, m, p);
+    p.k = (int)max_l;
+    p.max_subs = (int)max_subs;
+    p.max_ins = (int)max_ins;
+    p.max_dels = (int)max_dels;
+    int rc = check_halo(h, (uint64_t)m + max_l);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    if (!ngrams) {
+        CK(cudaEventRecord(h->ev[0], h->stream));
+        CK(cudaEventRecord(h->ev[1], h->stream));
+        res->stats.route = 6;
+        res->stats.bytes_scanned = h->buf_len;
+        rc = run_lp(h, res, [&](int grid, int cap) {
+            k_generic_lp<<<grid, kLpThreads, 0, h->stream>>>(p, h->d_scratch, cap, h->d_out, h->out_cap,
+                                                             h->d_counters);
+        });
+        if (rc) return rc;
+        finish_stats(h, res, false);
+        res->stats.filter_ms = res->stats.gpu_ms;
+        sort_canonical(res->raw);
+        return FZB_OK;
+    }
+    p.L = (int)(m / (max_l + 1));
+    if (p.L == 0) return fail(FZB_E_NGRAM_ZERO, "the subsequence length must be greater than max_l_dist");
+    p.n_ngrams = (int)m / p.L;
+    const bool sampled = !(flags & FZB_F_FORCE_DENSE) && m >= 4 && (int)m - (int)max_l - 3 >= 0 &&
+                         ((int)m - (int)max_l - 3) / 4 >= (int)max_l + 1;
+    p.q = sampled ? 4 : std::min(p.L, 4);
+    res->stats.route = 5;
+    const int64_t nvec = (int64_t)(round_up(h->buf_len, 16) / 16);
+    const int64_t ntiles = (nvec + kTileVecs - 1) / kTileVecs;
+    const size_t smem = kTblSize + 256 * sizeof(uint32_t);
+    rc = set_filter_attrs(smem);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(h->d_bitmap, 0, h->bitmap_words * sizeof(uint32_t), h->stream));
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    if (ntiles > 0) {
+        int grid = (int)std::min<int64_t>(ntiles, (int64_t)h->sm_count * 4);
+        if (sampled)
+            k_filter_sampled<<<grid, kFilterThreads, smem, h->stream>>>(p, nvec, ntiles);
+        else
+            k_filter_dense<<<grid, kFilterThreads, smem, h->stream>>>(p, nvec, ntiles);
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(h->ev[1], h->stream));
+    res->stats.n_launches = 1;
+    res->stats.bytes_scanned = h->buf_len;
+    rc = run_lp(h, res, [&](int grid, int cap) {
+        k_verify_generic<<<grid, kLpThreads, 0, h->stream>>>(p, h->bitmap_words, h->d_scratch, cap, h->d_out,
+                                                             h->out_cap, h->d_counters);
+    });
+    if (rc) return rc;
+    finish_stats(h, res, true);
+    // generation order: n-gram major, hit index, then the window's matches in canonical order
+    std::sort(res->raw.begin(), res->raw.end(), [](const RawRec &a, const RawRec &b) {
+        if (a.ngram != b.ngram) return a.ngram < b.ngram;
+        if (a.idx != b.idx) return a.idx < b.idx;
+        if (a.start != b.start) return a.start < b.start;
+        if (a.end != b.end) return a.end < b.end;
+        return a.dist < b.dist;
+    });
+    return FZB_OK;
+}
+
+static int make_result(fzb_result **out, fzb_result **res) {
+    if (!out) return fail(FZB_E_INVALID, "out is NULL");
+    *out = nullptr;
+    *res = new (std::nothrow) fzb_result();
+    if (!*res) return fail(FZB_E_CUDA, "out of host memory");
+    return FZB_OK;
+}
+
+static int check_pattern(const fzb_haystack *h, const uint8_t *pattern, uint32_t m) {
+    if (!h) return fail(FZB_E_INVALID, "haystack handle is NULL");
+    if (!pattern || m == 0) return fail(FZB_E_INVALID, "Given subsequence is empty!");
+    if (m > FZB_MAX_PATTERN) return fail(FZB_E_UNSUPPORTED, "pattern longer than %d bytes", FZB_MAX_PATTERN);
+    return FZB_OK;
+}
+
+extern "C" int fzb_search_levenshtein(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint32_t k,
+                                      uint32_t flags, fzb_result **out) {
+    fzb_result *res;
+    int rc = make_result(out, &res);
+    if (rc) return rc;
+    rc = check_pattern(h, pattern, m);
+    if (rc == FZB_OK) {
+        // find_near_matches_levenshtein (levenshtein.py:9-38)
+        bool ngrams = (k == 0) || (m / (k + 1) >= 3);
+        if (flags & FZB_F_FORCE_NGRAMS) ngrams = true;
+        if (flags & FZB_F_FORCE_LP) ngrams = false;
+        if (ngrams)
+            rc = search_lev_ngrams(h, pattern, m, k, flags, res);
+        else
+            rc = search_lev_lp(h, pattern, m, k, res);
+    }
+    if (rc == FZB_OK && !(flags & FZB_F_NO_FINAL)) {
+        // LevenshteinSearch.consolidate_matches (levenshtein.py:158-160) also applies when k == 0
+        consolidate_recs(res->raw, res->fin);
+    }
+    if (rc) {
+        delete res;
+        return rc;
+    }
+    *out = res;
+    return FZB_OK;
+}
+
+extern "C" int fzb_search_exact(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint32_t flags,
+                                fzb_result **out) {
+    fzb_result *res;
+    int rc = make_result(out, &res);
+    if (rc) return rc;
+    rc = check_pattern(h, pattern, m);
+    if (rc == FZB_E_INVALID && h) rc = fail(FZB_E_INVALID, "subsequence must not be empty");
+    if (rc == FZB_OK) rc = search_lev_ngrams(h, pattern, m, 0, flags, res);
+    if (rc) {
+        delete res;
+        return rc;
+    }
+    res->final_is_raw = true;  // ExactSearch.consolidate_matches is the base no-op (common.py:198-205)
+    *out = res;
+    return FZB_OK;
+}
+
+extern "C" int fzb_search_hamming(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint32_t k,
+                                  uint32_t flags, fzb_result **out) {
+    (void)flags;
+    fzb_result *res;
+    int rc = make_result(out, &res);
+    if (rc) return rc;
+    rc = check_pattern(h, pattern, m);
+    if (rc == FZB_OK) rc = check_halo(h, m);
+    if (rc == FZB_OK) {
+        rc = [&]() -> int {
+            ScanParams p;
+            fill_params(h, pattern, m, p);
+            p.k = (int)std::min<uint32_t>(k, m);
+            CK(cudaSetDevice(h->device));
+            CK(cudaEventRecord(h->ev[0], h->stream));
+            CK(cudaEventRecord(h->ev[1], h->stream));
+            res->stats.route = 4;
+            res->stats.bytes_scanned = h->buf_len;
+            int r2 = run_emitting(h, res, [&]() -> int {
+                k_hamming_scan<<<h->sm_count * 8, kHamThreads, 0, h->stream>>>(p, h->d_out, h->out_cap,
+                                                                               h->d_counters);
+                res->stats.n_launches++;
+                return FZB_OK;
+            });
+            if (r2) return r2;
+            finish_stats(h, res, false);
+            res->stats.filter_ms = res->stats.gpu_ms;
+            sort_canonical(res->raw);
+            for (auto &r : res->raw) r.ngram = -1;
+            return FZB_OK;
+        }();
+    }
+    if (rc) {
+        delete res;
+        return rc;
+    }
+    res->final_is_raw = true;
+    *out = res;
+    return FZB_OK;
+}
+
+extern "C" int fzb_search_generic(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint32_t max_subs,
+                                  uint32_t max_ins, uint32_t max_dels, uint32_t max_l, uint32_t flags,
+                                  fzb_result **out) {
+    fzb_result *res;
+    int rc = make_result(out, &res);
+    if (rc) return rc;
+    rc = check_pattern(h, pattern, m);
+    if (rc == FZB_OK) {
+        // find_near_matches_generic (generic_search.py:25-54)
+        if (max_l == 0 && !(flags & (FZB_F_FORCE_LP | FZB_F_FORCE_NGRAMS))) {
+            rc = search_lev_ngrams(h, pattern, m, 0, flags, res);
+        } else {
+            bool ngrams = m / (max_l + 1) >= 3;
+            if (flags & FZB_F_FORCE_NGRAMS) ngrams = true;
+            if (flags & FZB_F_FORCE_LP) ngrams = false;
+            rc = search_generic(h, pattern, m, max_subs, max_ins, max_dels, max_l, ngrams, flags, res);
+        }
+    }
+    if (rc == FZB_OK && !(flags & FZB_F_NO_FINAL)) consolidate_recs(res->raw, res->fin);
+    if (rc) {
+        delete res;
+        return rc;
+    }
+    *out = res;
+    return FZB_OK;
+}
+
+extern "C" int fzb_find_near_matches(const uint8_t *pattern, uint32_t m, const uint8_t *haystack, uint64_t n,
+                                     uint32_t max_subs, uint32_t max_ins, uint32_t max_dels, uint32_t max_l,
+                                     int device, fzb_result **out) {
+    if (!out) return fail(FZB_E_INVALID, "out is NULL");
+    *out = nullptr;
+    fzb_haystack *h = nullptr;
+    int rc = fzb_haystack_create(haystack, n, device, &h);
+    if (rc) return rc;
+    // choose_search_class (__init__.py:60-83) on normalised limits
+    if (max_l == 0)
+        rc = fzb_search_exact(h, pattern, m, 0, out);
+    else if (max_ins == 0 && max_dels == 0)
+        rc = fzb_search_hamming(h, pattern, m, std::min(max_l, max_subs), 0, out);
+    else if (max_l <= std::min(max_subs, std::min(max_ins, max_dels)))
+        rc = fzb_search_levenshtein(h, pattern, m, max_l, 0, out);
+    else
+        rc = fzb_search_generic(h, pattern, m, max_subs, max_ins, max_dels, max_l, 0, out);
+    fzb_haystack_destroy(h);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// results
+// ------------------------------------------------------------------------------------------------
+extern "C" uint64_t fzb_result_count(const fzb_result *r, int which) {
+    if (!r) return 0;
+    if (which == FZB_RAW || r->final_is_raw) return r->raw.size();
+    return r->fin.size();
+}
+
+extern "C" int fzb_result_copy(const fzb_result *r, int which, int64_t *start, int64_t *end, int32_t *dist,
+                               int32_t *anchor_ngram, int64_t *anchor_idx) {
+    if (!r) return fail(FZB_E_INVALID, "result is NULL");
+    const std::vector<RawRec> &v = (which == FZB_RAW || r->final_is_raw) ? r->raw : r->fin;
+    const bool anchors = (which == FZB_RAW) && (r->stats.route <= 2);
+    for (size_t i = 0; i < v.size(); i++) {
+        if (start) start[i] = v[i].start;
+        if (end) end[i] = v[i].end;
+        if (dist) dist[i] = v[i].dist;
+        if (anchor_ngram) anchor_ngram[i] = anchors ? v[i].ngram : -1;
+        if (anchor_idx) anchor_idx[i] = anchors ? v[i].idx : -1;
+    }
+    return FZB_OK;
+}
+
+extern "C" int fzb_result_stats(const fzb_result *r, fzb_stats *out) {
+    if (!r || !out) return fail(FZB_E_INVALID, "NULL argument");
+    *out = r->stats;
+    return FZB_OK;
+}
+
+extern "C" void fzb_result_destroy(fzb_result *r) { delete r; }

@@ -1,0 +1,418 @@
+// kernels.cuh -- sm_100a kernels of libfuzzb200 (Levenshtein n-gram route, exact search, Hamming).
+//
+// Pipeline of one n-gram search:
+//   k_filter_sampled / k_filter_dense : ONE pass over the haystack (the HBM-bound kernel); marks
+//        64-position "granules" that may contain an n-gram hit of a <=k-error occurrence.
+//   k_verify_lev : re-examines only the marked granules: exact n-gram test at every position,
+//        then the reference's right/left expansion DP per hit; emits raw (start,end,dist) triples.
+#pragma once
+#include "common.cuh"
+
+namespace fzb {
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+constexpr int kTblBits = 15;                   // hashed byte table: 32 KiB of shared memory
+constexpr int kTblSize = 1 << kTblBits;
+constexpr uint32_t kHashMul = 0x9E3779B1u;
+constexpr int kFilterThreads = 256;
+constexpr int kFilterUnroll = 4;               // uint4 loads in flight per thread
+constexpr int kTileVecs = kFilterThreads * kFilterUnroll;  // uint4s per CTA tile (16 KiB)
+
+__device__ __forceinline__ uint32_t hash_word(uint32_t w) { return (w * kHashMul) >> (32 - kTblBits); }
+
+__device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ void mark_range(const ScanParams &p, int64_t lo, int64_t hi) {
+    // mark the granules covering anchors [lo, hi] (global coords), clipped to the owned range
+    if (lo < p.own_lo) lo = p.own_lo;
+    if (hi > p.own_hi - 1) hi = p.own_hi - 1;
+    if (lo > hi) return;
+    int64_t g0 = (lo - p.buf_lo) >> kGranuleShift, g1 = (hi - p.buf_lo) >> kGranuleShift;
+    for (int64_t g = g0; g <= g1; g++) atomicOr(&p.bitmap[g >> 5], 1u << (g & 31));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sampled filter (stride 4).  Soundness (q-sample lemma): a raw match (start,end,dist<=k) of the
+// n-gram search spans an occurrence O=H[start:end] with ED(P,O)<=k and |O|>=m-k.  O contains at
+// least floor((m-k-3)/4) 4-byte-aligned words; k edits touch at most k of them; the host selects
+// this kernel only if floor((m-k-3)/4) >= k+1, so at least one aligned word inside O equals some
+// 4-gram of P.  Each aligned word is looked up (multiplicative hash -> byte table in shared
+// memory); table hits are re-checked exactly against the pattern's 4-grams and then mark every
+// granule that can hold an n-gram anchor of an occurrence containing that word.
+// Per 4 haystack bytes: IMAD (hash) + SHF + LDS.U8 + IMAD (accumulate): ~1 issue slot per byte.
+// ------------------------------------------------------------------------------------------------
+__device__ __noinline__ void sampled_slow_path(const ScanParams &p, const uint32_t *grams, int ngr,
+                                               int64_t word_off, uint32_t w) {
+    bool real = false;
+    for (int o = 0; o < ngr; o++) real |= (grams[o] == w);
+    if (!real) return;
+    int64_t g = p.buf_lo + word_off;
+    // anchor idx of n-gram j (pattern offset s_j in [0, m-L]) of an occurrence containing the word:
+    // idx - s_j - k <= g  and  g + 4 <= idx - s_j + m + k
+    mark_range(p, g - (p.m + p.k - 4), g + (p.m - p.L + p.k));
+}
+
+__global__ void __launch_bounds__(kFilterThreads)
+k_filter_sampled(const ScanParams p, int64_t nvec, int64_t ntiles) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t *tbl = smem;
+    uint32_t *grams = reinterpret_cast<uint32_t *>(smem + kTblSize);
+    for (int i = threadIdx.x; i < kTblSize / 16; i += blockDim.x)
+        reinterpret_cast<uint4 *>(tbl)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    const int ngr = p.m - 3;
+    for (int o = threadIdx.x; o < ngr; o += blockDim.x) {
+        uint32_t w = (uint32_t)p.P[o] | ((uint32_t)p.P[o + 1] << 8) | ((uint32_t)p.P[o + 2] << 16) |
+                     ((uint32_t)p.P[o + 3] << 24);
+        grams[o] = w;
+        tbl[hash_word(w)] = 1;
+    }
+    __syncthreads();
+
+    const uint4 *base = reinterpret_cast<const uint4 *>(p.H);
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t v0 = t * kTileVecs + threadIdx.x;
+        uint4 d[kFilterUnroll];
+#pragma unroll
+        for (int u = 0; u < kFilterUnroll; u++) {
+            int64_t v = v0 + (int64_t)u * kFilterThreads;
+            d[u] = (v < nvec) ? ldg_stream(base + v) : make_uint4(0, 0, 0, 0);
+        }
+        uint32_t acc = 0;  // bit (15 - 4u - i) <-> word i of load u
+#pragma unroll
+        for (int u = 0; u < kFilterUnroll; u++) {
+            acc = acc * 2u + tbl[hash_word(d[u].x)];
+            acc = acc * 2u + tbl[hash_word(d[u].y)];
+            acc = acc * 2u + tbl[hash_word(d[u].z)];
+            acc = acc * 2u + tbl[hash_word(d[u].w)];
+        }
+        if (acc) {
+#pragma unroll
+            for (int u = 0; u < kFilterUnroll; u++) {
+                int64_t v = v0 + (int64_t)u * kFilterThreads;
+                if (v >= nvec) continue;
+                const uint32_t ws[4] = {d[u].x, d[u].y, d[u].z, d[u].w};
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    if (acc & (1u << (4 * kFilterUnroll - 1 - 4 * u - i)))
+                        sampled_slow_path(p, grams, ngr, v * 16 + 4 * i, ws[i]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dense filter (every position): the fallback when the q-sample lemma does not apply (short
+// patterns / large k).  Tests the first q=min(L,4) bytes at EVERY position against the n-gram
+// prefixes (hashed byte table + exact re-check); a hit marks the granule of that position.
+// ------------------------------------------------------------------------------------------------
+__device__ __noinline__ void dense_slow_path(const ScanParams &p, const uint32_t *grams,
+                                             int64_t off, uint32_t w) {
+    bool real = false;
+    for (int j = 0; j < p.n_ngrams; j++) real |= (grams[j] == w);
+    if (!real) return;
+    int64_t g = p.buf_lo + off;
+    mark_range(p, g, g);
+}
+
+__global__ void __launch_bounds__(kFilterThreads)
+k_filter_dense(const ScanParams p, int64_t nvec, int64_t ntiles) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t *tbl = smem;
+    uint32_t *grams = reinterpret_cast<uint32_t *>(smem + kTblSize);
+    for (int i = threadIdx.x; i < kTblSize / 16; i += blockDim.x)
+        reinterpret_cast<uint4 *>(tbl)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    const uint32_t qmask = p.q >= 4 ? 0xFFFFFFFFu : ((1u << (8 * p.q)) - 1u);
+    for (int j = threadIdx.x; j < p.n_ngrams; j += blockDim.x) {
+        uint32_t w = 0;
+        for (int b = 0; b < p.q; b++) w |= (uint32_t)p.P[j * p.L + b] << (8 * b);
+        grams[j] = w;
+        tbl[hash_word(w)] = 1;
+    }
+    __syncthreads();
+
+    const uint4 *base = reinterpret_cast<const uint4 *>(p.H);
+    const uint32_t *words = reinterpret_cast<const uint32_t *>(p.H);
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t v0 = t * kTileVecs + threadIdx.x;
+#pragma unroll 1
+        for (int u = 0; u < kFilterUnroll; u++) {
+            int64_t v = v0 + (int64_t)u * kFilterThreads;
+            if (v >= nvec) continue;
+            uint4 d = __ldg(base + v);
+            uint32_t nx = __ldg(words + (v + 1) * 4);  // buffer is padded by >= 64 bytes
+            const uint32_t ws[5] = {d.x, d.y, d.z, d.w, nx};
+            uint32_t acc = 0;
+#pragma unroll
+            for (int b = 0; b < 16; b++) {
+                uint32_t w = __funnelshift_r(ws[b >> 2], ws[(b >> 2) + 1], 8 * (b & 3)) & qmask;
+                acc = acc * 2u + tbl[hash_word(w)];
+            }
+            if (acc) {
+#pragma unroll
+                for (int b = 0; b < 16; b++) {
+                    if (acc & (1u << (15 - b))) {
+                        uint32_t w = __funnelshift_r(ws[b >> 2], ws[(b >> 2) + 1], 8 * (b & 3)) & qmask;
+                        dense_slow_path(p, grams, v * 16 + b, w);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Expansion DP -- literal device restatement of levenshtein_ngram.py:8-143 (see oracle/fzoracle.c
+// for the same statements on the CPU).  `sub` lives in shared memory, `seq` in global memory; both
+// are walked with a stride of +1 (right expansion) or -1 (left expansion, reversed slices of
+// levenshtein_ngram.py:186-188).  Returns true and (dist,len), or false for (None, None).
+// ------------------------------------------------------------------------------------------------
+struct DpScratch {
+    uint16_t scores[kMaxPattern + 1];
+};
+
+template <int DIR>
+__device__ bool expand_short(const uint8_t *sub, int sublen, const uint8_t *seq, int seqlen, int max_l,
+                             DpScratch &S, int &dist, int &len) {
+    if (sublen == 0) {  // :42-43
+        dist = 0;
+        len = 0;
+        return true;
+    }
+    for (int j = 0; j < sublen; j++) S.scores[j] = (uint16_t)(j + 1);  // :47
+    int min_score = sublen, min_idx = -1;                             // :49-50
+    for (int si = 0; si < seqlen; si++) {                             // :52
+        const uint8_t ch = __ldg(seq + DIR * si);
+        int a = si, c = si + 1;  // :54-55
+        int row_min = 1 << 30;
+        for (int j = 0; j < sublen; j++) {  // :56-63
+            int b = S.scores[j];
+            int v = a + (ch != sub[DIR * j]);
+            v = min(v, min(b + 1, c + 1));
+            c = v;
+            S.scores[j] = (uint16_t)v;
+            row_min = min(row_min, v);
+            a = b;
+        }
+        if (c <= min_score) {  // :66-68
+            min_score = c;
+            min_idx = si;
+        } else if (row_min >= min_score) {  // :71-72
+            break;
+        }
+    }
+    if (min_score <= max_l) {  // :74
+        dist = min_score;
+        len = min_idx + 1;
+        return true;
+    }
+    return false;
+}
+
+template <int DIR>
+__device__ bool expand_long(const uint8_t *sub, int sublen, const uint8_t *seq, int seqlen, int max_l,
+                            DpScratch &S, int &dist, int &len) {
+    if (sublen == 0) {  // :86-88
+        dist = 0;
+        len = 0;
+        return true;
+    }
+    for (int j = 0; j < sublen; j++) S.scores[j] = (uint16_t)(j + 1);  // :92
+    int min_score = sublen, min_idx = -1;                             // :94-95
+    int max_good = max_l;                                             // :96
+    int new_start = 0, new_end = sublen - 1;                          // :97-98
+    bool ns_none = false;
+    for (int si = 0; si < seqlen; si++) {  // :100
+        const uint8_t ch = __ldg(seq + DIR * si);
+        const int rstart = new_start;                 // :102
+        const int rend = min(sublen, new_end + 1);    // :103
+        int a = si, c = si + 1;                       // :105-106
+        if (c <= max_good) {                          // :108-113
+            new_start = 0;
+            ns_none = false;
+            new_end = 0;
+        } else {
+            new_start = 0;
+            ns_none = true;
+            new_end = -1;
+        }
+        for (int j = rstart; j < rend; j++) {  // :115-122
+            int b = S.scores[j];
+            int v = a + (ch != sub[DIR * j]);
+            v = min(v, min(b + 1, c + 1));
+            c = v;
+            S.scores[j] = (uint16_t)v;
+            a = b;
+            if (c <= max_good) {  // :124-130
+                if (ns_none) {
+                    ns_none = false;
+                    new_start = j;
+                }
+                new_end = max(new_end, j + 1 + (max_good - c));
+            }
+        }
+        if (ns_none) break;                     // :133-134
+        if (rend == sublen && c <= min_score) {  // :137-141
+            min_score = c;
+            min_idx = si;
+            if (min_score < max_good) max_good = min_score;
+        }
+    }
+    if (min_score <= max_l) {  // :143
+        dist = min_score;
+        len = min_idx + 1;
+        return true;
+    }
+    return false;
+}
+
+template <int DIR>
+__device__ __forceinline__ bool expand_any(const uint8_t *sub, int sublen, const uint8_t *seq,
+                                           int seqlen, int max_l, DpScratch &S, int &dist, int &len) {
+    if (sublen > max(2 * max_l, 10))  // levenshtein_ngram.py:16
+        return expand_long<DIR>(sub, sublen, seq, seqlen, max_l, S, dist, len);
+    return expand_short<DIR>(sub, sublen, seq, seqlen, max_l, S, dist, len);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Verify kernel for the Levenshtein n-gram route (levenshtein_ngram.py:159-198).  One warp per
+// marked granule; lane <-> anchor position.  Boundary rules are evaluated in GLOBAL coordinates
+// (0 and N), never at shard seams.
+// ------------------------------------------------------------------------------------------------
+constexpr int kVerifyThreads = 128;
+
+__device__ __forceinline__ void emit(RawRec *out, uint32_t cap, uint32_t *counters, int64_t start,
+                                     int64_t end, int64_t idx, int dist, int ngram) {
+    uint32_t slot = atomicAdd(&counters[CNT_OUT], 1u);
+    if (slot < cap) {
+        RawRec r;
+        r.start = start;
+        r.end = end;
+        r.idx = idx;
+        r.dist = dist;
+        r.ngram = ngram;
+        out[slot] = r;
+    }
+}
+
+__device__ void verify_anchor_lev(const ScanParams &p, const uint8_t *sP, int64_t idx, DpScratch &S,
+                                  RawRec *out, uint32_t cap, uint32_t *counters) {
+    const int m = p.m, k = p.k, L = p.L;
+    const int64_t N = p.N;
+    for (int j = 0; j < p.n_ngrams; j++) {
+        const int s = j * L;  // :170
+        // search window of n-gram j, clamped like search_exact.py:29-30   (:174-176)
+        int64_t ws = max((int64_t)0, (int64_t)(s - k));
+        int64_t we = min(N, N - m + s + L + k);
+        ws = max((int64_t)0, min(ws, N));
+        we = max(ws, min(we, N));
+        if (idx < ws || idx + L > we) continue;
+        const uint8_t *h = p.H + (idx - p.buf_lo);
+        bool eq = true;
+        for (int i = 0; i < L; i++) {
+            if (__ldg(h + i) != sP[s + i]) {
+                eq = false;
+                break;
+            }
+        }
+        if (!eq) continue;
+        const int64_t p0 = idx - s;
+        // right: _expand(P[s+L:], H[idx+L : p0+m+k], k)   (:178-182)
+        int64_t rhi = min(N, p0 + m + k);
+        int rlen = (int)max((int64_t)0, rhi - (idx + L));
+        int dr, rs;
+        if (!expand_any<1>(sP + s + L, m - s - L, h + L, rlen, k, S, dr, rs)) continue;
+        // left: _expand(P[:s][::-1], H[max(0,p0-(k-dr)) : idx][::-1], k-dr)   (:185-189)
+        int64_t llo = max((int64_t)0, p0 - (k - dr));
+        int llen = (int)max((int64_t)0, idx - llo);
+        int dl, ls;
+        if (!expand_any<-1>(sP + s - 1, s, h - 1, llen, k - dr, S, dl, ls)) continue;
+        emit(out, cap, counters, idx - ls, idx + L + rs, idx, dl + dr, j);  // :194-198
+    }
+}
+
+__global__ void __launch_bounds__(kVerifyThreads)
+k_verify_lev(const ScanParams p, uint64_t bitmap_words, RawRec *out, uint32_t cap, uint32_t *counters) {
+    __shared__ uint8_t sP[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sP[i] = p.P[i];
+    __syncthreads();
+    DpScratch S;
+    const int lane = threadIdx.x & 31;
+    const uint64_t gwarp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t wbase = gwarp * 32; wbase < bitmap_words; wbase += nwarps * 32) {
+        const uint64_t wi = wbase + lane;
+        uint32_t bits = wi < bitmap_words ? p.bitmap[wi] : 0u;
+        unsigned active = __ballot_sync(0xFFFFFFFFu, bits != 0);
+        while (active) {
+            const int src = __ffs(active) - 1;
+            active &= active - 1;
+            uint32_t b = __shfl_sync(0xFFFFFFFFu, bits, src);
+            if (lane == 0) atomicAdd(&counters[CNT_CAND], (uint32_t)__popc(b));
+            while (b) {
+                const int bit = __ffs(b) - 1;
+                b &= b - 1;
+                const int64_t gbase = p.buf_lo + (((int64_t)(wbase + src) * 32 + bit) << kGranuleShift);
+#pragma unroll 1
+                for (int half = 0; half < kGranule / 32; half++) {
+                    const int64_t idx = gbase + half * 32 + lane;
+                    if (idx >= p.own_lo && idx < p.own_hi)
+                        verify_anchor_lev(p, sP, idx, S, out, cap, counters);
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Hamming (substitutions only): every start p in [0, N-m] with Hamming(P, H[p:p+m]) <= k
+// (substitutions_only.py:37-215 == brute force).  v1: direct per-position count with
+// early exit at k+1 mismatches, 4 bytes per step.
+// ------------------------------------------------------------------------------------------------
+constexpr int kHamThreads = 256;
+
+__global__ void __launch_bounds__(kHamThreads)
+k_hamming_scan(const ScanParams p, RawRec *out, uint32_t cap, uint32_t *counters) {
+    __shared__ uint8_t sP[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sP[i] = p.P[i];
+    __syncthreads();
+    const int m = p.m, k = p.k;
+    const int64_t last = min(p.own_hi, p.N - m + 1);  // exclusive bound on starts
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t pos = p.own_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pos < last;
+         pos += stride) {
+        const uint8_t *h = p.H + (pos - p.buf_lo);
+        int nd = 0;
+        for (int i = 0; i < m; i++) {
+            nd += (__ldg(h + i) != sP[i]);
+            if (nd > k) break;
+        }
+        if (nd <= k) emit(out, cap, counters, pos, pos + m, pos, nd, 0);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Synthetic corpus fill (bench / tests): byte i = alphabet[hash(seed, i)], counter based.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_fill_synth(uint8_t *H, int64_t buf_lo, int64_t nwords, uint64_t seed,
+                             const uint8_t *alphabet_g, uint32_t alen) {
+    __shared__ uint8_t alphabet[256];
+    for (int i = threadIdx.x; i < (int)alen; i += blockDim.x) alphabet[i] = alphabet_g[i];
+    __syncthreads();
+    uint32_t *W = reinterpret_cast<uint32_t *>(H);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    // buf_lo is required to be a multiple of 4 by the host
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += stride)
+        W[i] = synth_word(seed, (uint64_t)(buf_lo / 4 + i), alphabet, alen);
+}
+
+}  // namespace fzb

@@ -1,0 +1,283 @@
+// lp_kernels.cuh -- the "linear programming" NFA routes and the generic (per-operation-limit) search.
+//
+// Both reference NFAs keep a list of candidates that never interact, so the search
+// decomposes by START POSITION: one thread simulates the candidates born at one start, statement
+// by statement as the reference does (duplicate candidates are kept as separate list entries, so
+// the raw output is the reference's multiset, not merely its set).  The two candidate lists of a
+// thread live in a global scratch slab (cap entries each); an overflow sets CNT_OVERFLOW and the
+// host retries with a larger slab.
+//
+//   k_lev_lp            levenshtein.py:52-148   (route L = m//(k+1) < 3)
+//   k_generic_lp        generic_search.py:57-177 over the whole sequence
+//   k_verify_generic    generic_search.py:198-237: per n-gram hit, the same NFA on the clipped
+//                       window H[max(0,p0-k) : min(N,p0+m+k)] (window end acts as end of input)
+#pragma once
+#include "kernels.cuh"
+
+namespace fzb {
+
+enum { CNT_OVERFLOW = 2 };
+
+// ---- Levenshtein LP ------------------------------------------------------------------------------
+// candidate = (subseq_index j, dist d) packed j | d<<16
+__device__ __forceinline__ bool lp_push(uint32_t *list, int &n, int cap, int j, int d) {
+    if (n >= cap) return false;
+    list[n++] = (uint32_t)j | ((uint32_t)d << 16);
+    return true;
+}
+
+// Simulates the candidates whose start is `start` (global).  Returns false on list overflow.
+__device__ bool sim_lev_lp(const ScanParams &p, const uint8_t *sP, int64_t start, uint32_t *A, uint32_t *B,
+                           int cap, RawRec *out, uint32_t ocap, uint32_t *counters) {
+    const int m = p.m, k = p.k;
+    const int64_t N = p.N;
+    const uint8_t *H = p.H - p.buf_lo;  // index with global positions
+    int nA = 0;
+    {
+        const uint8_t ch = __ldg(H + start);
+        // make_char2first_subseq_index (levenshtein.py:44-49): first index of ch in P[:k+1]
+        int j0 = -1;
+        const int lim = min(k, m - 1);
+        for (int j = 0; j <= lim; j++)
+            if (sP[j] == ch) {
+                j0 = j;
+                break;
+            }
+        if (j0 < 0) return true;  // :76-77
+        if (j0 + 1 == m) {        // :78-79
+            emit(out, ocap, counters, start, start + 1, start, j0, 1);
+            return true;
+        }
+        A[0] = (uint32_t)(j0 + 1) | ((uint32_t)j0 << 16);  // :80-81
+        nA = 1;
+    }
+    int64_t i = start + 1;
+    for (; i < N && nA > 0; i++) {  // :73
+        const uint8_t ch = __ldg(H + i);
+        int nB = 0;
+        for (int c = 0; c < nA; c++) {  // :83
+            const int j = (int)(A[c] & 0xFFFFu), d = (int)(A[c] >> 16);
+            if (sP[j] == ch) {  // :85
+                if (j + 1 == m)
+                    emit(out, ocap, counters, start, i + 1, start, d, 1);  // :87-88
+                else if (!lp_push(B, nB, cap, j + 1, d))                  // :90-93
+                    return false;
+            } else {
+                if (d == k) continue;                                 // :100-101
+                if (!lp_push(B, nB, cap, j, d + 1)) return false;     // :104
+                if (i + 1 < N && j + 1 < m)                           // :106
+                    if (!lp_push(B, nB, cap, j + 1, d + 1)) return false;  // :109-112
+                for (int t = 1; t <= k - d; t++) {                    // :115
+                    if (j + t == m) {                                 // :118
+                        emit(out, ocap, counters, start, i + 1, start, d + t, 1);
+                        break;
+                    } else if (sP[j + t] == ch) {  // :126
+                        if (j + t + 1 == m)        // :129
+                            emit(out, ocap, counters, start, i + 1, start, d + t, 1);
+                        else if (!lp_push(B, nB, cap, j + 1 + t, d + t))  // :135-138
+                            return false;
+                        break;
+                    }
+                }
+            }
+        }
+        uint32_t *T = A;  // :143
+        A = B;
+        B = T;
+        nA = nB;
+    }
+    if (i >= N) {  // reached the end of the sequence with live candidates (:145-148)
+        for (int c = 0; c < nA; c++) {
+            const int j = (int)(A[c] & 0xFFFFu), d = (int)(A[c] >> 16);
+            const int dist = d + m - j;
+            if (dist <= k) emit(out, ocap, counters, start, N, start, dist, 1);
+        }
+    }
+    return true;
+}
+
+constexpr int kLpThreads = 128;
+
+__global__ void __launch_bounds__(kLpThreads)
+k_lev_lp(const ScanParams p, uint32_t *scratch, int cap, RawRec *out, uint32_t ocap, uint32_t *counters) {
+    __shared__ uint8_t sP[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sP[i] = p.P[i];
+    __syncthreads();
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    uint32_t *A = scratch + tid * 2 * (int64_t)cap, *B = A + cap;
+    if (p.k >= p.m) {  // levenshtein.py:62-65: an empty match (i,i,m) at every index 0..N
+        const int64_t hi = (p.own_hi == p.N) ? p.N + 1 : p.own_hi;
+        for (int64_t i = p.own_lo + tid; i < hi; i += stride) emit(out, ocap, counters, i, i, i, p.m, 1);
+        return;
+    }
+    const int64_t hi = min(p.own_hi, p.N);
+    for (int64_t s = p.own_lo + tid; s < hi; s += stride)
+        if (!sim_lev_lp(p, sP, s, A, B, cap, out, ocap, counters)) atomicExch(&counters[CNT_OVERFLOW], 1u);
+}
+
+// ---- generic NFA ---------------------------------------------------------------------------------
+// candidate = (subseq_index j, l_dist, n_subs, n_ins, n_dels) packed 8|6|6|6|6 bits
+__device__ __forceinline__ uint32_t gpack(int j, int l, int ns, int ni, int nd) {
+    return (uint32_t)j | ((uint32_t)l << 8) | ((uint32_t)ns << 14) | ((uint32_t)ni << 20) | ((uint32_t)nd << 26);
+}
+__device__ __forceinline__ bool g_push(uint32_t *list, int &n, int cap, uint32_t v) {
+    if (n >= cap) return false;
+    list[n++] = v;
+    return true;
+}
+
+// Candidates born at `start`, over the sequence that ends (exclusive) at `seq_end` (both global).
+// anchor_idx / anchor_ngram tag the emitted records (n-gram hit that opened the window, or start).
+__device__ bool sim_generic(const ScanParams &p, const uint8_t *sP, int64_t start, int64_t seq_end, uint32_t *A,
+                            uint32_t *B, int cap, int64_t anchor_idx, int anchor_ngram, RawRec *out,
+                            uint32_t ocap, uint32_t *counters) {
+    const int m = p.m, max_l = p.k, max_subs = p.max_subs, max_ins = p.max_ins, max_dels = p.max_dels;
+    const uint8_t *H = p.H - p.buf_lo;
+    A[0] = gpack(0, 0, 0, 0, 0);  // generic_search.py:81
+    int nA = 1;
+    int64_t i = start;
+    for (; i < seq_end && nA > 0; i++) {  // :79
+        const uint8_t ch = __ldg(H + i);
+        int nB = 0;
+        for (int c = 0; c < nA; c++) {  // :84
+            const uint32_t v = A[c];
+            const int j = (int)(v & 0xFFu), l = (int)((v >> 8) & 63u), ns = (int)((v >> 14) & 63u),
+                      ni = (int)((v >> 20) & 63u), nd = (int)((v >> 26) & 63u);
+            if (ch == sP[j]) {  // :86
+                if (j + 1 == m)
+                    emit(out, ocap, counters, start, i + 1, anchor_idx, l, anchor_ngram);  // :88-89
+                else if (!g_push(B, nB, cap, gpack(j + 1, l, ns, ni, nd)))                // :91-94
+                    return false;
+            } else {
+                if (l == max_l) continue;  // :101-102
+                if (ni < max_ins)          // :104-109
+                    if (!g_push(B, nB, cap, gpack(j, l + 1, ns, ni + 1, nd))) return false;
+                if (j + 1 < m) {            // :111
+                    if (ns < max_subs) {    // :112-119
+                        if (!g_push(B, nB, cap, gpack(j + 1, l + 1, ns + 1, ni, nd))) return false;
+                    } else if (nd < max_dels && ni < max_ins) {  // :120-128
+                        if (!g_push(B, nB, cap, gpack(j + 1, l + 1, ns, ni + 1, nd + 1))) return false;
+                    }
+                } else {  // :129-138
+                    if (ns < max_subs || (nd < max_dels && ni < max_ins))
+                        emit(out, ocap, counters, start, i + 1, anchor_idx, l + 1, anchor_ngram);
+                }
+                const int lim = min(max_dels - nd, max_l - l);  // :141
+                for (int t = 1; t <= lim; t++) {
+                    if (j + t == m) {  // :144-147  (end excludes the current char)
+                        emit(out, ocap, counters, start, i, anchor_idx, l + t, anchor_ngram);
+                        break;
+                    } else if (sP[j + t] == ch) {  // :151
+                        if (j + t + 1 == m)        // :154-156
+                            emit(out, ocap, counters, start, i, anchor_idx, l + t, anchor_ngram);
+                        else if (!g_push(B, nB, cap, gpack(j + 1 + t, l + t, ns, ni, nd + t)))  // :159-164
+                            return false;
+                        break;
+                    }
+                }
+            }
+        }
+        uint32_t *T = A;  // :170
+        A = B;
+        B = T;
+        nA = nB;
+    }
+    if (i >= seq_end) {  // :172-177
+        for (int c = 0; c < nA; c++) {
+            const uint32_t v = A[c];
+            const int j = (int)(v & 0xFFu), l = (int)((v >> 8) & 63u), nd = (int)((v >> 26) & 63u);
+            const int t = m - j;
+            if (nd + t <= max_dels && l + t <= max_l)
+                emit(out, ocap, counters, start, seq_end, anchor_idx, l + t, anchor_ngram);
+        }
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(kLpThreads)
+k_generic_lp(const ScanParams p, uint32_t *scratch, int cap, RawRec *out, uint32_t ocap, uint32_t *counters) {
+    __shared__ uint8_t sP[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sP[i] = p.P[i];
+    __syncthreads();
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    uint32_t *A = scratch + tid * 2 * (int64_t)cap, *B = A + cap;
+    const int64_t hi = min(p.own_hi, p.N);
+    for (int64_t s = p.own_lo + tid; s < hi; s += stride)
+        if (!sim_generic(p, sP, s, p.N, A, B, cap, s, 1, out, ocap, counters))
+            atomicExch(&counters[CNT_OVERFLOW], 1u);
+}
+
+// Generic n-gram route: one warp per marked granule.  Phase 1: lane <-> anchor position, exact
+// n-gram test (generic_search.py:221-227).  Phase 2: for every hit, the lanes of the warp split
+// the starts of the clipped window (:229-237) and run the NFA.
+__global__ void __launch_bounds__(kLpThreads)
+k_verify_generic(const ScanParams p, uint64_t bitmap_words, uint32_t *scratch, int cap, RawRec *out,
+                 uint32_t ocap, uint32_t *counters) {
+    __shared__ uint8_t sP[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sP[i] = p.P[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t *A = scratch + tid * 2 * (int64_t)cap, *B = A + cap;
+    const uint64_t gwarp = (uint64_t)tid >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const int m = p.m, k = p.k, L = p.L;
+    const int64_t N = p.N;
+    for (uint64_t wbase = gwarp * 32; wbase < bitmap_words; wbase += nwarps * 32) {
+        const uint64_t wi = wbase + lane;
+        uint32_t bits = wi < bitmap_words ? p.bitmap[wi] : 0u;
+        unsigned active = __ballot_sync(0xFFFFFFFFu, bits != 0);
+        while (active) {
+            const int src = __ffs(active) - 1;
+            active &= active - 1;
+            uint32_t b = __shfl_sync(0xFFFFFFFFu, bits, src);
+            if (lane == 0) atomicAdd(&counters[CNT_CAND], (uint32_t)__popc(b));
+            while (b) {
+                const int bit = __ffs(b) - 1;
+                b &= b - 1;
+                const int64_t gbase = p.buf_lo + (((int64_t)(wbase + src) * 32 + bit) << kGranuleShift);
+                for (int half = 0; half < kGranule / 32; half++) {
+                    const int64_t idx = gbase + half * 32 + lane;
+                    const bool owned = idx >= p.own_lo && idx < p.own_hi;
+                    for (int j = 0; j < p.n_ngrams; j++) {
+                        const int s = j * L;
+                        bool hit = false;
+                        if (owned) {
+                            int64_t ws = max((int64_t)0, (int64_t)(s - k));  // :223
+                            int64_t we = min(N, N - m + s + L + k);          // :224
+                            if (we > ws) {                                   // :225-226
+                                ws = max((int64_t)0, min(ws, N));
+                                we = max(ws, min(we, N));
+                                if (idx >= ws && idx + L <= we) {
+                                    const uint8_t *h = p.H + (idx - p.buf_lo);
+                                    hit = true;
+                                    for (int i = 0; i < L; i++)
+                                        if (__ldg(h + i) != sP[s + i]) {
+                                            hit = false;
+                                            break;
+                                        }
+                                }
+                            }
+                        }
+                        unsigned hits = __ballot_sync(0xFFFFFFFFu, hit);
+                        while (hits) {
+                            const int hl = __ffs(hits) - 1;
+                            hits &= hits - 1;
+                            const int64_t hidx = gbase + half * 32 + hl;
+                            const int64_t p0 = hidx - s;
+                            const int64_t wlo = max((int64_t)0, p0 - k);      // :231
+                            const int64_t whi = min(N, p0 + m + k);
+                            for (int64_t st = wlo + lane; st < whi; st += 32)
+                                if (!sim_generic(p, sP, st, whi, A, B, cap, hidx, j, out, ocap, counters))
+                                    atomicExch(&counters[CNT_OVERFLOW], 1u);
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace fzb

@@ -1,0 +1,178 @@
+/*
+ * fuzzb200.h -- C-ABI of libfuzzb200.so: the B200-native (sm_100a) replacement for the
+ * fuzzysearch hot path (bounded-Levenshtein / Hamming / generic near-match search of a short
+ * byte pattern in a long byte haystack).
+ *
+ * Boundary.  In the reference the hot path sits behind the four search classes selected by
+ * fuzzysearch.choose_search_class (src/fuzzysearch/__init__.py:60-83) -- ExactSearch,
+ * SubstitutionsOnlySearch, LevenshteinSearch, GenericSearch -- each a FuzzySearchBase
+ * (src/fuzzysearch/common.py:192-209) with search(subsequence, sequence, search_params) and
+ * consolidate_matches(matches).  The reference's own native seams (search_exact_byteslike,
+ * _common.c:5-112; c_expand_short/long, _levenshtein_ngrams.pyx:9-154;
+ * substitutions_only_find_near_matches_ngrams_byteslike, _substitutions_only.c:4-50;
+ * c_find_near_matches_generic_linear_programming, _generic_search.pyx:25-56) are per-candidate /
+ * per-pass calls -- the wrong granularity for a GPU -- so each entry point below replaces one whole
+ * search-class call instead.  INTEGRATION.md shows the ctypes stub that binds them.
+ *
+ * Conventions: every function returns 0 on success or a negative FZB_E_* code; the message is
+ * available from fzb_last_error() (thread-local).  No C++ exceptions, Python objects or torch types
+ * cross the ABI.  The caller owns every input buffer (copied during the call, never retained) and
+ * every handle (explicit destroy).  Distinct handles may be used from distinct threads.
+ *
+ * Semantics are bit-exact with the reference's PURE-PYTHON path: raw match
+ * streams are element-for-element those of the cited generators; the consolidated list follows
+ * consolidate_overlapping_matches (common.py:185-189) with ties inside a group (which the reference
+ * leaves to set-iteration order) broken towards the smallest (start, end).
+ */
+#ifndef FUZZB200_H
+#define FUZZB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+
+#define FZB_VERSION 100 /* 0.1.0 */
+
+/* error codes */
+#define FZB_OK 0
+#define FZB_E_INVALID (-1)     /* bad argument (reference raises ValueError/TypeError) */
+#define FZB_E_CUDA (-2)        /* CUDA runtime failure (no device, OOM, launch error) */
+#define FZB_E_UNSUPPORTED (-3) /* valid for the reference but outside this library's limits */
+#define FZB_E_NGRAM_ZERO (-4)  /* "the subsequence length must be greater than max_l_dist" */
+
+#define FZB_MAX_PATTERN 255 /* bytes */
+
+/* which result list */
+#define FZB_RAW 0   /* the raw match stream, reference generation order */
+#define FZB_FINAL 1 /* after the search class's consolidate_matches() */
+
+/* fzb_search_* flags */
+#define FZB_F_NO_FINAL 1u     /* skip consolidation (raw stream only) */
+#define FZB_F_FORCE_DENSE 2u  /* force the every-position candidate filter (testing) */
+#define FZB_F_FORCE_LP 4u     /* Levenshtein/generic: force the "linear programming" route */
+#define FZB_F_FORCE_NGRAMS 8u /* Levenshtein/generic/Hamming: force the n-gram route */
+
+typedef struct fzb_haystack fzb_haystack; /* a device-resident sequence (or one shard of it) */
+typedef struct fzb_result fzb_result;     /* the matches of one search */
+
+int fzb_version(void);
+/* number of usable CUDA devices (0 if none / driver missing); never fails */
+int fzb_device_count(void);
+const char *fzb_last_error(void);
+
+/* Upload `n` bytes of host memory to `device` as a whole sequence [0, n). */
+int fzb_haystack_create(const uint8_t *host, uint64_t n, int device, fzb_haystack **out);
+
+/*
+ * Multi-GPU shard: the global sequence has `global_len` bytes; this handle
+ * holds bytes [buf_lo, buf_lo + buf_len) of it (`host` points at byte buf_lo) and OWNS the matches
+ * whose anchor (n-gram hit index / Hamming start / LP start) lies in [own_lo, own_hi).  The caller
+ * must supply a halo: buf_lo <= max(0, own_lo - halo) and buf_lo + buf_len >= min(global_len,
+ * own_hi + halo) with halo = len(pattern) + max_l_dist of the searches to be run (checked per
+ * search).  Window clipping rules of the reference apply at 0 and global_len only, never at shard
+ * seams, so the union of the shards' raw streams equals the single-device raw stream.
+ */
+int fzb_haystack_create_shard(const uint8_t *host, uint64_t buf_len, uint64_t buf_lo,
+                              uint64_t global_len, uint64_t own_lo, uint64_t own_hi, int device,
+                              fzb_haystack **out);
+
+/* Adopt an existing device allocation (not freed by destroy).  `dev_ptr` must be 16-byte aligned
+ * and readable for buf_len rounded up to a multiple of 16 bytes plus 64. Used by bench.py to scan
+ * corpora generated on the device. */
+int fzb_haystack_adopt_device(const void *dev_ptr, uint64_t buf_len, uint64_t buf_lo,
+                              uint64_t global_len, uint64_t own_lo, uint64_t own_hi, int device,
+                              fzb_haystack **out);
+
+/* Allocate an uninitialised device-resident sequence of n bytes and return its device pointer (for
+ * callers that fill it with their own kernels / cudaMemcpy). */
+int fzb_haystack_alloc(uint64_t n, int device, fzb_haystack **out, void **dev_ptr);
+
+/* Fill an fzb_haystack_alloc'ed sequence with a seeded synthetic corpus ON THE DEVICE: byte i =
+ * alphabet[hash64(seed, i) % alphabet_len] (counter-based, so any shard of the global sequence can
+ * be generated independently); host code can reproduce any slice with fzb_synth_host. */
+int fzb_haystack_fill_synthetic(fzb_haystack *h, const uint8_t *alphabet, uint32_t alphabet_len,
+                                uint64_t seed);
+void fzb_synth_host(uint8_t *dst, uint64_t global_offset, uint64_t n, const uint8_t *alphabet,
+                    uint32_t alphabet_len, uint64_t seed);
+/* Overwrite bytes [global_offset, global_offset+n) of the sequence (must lie inside the buffer). */
+int fzb_haystack_write(fzb_haystack *h, uint64_t global_offset, const uint8_t *src, uint64_t n);
+/* Read bytes back (for Match.matched and tests). */
+int fzb_haystack_read(fzb_haystack *h, uint64_t global_offset, uint8_t *dst, uint64_t n);
+
+uint64_t fzb_haystack_len(const fzb_haystack *h); /* global length */
+void fzb_haystack_destroy(fzb_haystack *h);
+
+/*
+ * LevenshteinSearch.search (levenshtein.py:151-156 -> find_near_matches_levenshtein :9-38):
+ * k == 0 exact; len(pattern)//(k+1) >= 3 the n-gram search (levenshtein_ngram.py:159-198);
+ * else the "linear programming" NFA (levenshtein.py:52-148).  FINAL =
+ * consolidate_overlapping_matches.
+ */
+int fzb_search_levenshtein(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint32_t max_l_dist,
+                           uint32_t flags, fzb_result **out);
+
+/*
+ * SubstitutionsOnlySearch.search (substitutions_only.py:288-297 ->
+ * find_near_matches_substitutions :37-63): every start p in [0, n-m] with
+ * Hamming(pattern, H[p:p+m]) <= max_subs, ascending, dist = exact Hamming distance.
+ * FINAL == RAW (consolidate_matches is the base no-op, common.py:198-205).
+ */
+int fzb_search_hamming(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint32_t max_subs,
+                       uint32_t flags, fzb_result **out);
+
+/*
+ * GenericSearch.search (generic_search.py:256-261 -> find_near_matches_generic :25-54) with the
+ * normalised limits of LevenshteinSearchParams (common.py:100-116).
+ */
+int fzb_search_generic(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint32_t max_subs,
+                       uint32_t max_ins, uint32_t max_dels, uint32_t max_l_dist, uint32_t flags,
+                       fzb_result **out);
+
+/* ExactSearch.search (search_exact.py:80-85): all (overlapping) occurrences. FINAL == RAW. */
+int fzb_search_exact(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint32_t flags,
+                     fzb_result **out);
+
+/*
+ * One-shot convenience with HOST buffers (what find_near_matches() does): upload, dispatch like
+ * choose_search_class (__init__.py:60-83) on the already normalised limits, search, consolidate.
+ */
+int fzb_find_near_matches(const uint8_t *pattern, uint32_t m, const uint8_t *haystack, uint64_t n,
+                          uint32_t max_subs, uint32_t max_ins, uint32_t max_dels,
+                          uint32_t max_l_dist, int device, fzb_result **out);
+
+uint64_t fzb_result_count(const fzb_result *r, int which);
+/* Copy out `which` list; any pointer may be NULL.  anchor_ngram / anchor_idx are only meaningful
+ * for the RAW list of n-gram searches (n-gram ordinal and hit index), else -1. */
+int fzb_result_copy(const fzb_result *r, int which, int64_t *start, int64_t *end, int32_t *dist,
+                    int32_t *anchor_ngram, int64_t *anchor_idx);
+
+typedef struct {
+    double gpu_ms;          /* CUDA-event time of all kernels of the search */
+    double filter_ms;       /* ... of the haystack scan (filter) kernel alone */
+    uint64_t bytes_scanned; /* haystack bytes the scan kernel read (algorithmic bytes) */
+    uint64_t n_candidates;  /* granules / windows handed to the verify stage */
+    uint32_t n_launches;    /* kernels launched */
+    uint32_t route;         /* 0 exact, 1 n-grams (sampled filter), 2 n-grams (dense filter), 3 LP,
+                               4 hamming, 5 generic n-grams, 6 generic LP */
+} fzb_stats;
+int fzb_result_stats(const fzb_result *r, fzb_stats *out);
+void fzb_result_destroy(fzb_result *r);
+
+/* consolidate_overlapping_matches (common.py:185-189) on caller-supplied triples (used to merge
+ * per-shard raw streams after the multi-GPU gather).  Writes at most n winners; returns the count
+ * (>= 0) or a negative error. */
+int64_t fzb_consolidate(const int64_t *start, const int64_t *end, const int32_t *dist, uint64_t n,
+                        int64_t *out_start, int64_t *out_end, int32_t *out_dist);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* FUZZB200_H */

@@ -1,0 +1,101 @@
+"""GPU parity against the committed golden fixtures (outputs of the real reference), through the
+C-ABI of libfuzzb200.so.  Every record of tests/golden/*.json that names a hot-path function is
+replayed on the device; results must be bit-exact (raw streams) / tie-aware equal (final lists)."""
+import pytest
+
+import oracle
+from fuzzysearch_b200 import _native, find_near_matches
+from parity import assert_final_parity, load_golden, tup
+
+pytestmark = pytest.mark.gpu
+
+F = _native
+
+
+def _b(h):
+    return bytes.fromhex(h)
+
+
+def _replay(records, cuda_device):
+    counts = {}
+    for rec in records:
+        fn, a = rec["fn"], rec["args"]
+        ctx = "%s%r" % (fn, a)
+        if fn in ("expand", "expand_short", "expand_long", "consolidate", "lev_raw", "generic_raw", "subs"):
+            continue  # internal helpers: covered through the search entry points below
+        if fn == "find_near_matches":
+            pat, hay = _b(a[0]), _b(a[1])
+            if "exc" in rec:
+                with pytest.raises((ValueError, TypeError)):
+                    find_near_matches(pat, hay, *a[2:6])
+                counts[fn] = counts.get(fn, 0) + 1
+                continue
+            ours = [(m.start, m.end, m.dist) for m in find_near_matches(pat, hay, *a[2:6])]
+            subs, ins, dels, l = oracle.normalize_params(*a[2:6])
+            if l == 0 or (ins == 0 and dels == 0):
+                assert ours == tup(rec["result"]), ctx
+            else:
+                _, raw = oracle.find_near_matches(pat, hay, *a[2:6], return_raw=True)
+                assert_final_parity(ours, rec["result"], raw, ctx)
+            counts[fn] = counts.get(fn, 0) + 1
+            continue
+        if "exc" in rec:
+            continue
+        pat, hay = _b(a[0]), _b(a[1])
+        if len(pat) == 0 or len(pat) > F.FZB_MAX_PATTERN:
+            continue
+        exp = rec["result"]
+        hs = F.Haystack.from_host(hay)
+        try:
+            if fn == "lev_ngrams_raw":
+                for flags in (F.F_FORCE_NGRAMS | F.F_NO_FINAL,
+                              F.F_FORCE_NGRAMS | F.F_NO_FINAL | F.F_FORCE_DENSE):
+                    r = hs.search_levenshtein(pat, a[2], flags)
+                    assert r.triples(F.RAW) == tup(exp), ctx  # generation order
+                    r.close()
+            elif fn == "lev_lp_raw":
+                r = hs.search_levenshtein(pat, a[2], F.F_FORCE_LP | F.F_NO_FINAL)
+                assert sorted(r.triples(F.RAW)) == sorted(tup(exp)), ctx
+                r.close()
+            elif fn == "generic_lp_raw":
+                if a[5] > 63:
+                    continue
+                r = hs.search_generic(pat, a[2], a[3], a[4], a[5], F.F_FORCE_LP | F.F_NO_FINAL)
+                assert sorted(r.triples(F.RAW)) == sorted(tup(exp)), ctx
+                r.close()
+            elif fn == "generic_ngrams_raw":
+                if a[5] > 63:
+                    continue
+                for flags in (F.F_FORCE_NGRAMS | F.F_NO_FINAL,
+                              F.F_FORCE_NGRAMS | F.F_NO_FINAL | F.F_FORCE_DENSE):
+                    r = hs.search_generic(pat, a[2], a[3], a[4], a[5], flags)
+                    assert sorted(r.triples(F.RAW)) == sorted(tup(exp)), ctx
+                    r.close()
+            elif fn in ("subs_lp", "subs_ngrams"):
+                r = hs.search_hamming(pat, a[2])
+                assert r.triples(F.RAW) == tup(exp), ctx
+                r.close()
+            elif fn == "search_exact":
+                if a[2] != 0 or a[3] is not None:
+                    continue
+                r = hs.search_exact(pat)
+                assert [s for s, _, _ in r.triples(F.RAW)] == list(exp), ctx
+                r.close()
+            else:
+                raise KeyError(fn)
+            counts[fn] = counts.get(fn, 0) + 1
+        finally:
+            hs.close()
+    return counts
+
+
+def test_gpu_replays_reference_suite_calls(cuda_device):
+    counts = _replay(load_golden("ref_suite_calls.json"), cuda_device)
+    for fn in ("lev_ngrams_raw", "lev_lp_raw", "generic_lp_raw", "generic_ngrams_raw", "subs_lp",
+               "subs_ngrams", "search_exact", "find_near_matches"):
+        assert counts.get(fn, 0) > 0, fn
+
+
+def test_gpu_replays_reference_fuzz(cuda_device):
+    counts = _replay(load_golden("ref_fuzz.json"), cuda_device)
+    assert sum(counts.values()) > 3000

@@ -1,0 +1,163 @@
+"""GPU vs CPU oracle on seeded corpora with planted near-matches (sizes the oracle handles in
+seconds), incl. sharded searches whose union must equal the single-shard raw stream."""
+import numpy as np
+import pytest
+
+import oracle
+from corpus import ASCII, DNA, make_corpus
+from fuzzysearch_b200 import _native as F
+from parity import tup
+
+pytestmark = pytest.mark.gpu
+
+
+def _raw(res):
+    s, e, d, ng, ix = res.arrays(F.RAW, anchors=True)
+    return list(zip(s.tolist(), e.tolist(), d.tolist())), ng.tolist(), ix.tolist()
+
+
+@pytest.mark.parametrize("alphabet,n,m,k,flags", [
+    (ASCII, 1 << 22, 20, 2, 0),
+    (ASCII, 1 << 22, 20, 2, F.F_FORCE_DENSE),
+    (ASCII, (1 << 20) + 13, 32, 3, 0),
+    (ASCII, 1 << 20, 9, 2, 0),          # L = 3: dense filter, q = 3
+    (ASCII, 1 << 20, 64, 4, 0),
+    (DNA, 1 << 20, 20, 2, 0),           # config 1 of BASELINE.json
+    (DNA, 1 << 18, 20, 2, F.F_FORCE_DENSE),
+    (DNA, 1 << 18, 12, 1, 0),
+    (b"ab", 1 << 14, 12, 2, 0),
+])
+def test_levenshtein_ngrams_matches_oracle(cuda_device, alphabet, n, m, k, flags):
+    pat, hay, _ = make_corpus(11, n, alphabet, m, 64, k + 1)
+    raw_cpu, ng_cpu, ix_cpu = oracle.levenshtein_ngrams_raw(pat, hay, k, with_anchor=True)
+    hs = F.Haystack.from_host(hay)
+    res = hs.search_levenshtein(pat, k, flags)
+    raw_gpu, ng, ix = _raw(res)
+    assert raw_gpu == tup(raw_cpu)
+    assert ng == ng_cpu.tolist() and ix == ix_cpu.tolist()
+    assert res.triples(F.FINAL) == tup(oracle.consolidate(raw_cpu))
+    assert len(raw_gpu) >= 32
+    res.close()
+    hs.close()
+
+
+@pytest.mark.parametrize("alphabet,n,m,k", [
+    (DNA, 1 << 20, 32, 3),   # config 3 of BASELINE.json (scaled)
+    (ASCII, 1 << 20, 32, 3),
+    (DNA, 1 << 16, 8, 2),
+    (b"ab", 1 << 12, 6, 5),
+    (ASCII, 1 << 12, 5, 7),  # k >= m: every start matches
+])
+def test_hamming_matches_oracle(cuda_device, alphabet, n, m, k):
+    pat, hay, _ = make_corpus(5, n, alphabet, m, 64, k + 1, subs_only=True)
+    cpu = oracle.substitutions(pat, hay, k)
+    hs = F.Haystack.from_host(hay)
+    res = hs.search_hamming(pat, k)
+    assert res.triples(F.RAW) == tup(cpu)
+    assert res.triples(F.FINAL) == tup(cpu)
+    res.close()
+    hs.close()
+
+
+@pytest.mark.parametrize("alphabet,n,m,k", [
+    (ASCII, 1 << 18, 8, 2),
+    (DNA, 1 << 14, 8, 2),
+    (DNA, 1 << 12, 5, 3),
+    (b"ab", 1 << 9, 4, 2),
+    (ASCII, 1 << 10, 3, 4),  # k >= m
+])
+def test_levenshtein_lp_matches_oracle(cuda_device, alphabet, n, m, k):
+    pat, hay, _ = make_corpus(3, n, alphabet, m, 32, k + 1)
+    cpu = oracle.levenshtein_lp_raw(pat, hay, k)
+    hs = F.Haystack.from_host(hay)
+    res = hs.search_levenshtein(pat, k, F.F_FORCE_LP)
+    assert sorted(res.triples(F.RAW)) == sorted(tup(cpu))
+    assert res.triples(F.FINAL) == tup(oracle.consolidate(cpu))
+    res.close()
+    hs.close()
+
+
+@pytest.mark.parametrize("alphabet,n,m,limits,flags", [
+    (ASCII, 1 << 18, 20, (2, 1, 1, 3), 0),
+    (ASCII, 1 << 16, 20, (2, 1, 1, 3), F.F_FORCE_DENSE),
+    (DNA, 1 << 13, 20, (2, 1, 1, 3), 0),
+    (DNA, 1 << 12, 12, (1, 1, 0, 2), 0),
+    (ASCII, 1 << 14, 8, (1, 2, 1, 3), F.F_FORCE_LP),
+    (DNA, 1 << 11, 6, (2, 0, 2, 3), F.F_FORCE_LP),
+])
+def test_generic_matches_oracle(cuda_device, alphabet, n, m, limits, flags):
+    pat, hay, _ = make_corpus(9, n, alphabet, m, 32, limits[3] + 1)
+    if flags & F.F_FORCE_LP:
+        cpu = oracle.generic_lp_raw(pat, hay, *limits)
+    else:
+        cpu = oracle.generic_ngrams_raw(pat, hay, *limits)
+    hs = F.Haystack.from_host(hay)
+    res = hs.search_generic(pat, *limits, flags=flags)
+    assert sorted(res.triples(F.RAW)) == sorted(tup(cpu))
+    assert res.triples(F.FINAL) == tup(oracle.consolidate(cpu))
+    res.close()
+    hs.close()
+
+
+@pytest.mark.parametrize("nshards", [2, 3, 7])
+def test_sharded_union_equals_whole(cuda_device, nshards):
+    """shards own anchors in [lo,hi) and carry a halo of m+k; the union of the shards'
+    raw streams is the single-device raw stream (matches straddling every seam are planted)."""
+    m, k, n = 20, 2, (1 << 20) + 5
+    pat, hay, _ = make_corpus(21, n, ASCII, m, 64, 3)
+    bounds = [((n * i // nshards) // 16) * 16 for i in range(nshards)] + [n]
+    for b in bounds[1:-1]:  # straddle every seam at the deltas of test_find_near_matches_in_file.py:84-86
+        for j, delta in enumerate((-m, -m + 1, -4, -2, -1, 0, 1)):
+            pos = b + delta + 64 * (j - 3)
+            hay[pos:pos + m] = np.frombuffer(pat, dtype=np.uint8)
+        hay[b - 7:b - 7 + m] = np.frombuffer(pat, dtype=np.uint8)
+    whole = tup(oracle.levenshtein_ngrams_raw(pat, hay, k))
+    halo = m + k
+    got = []
+    for i in range(nshards):
+        lo, hi = bounds[i], bounds[i + 1]
+        blo = max(0, lo - halo) // 16 * 16
+        bhi = min(n, hi + halo)
+        hs = F.Haystack.from_host(hay[blo:bhi], buf_lo=blo, global_len=n, own_lo=lo, own_hi=hi)
+        res = hs.search_levenshtein(pat, k, F.F_NO_FINAL)
+        s, e, d, ng, ix = res.arrays(F.RAW, anchors=True)
+        got += list(zip(ng.tolist(), ix.tolist(), s.tolist(), e.tolist(), d.tolist()))
+        res.close()
+        hs.close()
+    got.sort()
+    assert [(s, e, d) for _, _, s, e, d in got] == whole
+    hs = F.Haystack.from_host(hay)
+    ham_whole = hs.search_hamming(pat, 3).triples(F.RAW)
+    hs.close()
+    ham = []
+    for i in range(nshards):
+        lo, hi = bounds[i], bounds[i + 1]
+        blo = max(0, lo - halo) // 16 * 16
+        bhi = min(n, hi + halo)
+        hs = F.Haystack.from_host(hay[blo:bhi], buf_lo=blo, global_len=n, own_lo=lo, own_hi=hi)
+        ham += hs.search_hamming(pat, 3).triples(F.RAW)
+        hs.close()
+    assert sorted(ham) == ham_whole
+
+
+def test_edge_cases(cuda_device):
+    from fuzzysearch_b200 import find_near_matches
+    t = lambda ms: [(m.start, m.end, m.dist) for m in ms]  # noqa: E731
+    assert t(find_near_matches(b"abc", b"", max_l_dist=1)) == []
+    assert t(find_near_matches(b"ab", b"xyz", max_l_dist=2)) == [(0, 0, 2), (1, 1, 2), (2, 2, 2), (3, 3, 2)]
+    assert t(find_near_matches(b"abc", b"ab", max_l_dist=1)) == [(0, 2, 1)]
+    assert t(find_near_matches(b"abc", b"xbz", max_substitutions=5, max_insertions=0, max_deletions=0)) == \
+        [(0, 3, 2)]
+    assert t(find_near_matches(b"abcd", b"ab", max_substitutions=1, max_insertions=0, max_deletions=0)) == []
+    ms = find_near_matches(b"PATTERN", b"---PATERN---", max_l_dist=1)
+    assert t(ms) == [(3, 9, 1)] and ms[0].matched == b"PATERN"
+    ms = find_near_matches("PATTERN", "---PATERN---", max_l_dist=1)
+    assert ms[0].matched == "PATERN"
+    with pytest.raises(ValueError):
+        find_near_matches(b"", b"TEXT", max_l_dist=1)
+    with pytest.raises(ValueError):
+        find_near_matches(b"a", b"a")
+    with pytest.raises(TypeError):
+        find_near_matches(b"a", b"a", max_l_dist=-1)
+    with pytest.raises(TypeError):
+        find_near_matches(["a"], ["a"], max_l_dist=1)

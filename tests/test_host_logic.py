@@ -1,0 +1,138 @@
+"""CPU-only tests: the host-side mirror of the reference interface, the C-ABI surface, and the
+native consolidation (pure host code inside libfuzzb200.so) against the oracle."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle
+from fuzzysearch_b200 import (ExactSearch, GenericSearch, LevenshteinSearch, LevenshteinSearchParams,
+                              Match, SubstitutionsOnlySearch, _native, choose_search_class,
+                              find_near_matches)
+from parity import assert_final_parity, load_golden, tup
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "fuzzb200.h")).read()
+    declared = set(re.findall(r"\b(fzb_[a-z_0-9]+)\s*\(", header))
+    assert len(declared) >= 20
+    lib = _native.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(_native.SYMBOLS), declared ^ set(_native.SYMBOLS)
+    assert lib.fzb_version() == 100
+
+
+def test_match_semantics():
+    # common.py:15-32: eq/hash/order on (start,end,dist); matched excluded; frozen
+    a, b = Match(1, 3, 0, matched=b"xy"), Match(1, 3, 0, matched=b"zz")
+    assert a == b and hash(a) == hash(b) and len({a, b}) == 1
+    assert Match(1, 3, 0, b"a") < Match(1, 3, 1, b"a") < Match(1, 4, 0, b"a") < Match(2, 2, 0, b"")
+    assert sorted([Match(5, 6, 0, b"a"), Match(1, 9, 2, b"a")])[0].start == 1
+    assert repr(a) == "Match(start=1, end=3, dist=0, matched=b'xy')"
+    with pytest.raises(AttributeError):
+        a.start = 4
+    for bad in [(-1, 2, 0), (3, 2, 0), (1, 2, -1)]:
+        with pytest.raises(ValueError):
+            Match(*bad, matched=b"")
+    with pytest.raises(ValueError):
+        Match(1, 2, 0)
+
+
+def test_params_normalisation_matches_oracle_restatement():
+    vals = [None, 0, 1, 2, 5]
+    for s in vals:
+        for i in vals:
+            for d in vals:
+                for l in vals:
+                    try:
+                        exp = oracle.normalize_params(s, i, d, l)
+                    except (ValueError, TypeError) as e:
+                        with pytest.raises(type(e)):
+                            LevenshteinSearchParams(s, i, d, l)
+                        continue
+                    assert LevenshteinSearchParams(s, i, d, l).unpacked == exp
+    for bad in [(-1, None, None, 2), ("1", 1, 1, 1), (1.5, 1, 1, None)]:
+        with pytest.raises(TypeError):
+            LevenshteinSearchParams(*bad)
+    with pytest.raises(ValueError):
+        LevenshteinSearchParams()
+    with pytest.raises(ValueError):
+        LevenshteinSearchParams(max_substitutions=1)
+
+
+def test_choose_search_class():
+    # tests/test_find_near_matches.py:53-199 (dispatch rules of __init__.py:60-83)
+    c = lambda *a: choose_search_class(LevenshteinSearchParams(*a))  # noqa: E731
+    assert c(None, None, None, 0) is ExactSearch
+    assert c(0, 0, 0, None) is ExactSearch
+    assert c(1, 0, 0, None) is SubstitutionsOnlySearch
+    assert c(3, 0, 0, 2) is SubstitutionsOnlySearch
+    assert c(None, None, None, 2) is LevenshteinSearch
+    assert c(2, 2, 2, 2) is LevenshteinSearch
+    assert c(3, 4, 5, 2) is LevenshteinSearch
+    assert c(1, 2, 2, 2) is GenericSearch
+    assert c(2, 1, 1, None) is GenericSearch
+    assert c(2, 0, 1, 3) is GenericSearch
+
+
+def test_no_gpu_fails_loudly():
+    if _native.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(_native.CudaError):
+        find_near_matches(b"abc", b"xxabcxx", max_l_dist=1)
+
+
+def test_argument_errors_before_any_device_work():
+    with pytest.raises(ValueError):
+        find_near_matches(b"", b"TEXT", max_l_dist=1)
+    with pytest.raises(TypeError):
+        find_near_matches(["a"], ["a", "b"], max_l_dist=1)
+    with pytest.raises(TypeError):
+        find_near_matches(b"a", "aሴ", max_l_dist=1)
+
+
+def _random_raw(rng, n, span, with_empty):
+    out = []
+    for _ in range(n):
+        s = int(rng.integers(0, span))
+        ln = int(rng.integers(0 if with_empty else 1, 9))
+        out.append((s, s + ln, int(rng.integers(0, 4))))
+    return out
+
+
+def test_native_consolidate_equals_literal_grouping():
+    """fzb_consolidate (sort + sweep) vs the oracle's literal group_matches (common.py:145-189),
+    incl. empty matches, duplicates and dense chains."""
+    rng = np.random.default_rng(123)
+    for trial in range(400):
+        raw = _random_raw(rng, int(rng.integers(0, 40)), int(rng.integers(5, 120)), trial % 2 == 0)
+        if trial % 7 == 0:
+            raw = raw + raw[:3]
+        a = np.array(raw, dtype=np.int64).reshape(-1, 3)
+        s, e, d = _native.consolidate(a[:, 0], a[:, 1], a[:, 2].astype(np.int32))
+        ours = list(zip(s.tolist(), e.tolist(), d.tolist()))
+        assert ours == tup(oracle.consolidate(a)), raw
+
+
+def test_native_consolidate_on_reference_records():
+    n = 0
+    for rec in load_golden("ref_suite_calls.json"):
+        if rec["fn"] != "consolidate":
+            continue
+        raw = np.array(rec["args"][0], dtype=np.int64).reshape(-1, 3)
+        s, e, d = _native.consolidate(raw[:, 0], raw[:, 1], raw[:, 2].astype(np.int32))
+        assert_final_parity(list(zip(s.tolist(), e.tolist(), d.tolist())), rec["result"], raw)
+        n += 1
+    assert n > 50
+
+
+def test_synth_host_is_counter_based():
+    a = _native.synth_host(0, 1000, b"ACGT", 42)
+    b = _native.synth_host(333, 100, b"ACGT", 42)
+    assert a[333:433].tobytes() == b.tobytes()
+    assert set(a.tolist()) == set(b"ACGT")
+    assert _native.synth_host(0, 64, b"ACGT", 43).tobytes() != a[:64].tobytes()
