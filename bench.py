@@ -1,0 +1,457 @@
+#!/usr/bin/env python
+"""bench.py -- the driver's benchmark contract for the fuzzysearch hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
+
+A "step" is one pass of the hot path over one batch of synthetic input: ONE bounded-Levenshtein
+search (``find_near_matches(pattern, haystack, max_l_dist=2)``, |pattern| = 20) of a 4 GiB
+95-symbol ASCII haystack per GPU (BASELINE.json configs[1]; with N GPUs the global sequence is
+N x 4 GiB, sharded with a halo of |pattern|+k = configs[3], weak scaling).
+
+* ``value``  = haystack GB/s scanned, whole job, inputs resident in HBM, timed on the device (CUDA
+  events on the library's stream around exactly K searches incl. result read-back; max over ranks).
+* ``e2e``    = same metric through the C-ABI one-shot call with HOST (pinned) buffers: H2D copy of
+  the haystack and D2H of the matches inside the timed region.
+* ``roofline`` = the dominant kernel (k_filter_sampled): algorithmic bytes (1 per haystack byte) /
+  its CUDA-event duration, against the measured HBM peak of MEASURED_PEAKS.json.
+* ``cpu_baseline`` / ``--impl reference`` = the reference itself (oracle/_ref, compiled from
+  /root/reference by oracle/build_ref.py) on the box's host cores, on a bounded sample.
+
+Inputs are far larger than L2 (4 GiB vs 126 MB), so no explicit L2 flush is needed between steps.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ASCII = bytes(range(32, 127))
+DNA = b"ACGT"
+GiB = 1 << 30
+
+WORKLOADS = {
+    # name: (alphabet, bytes per GPU, m, search kind, k)
+    "ascii4g_lev_m20_k2": (ASCII, 4 * GiB, 20, "lev", 2),
+    "dna4g_ham_m32_k3": (DNA, 4 * GiB, 32, "ham", 3),
+    "ascii64m_lev_m20_k2": (ASCII, 64 << 20, 20, "lev", 2),  # quick self-test size
+}
+
+
+def mutate(rng, pat, alphabet, nedits, subs_only):
+    s = bytearray(pat)
+    for _ in range(nedits):
+        op = 0 if subs_only else int(rng.integers(3))
+        if op == 0:
+            s[int(rng.integers(len(s)))] = alphabet[int(rng.integers(len(alphabet)))]
+        elif op == 1:
+            s.insert(int(rng.integers(len(s) + 1)), alphabet[int(rng.integers(len(alphabet)))])
+        else:
+            del s[int(rng.integers(len(s)))]
+    return bytes(s)
+
+
+def make_plants(seed, lo, hi, m, k, pat, alphabet, n_plants, subs_only):
+    """Deterministic plants inside [lo, hi): (global offset, bytes).  0..k+1 edits each (k+1 are
+    negatives), plus overlapping clusters for the consolidation."""
+    rng = np.random.default_rng(seed)
+    out = []
+    span = (hi - lo - 8 * m) // n_plants
+    for i in range(n_plants):
+        pos = lo + 4 * m + i * span + int(rng.integers(0, span - 4 * m))
+        out.append((pos, mutate(rng, pat, alphabet, int(rng.integers(0, k + 2)), subs_only)))
+    for c in range(16):
+        pos = lo + 4 * m + int(rng.integers(0, hi - lo - 16 * m))
+        out.append((pos, pat + pat[m // 2:] + pat))
+    return out
+
+
+def clocks_monitor_start(path, gpu_index):
+    try:
+        return subprocess.Popen(
+            ["nvidia-smi", "-i", str(gpu_index),
+             "--query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
+             "--format=csv,noheader,nounits", "-lms", "100"],
+            stdout=open(path, "w"), stderr=subprocess.DEVNULL)
+    except OSError:
+        return None
+
+
+def clocks_monitor_stop(proc, path):
+    if proc is None:
+        return None
+    proc.terminate()
+    try:
+        proc.wait(timeout=5)
+    except subprocess.TimeoutExpired:
+        proc.kill()
+    sm, mx, reasons = [], [], set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    try:
+        for line in open(path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+    except OSError:
+        return None
+    if not sm:
+        return None
+    # "under load": the upper half of the samples (the monitor also sees the idle edges)
+    load = sorted(sm)[len(sm) // 2:]
+    return {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(max(mx)), "samples": len(sm),
+            "reasons": sorted(reasons)}
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        v = json.load(open(p))
+        return float(v["hbm_gbs"]), "measured (MEASURED_PEAKS.json, copy read+write)"
+    except (OSError, KeyError, ValueError):
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "filter_traffic.json")))
+    except (OSError, ValueError):
+        return None
+
+
+# -------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation (oracle/_ref), all host cores
+# -------------------------------------------------------------------------------------------------
+_REF_STATE = {}
+
+
+def _ref_worker(args):
+    lo, hi, kind, k = args
+    fz = _REF_STATE["fz"]
+    pat = _REF_STATE["pat"]
+    chunk = _REF_STATE["hay"][lo:hi].tobytes()
+    if kind == "lev":
+        ms = fz.find_near_matches(pat, chunk, max_l_dist=k)
+    else:
+        ms = fz.find_near_matches(pat, chunk, max_substitutions=k, max_insertions=0, max_deletions=0)
+    return [(m.start + lo, m.end + lo, m.dist) for m in ms]
+
+
+def reference_available():
+    return os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "fuzzysearch"))
+
+
+def import_reference():
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+    import fuzzysearch
+    return fuzzysearch
+
+
+def run_reference_sample(hay, pat, kind, k, cores, repeats=1):
+    """Time the reference on `hay` (numpy uint8) split into overlapping chunks over `cores`
+    processes (the reference's own chunk + carry-over rule, __init__.py:135-138).  Returns
+    (seconds, n_matches).  With cores == 1 it is one plain find_near_matches call."""
+    import multiprocessing as mp
+    fz = import_reference()
+    _REF_STATE.update(fz=fz, pat=pat, hay=hay)
+    n = hay.size
+    m = len(pat)
+    keep = m - 1 + (k if kind == "lev" else 0)
+    best = None
+    nm = 0
+    if cores == 1:
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            res = _ref_worker((0, n, kind, k))
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+            nm = len(res)
+        return best, nm
+    nchunks = cores * 4
+    step = (n + nchunks - 1) // nchunks
+    tasks = [(max(0, i * step), min(n, (i + 1) * step + keep), kind, k) for i in range(nchunks)
+             if i * step < n]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        pool.map(_ref_worker, tasks[:cores])  # warm the workers
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            parts = pool.map(_ref_worker, tasks, chunksize=1)
+            allm = [x for p in parts for x in p]
+            if kind == "lev" and allm:
+                # one global consolidation of the per-chunk winners (find_near_matches_in_file,
+                # __init__.py:126), with the reference's own function
+                Match = fz.Match
+                from fuzzysearch.common import consolidate_overlapping_matches
+                allm = consolidate_overlapping_matches([Match(s, e, d, b"") for s, e, d in allm])
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+            nm = len(allm)
+    return best, nm
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def synth_sample_host(native, alphabet, seed, pat, nbytes, m, k, kind):
+    """The first `nbytes` of rank 0's corpus, regenerated on the host (counter-based generator +
+    the same plants), so the CPU baseline scans the same bytes the GPU scans."""
+    hay = native.synth_host(0, nbytes, alphabet, seed)
+    for pos, b in make_plants(seed + 1, 0, nbytes, m, k, pat, alphabet, max(8, nbytes >> 20), kind == "ham"):
+        b = b[:max(0, nbytes - pos)]
+        hay[pos:pos + len(b)] = np.frombuffer(b, dtype=np.uint8)
+    return hay
+
+
+# -------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ascii4g_lev_m20_k2", choices=sorted(WORKLOADS))
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-mib", type=int, default=0, help="0 = auto (about 10-20 s of CPU work)")
+    ap.add_argument("--ref-cores", type=int, default=0, help="reference arm: processes to use (0 = all cores)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    alphabet, per_gpu, m, kind, k = WORKLOADS[args.workload]
+    seed = 20260923
+    metric = "haystack_GB_per_s_scanned"
+    unit = "GB/s"
+    config = {"workload": args.workload, "alphabet": len(alphabet), "pattern_len": m,
+              "max_l_dist" if kind == "lev" else "max_substitutions": k,
+              "bytes_per_gpu": per_gpu, "global_bytes": per_gpu * world,
+              "sharding": "contiguous shards, halo=%d, no data-path collective" % (m + k),
+              "l2": "inputs larger than L2 (no flush needed)"}
+
+    from fuzzysearch_b200 import _native as F
+    rng = np.random.default_rng(seed)
+    pat = bytes(np.frombuffer(alphabet, dtype=np.uint8)[rng.integers(0, len(alphabet), size=m)])
+
+    # ---------------------------------------------------------------------------------------------
+    if args.impl == "reference":
+        if world > 1 and rank != 0:
+            return 0
+        cores = args.ref_cores or host_cores()
+        sample = (args.cpu_sample_mib << 20) if args.cpu_sample_mib else min(per_gpu, 1 * GiB)
+        hay = synth_sample_host(F, alphabet, seed, pat, sample, m, k, kind)
+        kindname = "reference" if reference_available() else "port"
+        if not reference_available():
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built"}))
+            return 0
+        times = []
+        for i in range(args.warmup + args.steps):
+            dt, nm = run_reference_sample(hay, pat, kind, k, cores)
+            if i >= args.warmup:
+                times.append(dt)
+            if sum(times) > 240:
+                break
+        sec = float(np.mean(times))
+        val = sample / sec / 1e9
+        line = {"impl": "reference", "metric": metric, "value": val, "unit": unit, "n_gpus": args.gpus,
+                "steps": len(times), "warmup": args.warmup, "ms_per_step": sec * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+                "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": unit, "cores": cores, "kind": kindname,
+                                 "sample": "first %d MiB of rank 0's corpus per step, split over %d "
+                                           "processes with the reference's chunk overlap" % (sample >> 20, cores)},
+                "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0, "matches": nm}
+        print(json.dumps(line))
+        return 0
+
+    # ---------------------------------------------------------------------------------------------
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from fuzzysearch_b200.sharding import gather_rows, merge_raw_streams, shard_bounds
+
+    global_len = per_gpu * world
+    halo = m + k
+    blo, bhi, own_lo, own_hi = shard_bounds(global_len, world, rank, halo)
+    # device-resident shard generated ON the device (counter-based corpus keyed by global offset)
+    hs = F.Haystack.alloc(bhi - blo, device=local_rank, buf_lo=blo, global_len=global_len, own_lo=own_lo,
+                          own_hi=own_hi)
+    hs.fill_synthetic(alphabet, seed)
+    plants = []
+    for r in range(world):  # every rank knows every plant (needed for seam plants + checking)
+        lo_r, hi_r = shard_bounds(global_len, world, r, halo)[2:]
+        plants += make_plants(seed + 1 + r, lo_r, hi_r, m, k, pat, alphabet, 4096, kind == "ham")
+        if r > 0:  # straddle the seam (tests/test_find_near_matches_in_file.py:84-86 deltas)
+            for j, delta in enumerate((-m, -m + 1, -4, -2, -1, 0, 1)):
+                plants.append((lo_r + delta + 256 * (j - 3), pat))
+    for pos, b in plants:
+        if pos >= blo and pos + len(b) <= bhi:
+            hs.write(pos, b)
+
+    def one_search():
+        if kind == "lev":
+            return hs.search_levenshtein(pat, k, F.F_NO_FINAL if world > 1 else 0)
+        return hs.search_hamming(pat, k)
+
+    def step():
+        res = one_search()
+        st = res.stats()
+        if world > 1:
+            s, e, d, ng, ix = res.arrays(F.RAW, anchors=True)
+            rows = np.column_stack([s, e, d.astype(np.int64), ng.astype(np.int64), ix])
+            allrows = gather_rows(rows)
+            _, final = merge_raw_streams(allrows, ngram_route=(kind == "lev"))
+            nfinal = len(final)
+        else:
+            nfinal = res.count(F.FINAL)
+        res.close()
+        return st, nfinal
+
+    def sync_all():
+        if dist is not None:
+            dist.barrier()
+            import torch
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    clock_path = os.path.join(tempfile.gettempdir(), "fzb_clocks_%d.csv" % rank)
+    mon = clocks_monitor_start(clock_path, local_rank) if rank == 0 else None
+    time.sleep(0.3)
+    sync_all()
+    filt_ms, launches, nfinal = [], 0, 0
+    hs.timer_start()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        st, nfinal = step()
+        filt_ms.append(st["filter_ms"])
+        launches += st["n_launches"]
+    dev_ms = hs.timer_stop()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    sync_all()
+    time.sleep(0.3)
+    clocks = clocks_monitor_stop(mon, clock_path)
+    ms_per_step = dev_ms / args.steps
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms_per_step], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_per_step = float(t.item())
+    value = global_len / (ms_per_step * 1e-3) / 1e9
+
+    # ---- end to end through the one-shot C-ABI call with pinned HOST buffers -----------------------
+    e2e = None
+    if args.e2e_steps > 0:
+        pinned = F.PinnedBuffer(bhi - blo)
+        chunk = 256 << 20
+        for off in range(0, bhi - blo, chunk):  # host copy of the shard (setup, untimed)
+            nb = min(chunk, bhi - blo - off)
+            pinned.array[off:off + nb] = np.frombuffer(hs.read(blo + off, nb), dtype=np.uint8)
+        subs, ins, dels, l = (k, k, k, k) if kind == "lev" else (k, 0, 0, k)
+
+        def e2e_step():
+            if world == 1:
+                r = F.find_near_matches_host(pat, pinned.array, subs, ins, dels, l, device=local_rank)
+                cnt = r.count(F.FINAL)
+                d2h = cnt * 20
+                r.close()
+                return cnt, d2h
+            h2 = F.Haystack.from_host(pinned.array, device=local_rank, buf_lo=blo, global_len=global_len,
+                                      own_lo=own_lo, own_hi=own_hi)
+            r = h2.search_levenshtein(pat, k, F.F_NO_FINAL) if kind == "lev" else h2.search_hamming(pat, k)
+            s, e, d, ng, ix = r.arrays(F.RAW, anchors=True)
+            rows = np.column_stack([s, e, d.astype(np.int64), ng.astype(np.int64), ix])
+            _, final = merge_raw_streams(gather_rows(rows), ngram_route=(kind == "lev"))
+            r.close()
+            h2.close()
+            return len(final), rows.shape[0] * 40
+
+        e2e_step()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            cnt_e2e, d2h_bytes = e2e_step()
+        sync_all()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / args.e2e_steps
+        if dist is not None:
+            import torch
+            t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t.item())
+        e2e = {"value": global_len / (e2e_ms * 1e-3) / 1e9, "unit": unit, "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": (bhi - blo) + m, "d2h_bytes_per_step": int(d2h_bytes),
+               "steps": args.e2e_steps, "timer": "host clock around the C-ABI call (includes H2D/D2H)",
+               "matches": int(cnt_e2e)}
+        pinned.close()
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = hbm_peak()
+    filt = float(np.mean(filt_ms))
+    achieved = (bhi - blo) / (filt * 1e-3) / 1e9 if filt > 0 else 0.0
+    traffic = ncu_traffic()
+    line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
+            "matches_per_step": int(nfinal), "wall_ms_per_step": wall_ms / args.steps,
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_filter_sampled" if kind == "lev" else "k_hamming_scan",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": peak_src, "kernel_ms": filt,
+                         "algorithmic_bytes_per_launch": bhi - blo,
+                         "traffic": (traffic or {}).get("dram_bytes_per_launch")},
+            "clocks": clocks}
+    if e2e is not None:
+        line["e2e"] = e2e
+    if not args.no_cpu_baseline and world == 1 and reference_available():
+        # run in a fresh process: the reference arm forks worker processes, which must not inherit
+        # this process's CUDA context
+        def ref_run(extra):
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload",
+                                  args.workload, "--steps", "1", "--warmup", "0"] + extra,
+                                 capture_output=True, text=True, timeout=900)
+            return json.loads(out.stdout.strip().splitlines()[-1])
+        try:
+            sample_mib = args.cpu_sample_mib or min(per_gpu >> 20, 1024)
+            allc = ref_run(["--cpu-sample-mib", str(sample_mib)])
+            one = ref_run(["--cpu-sample-mib", str(min(sample_mib, 256)), "--ref-cores", "1"])
+            line["cpu_baseline"] = dict(allc["cpu_baseline"], single_core_value=one["value"],
+                                        matches=allc.get("matches"))
+        except Exception as e:  # noqa: BLE001 -- the GPU line must still be printed
+            line["cpu_baseline"] = {"error": repr(e)[:200]}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

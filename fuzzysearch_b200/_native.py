@@ -54,11 +54,16 @@ SYMBOLS = {
     "fzb_haystack_create": (_i32, [_u8p, _u64, _i32, _vpp]),
     "fzb_haystack_create_shard": (_i32, [_u8p, _u64, _u64, _u64, _u64, _u64, _i32, _vpp]),
     "fzb_haystack_adopt_device": (_i32, [_vp, _u64, _u64, _u64, _u64, _u64, _i32, _vpp]),
-    "fzb_haystack_alloc": (_i32, [_u64, _i32, _vpp, _vpp]),
+    "fzb_haystack_alloc": (_i32, [_u64, _u64, _u64, _u64, _u64, _i32, _vpp, _vpp]),
     "fzb_haystack_fill_synthetic": (_i32, [_vp, _u8p, _u32, _u64]),
     "fzb_synth_host": (None, [_u8p, _u64, _u64, _u8p, _u32, _u64]),
     "fzb_haystack_write": (_i32, [_vp, _u64, _u8p, _u64]),
     "fzb_haystack_read": (_i32, [_vp, _u64, _u8p, _u64]),
+    "fzb_haystack_upload": (_i32, [_vp, _u8p, _u64]),
+    "fzb_host_alloc": (_vp, [_u64]),
+    "fzb_host_free": (None, [_vp]),
+    "fzb_timer_start": (_i32, [_vp]),
+    "fzb_timer_stop": (_i32, [_vp, ctypes.POINTER(ctypes.c_double)]),
     "fzb_haystack_len": (_u64, [_vp]),
     "fzb_haystack_destroy": (None, [_vp]),
     "fzb_search_levenshtein": (_i32, [_vp, _u8p, _u32, _u32, _u32, _vpp]),
@@ -191,10 +196,13 @@ class Haystack(object):
         return cls(h)
 
     @classmethod
-    def alloc(cls, n, device=0):
+    def alloc(cls, buf_len, device=0, buf_lo=0, global_len=None, own_lo=None, own_hi=None):
+        if global_len is None:
+            global_len, own_lo, own_hi = buf_len, 0, buf_len
         h = ctypes.c_void_p()
         dp = ctypes.c_void_p()
-        check(lib().fzb_haystack_alloc(n, device, ctypes.byref(h), ctypes.byref(dp)))
+        check(lib().fzb_haystack_alloc(buf_len, buf_lo, global_len, own_lo, own_hi, device,
+                                       ctypes.byref(h), ctypes.byref(dp)))
         return cls(h, dp.value)
 
     @classmethod
@@ -215,6 +223,18 @@ class Haystack(object):
 
     def __len__(self):
         return int(lib().fzb_haystack_len(self._h))
+
+    def upload(self, data):
+        a = as_u8(data)
+        check(lib().fzb_haystack_upload(self._h, ptr(a), a.size))
+
+    def timer_start(self):
+        check(lib().fzb_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = ctypes.c_double()
+        check(lib().fzb_timer_stop(self._h, ctypes.byref(ms)))
+        return ms.value
 
     def fill_synthetic(self, alphabet, seed):
         a = as_u8(alphabet)
@@ -257,6 +277,24 @@ class Haystack(object):
         r = ctypes.c_void_p()
         check(lib().fzb_search_exact(self._h, pp, m, flags, ctypes.byref(r)))
         return Result(r)
+
+
+class PinnedBuffer(object):
+    """Page-locked host memory exposed as a numpy uint8 array (``.array``)."""
+
+    def __init__(self, n):
+        self._p = lib().fzb_host_alloc(n)
+        if not self._p:
+            raise CudaError(last_error())
+        self.array = np.ctypeslib.as_array(ctypes.cast(self._p, ctypes.POINTER(ctypes.c_uint8)), shape=(n,))
+
+    def close(self):
+        if self._p:
+            self.array = None
+            lib().fzb_host_free(self._p)
+            self._p = None
+
+    __del__ = close
 
 
 def synth_host(global_offset, n, alphabet, seed):

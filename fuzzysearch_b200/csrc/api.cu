@@ -61,6 +61,8 @@ struct fzb_haystack {
     bool owned = true;
     uint64_t buf_len = 0, buf_lo = 0, global_len = 0, own_lo = 0, own_hi = 0;
     uint64_t padded_len = 0;
+    uint64_t capacity = 0;  // bytes allocated at d (owned buffers)
+    cudaEvent_t ev_stop = nullptr;
     cudaStream_t stream = nullptr;
     uint32_t *d_bitmap = nullptr;
     uint64_t bitmap_words = 0;
@@ -87,6 +89,7 @@ static int haystack_common_init(fzb_haystack *h) {
     CK(cudaSetDevice(h->device));
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     for (auto &e : h->ev) CK(cudaEventCreate(&e));
+    CK(cudaEventCreate(&h->ev_stop));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, h->device));
     h->sm_count = prop.multiProcessorCount;
@@ -113,6 +116,7 @@ static int alloc_buffer(fzb_haystack *h) {
     h->padded_len = round_up(h->buf_len, 16) + 64;
     CK(cudaSetDevice(h->device));
     CK(cudaMalloc(&h->d, h->padded_len));
+    h->capacity = h->padded_len;
     CK(cudaMemset(h->d + h->buf_len, 0, h->padded_len - h->buf_len));
     return FZB_OK;
 }
@@ -129,6 +133,7 @@ extern "C" void fzb_haystack_destroy(fzb_haystack *h) {
     if (h->h_counters) cudaFreeHost(h->h_counters);
     for (auto &e : h->ev)
         if (e) cudaEventDestroy(e);
+    if (h->ev_stop) cudaEventDestroy(h->ev_stop);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -199,17 +204,22 @@ extern "C" int fzb_haystack_adopt_device(const void *dev_ptr, uint64_t buf_len, 
     return FZB_OK;
 }
 
-extern "C" int fzb_haystack_alloc(uint64_t n, int device, fzb_haystack **out, void **dev_ptr) {
+extern "C" int fzb_haystack_alloc(uint64_t buf_len, uint64_t buf_lo, uint64_t global_len, uint64_t own_lo,
+                                  uint64_t own_hi, int device, fzb_haystack **out, void **dev_ptr) {
     if (!out) return fail(FZB_E_INVALID, "out is NULL");
     *out = nullptr;
+    int rc = check_shard(buf_len, buf_lo, global_len, own_lo, own_hi);
+    if (rc) return rc;
     if (fzb_device_count() <= device || device < 0) return fail(FZB_E_CUDA, "CUDA device %d not available", device);
     fzb_haystack *h = new (std::nothrow) fzb_haystack();
     if (!h) return fail(FZB_E_CUDA, "out of host memory");
     h->device = device;
-    h->buf_len = n;
-    h->global_len = n;
-    h->own_hi = n;
-    int rc = alloc_buffer(h);
+    h->buf_len = buf_len;
+    h->buf_lo = buf_lo;
+    h->global_len = global_len;
+    h->own_lo = own_lo;
+    h->own_hi = own_hi;
+    rc = alloc_buffer(h);
     if (rc == FZB_OK) rc = haystack_common_init(h);
     if (rc) {
         fzb_haystack_destroy(h);
@@ -271,6 +281,52 @@ extern "C" int fzb_haystack_read(fzb_haystack *h, uint64_t global_offset, uint8_
 }
 
 extern "C" uint64_t fzb_haystack_len(const fzb_haystack *h) { return h ? h->global_len : 0; }
+
+extern "C" int fzb_haystack_upload(fzb_haystack *h, const uint8_t *host, uint64_t n) {
+    if (!h || (!host && n)) return fail(FZB_E_INVALID, "bad arguments");
+    if (!h->owned || h->buf_lo != 0) return fail(FZB_E_INVALID, "upload needs an owned whole-sequence handle");
+    if (round_up(n, 16) + 64 > h->capacity) return fail(FZB_E_INVALID, "upload larger than the handle's capacity");
+    CK(cudaSetDevice(h->device));
+    h->buf_len = h->global_len = h->own_hi = n;
+    h->own_lo = 0;
+    h->padded_len = round_up(n, 16) + 64;
+    if (n) CK(cudaMemcpyAsync(h->d, host, n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(h->d + n, 0, h->padded_len - n, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return FZB_OK;
+}
+
+extern "C" void *fzb_host_alloc(uint64_t n) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, n ? n : 1, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        fail(FZB_E_CUDA, "cudaHostAlloc(%llu) failed", (unsigned long long)n);
+        return nullptr;
+    }
+    return p;
+}
+
+extern "C" void fzb_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+extern "C" int fzb_timer_start(fzb_haystack *h) {
+    if (!h) return fail(FZB_E_INVALID, "NULL handle");
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventRecord(h->ev[3], h->stream));
+    return FZB_OK;
+}
+
+extern "C" int fzb_timer_stop(fzb_haystack *h, double *ms) {
+    if (!h || !ms) return fail(FZB_E_INVALID, "NULL argument");
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventRecord(h->ev_stop, h->stream));
+    CK(cudaEventSynchronize(h->ev_stop));
+    float f = 0.f;
+    CK(cudaEventElapsedTime(&f, h->ev[3], h->ev_stop));
+    *ms = f;
+    return FZB_OK;
+}
 
 // ------------------------------------------------------------------------------------------------
 // consolidation (common.py:145-189).  Groups are the connected components of interval overlap

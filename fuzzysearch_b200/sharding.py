@@ -1,0 +1,87 @@
+"""Multi-GPU layout of one long sequence: contiguous shards with a halo, one process per GPU.
+
+SURVEY.md section 8e.  Every raw match is a pure function of a bounded window around its *anchor*
+(n-gram hit index / Hamming start / LP start), so rank g OWNS the anchors in ``[own_lo, own_hi)``,
+loads ``H[own_lo - halo : own_hi + halo)`` with ``halo = len(pattern) + max_l_dist`` and emits only
+matches it owns.  The reference's clipping rules are evaluated at the global ends only, so the union
+of the per-rank raw streams IS the single-device raw stream -- no haystack byte ever crosses NVLink.
+The only exchange is the (tiny) match list: an all-gather of per-rank counts followed by one padded
+all-gather of ``(start, end, dist, ngram, idx)`` rows over ``torch.distributed`` (NCCL on GPUs, gloo
+in the CPU tests); the final consolidation (common.py:185-189) then runs once on the gathered list,
+because groups of overlapping matches can chain across seams.
+
+The reference's CPU analogue of this layout is the chunk + carry-over tail loop of
+``_search_binary_file`` (fuzzysearch/__init__.py:129-171).
+"""
+import numpy as np
+
+__all__ = ["shard_bounds", "gather_rows", "merge_raw_streams"]
+
+ALIGN = 16  # shard buffers start on 16-byte boundaries of the global sequence (uint4 loads)
+
+
+def shard_bounds(global_len, world_size, rank, halo):
+    """-> (buf_lo, buf_hi, own_lo, own_hi) for `rank` of `world_size`.
+
+    Owned ranges partition [0, global_len); seams are multiples of ALIGN; buffers extend the owned
+    range by `halo` on both sides, clipped to the sequence and aligned down at the start."""
+    if world_size < 1 or not (0 <= rank < world_size):
+        raise ValueError("bad rank/world_size")
+
+    def seam(i):
+        if i >= world_size:
+            return global_len
+        return (global_len * i // world_size) // ALIGN * ALIGN
+
+    own_lo, own_hi = seam(rank), seam(rank + 1)
+    buf_lo = max(0, own_lo - halo) // ALIGN * ALIGN
+    buf_hi = min(global_len, own_hi + halo)
+    return buf_lo, buf_hi, own_lo, own_hi
+
+
+def gather_rows(rows, group=None, device=None):
+    """All-gather a variable number of int64 rows ([n_i, C] per rank) -> [sum n_i, C] on every rank,
+    rank-major.  Uses torch.distributed when initialised (NCCL: tensors on `device`; gloo: CPU),
+    otherwise returns `rows` (single process)."""
+    rows = np.ascontiguousarray(rows, dtype=np.int64)
+    try:
+        import torch
+        import torch.distributed as dist
+    except ImportError:  # pragma: no cover
+        return rows
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return rows
+    world = dist.get_world_size(group)
+    backend = dist.get_backend(group)
+    dev = torch.device("cpu")
+    if backend == "nccl":
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    ncols = rows.shape[1]
+    count = torch.tensor([rows.shape[0]], dtype=torch.int64, device=dev)
+    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(counts, count, group=group)
+    counts = [int(c.item()) for c in counts]
+    width = max(max(counts), 1)
+    padded = torch.zeros((width, ncols), dtype=torch.int64, device=dev)
+    if rows.shape[0]:
+        padded[:rows.shape[0]] = torch.from_numpy(rows).to(dev)
+    out = [torch.zeros((width, ncols), dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(out, padded, group=group)
+    parts = [out[r][:counts[r]].cpu().numpy() for r in range(world)]
+    return np.concatenate(parts, axis=0) if parts else rows
+
+
+def merge_raw_streams(rows, ngram_route=True):
+    """Gathered rows (start, end, dist, ngram, idx) -> (raw rows in reference order, final triples).
+
+    Raw order: n-gram major then hit index for the n-gram routes (the reference's generation order),
+    (start, end, dist) otherwise.  Final = consolidate_overlapping_matches via the native sweep."""
+    from . import _native
+    rows = np.asarray(rows, dtype=np.int64).reshape(-1, 5)
+    if ngram_route:
+        order = np.lexsort((rows[:, 4], rows[:, 3]))
+    else:
+        order = np.lexsort((rows[:, 2], rows[:, 1], rows[:, 0]))
+    rows = rows[order]
+    s, e, d = _native.consolidate(rows[:, 0], rows[:, 1], rows[:, 2].astype(np.int32))
+    return rows, list(zip(s.tolist(), e.tolist(), d.tolist()))

@@ -88,9 +88,11 @@ int fzb_haystack_adopt_device(const void *dev_ptr, uint64_t buf_len, uint64_t bu
                               uint64_t global_len, uint64_t own_lo, uint64_t own_hi, int device,
                               fzb_haystack **out);
 
-/* Allocate an uninitialised device-resident sequence of n bytes and return its device pointer (for
- * callers that fill it with their own kernels / cudaMemcpy). */
-int fzb_haystack_alloc(uint64_t n, int device, fzb_haystack **out, void **dev_ptr);
+/* Allocate an uninitialised device-resident shard (same geometry arguments as
+ * fzb_haystack_create_shard; a whole sequence is buf_lo = own_lo = 0, buf_len = global_len = own_hi)
+ * and return its device pointer, for callers that fill it on the device. */
+int fzb_haystack_alloc(uint64_t buf_len, uint64_t buf_lo, uint64_t global_len, uint64_t own_lo,
+                       uint64_t own_hi, int device, fzb_haystack **out, void **dev_ptr);
 
 /* Fill an fzb_haystack_alloc'ed sequence with a seeded synthetic corpus ON THE DEVICE: byte i =
  * alphabet[hash64(seed, i) % alphabet_len] (counter-based, so any shard of the global sequence can
@@ -103,6 +105,21 @@ void fzb_synth_host(uint8_t *dst, uint64_t global_offset, uint64_t n, const uint
 int fzb_haystack_write(fzb_haystack *h, uint64_t global_offset, const uint8_t *src, uint64_t n);
 /* Read bytes back (for Match.matched and tests). */
 int fzb_haystack_read(fzb_haystack *h, uint64_t global_offset, uint8_t *dst, uint64_t n);
+
+/* Replace the contents of a whole-sequence handle with `n` new host bytes (n <= the capacity the
+ * handle was created with); the device allocations are reused -- the analogue of the reference's
+ * reusable chunk buffer in _search_binary_file (__init__.py:141-171). */
+int fzb_haystack_upload(fzb_haystack *h, const uint8_t *host, uint64_t n);
+
+/* Page-locked host memory for fast host<->device copies (cudaHostAlloc); NULL on failure. */
+void *fzb_host_alloc(uint64_t n);
+void fzb_host_free(void *p);
+
+/* Device-side stopwatch on the handle's stream: start records a CUDA event, stop records another,
+ * waits for it and returns the elapsed milliseconds (covers every kernel and copy the handle
+ * enqueued in between, including idle gaps). */
+int fzb_timer_start(fzb_haystack *h);
+int fzb_timer_stop(fzb_haystack *h, double *ms);
 
 uint64_t fzb_haystack_len(const fzb_haystack *h); /* global length */
 void fzb_haystack_destroy(fzb_haystack *h);
