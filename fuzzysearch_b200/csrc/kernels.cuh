@@ -49,15 +49,20 @@ __device__ __forceinline__ void mark_range(const ScanParams &p, int64_t lo, int6
 // granule that can hold an n-gram anchor of an occurrence containing that word.
 // Per 4 haystack bytes: IMAD (hash) + SHF + LDS.U8 + IMAD (accumulate): ~1 issue slot per byte.
 // ------------------------------------------------------------------------------------------------
-__device__ __noinline__ void sampled_slow_path(const ScanParams &p, const uint32_t *grams, int ngr,
-                                               int64_t word_off, uint32_t w) {
+// Confirmation of table hits is warp-cooperative and branch-uniform: the flagged lane's word is
+// broadcast and lane o compares it with the pattern's o-th 4-gram (one compare per lane), so the
+// common case (no lane flagged: one ballot) and the rare case (a false positive of the hash) both
+// cost a handful of warp instructions and nothing is spilled to local memory.
+__device__ __forceinline__ void confirm_word(const ScanParams &p, const uint32_t *grams, int ngr, int lane,
+                                             uint32_t w, int64_t word_off) {
     bool real = false;
-    for (int o = 0; o < ngr; o++) real |= (grams[o] == w);
-    if (!real) return;
-    int64_t g = p.buf_lo + word_off;
-    // anchor idx of n-gram j (pattern offset s_j in [0, m-L]) of an occurrence containing the word:
-    // idx - s_j - k <= g  and  g + 4 <= idx - s_j + m + k
-    mark_range(p, g - (p.m + p.k - 4), g + (p.m - p.L + p.k));
+    for (int o = lane; o < ngr; o += 32) real |= (grams[o] == w);
+    if (__ballot_sync(0xFFFFFFFFu, real) != 0 && lane == 0) {
+        const int64_t g = p.buf_lo + word_off;
+        // anchor idx of n-gram j (pattern offset s_j in [0, m-L]) of an occurrence containing the
+        // word:  idx - s_j - k <= g  and  g + 4 <= idx - s_j + m + k
+        mark_range(p, g - (p.m + p.k - 4), g + (p.m - p.L + p.k));
+    }
 }
 
 __global__ void __launch_bounds__(kFilterThreads)
@@ -77,6 +82,7 @@ k_filter_sampled(const ScanParams p, int64_t nvec, int64_t ntiles) {
     }
     __syncthreads();
 
+    const int lane = threadIdx.x & 31;
     const uint4 *base = reinterpret_cast<const uint4 *>(p.H);
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int64_t v0 = t * kTileVecs + threadIdx.x;
@@ -86,7 +92,7 @@ k_filter_sampled(const ScanParams p, int64_t nvec, int64_t ntiles) {
             int64_t v = v0 + (int64_t)u * kFilterThreads;
             d[u] = (v < nvec) ? ldg_stream(base + v) : make_uint4(0, 0, 0, 0);
         }
-        uint32_t acc = 0;  // bit (15 - 4u - i) <-> word i of load u
+        uint32_t acc = 0;  // bit (4*kFilterUnroll - 1 - 4u - i) <-> word i of load u
 #pragma unroll
         for (int u = 0; u < kFilterUnroll; u++) {
             acc = acc * 2u + tbl[hash_word(d[u].x)];
@@ -94,16 +100,26 @@ k_filter_sampled(const ScanParams p, int64_t nvec, int64_t ntiles) {
             acc = acc * 2u + tbl[hash_word(d[u].z)];
             acc = acc * 2u + tbl[hash_word(d[u].w)];
         }
-        if (acc) {
+        unsigned flagged = __ballot_sync(0xFFFFFFFFu, acc != 0);
+        while (flagged) {  // warp-uniform
+            const int src = __ffs(flagged) - 1;
+            flagged &= flagged - 1;
+            const uint32_t a = __shfl_sync(0xFFFFFFFFu, acc, src);
+            const int64_t vsrc = t * kTileVecs + (threadIdx.x - lane + src);
 #pragma unroll
             for (int u = 0; u < kFilterUnroll; u++) {
-                int64_t v = v0 + (int64_t)u * kFilterThreads;
-                if (v >= nvec) continue;
-                const uint32_t ws[4] = {d[u].x, d[u].y, d[u].z, d[u].w};
-#pragma unroll
-                for (int i = 0; i < 4; i++)
-                    if (acc & (1u << (4 * kFilterUnroll - 1 - 4 * u - i)))
-                        sampled_slow_path(p, grams, ngr, v * 16 + 4 * i, ws[i]);
+                if ((a >> (4 * (kFilterUnroll - 1 - u))) & 0xFu) {  // uniform
+                    const int64_t off = (vsrc + (int64_t)u * kFilterThreads) * 16;
+                    const uint32_t wx = __shfl_sync(0xFFFFFFFFu, d[u].x, src);
+                    const uint32_t wy = __shfl_sync(0xFFFFFFFFu, d[u].y, src);
+                    const uint32_t wz = __shfl_sync(0xFFFFFFFFu, d[u].z, src);
+                    const uint32_t ww = __shfl_sync(0xFFFFFFFFu, d[u].w, src);
+                    const uint32_t nib = a >> (4 * (kFilterUnroll - 1 - u));
+                    if (nib & 8u) confirm_word(p, grams, ngr, lane, wx, off);
+                    if (nib & 4u) confirm_word(p, grams, ngr, lane, wy, off + 4);
+                    if (nib & 2u) confirm_word(p, grams, ngr, lane, wz, off + 8);
+                    if (nib & 1u) confirm_word(p, grams, ngr, lane, ww, off + 12);
+                }
             }
         }
     }
