@@ -70,8 +70,12 @@ struct fzb_haystack {
     uint32_t out_cap = 0;
     uint32_t *d_counters = nullptr;
     uint32_t *h_counters = nullptr;  // pinned
+    RawRec *h_stage = nullptr;       // pinned staging for the first kSpecRecs records
+    bool ev1_recorded = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     int sm_count = 148;
+    uint32_t *d_glist = nullptr;    // compacted list of marked granules
+    uint32_t glist_cap = 0;
     uint32_t *d_scratch = nullptr;  // candidate lists of the LP / generic kernels
     uint64_t scratch_words = 0;
 };
@@ -98,6 +102,10 @@ static int haystack_common_init(fzb_haystack *h) {
     CK(cudaMalloc(&h->d_bitmap, h->bitmap_words * sizeof(uint32_t)));
     CK(cudaMalloc(&h->d_counters, CNT_COUNT * sizeof(uint32_t)));
     CK(cudaMallocHost(&h->h_counters, CNT_COUNT * sizeof(uint32_t)));
+    CK(cudaMallocHost(&h->h_stage, (size_t)16384 * sizeof(RawRec)));
+    CK(cudaMemset(h->d_bitmap, 0, h->bitmap_words * sizeof(uint32_t)));  // stays all-zero between searches
+    h->glist_cap = (uint32_t)std::min<uint64_t>(granules, 1u << 20);
+    CK(cudaMalloc(&h->d_glist, (size_t)std::max<uint32_t>(h->glist_cap, 1) * sizeof(uint32_t)));
     h->out_cap = 1u << 16;
     CK(cudaMalloc(&h->d_out, (size_t)h->out_cap * sizeof(RawRec)));
     return FZB_OK;
@@ -130,7 +138,9 @@ extern "C" void fzb_haystack_destroy(fzb_haystack *h) {
     if (h->d_out) cudaFree(h->d_out);
     if (h->d_counters) cudaFree(h->d_counters);
     if (h->d_scratch) cudaFree(h->d_scratch);
+    if (h->d_glist) cudaFree(h->d_glist);
     if (h->h_counters) cudaFreeHost(h->h_counters);
+    if (h->h_stage) cudaFreeHost(h->h_stage);
     for (auto &e : h->ev)
         if (e) cudaEventDestroy(e);
     if (h->ev_stop) cudaEventDestroy(h->ev_stop);
@@ -428,27 +438,46 @@ static int ensure_out_cap(fzb_haystack *h, uint64_t need) {
     return FZB_OK;
 }
 
-// Runs `launch_verify` (which must enqueue the emitting kernel(s) on h->stream) until the output
-// buffer was large enough; leaves the records in res->raw.
+// Runs one search attempt after another until the output buffer was large enough.  `enqueue` must
+// put EVERY kernel of the search on h->stream (filter included: the verify kernels clear the dirty
+// bitmap as they consume it, so a retry has to re-mark it) and may record h->ev[1] after its scan
+// kernel.  One attempt = one stream synchronisation: the counters and the first kSpecRecs records
+// are copied speculatively into pinned staging memory behind the kernels.
+constexpr uint32_t kSpecRecs = 16384;
+
 template <class F>
-static int run_emitting(fzb_haystack *h, fzb_result *res, F launch_verify) {
+static int run_emitting(fzb_haystack *h, fzb_result *res, F enqueue) {
     for (int attempt = 0; attempt < 8; attempt++) {
         CK(cudaMemsetAsync(h->d_counters, 0, CNT_COUNT * sizeof(uint32_t), h->stream));
-        int rc = launch_verify();
+        CK(cudaEventRecord(h->ev[0], h->stream));
+        h->ev1_recorded = false;
+        int rc = enqueue();
         if (rc) return rc;
         CK(cudaGetLastError());
         CK(cudaEventRecord(h->ev[2], h->stream));
+        const uint32_t spec = std::min(kSpecRecs, h->out_cap);
         CK(cudaMemcpyAsync(h->h_counters, h->d_counters, CNT_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                            h->stream));
+        CK(cudaMemcpyAsync(h->h_stage, h->d_out, (size_t)spec * sizeof(RawRec), cudaMemcpyDeviceToHost,
+                           h->stream));
         CK(cudaStreamSynchronize(h->stream));
-        uint32_t n = h->h_counters[CNT_OUT];
+        const uint32_t n = h->h_counters[CNT_OUT];
         res->stats.n_candidates = h->h_counters[CNT_CAND];
         if (n <= h->out_cap) {
             res->raw.resize(n);
-            if (n) {
-                CK(cudaMemcpyAsync(res->raw.data(), h->d_out, (size_t)n * sizeof(RawRec), cudaMemcpyDeviceToHost,
-                                   h->stream));
+            if (n) memcpy(res->raw.data(), h->h_stage, (size_t)std::min(n, spec) * sizeof(RawRec));
+            if (n > spec) {
+                CK(cudaMemcpyAsync(res->raw.data() + spec, h->d_out + spec, (size_t)(n - spec) * sizeof(RawRec),
+                                   cudaMemcpyDeviceToHost, h->stream));
                 CK(cudaStreamSynchronize(h->stream));
+            }
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, h->ev[0], h->ev[2]);
+            res->stats.gpu_ms = ms;
+            res->stats.filter_ms = ms;
+            if (h->ev1_recorded) {
+                cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+                res->stats.filter_ms = ms;
             }
             return FZB_OK;
         }
@@ -456,16 +485,6 @@ static int run_emitting(fzb_haystack *h, fzb_result *res, F launch_verify) {
         if (rc) return rc;
     }
     return fail(FZB_E_CUDA, "output buffer kept overflowing");
-}
-
-static void finish_stats(fzb_haystack *h, fzb_result *res, bool has_filter) {
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, h->ev[0], h->ev[2]);
-    res->stats.gpu_ms = ms;
-    if (has_filter) {
-        cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
-        res->stats.filter_ms = ms;
-    }
 }
 
 static void sort_generation_order(std::vector<RawRec> &v) {
@@ -490,6 +509,33 @@ static int set_filter_attrs(size_t smem) {
     return FZB_OK;
 }
 
+constexpr size_t kFilterSmem = kTblSize + 256 * sizeof(uint32_t);
+
+// The q-sample lemma of k_filter_sampled needs floor((m-k-3)/4) >= k+1 aligned words per occurrence.
+static bool sampled_filter_applies(uint32_t m, uint32_t k, uint32_t flags) {
+    if (flags & FZB_F_FORCE_DENSE) return false;
+    if (m < 4 || m < k + 3) return false;
+    return (m - k - 3) / 4 >= k + 1;
+}
+
+// Enqueue the one pass over the haystack that marks candidate granules; records ev[1] behind it.
+static int enqueue_filter(fzb_haystack *h, const ScanParams &p, bool sampled, fzb_result *res) {
+    const int64_t nvec = (int64_t)(round_up(h->buf_len, 16) / 16);
+    const int64_t ntiles = (nvec + kTileVecs - 1) / kTileVecs;
+    if (ntiles > 0) {
+        int grid = (int)std::min<int64_t>(ntiles, (int64_t)h->sm_count * 4);
+        if (sampled)
+            k_filter_sampled<<<grid, kFilterThreads, kFilterSmem, h->stream>>>(p, nvec, ntiles);
+        else
+            k_filter_dense<<<grid, kFilterThreads, kFilterSmem, h->stream>>>(p, nvec, ntiles);
+        CK(cudaGetLastError());
+        res->stats.n_launches++;
+    }
+    CK(cudaEventRecord(h->ev[1], h->stream));
+    h->ev1_recorded = true;
+    return FZB_OK;
+}
+
 // n-gram Levenshtein search (also serves exact search as k == 0, L == m)
 static int search_lev_ngrams(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint32_t k, uint32_t flags,
                              fzb_result *res) {
@@ -501,43 +547,29 @@ static int search_lev_ngrams(fzb_haystack *h, const uint8_t *pattern, uint32_t m
     p.n_ngrams = (int)m / p.L;  // range(0, m-L+1, L)
     int rc = check_halo(h, (uint64_t)m + k);
     if (rc) return rc;
-    const bool sampled = !(flags & FZB_F_FORCE_DENSE) && m >= 4 && ((int)m - (int)k - 3) / 4 >= (int)k + 1 &&
-                         (int)m - (int)k - 3 >= 0;
+    const bool sampled = sampled_filter_applies(m, k, flags);
     p.q = sampled ? 4 : std::min(p.L, 4);
     res->stats.route = k == 0 ? 0 : (sampled ? 1 : 2);
-
-    CK(cudaSetDevice(h->device));
-    const int64_t nvec = (int64_t)(round_up(h->buf_len, 16) / 16);
-    const int64_t ntiles = (nvec + kTileVecs - 1) / kTileVecs;
-    const size_t smem = kTblSize + 256 * sizeof(uint32_t);
-    rc = set_filter_attrs(smem);
-    if (rc) return rc;
-    CK(cudaMemsetAsync(h->d_bitmap, 0, h->bitmap_words * sizeof(uint32_t), h->stream));
-    CK(cudaEventRecord(h->ev[0], h->stream));
-    if (ntiles > 0) {
-        int grid = (int)std::min<int64_t>(ntiles, (int64_t)h->sm_count * 4);
-        if (sampled)
-            k_filter_sampled<<<grid, kFilterThreads, smem, h->stream>>>(p, nvec, ntiles);
-        else
-            k_filter_dense<<<grid, kFilterThreads, smem, h->stream>>>(p, nvec, ntiles);
-        CK(cudaGetLastError());
-    }
-    CK(cudaEventRecord(h->ev[1], h->stream));
-    res->stats.n_launches = 1;
     res->stats.bytes_scanned = h->buf_len;
+    CK(cudaSetDevice(h->device));
+    rc = set_filter_attrs(kFilterSmem);
+    if (rc) return rc;
     rc = run_emitting(h, res, [&]() -> int {
-        int grid = h->sm_count * 4;
-        k_verify_lev<<<grid, kVerifyThreads, 0, h->stream>>>(p, h->bitmap_words, h->d_out, h->out_cap,
-                                                             h->d_counters);
-        res->stats.n_launches++;
+        int r2 = enqueue_filter(h, p, sampled, res);
+        if (r2) return r2;
+        const uint32_t gcap = (flags & FZB_F_TINY_LIST) ? std::min(h->glist_cap, 8u) : h->glist_cap;
+        k_compact_granules<<<h->sm_count * 4, 256, 0, h->stream>>>(h->d_bitmap, h->bitmap_words, h->d_glist, gcap,
+                                                                   h->d_counters);
+        for (int scan_mode = 0; scan_mode < 2; scan_mode++)
+            k_verify_lev<<<h->sm_count * 4, kVerifyThreads, 0, h->stream>>>(
+                p, h->bitmap_words, h->d_glist, gcap, scan_mode, h->d_out, h->out_cap, h->d_counters);
+        res->stats.n_launches += 3;
         return FZB_OK;
     });
     if (rc) return rc;
-    finish_stats(h, res, true);
     sort_generation_order(res->raw);
     return FZB_OK;
 }
-
 
 // ------------------------------------------------------------------------------------------------
 // LP / generic routes (lp_kernels.cuh)
@@ -552,19 +584,16 @@ static int ensure_scratch(fzb_haystack *h, uint64_t words) {
     return FZB_OK;
 }
 
-// Runs an LP-style kernel with growing per-thread candidate capacity until no list overflowed.
+// Runs an LP-style search with growing per-thread candidate capacity until no list overflowed.
+// `enqueue(grid, cap)` must put every kernel of one attempt on the stream.
 template <class F>
-static int run_lp(fzb_haystack *h, fzb_result *res, F launch) {
+static int run_lp(fzb_haystack *h, fzb_result *res, F enqueue) {
     const int grid = h->sm_count * 4;
     const uint64_t threads = (uint64_t)grid * kLpThreads;
     for (int cap = 256; cap <= (1 << 16); cap *= 8) {
         int rc = ensure_scratch(h, threads * 2 * (uint64_t)cap);
         if (rc) return rc;
-        rc = run_emitting(h, res, [&]() -> int {
-            launch(grid, cap);
-            res->stats.n_launches++;
-            return FZB_OK;
-        });
+        rc = run_emitting(h, res, [&]() -> int { return enqueue(grid, cap); });
         if (rc) return rc;
         if (!h->h_counters[CNT_OVERFLOW]) return FZB_OK;
     }
@@ -579,27 +608,24 @@ static int search_lev_lp(fzb_haystack *h, const uint8_t *pattern, uint32_t m, ui
     int rc = check_halo(h, (uint64_t)m + k);
     if (rc) return rc;
     CK(cudaSetDevice(h->device));
-    CK(cudaEventRecord(h->ev[0], h->stream));
-    CK(cudaEventRecord(h->ev[1], h->stream));
     res->stats.route = 3;
     res->stats.bytes_scanned = h->buf_len;
-    rc = run_lp(h, res, [&](int grid, int cap) {
+    rc = run_lp(h, res, [&](int grid, int cap) -> int {
         k_lev_lp<<<grid, kLpThreads, 0, h->stream>>>(p, h->d_scratch, cap, h->d_out, h->out_cap, h->d_counters);
+        res->stats.n_launches++;
+        return FZB_OK;
     });
     if (rc) return rc;
-    finish_stats(h, res, false);
-    res->stats.filter_ms = res->stats.gpu_ms;
     sort_canonical(res->raw);
     return FZB_OK;
 }
 
 static int search_generic(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint32_t max_subs, uint32_t max_ins,
                           uint32_t max_dels, uint32_t max_l, bool ngrams, uint32_t flags, fzb_result *res) {
-    // after LevenshteinSearchParams normalisation (common.py:100-116) every limit is <= max_l or
-    // max_l <= their sum; the packed candidate keeps 6 bits per counter
-    const uint32_t lim = 63;
-    if (max_l > lim) return fail(FZB_E_UNSUPPORTED, "max_l_dist > 63 is not supported by the generic search");
-    // counters can never exceed max_l (each op costs >= 1 except dels inside ins+del pairs, <= max_l too)
+    // the packed candidate of sim_generic keeps 6 bits per counter
+    if (max_l > 63) return fail(FZB_E_UNSUPPORTED, "max_l_dist > 63 is not supported by the generic search");
+    // no counter can exceed max_l (every operation that increments one costs >= 1), so clamping the
+    // per-operation limits to max_l changes nothing (LevenshteinSearchParams does the same, common.py:108-116)
     max_subs = std::min(max_subs, max_l);
     max_ins = std::min(max_ins, max_l);
     max_dels = std::min(max_dels, max_l);
@@ -612,52 +638,36 @@ static int search_generic(fzb_haystack *h, const uint8_t *pattern, uint32_t m, u
     int rc = check_halo(h, (uint64_t)m + max_l);
     if (rc) return rc;
     CK(cudaSetDevice(h->device));
+    res->stats.bytes_scanned = h->buf_len;
     if (!ngrams) {
-        CK(cudaEventRecord(h->ev[0], h->stream));
-        CK(cudaEventRecord(h->ev[1], h->stream));
         res->stats.route = 6;
-        res->stats.bytes_scanned = h->buf_len;
-        rc = run_lp(h, res, [&](int grid, int cap) {
+        rc = run_lp(h, res, [&](int grid, int cap) -> int {
             k_generic_lp<<<grid, kLpThreads, 0, h->stream>>>(p, h->d_scratch, cap, h->d_out, h->out_cap,
                                                              h->d_counters);
+            res->stats.n_launches++;
+            return FZB_OK;
         });
         if (rc) return rc;
-        finish_stats(h, res, false);
-        res->stats.filter_ms = res->stats.gpu_ms;
         sort_canonical(res->raw);
         return FZB_OK;
     }
     p.L = (int)(m / (max_l + 1));
     if (p.L == 0) return fail(FZB_E_NGRAM_ZERO, "the subsequence length must be greater than max_l_dist");
     p.n_ngrams = (int)m / p.L;
-    const bool sampled = !(flags & FZB_F_FORCE_DENSE) && m >= 4 && (int)m - (int)max_l - 3 >= 0 &&
-                         ((int)m - (int)max_l - 3) / 4 >= (int)max_l + 1;
+    const bool sampled = sampled_filter_applies(m, max_l, flags);
     p.q = sampled ? 4 : std::min(p.L, 4);
     res->stats.route = 5;
-    const int64_t nvec = (int64_t)(round_up(h->buf_len, 16) / 16);
-    const int64_t ntiles = (nvec + kTileVecs - 1) / kTileVecs;
-    const size_t smem = kTblSize + 256 * sizeof(uint32_t);
-    rc = set_filter_attrs(smem);
+    rc = set_filter_attrs(kFilterSmem);
     if (rc) return rc;
-    CK(cudaMemsetAsync(h->d_bitmap, 0, h->bitmap_words * sizeof(uint32_t), h->stream));
-    CK(cudaEventRecord(h->ev[0], h->stream));
-    if (ntiles > 0) {
-        int grid = (int)std::min<int64_t>(ntiles, (int64_t)h->sm_count * 4);
-        if (sampled)
-            k_filter_sampled<<<grid, kFilterThreads, smem, h->stream>>>(p, nvec, ntiles);
-        else
-            k_filter_dense<<<grid, kFilterThreads, smem, h->stream>>>(p, nvec, ntiles);
-        CK(cudaGetLastError());
-    }
-    CK(cudaEventRecord(h->ev[1], h->stream));
-    res->stats.n_launches = 1;
-    res->stats.bytes_scanned = h->buf_len;
-    rc = run_lp(h, res, [&](int grid, int cap) {
+    rc = run_lp(h, res, [&](int grid, int cap) -> int {
+        int r2 = enqueue_filter(h, p, sampled, res);
+        if (r2) return r2;
         k_verify_generic<<<grid, kLpThreads, 0, h->stream>>>(p, h->bitmap_words, h->d_scratch, cap, h->d_out,
                                                              h->out_cap, h->d_counters);
+        res->stats.n_launches++;
+        return FZB_OK;
     });
     if (rc) return rc;
-    finish_stats(h, res, true);
     // generation order: n-gram major, hit index, then the window's matches in canonical order
     std::sort(res->raw.begin(), res->raw.end(), [](const RawRec &a, const RawRec &b) {
         if (a.ngram != b.ngram) return a.ngram < b.ngram;
@@ -743,8 +753,6 @@ extern "C" int fzb_search_hamming(fzb_haystack *h, const uint8_t *pattern, uint3
             fill_params(h, pattern, m, p);
             p.k = (int)std::min<uint32_t>(k, m);
             CK(cudaSetDevice(h->device));
-            CK(cudaEventRecord(h->ev[0], h->stream));
-            CK(cudaEventRecord(h->ev[1], h->stream));
             res->stats.route = 4;
             res->stats.bytes_scanned = h->buf_len;
             int r2 = run_emitting(h, res, [&]() -> int {
@@ -754,8 +762,6 @@ extern "C" int fzb_search_hamming(fzb_haystack *h, const uint8_t *pattern, uint3
                 return FZB_OK;
             });
             if (r2) return r2;
-            finish_stats(h, res, false);
-            res->stats.filter_ms = res->stats.gpu_ms;
             sort_canonical(res->raw);
             for (auto &r : res->raw) r.ngram = -1;
             return FZB_OK;

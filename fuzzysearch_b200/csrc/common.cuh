@@ -36,7 +36,7 @@ struct ScanParams {
 };
 
 // counters[] slots (device, uint32 each unless noted)
-enum { CNT_OUT = 0, CNT_CAND = 1, CNT_COUNT = 8 };
+enum { CNT_OUT = 0, CNT_CAND = 1, CNT_OVERFLOW = 2, CNT_GRAN = 3, CNT_WORK = 4, CNT_COUNT = 8 };
 
 __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
     x += 0x9E3779B97F4A7C15ull;

@@ -207,7 +207,7 @@ __device__ bool expand_short(const uint8_t *sub, int sublen, const uint8_t *seq,
     for (int j = 0; j < sublen; j++) S.scores[j] = (uint16_t)(j + 1);  // :47
     int min_score = sublen, min_idx = -1;                             // :49-50
     for (int si = 0; si < seqlen; si++) {                             // :52
-        const uint8_t ch = __ldg(seq + DIR * si);
+        const uint8_t ch = seq[DIR * si];
         int a = si, c = si + 1;  // :54-55
         int row_min = 1 << 30;
         for (int j = 0; j < sublen; j++) {  // :56-63
@@ -248,7 +248,7 @@ __device__ bool expand_long(const uint8_t *sub, int sublen, const uint8_t *seq, 
     int new_start = 0, new_end = sublen - 1;                          // :97-98
     bool ns_none = false;
     for (int si = 0; si < seqlen; si++) {  // :100
-        const uint8_t ch = __ldg(seq + DIR * si);
+        const uint8_t ch = seq[DIR * si];
         const int rstart = new_start;                 // :102
         const int rend = min(sublen, new_end + 1);    // :103
         int a = si, c = si + 1;                       // :105-106
@@ -320,10 +320,34 @@ __device__ __forceinline__ void emit(RawRec *out, uint32_t cap, uint32_t *counte
     }
 }
 
-__device__ void verify_anchor_lev(const ScanParams &p, const uint8_t *sP, int64_t idx, DpScratch &S,
-                                  RawRec *out, uint32_t cap, uint32_t *counters) {
+// Window staging: a marked granule [gbase, gbase+64) only ever needs H[gbase-(m+k) : gbase+64+m+k)
+// (every anchor's n-gram test and both expansions stay inside it), so the warp copies that window
+// into shared memory with ONE round trip to DRAM and all further reads are shared-memory reads --
+// the compares and the DP are chains of dependent byte reads, which would otherwise each pay the
+// full DRAM latency (the scan streamed the haystack past the caches).
+constexpr int kWinBytes = 64 + 2 * (2 * kMaxPattern) + 32;  // 1116
+constexpr int kWinWords = (kWinBytes + 3) / 4;
+
+// Loads the window of granule `gbase` into sWin; returns the global position of sWin[0].
+__device__ __forceinline__ int64_t stage_window(const ScanParams &p, int64_t gbase, int halo, int lane,
+                                                uint32_t *sWin) {
+    int64_t wlo = max(gbase - halo, p.buf_lo);
+    int64_t whi = min(gbase + kGranule + halo, p.buf_lo + p.buf_len);
+    const int64_t alo = wlo & ~(int64_t)3;  // buf_lo is a multiple of 16, so global and buffer alignment agree
+    const int nwords = (int)((whi - alo + 3) >> 2);
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(p.H + (alo - p.buf_lo));
+    __syncwarp();
+    for (int w = lane; w < nwords; w += 32) sWin[w] = __ldg(src + w);  // padded buffer: reads past whi are safe
+    __syncwarp();
+    return alo;
+}
+
+__device__ void verify_anchor_lev(const ScanParams &p, const uint8_t *sP, const uint8_t *W, int64_t idx,
+                                  DpScratch &S, RawRec *out, uint32_t cap, uint32_t *counters) {
+    // W[g] is the haystack byte at global position g (shared-memory window)
     const int m = p.m, k = p.k, L = p.L;
     const int64_t N = p.N;
+    const uint8_t *h = W + idx;
     for (int j = 0; j < p.n_ngrams; j++) {
         const int s = j * L;  // :170
         // search window of n-gram j, clamped like search_exact.py:29-30   (:174-176)
@@ -332,10 +356,9 @@ __device__ void verify_anchor_lev(const ScanParams &p, const uint8_t *sP, int64_
         ws = max((int64_t)0, min(ws, N));
         we = max(ws, min(we, N));
         if (idx < ws || idx + L > we) continue;
-        const uint8_t *h = p.H + (idx - p.buf_lo);
         bool eq = true;
         for (int i = 0; i < L; i++) {
-            if (__ldg(h + i) != sP[s + i]) {
+            if (h[i] != sP[s + i]) {
                 eq = false;
                 break;
             }
@@ -356,18 +379,77 @@ __device__ void verify_anchor_lev(const ScanParams &p, const uint8_t *sP, int64_
     }
 }
 
+// Work distribution.  The marked granules are first compacted into a list (k_compact_granules: one
+// thread per bitmap word, ~8 MB for a 4 GiB haystack) and the verify kernel hands ONE GRANULE TO ONE
+// WARP through an atomic work counter, so clustered matches (the realistic case) spread over the
+// whole GPU instead of serialising on the warp that owns their bitmap words.  Each processed granule
+// clears its own bit; if the list overflows (dense candidates, e.g. small alphabets) the bits left
+// set are swept by the bitmap-scanning fallback loop of the same kernel launched in "scan" mode.
+__global__ void __launch_bounds__(256)
+k_compact_granules(const uint32_t *bitmap, uint64_t bitmap_words, uint32_t *glist, uint32_t glist_cap,
+                   uint32_t *counters) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t wi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; wi < bitmap_words; wi += stride) {
+        uint32_t bits = bitmap[wi];
+        if (!bits) continue;
+        const uint32_t n = (uint32_t)__popc(bits);
+        uint32_t slot = atomicAdd(&counters[CNT_GRAN], n);
+        while (bits) {
+            const int bit = __ffs(bits) - 1;
+            bits &= bits - 1;
+            if (slot < glist_cap) glist[slot] = (uint32_t)(wi * 32 + bit);
+            slot++;
+        }
+    }
+}
+
+__device__ __forceinline__ void verify_granule_lev(const ScanParams &p, const uint8_t *sP, uint32_t *sWin,
+                                                   int64_t granule, int lane, DpScratch &S, RawRec *out,
+                                                   uint32_t cap, uint32_t *counters) {
+    const int64_t gbase = p.buf_lo + (granule << kGranuleShift);
+    const int64_t alo = stage_window(p, gbase, p.m + p.k, lane, sWin);
+    const uint8_t *W = reinterpret_cast<const uint8_t *>(sWin) - alo;
+#pragma unroll 1
+    for (int half = 0; half < kGranule / 32; half++) {
+        const int64_t idx = gbase + half * 32 + lane;
+        if (idx >= p.own_lo && idx < p.own_hi) verify_anchor_lev(p, sP, W, idx, S, out, cap, counters);
+    }
+}
+
+// scan_mode == 0: process glist[0 .. min(CNT_GRAN, glist_cap)) one granule per warp.
+// scan_mode == 1: only if the list overflowed, sweep the bitmap for the bits still set.
 __global__ void __launch_bounds__(kVerifyThreads)
-k_verify_lev(const ScanParams p, uint64_t bitmap_words, RawRec *out, uint32_t cap, uint32_t *counters) {
+k_verify_lev(const ScanParams p, uint64_t bitmap_words, const uint32_t *glist, uint32_t glist_cap, int scan_mode,
+             RawRec *out, uint32_t cap, uint32_t *counters) {
     __shared__ uint8_t sP[256];
+    __shared__ uint32_t sWinAll[kVerifyThreads / 32][kWinWords];
+    const uint32_t ngran = counters[CNT_GRAN];
+    if (scan_mode && ngran <= glist_cap) return;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) sP[i] = p.P[i];
     __syncthreads();
     DpScratch S;
     const int lane = threadIdx.x & 31;
+    uint32_t *sWin = sWinAll[threadIdx.x >> 5];
+    if (!scan_mode) {
+        const uint32_t nitems = min(ngran, glist_cap);
+        for (;;) {
+            uint32_t item = 0;
+            if (lane == 0) item = atomicAdd(&counters[CNT_WORK], 1u);
+            item = __shfl_sync(0xFFFFFFFFu, item, 0);
+            if (item >= nitems) break;
+            const uint32_t g = glist[item];
+            verify_granule_lev(p, sP, sWin, (int64_t)g, lane, S, out, cap, counters);
+            if (lane == 0) atomicAnd(&p.bitmap[g >> 5], ~(1u << (g & 31)));
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counters[CNT_CAND], nitems);
+        return;
+    }
     const uint64_t gwarp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     for (uint64_t wbase = gwarp * 32; wbase < bitmap_words; wbase += nwarps * 32) {
         const uint64_t wi = wbase + lane;
         uint32_t bits = wi < bitmap_words ? p.bitmap[wi] : 0u;
+        if (bits) p.bitmap[wi] = 0u;  // consumed: the bitmap is all-zero again when the kernel ends
         unsigned active = __ballot_sync(0xFFFFFFFFu, bits != 0);
         while (active) {
             const int src = __ffs(active) - 1;
@@ -377,13 +459,7 @@ k_verify_lev(const ScanParams p, uint64_t bitmap_words, RawRec *out, uint32_t ca
             while (b) {
                 const int bit = __ffs(b) - 1;
                 b &= b - 1;
-                const int64_t gbase = p.buf_lo + (((int64_t)(wbase + src) * 32 + bit) << kGranuleShift);
-#pragma unroll 1
-                for (int half = 0; half < kGranule / 32; half++) {
-                    const int64_t idx = gbase + half * 32 + lane;
-                    if (idx >= p.own_lo && idx < p.own_hi)
-                        verify_anchor_lev(p, sP, idx, S, out, cap, counters);
-                }
+                verify_granule_lev(p, sP, sWin, (int64_t)(wbase + src) * 32 + bit, lane, S, out, cap, counters);
             }
         }
     }

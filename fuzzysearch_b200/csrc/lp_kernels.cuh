@@ -16,7 +16,6 @@
 
 namespace fzb {
 
-enum { CNT_OVERFLOW = 2 };
 
 // ---- Levenshtein LP ------------------------------------------------------------------------------
 // candidate = (subseq_index j, dist d) packed j | d<<16
@@ -129,16 +128,16 @@ __device__ __forceinline__ bool g_push(uint32_t *list, int &n, int cap, uint32_t
 
 // Candidates born at `start`, over the sequence that ends (exclusive) at `seq_end` (both global).
 // anchor_idx / anchor_ngram tag the emitted records (n-gram hit that opened the window, or start).
-__device__ bool sim_generic(const ScanParams &p, const uint8_t *sP, int64_t start, int64_t seq_end, uint32_t *A,
-                            uint32_t *B, int cap, int64_t anchor_idx, int anchor_ngram, RawRec *out,
-                            uint32_t ocap, uint32_t *counters) {
+// H[g] must be the haystack byte at global position g (global memory, or the staged window).
+__device__ bool sim_generic(const ScanParams &p, const uint8_t *sP, const uint8_t *H, int64_t start,
+                            int64_t seq_end, uint32_t *A, uint32_t *B, int cap, int64_t anchor_idx,
+                            int anchor_ngram, RawRec *out, uint32_t ocap, uint32_t *counters) {
     const int m = p.m, max_l = p.k, max_subs = p.max_subs, max_ins = p.max_ins, max_dels = p.max_dels;
-    const uint8_t *H = p.H - p.buf_lo;
     A[0] = gpack(0, 0, 0, 0, 0);  // generic_search.py:81
     int nA = 1;
     int64_t i = start;
     for (; i < seq_end && nA > 0; i++) {  // :79
-        const uint8_t ch = __ldg(H + i);
+        const uint8_t ch = H[i];
         int nB = 0;
         for (int c = 0; c < nA; c++) {  // :84
             const uint32_t v = A[c];
@@ -205,7 +204,7 @@ k_generic_lp(const ScanParams p, uint32_t *scratch, int cap, RawRec *out, uint32
     uint32_t *A = scratch + tid * 2 * (int64_t)cap, *B = A + cap;
     const int64_t hi = min(p.own_hi, p.N);
     for (int64_t s = p.own_lo + tid; s < hi; s += stride)
-        if (!sim_generic(p, sP, s, p.N, A, B, cap, s, 1, out, ocap, counters))
+        if (!sim_generic(p, sP, p.H - p.buf_lo, s, p.N, A, B, cap, s, 1, out, ocap, counters))
             atomicExch(&counters[CNT_OVERFLOW], 1u);
 }
 
@@ -216,9 +215,11 @@ __global__ void __launch_bounds__(kLpThreads)
 k_verify_generic(const ScanParams p, uint64_t bitmap_words, uint32_t *scratch, int cap, RawRec *out,
                  uint32_t ocap, uint32_t *counters) {
     __shared__ uint8_t sP[256];
+    __shared__ uint32_t sWinAll[kLpThreads / 32][kWinWords];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) sP[i] = p.P[i];
     __syncthreads();
     const int lane = threadIdx.x & 31;
+    uint32_t *sWin = sWinAll[threadIdx.x >> 5];
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t *A = scratch + tid * 2 * (int64_t)cap, *B = A + cap;
     const uint64_t gwarp = (uint64_t)tid >> 5;
@@ -228,6 +229,7 @@ k_verify_generic(const ScanParams p, uint64_t bitmap_words, uint32_t *scratch, i
     for (uint64_t wbase = gwarp * 32; wbase < bitmap_words; wbase += nwarps * 32) {
         const uint64_t wi = wbase + lane;
         uint32_t bits = wi < bitmap_words ? p.bitmap[wi] : 0u;
+        if (bits) p.bitmap[wi] = 0u;  // consumed: the bitmap is all-zero again when the kernel ends
         unsigned active = __ballot_sync(0xFFFFFFFFu, bits != 0);
         while (active) {
             const int src = __ffs(active) - 1;
@@ -238,6 +240,8 @@ k_verify_generic(const ScanParams p, uint64_t bitmap_words, uint32_t *scratch, i
                 const int bit = __ffs(b) - 1;
                 b &= b - 1;
                 const int64_t gbase = p.buf_lo + (((int64_t)(wbase + src) * 32 + bit) << kGranuleShift);
+                const int64_t alo = stage_window(p, gbase, m + k, lane, sWin);
+                const uint8_t *W = reinterpret_cast<const uint8_t *>(sWin) - alo;  // W[g]: byte at global g
                 for (int half = 0; half < kGranule / 32; half++) {
                     const int64_t idx = gbase + half * 32 + lane;
                     const bool owned = idx >= p.own_lo && idx < p.own_hi;
@@ -251,10 +255,10 @@ k_verify_generic(const ScanParams p, uint64_t bitmap_words, uint32_t *scratch, i
                                 ws = max((int64_t)0, min(ws, N));
                                 we = max(ws, min(we, N));
                                 if (idx >= ws && idx + L <= we) {
-                                    const uint8_t *h = p.H + (idx - p.buf_lo);
+                                    const uint8_t *h = W + idx;
                                     hit = true;
                                     for (int i = 0; i < L; i++)
-                                        if (__ldg(h + i) != sP[s + i]) {
+                                        if (h[i] != sP[s + i]) {
                                             hit = false;
                                             break;
                                         }
@@ -270,7 +274,7 @@ k_verify_generic(const ScanParams p, uint64_t bitmap_words, uint32_t *scratch, i
                             const int64_t wlo = max((int64_t)0, p0 - k);      // :231
                             const int64_t whi = min(N, p0 + m + k);
                             for (int64_t st = wlo + lane; st < whi; st += 32)
-                                if (!sim_generic(p, sP, st, whi, A, B, cap, hidx, j, out, ocap, counters))
+                                if (!sim_generic(p, sP, W, st, whi, A, B, cap, hidx, j, out, ocap, counters))
                                     atomicExch(&counters[CNT_OVERFLOW], 1u);
                         }
                     }

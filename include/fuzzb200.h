@@ -56,6 +56,7 @@ extern "C" {
 #define FZB_F_FORCE_DENSE 2u  /* force the every-position candidate filter (testing) */
 #define FZB_F_FORCE_LP 4u     /* Levenshtein/generic: force the "linear programming" route */
 #define FZB_F_FORCE_NGRAMS 8u /* Levenshtein/generic/Hamming: force the n-gram route */
+#define FZB_F_TINY_LIST 16u   /* testing: cap the granule work list at 8 entries (overflow path) */
 
 typedef struct fzb_haystack fzb_haystack; /* a device-resident sequence (or one shard of it) */
 typedef struct fzb_result fzb_result;     /* the matches of one search */

@@ -19,6 +19,8 @@ def _raw(res):
 @pytest.mark.parametrize("alphabet,n,m,k,flags", [
     (ASCII, 1 << 22, 20, 2, 0),
     (ASCII, 1 << 22, 20, 2, F.F_FORCE_DENSE),
+    (ASCII, 1 << 22, 20, 2, F.F_TINY_LIST),   # granule work list overflows -> bitmap sweep
+    (DNA, 1 << 18, 20, 2, F.F_TINY_LIST),
     (ASCII, (1 << 20) + 13, 32, 3, 0),
     (ASCII, 1 << 20, 9, 2, 0),          # L = 3: dense filter, q = 3
     (ASCII, 1 << 20, 64, 4, 0),
