@@ -14,6 +14,7 @@
 
 #include "kernels.cuh"
 #include "lp_kernels.cuh"
+#include "post_kernels.cuh"
 
 using namespace fzb;
 
@@ -71,6 +72,10 @@ struct fzb_haystack {
     uint32_t *d_counters = nullptr;
     uint32_t *h_counters = nullptr;  // pinned
     RawRec *h_stage = nullptr;       // pinned staging for the first kSpecRecs records
+    RawRec *d_raw_sorted = nullptr;  // k_post_small outputs (kPostMax entries each)
+    int64_t *d_fin = nullptr;
+    uint64_t *d_keys_sorted = nullptr;
+    int64_t *h_fin = nullptr;        // pinned
     bool ev1_recorded = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     int sm_count = 148;
@@ -84,6 +89,7 @@ struct fzb_result {
     std::vector<RawRec> raw;
     std::vector<RawRec> fin;
     bool final_is_raw = false;
+    bool device_post = false;  // raw already ordered (and fin filled) by k_post_small
     fzb_stats stats{};
 };
 
@@ -100,9 +106,14 @@ static int haystack_common_init(fzb_haystack *h) {
     uint64_t granules = (h->padded_len >> kGranuleShift) + 2;
     h->bitmap_words = round_up((granules + 31) / 32, 32);
     CK(cudaMalloc(&h->d_bitmap, h->bitmap_words * sizeof(uint32_t)));
-    CK(cudaMalloc(&h->d_counters, CNT_COUNT * sizeof(uint32_t)));
+    CK(cudaMalloc(&h->d_counters, (CNT_COUNT + 2 * (size_t)kPostMax) * sizeof(uint32_t)));  // + k_rank's ranks
     CK(cudaMallocHost(&h->h_counters, CNT_COUNT * sizeof(uint32_t)));
-    CK(cudaMallocHost(&h->h_stage, (size_t)16384 * sizeof(RawRec)));
+    CK(cudaMallocHost(&h->h_stage, (size_t)kPostMax * sizeof(RawRec)));
+    CK(cudaMallocHost(&h->h_fin, (size_t)kPostMax * 3 * sizeof(int64_t)));
+    CK(cudaMalloc(&h->d_raw_sorted, (size_t)kPostMax * sizeof(RawRec)));
+    CK(cudaMalloc(&h->d_fin, (size_t)kPostMax * 3 * sizeof(int64_t)));
+    CK(cudaMalloc(&h->d_keys_sorted, (size_t)kPostMax * sizeof(uint64_t)));
+    CK(cudaFuncSetAttribute(k_consolidate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConsSmem));
     CK(cudaMemset(h->d_bitmap, 0, h->bitmap_words * sizeof(uint32_t)));  // stays all-zero between searches
     h->glist_cap = (uint32_t)std::min<uint64_t>(granules, 1u << 20);
     CK(cudaMalloc(&h->d_glist, (size_t)std::max<uint32_t>(h->glist_cap, 1) * sizeof(uint32_t)));
@@ -141,6 +152,10 @@ extern "C" void fzb_haystack_destroy(fzb_haystack *h) {
     if (h->d_glist) cudaFree(h->d_glist);
     if (h->h_counters) cudaFreeHost(h->h_counters);
     if (h->h_stage) cudaFreeHost(h->h_stage);
+    if (h->h_fin) cudaFreeHost(h->h_fin);
+    if (h->d_raw_sorted) cudaFree(h->d_raw_sorted);
+    if (h->d_fin) cudaFree(h->d_fin);
+    if (h->d_keys_sorted) cudaFree(h->d_keys_sorted);
     for (auto &e : h->ev)
         if (e) cudaEventDestroy(e);
     if (h->ev_stop) cudaEventDestroy(h->ev_stop);
@@ -443,46 +458,87 @@ static int ensure_out_cap(fzb_haystack *h, uint64_t need) {
 // bitmap as they consume it, so a retry has to re-mark it) and may record h->ev[1] after its scan
 // kernel.  One attempt = one stream synchronisation: the counters and the first kSpecRecs records
 // are copied speculatively into pinned staging memory behind the kernels.
-constexpr uint32_t kSpecRecs = 16384;
+constexpr uint32_t kSpecRecs = 4096;
+
+// What k_post_small should do behind the emitting kernels (post.enable == false: host does it).
+struct PostPlan {
+    bool enable = false;
+    int raw_canonical = 0;
+    int do_consolidate = 0;
+};
 
 template <class F>
-static int run_emitting(fzb_haystack *h, fzb_result *res, F enqueue) {
+static int run_emitting(fzb_haystack *h, fzb_result *res, F enqueue, PostPlan post = PostPlan()) {
     for (int attempt = 0; attempt < 8; attempt++) {
-        CK(cudaMemsetAsync(h->d_counters, 0, CNT_COUNT * sizeof(uint32_t), h->stream));
+        CK(cudaMemsetAsync(h->d_counters, 0,
+                           (CNT_COUNT + (post.enable ? 2 * (size_t)kPostMax : 0)) * sizeof(uint32_t), h->stream));
         CK(cudaEventRecord(h->ev[0], h->stream));
         h->ev1_recorded = false;
         int rc = enqueue();
         if (rc) return rc;
         CK(cudaGetLastError());
-        CK(cudaEventRecord(h->ev[2], h->stream));
         const uint32_t spec = std::min(kSpecRecs, h->out_cap);
+        if (post.enable) {
+            uint32_t *ranks = h->d_counters + CNT_COUNT;
+            k_rank<<<dim3(kPostMax / kRankThreads, kPostMax / kRankChunk), kRankThreads, 0, h->stream>>>(
+                h->d_out, h->out_cap, post.raw_canonical, ranks, h->d_counters);
+            k_consolidate<<<1, kConsThreads, kConsSmem, h->stream>>>(h->d_out, ranks, h->d_raw_sorted,
+                                                                     h->d_keys_sorted, h->out_cap,
+                                                                     post.do_consolidate, h->d_fin, h->d_counters);
+            CK(cudaGetLastError());
+            res->stats.n_launches += 2;
+        }
+        CK(cudaEventRecord(h->ev[2], h->stream));
         CK(cudaMemcpyAsync(h->h_counters, h->d_counters, CNT_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                            h->stream));
-        CK(cudaMemcpyAsync(h->h_stage, h->d_out, (size_t)spec * sizeof(RawRec), cudaMemcpyDeviceToHost,
-                           h->stream));
+        CK(cudaMemcpyAsync(h->h_stage, post.enable ? h->d_raw_sorted : h->d_out, (size_t)spec * sizeof(RawRec),
+                           cudaMemcpyDeviceToHost, h->stream));
+        if (post.enable && post.do_consolidate)
+            CK(cudaMemcpyAsync(h->h_fin, h->d_fin, (size_t)spec * 3 * sizeof(int64_t), cudaMemcpyDeviceToHost,
+                               h->stream));
         CK(cudaStreamSynchronize(h->stream));
         const uint32_t n = h->h_counters[CNT_OUT];
         res->stats.n_candidates = h->h_counters[CNT_CAND];
-        if (n <= h->out_cap) {
-            res->raw.resize(n);
-            if (n) memcpy(res->raw.data(), h->h_stage, (size_t)std::min(n, spec) * sizeof(RawRec));
-            if (n > spec) {
-                CK(cudaMemcpyAsync(res->raw.data() + spec, h->d_out + spec, (size_t)(n - spec) * sizeof(RawRec),
-                                   cudaMemcpyDeviceToHost, h->stream));
-                CK(cudaStreamSynchronize(h->stream));
-            }
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, h->ev[0], h->ev[2]);
-            res->stats.gpu_ms = ms;
-            res->stats.filter_ms = ms;
-            if (h->ev1_recorded) {
-                cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
-                res->stats.filter_ms = ms;
-            }
-            return FZB_OK;
+        if (n > h->out_cap) {  // output buffer too small: grow and redo the whole attempt
+            rc = ensure_out_cap(h, n);
+            if (rc) return rc;
+            continue;
         }
-        rc = ensure_out_cap(h, n);
-        if (rc) return rc;
+        const bool posted = post.enable && h->h_counters[CNT_POST_DONE] != 0;
+        const RawRec *dsrc = posted ? h->d_raw_sorted : h->d_out;
+        res->raw.resize(n);
+        if (n && (posted || !post.enable)) memcpy(res->raw.data(), h->h_stage, (size_t)std::min(n, spec) * sizeof(RawRec));
+        const uint32_t have = (posted || !post.enable) ? std::min(n, spec) : 0;
+        if (n > have)
+            CK(cudaMemcpyAsync(res->raw.data() + have, dsrc + have, (size_t)(n - have) * sizeof(RawRec),
+                               cudaMemcpyDeviceToHost, h->stream));
+        if (posted && post.do_consolidate) {
+            const uint32_t nf = h->h_counters[CNT_NFINAL];
+            if (nf > spec)
+                CK(cudaMemcpyAsync(h->h_fin + (size_t)spec * 3, h->d_fin + (size_t)spec * 3,
+                                   (size_t)(nf - spec) * 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+            if (n > have || nf > spec) CK(cudaStreamSynchronize(h->stream));
+            res->fin.resize(nf);
+            for (uint32_t i = 0; i < nf; i++) {
+                res->fin[i].start = h->h_fin[3 * i];
+                res->fin[i].end = h->h_fin[3 * i + 1];
+                res->fin[i].dist = (int32_t)h->h_fin[3 * i + 2];
+                res->fin[i].idx = -1;
+                res->fin[i].ngram = -1;
+            }
+        } else if (n > have) {
+            CK(cudaStreamSynchronize(h->stream));
+        }
+        res->device_post = posted;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, h->ev[0], h->ev[2]);
+        res->stats.gpu_ms = ms;
+        res->stats.filter_ms = ms;
+        if (h->ev1_recorded) {
+            cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+            res->stats.filter_ms = ms;
+        }
+        return FZB_OK;
     }
     return fail(FZB_E_CUDA, "output buffer kept overflowing");
 }
@@ -538,7 +594,7 @@ static int enqueue_filter(fzb_haystack *h, const ScanParams &p, bool sampled, fz
 
 // n-gram Levenshtein search (also serves exact search as k == 0, L == m)
 static int search_lev_ngrams(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint32_t k, uint32_t flags,
-                             fzb_result *res) {
+                             fzb_result *res, bool want_final) {
     ScanParams p;
     fill_params(h, pattern, m, p);
     p.k = (int)k;
@@ -565,9 +621,9 @@ static int search_lev_ngrams(fzb_haystack *h, const uint8_t *pattern, uint32_t m
                 p, h->bitmap_words, h->d_glist, gcap, scan_mode, h->d_out, h->out_cap, h->d_counters);
         res->stats.n_launches += 3;
         return FZB_OK;
-    });
+    }, PostPlan{true, 0, want_final ? 1 : 0});
     if (rc) return rc;
-    sort_generation_order(res->raw);
+    if (!res->device_post) sort_generation_order(res->raw);
     return FZB_OK;
 }
 
@@ -587,20 +643,21 @@ static int ensure_scratch(fzb_haystack *h, uint64_t words) {
 // Runs an LP-style search with growing per-thread candidate capacity until no list overflowed.
 // `enqueue(grid, cap)` must put every kernel of one attempt on the stream.
 template <class F>
-static int run_lp(fzb_haystack *h, fzb_result *res, F enqueue) {
+static int run_lp(fzb_haystack *h, fzb_result *res, F enqueue, PostPlan post = PostPlan()) {
     const int grid = h->sm_count * 4;
     const uint64_t threads = (uint64_t)grid * kLpThreads;
     for (int cap = 256; cap <= (1 << 16); cap *= 8) {
         int rc = ensure_scratch(h, threads * 2 * (uint64_t)cap);
         if (rc) return rc;
-        rc = run_emitting(h, res, [&]() -> int { return enqueue(grid, cap); });
+        rc = run_emitting(h, res, [&]() -> int { return enqueue(grid, cap); }, post);
         if (rc) return rc;
         if (!h->h_counters[CNT_OVERFLOW]) return FZB_OK;
     }
     return fail(FZB_E_UNSUPPORTED, "candidate explosion: more than 65536 live candidates for one start");
 }
 
-static int search_lev_lp(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint32_t k, fzb_result *res) {
+static int search_lev_lp(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint32_t k, fzb_result *res,
+                         bool want_final) {
     if (k > 0xFFFF) return fail(FZB_E_UNSUPPORTED, "max_l_dist too large");
     ScanParams p;
     fill_params(h, pattern, m, p);
@@ -614,14 +671,15 @@ static int search_lev_lp(fzb_haystack *h, const uint8_t *pattern, uint32_t m, ui
         k_lev_lp<<<grid, kLpThreads, 0, h->stream>>>(p, h->d_scratch, cap, h->d_out, h->out_cap, h->d_counters);
         res->stats.n_launches++;
         return FZB_OK;
-    });
+    }, PostPlan{true, 1, want_final ? 1 : 0});
     if (rc) return rc;
-    sort_canonical(res->raw);
+    if (!res->device_post) sort_canonical(res->raw);
     return FZB_OK;
 }
 
 static int search_generic(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint32_t max_subs, uint32_t max_ins,
-                          uint32_t max_dels, uint32_t max_l, bool ngrams, uint32_t flags, fzb_result *res) {
+                          uint32_t max_dels, uint32_t max_l, bool ngrams, uint32_t flags, fzb_result *res,
+                          bool want_final) {
     // the packed candidate of sim_generic keeps 6 bits per counter
     if (max_l > 63) return fail(FZB_E_UNSUPPORTED, "max_l_dist > 63 is not supported by the generic search");
     // no counter can exceed max_l (every operation that increments one costs >= 1), so clamping the
@@ -646,9 +704,9 @@ static int search_generic(fzb_haystack *h, const uint8_t *pattern, uint32_t m, u
                                                              h->d_counters);
             res->stats.n_launches++;
             return FZB_OK;
-        });
+        }, PostPlan{true, 1, want_final ? 1 : 0});
         if (rc) return rc;
-        sort_canonical(res->raw);
+        if (!res->device_post) sort_canonical(res->raw);
         return FZB_OK;
     }
     p.L = (int)(m / (max_l + 1));
@@ -705,14 +763,13 @@ extern "C" int fzb_search_levenshtein(fzb_haystack *h, const uint8_t *pattern, u
         bool ngrams = (k == 0) || (m / (k + 1) >= 3);
         if (flags & FZB_F_FORCE_NGRAMS) ngrams = true;
         if (flags & FZB_F_FORCE_LP) ngrams = false;
-        if (ngrams)
-            rc = search_lev_ngrams(h, pattern, m, k, flags, res);
-        else
-            rc = search_lev_lp(h, pattern, m, k, res);
-    }
-    if (rc == FZB_OK && !(flags & FZB_F_NO_FINAL)) {
         // LevenshteinSearch.consolidate_matches (levenshtein.py:158-160) also applies when k == 0
-        consolidate_recs(res->raw, res->fin);
+        const bool want_final = !(flags & FZB_F_NO_FINAL);
+        if (ngrams)
+            rc = search_lev_ngrams(h, pattern, m, k, flags, res, want_final);
+        else
+            rc = search_lev_lp(h, pattern, m, k, res, want_final);
+        if (rc == FZB_OK && want_final && !res->device_post) consolidate_recs(res->raw, res->fin);
     }
     if (rc) {
         delete res;
@@ -729,7 +786,7 @@ extern "C" int fzb_search_exact(fzb_haystack *h, const uint8_t *pattern, uint32_
     if (rc) return rc;
     rc = check_pattern(h, pattern, m);
     if (rc == FZB_E_INVALID && h) rc = fail(FZB_E_INVALID, "subsequence must not be empty");
-    if (rc == FZB_OK) rc = search_lev_ngrams(h, pattern, m, 0, flags, res);
+    if (rc == FZB_OK) rc = search_lev_ngrams(h, pattern, m, 0, flags, res, false);
     if (rc) {
         delete res;
         return rc;
@@ -760,9 +817,9 @@ extern "C" int fzb_search_hamming(fzb_haystack *h, const uint8_t *pattern, uint3
                                                                                h->d_counters);
                 res->stats.n_launches++;
                 return FZB_OK;
-            });
+            }, PostPlan{true, 1, 0});
             if (r2) return r2;
-            sort_canonical(res->raw);
+            if (!res->device_post) sort_canonical(res->raw);
             for (auto &r : res->raw) r.ngram = -1;
             return FZB_OK;
         }();
@@ -785,16 +842,18 @@ extern "C" int fzb_search_generic(fzb_haystack *h, const uint8_t *pattern, uint3
     rc = check_pattern(h, pattern, m);
     if (rc == FZB_OK) {
         // find_near_matches_generic (generic_search.py:25-54)
+        const bool want_final = !(flags & FZB_F_NO_FINAL);
         if (max_l == 0 && !(flags & (FZB_F_FORCE_LP | FZB_F_FORCE_NGRAMS))) {
-            rc = search_lev_ngrams(h, pattern, m, 0, flags, res);
+            rc = search_lev_ngrams(h, pattern, m, 0, flags, res, want_final);
         } else {
             bool ngrams = m / (max_l + 1) >= 3;
             if (flags & FZB_F_FORCE_NGRAMS) ngrams = true;
             if (flags & FZB_F_FORCE_LP) ngrams = false;
-            rc = search_generic(h, pattern, m, max_subs, max_ins, max_dels, max_l, ngrams, flags, res);
+            rc = search_generic(h, pattern, m, max_subs, max_ins, max_dels, max_l, ngrams, flags, res, want_final);
         }
+        if (rc == FZB_OK && want_final && !(res->device_post && res->stats.route != 5))
+            consolidate_recs(res->raw, res->fin);
     }
-    if (rc == FZB_OK && !(flags & FZB_F_NO_FINAL)) consolidate_recs(res->raw, res->fin);
     if (rc) {
         delete res;
         return rc;
