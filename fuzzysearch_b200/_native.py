@@ -71,6 +71,7 @@ SYMBOLS = {
     "fzb_search_generic": (_i32, [_vp, _u8p, _u32, _u32, _u32, _u32, _u32, _u32, _vpp]),
     "fzb_search_exact": (_i32, [_vp, _u8p, _u32, _u32, _vpp]),
     "fzb_find_near_matches": (_i32, [_u8p, _u32, _u8p, _u64, _u32, _u32, _u32, _u32, _i32, _vpp]),
+    "fzb_release_workspace": (None, []),
     "fzb_result_count": (_u64, [_vp, _i32]),
     "fzb_result_copy": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "fzb_result_stats": (_i32, [_vp, ctypes.POINTER(Stats)]),

@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -317,7 +318,7 @@ extern "C" int fzb_haystack_upload(fzb_haystack *h, const uint8_t *host, uint64_
     h->padded_len = round_up(n, 16) + 64;
     if (n) CK(cudaMemcpyAsync(h->d, host, n, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemsetAsync(h->d + n, 0, h->padded_len - n, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaStreamSynchronize(h->stream));  // the caller may reuse `host` as soon as we return
     return FZB_OK;
 }
 
@@ -862,13 +863,37 @@ extern "C" int fzb_search_generic(fzb_haystack *h, const uint8_t *pattern, uint3
     return FZB_OK;
 }
 
+// One cached workspace per device for the one-shot call: the analogue of the reference's reusable
+// chunk buffer (__init__.py:141-145) -- a call then costs one H2D copy plus the kernels instead of
+// a 4 GiB cudaMalloc/cudaFree pair and a dozen small allocations.
+static std::mutex g_ws_mutex;
+static fzb_haystack *g_ws[64];
+
+extern "C" void fzb_release_workspace(void) {
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    for (auto &h : g_ws) {
+        if (h) fzb_haystack_destroy(h);
+        h = nullptr;
+    }
+}
+
 extern "C" int fzb_find_near_matches(const uint8_t *pattern, uint32_t m, const uint8_t *haystack, uint64_t n,
                                      uint32_t max_subs, uint32_t max_ins, uint32_t max_dels, uint32_t max_l,
                                      int device, fzb_result **out) {
     if (!out) return fail(FZB_E_INVALID, "out is NULL");
     *out = nullptr;
-    fzb_haystack *h = nullptr;
-    int rc = fzb_haystack_create(haystack, n, device, &h);
+    if (device < 0 || device >= 64 || device >= fzb_device_count())
+        return fail(FZB_E_CUDA, "CUDA device %d not available (%d devices)", device, fzb_device_count());
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    fzb_haystack *&h = g_ws[device];
+    if (!h || round_up(n, 16) + 64 > h->capacity) {
+        if (h) fzb_haystack_destroy(h);
+        h = nullptr;
+        const uint64_t cap = std::max<uint64_t>(n + n / 8, 1u << 20);  // head-room: repeated calls with growing inputs
+        int rc = fzb_haystack_alloc(cap, 0, cap, 0, cap, device, &h, nullptr);
+        if (rc) return rc;
+    }
+    int rc = fzb_haystack_upload(h, haystack, n);
     if (rc) return rc;
     // choose_search_class (__init__.py:60-83) on normalised limits
     if (max_l == 0)
@@ -879,7 +904,6 @@ extern "C" int fzb_find_near_matches(const uint8_t *pattern, uint32_t m, const u
         rc = fzb_search_levenshtein(h, pattern, m, max_l, 0, out);
     else
         rc = fzb_search_generic(h, pattern, m, max_subs, max_ins, max_dels, max_l, 0, out);
-    fzb_haystack_destroy(h);
     return rc;
 }
 

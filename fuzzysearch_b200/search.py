@@ -71,7 +71,8 @@ def _prepare(subsequence, sequence):
     host, is_str = _coerce(sequence)
     if is_str != pat_is_str:
         raise TypeError("subsequence and sequence must both be str or both be byte-like")
-    hay = _native.Haystack.from_host(host)
+    hay = _workspace(host.size)
+    hay.upload(host)
     if is_str:
         text = sequence
 
@@ -85,7 +86,30 @@ def _prepare(subsequence, sequence):
 
         def slicer(s, e):
             return bytes(mv[s:e])
-    return pat, hay, slicer, True
+    return pat, hay, slicer, False
+
+
+_WORKSPACE = {}
+
+
+def _workspace(nbytes, device=0):
+    """A cached device buffer for plain (host) sequences: like the reference's reusable chunk buffer
+    (__init__.py:141-145), a search then costs one H2D copy instead of allocations."""
+    ws = _WORKSPACE.get(device)
+    if ws is None or ws[1] < nbytes:
+        if ws is not None:
+            ws[0].close()
+        cap = max(nbytes + nbytes // 8, 1 << 20)
+        ws = (_native.Haystack.alloc(cap, device=device), cap)
+        _WORKSPACE[device] = ws
+    return ws[0]
+
+
+def release_workspace():
+    for ws in _WORKSPACE.values():
+        ws[0].close()
+    _WORKSPACE.clear()
+    _native.lib().fzb_release_workspace()
 
 
 def _to_matches(result, which, slicer):

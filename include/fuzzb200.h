@@ -163,6 +163,10 @@ int fzb_find_near_matches(const uint8_t *pattern, uint32_t m, const uint8_t *hay
                           uint32_t max_subs, uint32_t max_ins, uint32_t max_dels,
                           uint32_t max_l_dist, int device, fzb_result **out);
 
+/* fzb_find_near_matches keeps one device workspace per device (haystack buffer, bitmap, staging)
+ * alive between calls so that a call costs one H2D copy + the kernels; this frees them. */
+void fzb_release_workspace(void);
+
 uint64_t fzb_result_count(const fzb_result *r, int which);
 /* Copy out `which` list; any pointer may be NULL.  anchor_ngram / anchor_idx are only meaningful
  * for the RAW list of n-gram searches (n-gram ordinal and hit index), else -1. */
