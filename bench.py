@@ -293,7 +293,7 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from fuzzysearch_b200.sharding import gather_rows, merge_raw_streams, shard_bounds
+    from fuzzysearch_b200.sharding import gather_and_merge_groups, shard_bounds
 
     global_len = per_gpu * world
     halo = m + k
@@ -313,20 +313,18 @@ def main():
         if pos >= blo and pos + len(b) <= bhi:
             hs.write(pos, b)
 
-    def one_search():
+    def one_search(h):
         if kind == "lev":
-            return hs.search_levenshtein(pat, k, F.F_NO_FINAL if world > 1 else 0)
-        return hs.search_hamming(pat, k)
+            return h.search_levenshtein(pat, k)
+        return h.search_hamming(pat, k)
 
-    def step():
-        res = one_search()
+    def step(h=None):
+        # one search of this rank's shard (local consolidation on the device), then -- multi-GPU only --
+        # ONE all-gather of the per-shard groups and the linear merge into the global final list
+        res = one_search(h or hs)
         st = res.stats()
         if world > 1:
-            s, e, d, ng, ix = res.arrays(F.RAW, anchors=True)
-            rows = np.column_stack([s, e, d.astype(np.int64), ng.astype(np.int64), ix])
-            allrows = gather_rows(rows)
-            _, final = merge_raw_streams(allrows, ngram_route=(kind == "lev"))
-            nfinal = len(final)
+            nfinal = len(gather_and_merge_groups(res.group_rows()))
         else:
             nfinal = res.count(F.FINAL)
         res.close()
@@ -383,13 +381,9 @@ def main():
                 return cnt, d2h
             h2 = F.Haystack.from_host(pinned.array, device=local_rank, buf_lo=blo, global_len=global_len,
                                       own_lo=own_lo, own_hi=own_hi)
-            r = h2.search_levenshtein(pat, k, F.F_NO_FINAL) if kind == "lev" else h2.search_hamming(pat, k)
-            s, e, d, ng, ix = r.arrays(F.RAW, anchors=True)
-            rows = np.column_stack([s, e, d.astype(np.int64), ng.astype(np.int64), ix])
-            _, final = merge_raw_streams(gather_rows(rows), ngram_route=(kind == "lev"))
-            r.close()
+            _, nf = step(h2)
             h2.close()
-            return len(final), rows.shape[0] * 40
+            return nf, nf * 40
 
         e2e_step()
         sync_all()

@@ -74,6 +74,9 @@ SYMBOLS = {
     "fzb_release_workspace": (None, []),
     "fzb_result_count": (_u64, [_vp, _i32]),
     "fzb_result_copy": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "fzb_result_hulls": (_i32, [_vp, _vp, _vp]),
+    "fzb_merge_groups": (_i64, [_vp, _u64, _vp, _vp, _vp]),
+    "fzb_consolidate_groups": (_i64, [_vp, _vp, _vp, _u64, _vp]),
     "fzb_result_stats": (_i32, [_vp, ctypes.POINTER(Stats)]),
     "fzb_result_destroy": (None, [_vp]),
     "fzb_consolidate": (_i64, [_vp, _vp, _vp, _u64, _vp, _vp, _vp]),
@@ -165,6 +168,15 @@ class Result(object):
             return start, end, dist, ng, ix
         check(lib().fzb_result_copy(self._h, which, ptr(start), ptr(end), ptr(dist), None, None))
         return start, end, dist
+
+    def group_rows(self):
+        """FINAL list as int64 rows (start, end, dist, hull_start, hull_end): what a shard
+        contributes to the multi-GPU merge (fzb_merge_groups)."""
+        s, e, d = self.arrays(FINAL)
+        hs = np.empty(s.size, dtype=np.int64)
+        he = np.empty(s.size, dtype=np.int64)
+        check(lib().fzb_result_hulls(self._h, ptr(hs), ptr(he)))
+        return np.column_stack([s, e, d.astype(np.int64), hs, he]).reshape(-1, 5)
 
     def triples(self, which=FINAL):
         s, e, d = self.arrays(which)
@@ -313,6 +325,29 @@ def find_near_matches_host(pattern, haystack, max_subs, max_ins, max_dels, max_l
     check(lib().fzb_find_near_matches(ptr(p), p.size, ptr(a), a.size, max_subs, max_ins, max_dels, max_l,
                                       device, ctypes.byref(r)))
     return Result(r)
+
+
+def consolidate_groups(start, end, dist):
+    """-> int64 rows (start, end, dist, hull_start, hull_end), one per group of overlapping matches."""
+    start = np.ascontiguousarray(start, dtype=np.int64)
+    end = np.ascontiguousarray(end, dtype=np.int64)
+    dist = np.ascontiguousarray(dist, dtype=np.int32)
+    rows = np.empty((max(start.size, 1), 5), dtype=np.int64)
+    cnt = lib().fzb_consolidate_groups(ptr(start), ptr(end), ptr(dist), start.size, ptr(rows))
+    if cnt < 0:
+        check(int(cnt))
+    return rows[:cnt]
+
+
+def merge_groups(rows):
+    """fzb_merge_groups: rows[n,5] (start,end,dist,hull_start,hull_end) -> global final triples."""
+    rows = np.ascontiguousarray(rows, dtype=np.int64).reshape(-1, 5)
+    n = rows.shape[0]
+    os_, oe, od = np.empty(n, np.int64), np.empty(n, np.int64), np.empty(n, np.int32)
+    cnt = lib().fzb_merge_groups(ptr(rows), n, ptr(os_), ptr(oe), ptr(od))
+    if cnt < 0:
+        check(int(cnt))
+    return list(zip(os_[:cnt].tolist(), oe[:cnt].tolist(), od[:cnt].tolist()))
 
 
 def consolidate(start, end, dist):

@@ -89,6 +89,7 @@ struct fzb_haystack {
 struct fzb_result {
     std::vector<RawRec> raw;
     std::vector<RawRec> fin;
+    std::vector<int64_t> hulls;  // (hull_start, hull_end) of the group behind each final match
     bool final_is_raw = false;
     bool device_post = false;  // raw already ordered (and fin filled) by k_post_small
     fzb_stats stats{};
@@ -110,9 +111,9 @@ static int haystack_common_init(fzb_haystack *h) {
     CK(cudaMalloc(&h->d_counters, (CNT_COUNT + 2 * (size_t)kPostMax) * sizeof(uint32_t)));  // + k_rank's ranks
     CK(cudaMallocHost(&h->h_counters, CNT_COUNT * sizeof(uint32_t)));
     CK(cudaMallocHost(&h->h_stage, (size_t)kPostMax * sizeof(RawRec)));
-    CK(cudaMallocHost(&h->h_fin, (size_t)kPostMax * 3 * sizeof(int64_t)));
+    CK(cudaMallocHost(&h->h_fin, (size_t)kPostMax * kFinCols * sizeof(int64_t)));
     CK(cudaMalloc(&h->d_raw_sorted, (size_t)kPostMax * sizeof(RawRec)));
-    CK(cudaMalloc(&h->d_fin, (size_t)kPostMax * 3 * sizeof(int64_t)));
+    CK(cudaMalloc(&h->d_fin, (size_t)kPostMax * kFinCols * sizeof(int64_t)));
     CK(cudaMalloc(&h->d_keys_sorted, (size_t)kPostMax * sizeof(uint64_t)));
     CK(cudaFuncSetAttribute(k_consolidate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConsSmem));
     CK(cudaMemset(h->d_bitmap, 0, h->bitmap_words * sizeof(uint32_t)));  // stays all-zero between searches
@@ -361,16 +362,18 @@ extern "C" int fzb_timer_stop(fzb_haystack *h, double *ms) {
 // overlap anything they merely touch).  Winner = min (dist, -(end-start)), ties -> smallest
 // (start,end).  Output sorted by (start,end,dist).
 // ------------------------------------------------------------------------------------------------
-static void consolidate_recs(std::vector<RawRec> v, std::vector<RawRec> &out) {
+static void consolidate_recs(std::vector<RawRec> v, std::vector<RawRec> &out, std::vector<int64_t> *hulls = nullptr) {
     out.clear();
+    if (hulls) hulls->clear();
     if (v.empty()) return;
-    std::sort(v.begin(), v.end(), [](const RawRec &a, const RawRec &b) {
+    auto canonical = [](const RawRec &a, const RawRec &b) {
         if (a.start != b.start) return a.start < b.start;
         if (a.end != b.end) return a.end < b.end;
         return a.dist < b.dist;
-    });
+    };
+    std::sort(v.begin(), v.end(), canonical);
     RawRec best = v[0];
-    int64_t hull_end = v[0].end;
+    int64_t hull_start = v[0].start, hull_end = v[0].end;
     auto better = [](const RawRec &a, const RawRec &b) {  // a strictly better than b
         if (a.dist != b.dist) return a.dist < b.dist;
         int64_t la = a.end - a.start, lb = b.end - b.start;
@@ -378,22 +381,27 @@ static void consolidate_recs(std::vector<RawRec> v, std::vector<RawRec> &out) {
         if (a.start != b.start) return a.start < b.start;
         return a.end < b.end;
     };
+    auto close_group = [&]() {
+        out.push_back(best);
+        if (hulls) {
+            hulls->push_back(hull_start);
+            hulls->push_back(hull_end);
+        }
+    };
     for (size_t i = 1; i < v.size(); i++) {
         if (v[i].start < hull_end) {
             if (better(v[i], best)) best = v[i];
             hull_end = std::max(hull_end, v[i].end);
         } else {
-            out.push_back(best);
+            close_group();
             best = v[i];
+            hull_start = v[i].start;
             hull_end = v[i].end;
         }
     }
-    out.push_back(best);
-    std::sort(out.begin(), out.end(), [](const RawRec &a, const RawRec &b) {
-        if (a.start != b.start) return a.start < b.start;
-        if (a.end != b.end) return a.end < b.end;
-        return a.dist < b.dist;
-    });
+    close_group();
+    // winners come out in group order, which is already (start, end, dist) order: groups are
+    // disjoint and ordered, and an empty group at x sorts before a group starting at x
 }
 
 extern "C" int64_t fzb_consolidate(const int64_t *start, const int64_t *end, const int32_t *dist, uint64_t n,
@@ -414,6 +422,92 @@ extern "C" int64_t fzb_consolidate(const int64_t *start, const int64_t *end, con
         if (out_dist) out_dist[i] = o[i].dist;
     }
     return (int64_t)o.size();
+}
+
+extern "C" int64_t fzb_consolidate_groups(const int64_t *start, const int64_t *end, const int32_t *dist, uint64_t n,
+                                          int64_t *out_rows) {
+    if (n && (!start || !end || !dist || !out_rows)) return fail(FZB_E_INVALID, "NULL input");
+    std::vector<RawRec> v(n), o;
+    std::vector<int64_t> hulls;
+    for (uint64_t i = 0; i < n; i++) {
+        v[i].start = start[i];
+        v[i].end = end[i];
+        v[i].dist = dist[i];
+        v[i].idx = -1;
+        v[i].ngram = -1;
+    }
+    consolidate_recs(std::move(v), o, &hulls);
+    for (size_t i = 0; i < o.size(); i++) {
+        out_rows[5 * i + 0] = o[i].start;
+        out_rows[5 * i + 1] = o[i].end;
+        out_rows[5 * i + 2] = o[i].dist;
+        out_rows[5 * i + 3] = hulls[2 * i];
+        out_rows[5 * i + 4] = hulls[2 * i + 1];
+    }
+    return (int64_t)o.size();
+}
+
+extern "C" int fzb_result_hulls(const fzb_result *r, int64_t *hull_start, int64_t *hull_end) {
+    if (!r) return fail(FZB_E_INVALID, "result is NULL");
+    if (r->final_is_raw) {  // unconsolidated routes: every match is its own group
+        for (size_t i = 0; i < r->raw.size(); i++) {
+            if (hull_start) hull_start[i] = r->raw[i].start;
+            if (hull_end) hull_end[i] = r->raw[i].end;
+        }
+        return FZB_OK;
+    }
+    if (r->hulls.size() != r->fin.size() * 2) return fail(FZB_E_INVALID, "result was produced with FZB_F_NO_FINAL");
+    for (size_t i = 0; i < r->fin.size(); i++) {
+        if (hull_start) hull_start[i] = r->hulls[2 * i];
+        if (hull_end) hull_end[i] = r->hulls[2 * i + 1];
+    }
+    return FZB_OK;
+}
+
+// Merge per-shard consolidated lists.  Each input row is one GROUP of overlapping matches found by a
+// shard: its winner (start, end, dist) and the group's hull [hull_start, hull_end).  Groups of
+// different shards that overlap belong to one global group (a group's hull is covered by its
+// members, so hulls overlap iff members do), and the winner of a union is the better of the two
+// winners -- so the global consolidate_overlapping_matches (common.py:185-189) is the same sweep run
+// over the groups instead of the raw matches.
+extern "C" int64_t fzb_merge_groups(const int64_t *rows, uint64_t n, int64_t *out_start, int64_t *out_end,
+                                    int32_t *out_dist) {
+    if (n && !rows) return fail(FZB_E_INVALID, "NULL input");
+    struct G { int64_t s, e, d, hs, he; };
+    std::vector<G> g(n);
+    for (uint64_t i = 0; i < n; i++) g[i] = G{rows[5 * i], rows[5 * i + 1], rows[5 * i + 2], rows[5 * i + 3], rows[5 * i + 4]};
+    auto less = [](const G &a, const G &b) {
+        if (a.hs != b.hs) return a.hs < b.hs;
+        if (a.he != b.he) return a.he < b.he;
+        if (a.s != b.s) return a.s < b.s;
+        if (a.e != b.e) return a.e < b.e;
+        return a.d < b.d;
+    };
+    if (!std::is_sorted(g.begin(), g.end(), less)) std::sort(g.begin(), g.end(), less);  // shards arrive almost ordered
+    auto better = [](const G &a, const G &b) {
+        if (a.d != b.d) return a.d < b.d;
+        int64_t la = a.e - a.s, lb = b.e - b.s;
+        if (la != lb) return la > lb;
+        if (a.s != b.s) return a.s < b.s;
+        return a.e < b.e;
+    };
+    uint64_t w = 0;
+    for (uint64_t i = 0; i < n;) {
+        G best = g[i];
+        int64_t hull_end = g[i].he;
+        uint64_t j = i + 1;
+        while (j < n && g[j].hs < hull_end) {
+            if (better(g[j], best)) best = g[j];
+            hull_end = std::max(hull_end, g[j].he);
+            j++;
+        }
+        if (out_start) out_start[w] = best.s;
+        if (out_end) out_end[w] = best.e;
+        if (out_dist) out_dist[w] = (int32_t)best.d;
+        w++;
+        i = j;
+    }
+    return (int64_t)w;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -495,7 +589,7 @@ static int run_emitting(fzb_haystack *h, fzb_result *res, F enqueue, PostPlan po
         CK(cudaMemcpyAsync(h->h_stage, post.enable ? h->d_raw_sorted : h->d_out, (size_t)spec * sizeof(RawRec),
                            cudaMemcpyDeviceToHost, h->stream));
         if (post.enable && post.do_consolidate)
-            CK(cudaMemcpyAsync(h->h_fin, h->d_fin, (size_t)spec * 3 * sizeof(int64_t), cudaMemcpyDeviceToHost,
+            CK(cudaMemcpyAsync(h->h_fin, h->d_fin, (size_t)spec * kFinCols * sizeof(int64_t), cudaMemcpyDeviceToHost,
                                h->stream));
         CK(cudaStreamSynchronize(h->stream));
         const uint32_t n = h->h_counters[CNT_OUT];
@@ -516,16 +610,20 @@ static int run_emitting(fzb_haystack *h, fzb_result *res, F enqueue, PostPlan po
         if (posted && post.do_consolidate) {
             const uint32_t nf = h->h_counters[CNT_NFINAL];
             if (nf > spec)
-                CK(cudaMemcpyAsync(h->h_fin + (size_t)spec * 3, h->d_fin + (size_t)spec * 3,
-                                   (size_t)(nf - spec) * 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+                CK(cudaMemcpyAsync(h->h_fin + (size_t)spec * kFinCols, h->d_fin + (size_t)spec * kFinCols,
+                                   (size_t)(nf - spec) * kFinCols * sizeof(int64_t), cudaMemcpyDeviceToHost,
+                                   h->stream));
             if (n > have || nf > spec) CK(cudaStreamSynchronize(h->stream));
             res->fin.resize(nf);
+            res->hulls.resize((size_t)nf * 2);
             for (uint32_t i = 0; i < nf; i++) {
-                res->fin[i].start = h->h_fin[3 * i];
-                res->fin[i].end = h->h_fin[3 * i + 1];
-                res->fin[i].dist = (int32_t)h->h_fin[3 * i + 2];
+                res->fin[i].start = h->h_fin[kFinCols * i];
+                res->fin[i].end = h->h_fin[kFinCols * i + 1];
+                res->fin[i].dist = (int32_t)h->h_fin[kFinCols * i + 2];
                 res->fin[i].idx = -1;
                 res->fin[i].ngram = -1;
+                res->hulls[2 * i] = h->h_fin[kFinCols * i + 3];
+                res->hulls[2 * i + 1] = h->h_fin[kFinCols * i + 4];
             }
         } else if (n > have) {
             CK(cudaStreamSynchronize(h->stream));
@@ -770,7 +868,7 @@ extern "C" int fzb_search_levenshtein(fzb_haystack *h, const uint8_t *pattern, u
             rc = search_lev_ngrams(h, pattern, m, k, flags, res, want_final);
         else
             rc = search_lev_lp(h, pattern, m, k, res, want_final);
-        if (rc == FZB_OK && want_final && !res->device_post) consolidate_recs(res->raw, res->fin);
+        if (rc == FZB_OK && want_final && !res->device_post) consolidate_recs(res->raw, res->fin, &res->hulls);
     }
     if (rc) {
         delete res;
@@ -853,7 +951,7 @@ extern "C" int fzb_search_generic(fzb_haystack *h, const uint8_t *pattern, uint3
             rc = search_generic(h, pattern, m, max_subs, max_ins, max_dels, max_l, ngrams, flags, res, want_final);
         }
         if (rc == FZB_OK && want_final && !(res->device_post && res->stats.route != 5))
-            consolidate_recs(res->raw, res->fin);
+            consolidate_recs(res->raw, res->fin, &res->hulls);
     }
     if (rc) {
         delete res;

@@ -24,6 +24,7 @@ constexpr int kRankThreads = 256;
 constexpr int kConsThreads = 1024;
 enum { CNT_POST_DONE = 5, CNT_NFINAL = 6 };
 constexpr size_t kConsSmem = (size_t)kPostMax * 4;  // segbest
+constexpr int kFinCols = 5;  // start, end, dist, hull_start, hull_end of the group
 
 // canonical order (start, end, dist): start < 2^46, end-start < 2^10, dist < 2^8
 __device__ __forceinline__ uint64_t canonical_key(const RawRec &r) {
@@ -189,8 +190,13 @@ k_consolidate(const RawRec *recs, const uint32_t *ranks, RawRec *raw_sorted, uin
             if (c < chunk && i < (int)n) {
                 const uint64_t kx = mykeys[c];
                 const unsigned long long s = kx >> 18, len = (kx >> 8) & 1023u, e = s + len;
-                if (i == 0 || s >= hull) seg++;
+                if (i == 0 || s >= hull) {  // group head: hull_start of this group, hull_end of the previous
+                    seg++;
+                    fin[kFinCols * (seg - 1) + 3] = (int64_t)s;
+                    if (seg >= 2) fin[kFinCols * (seg - 2) + 4] = (int64_t)hull;
+                }
                 hull = max(hull, e);
+                if (i == (int)n - 1) fin[kFinCols * (seg - 1) + 4] = (int64_t)hull;  // last group
                 const uint32_t score = ((uint32_t)(kx & 255u) << 24) | ((uint32_t)(1023u - len) << 14) | (uint32_t)i;
                 atomicMin(&segbest[seg - 1], score);
             }
@@ -199,9 +205,9 @@ k_consolidate(const RawRec *recs, const uint32_t *ranks, RawRec *raw_sorted, uin
         for (int g = threadIdx.x; g < (int)nfinal; g += kConsThreads) {
             const uint64_t kx = keys[segbest[g] & 16383u];
             const int64_t s = (int64_t)(kx >> 18);
-            fin[3 * g + 0] = s;
-            fin[3 * g + 1] = s + (int64_t)((kx >> 8) & 1023u);
-            fin[3 * g + 2] = (int64_t)(kx & 255u);
+            fin[kFinCols * g + 0] = s;
+            fin[kFinCols * g + 1] = s + (int64_t)((kx >> 8) & 1023u);
+            fin[kFinCols * g + 2] = (int64_t)(kx & 255u);
         }
     }
     if (threadIdx.x == 0) {

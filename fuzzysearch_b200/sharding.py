@@ -5,17 +5,20 @@ SURVEY.md section 8e.  Every raw match is a pure function of a bounded window ar
 loads ``H[own_lo - halo : own_hi + halo)`` with ``halo = len(pattern) + max_l_dist`` and emits only
 matches it owns.  The reference's clipping rules are evaluated at the global ends only, so the union
 of the per-rank raw streams IS the single-device raw stream -- no haystack byte ever crosses NVLink.
-The only exchange is the (tiny) match list: an all-gather of per-rank counts followed by one padded
-all-gather of ``(start, end, dist, ngram, idx)`` rows over ``torch.distributed`` (NCCL on GPUs, gloo
-in the CPU tests); the final consolidation (common.py:185-189) then runs once on the gathered list,
-because groups of overlapping matches can chain across seams.
+The only exchange is the (tiny) match list over ``torch.distributed`` (NCCL on GPUs, gloo in the CPU
+tests).  Each rank consolidates its own raw stream on the device and contributes one row per GROUP of
+overlapping matches -- the winner and the group's hull; groups can chain across seams, but the winner
+of a union of groups is the better of their winners and hulls overlap iff members do, so the global
+consolidation (common.py:185-189) is ONE fixed-size all-gather plus a linear merge
+(``gather_and_merge_groups``).  ``gather_rows``/``merge_raw_streams`` gather the raw streams instead
+(parity tests).
 
 The reference's CPU analogue of this layout is the chunk + carry-over tail loop of
 ``_search_binary_file`` (fuzzysearch/__init__.py:129-171).
 """
 import numpy as np
 
-__all__ = ["shard_bounds", "gather_rows", "merge_raw_streams"]
+__all__ = ["shard_bounds", "gather_rows", "merge_raw_streams", "gather_and_merge_groups"]
 
 ALIGN = 16  # shard buffers start on 16-byte boundaries of the global sequence (uint4 loads)
 
@@ -69,6 +72,45 @@ def gather_rows(rows, group=None, device=None):
     dist.all_gather(out, padded, group=group)
     parts = [out[r][:counts[r]].cpu().numpy() for r in range(world)]
     return np.concatenate(parts, axis=0) if parts else rows
+
+
+_GATHER_CAP = {"rows": 4096}
+
+
+def gather_and_merge_groups(group_rows, group=None, device=None):
+    """The multi-GPU reduction of one search: every rank contributes its locally consolidated groups
+    (rows (start, end, dist, hull_start, hull_end), Result.group_rows()); ONE fixed-size all-gather
+    (slot = count + padded rows; grown and retried if a rank overflows it) and a linear merge of the
+    almost-ordered shard lists (fzb_merge_groups) yield the global final list on every rank."""
+    from . import _native
+    rows = np.ascontiguousarray(group_rows, dtype=np.int64).reshape(-1, 5)
+    try:
+        import torch
+        import torch.distributed as dist
+        ready = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    except ImportError:  # pragma: no cover
+        ready = False
+    if not ready:
+        return _native.merge_groups(rows)
+    world = dist.get_world_size(group)
+    dev = torch.device("cpu")
+    if dist.get_backend(group) == "nccl":
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    while True:
+        cap = _GATHER_CAP["rows"]
+        slot = np.zeros((cap + 1, 5), dtype=np.int64)
+        slot[0, 0] = rows.shape[0]
+        slot[1:1 + min(cap, rows.shape[0])] = rows[:cap]
+        mine = torch.from_numpy(slot).to(dev, non_blocking=False)
+        out = torch.empty((world, cap + 1, 5), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(out.view(-1), mine.view(-1), group=group)
+        allr = out.cpu().numpy()
+        counts = allr[:, 0, 0]
+        if int(counts.max()) <= cap:
+            parts = [allr[r, 1:1 + int(counts[r])] for r in range(world)]
+            return _native.merge_groups(np.concatenate(parts, axis=0))
+        while _GATHER_CAP["rows"] < int(counts.max()):
+            _GATHER_CAP["rows"] *= 2
 
 
 def merge_raw_streams(rows, ngram_route=True):

@@ -173,6 +173,10 @@ uint64_t fzb_result_count(const fzb_result *r, int which);
 int fzb_result_copy(const fzb_result *r, int which, int64_t *start, int64_t *end, int32_t *dist,
                     int32_t *anchor_ngram, int64_t *anchor_idx);
 
+/* For the FINAL list: the hull [hull_start, hull_end) of the group of overlapping raw matches each
+ * final match won (for the unconsolidated routes: the match itself). */
+int fzb_result_hulls(const fzb_result *r, int64_t *hull_start, int64_t *hull_end);
+
 typedef struct {
     double gpu_ms;          /* CUDA-event time of all kernels of the search */
     double filter_ms;       /* ... of the haystack scan (filter) kernel alone */
@@ -190,6 +194,17 @@ void fzb_result_destroy(fzb_result *r);
  * (>= 0) or a negative error. */
 int64_t fzb_consolidate(const int64_t *start, const int64_t *end, const int32_t *dist, uint64_t n,
                         int64_t *out_start, int64_t *out_end, int32_t *out_dist);
+
+/* Like fzb_consolidate but writes one row (start, end, dist, hull_start, hull_end) per group into
+ * out_rows[n][5] -- the per-shard input of fzb_merge_groups. Returns the number of groups. */
+int64_t fzb_consolidate_groups(const int64_t *start, const int64_t *end, const int32_t *dist, uint64_t n,
+                               int64_t *out_rows);
+
+/* Multi-GPU merge: rows[n][5] = (start, end, dist, hull_start, hull_end), one row per group found by
+ * any shard (fzb_result_copy(FINAL) + fzb_result_hulls of every shard, concatenated).  Writes the
+ * global consolidated list (at most n rows); returns its length or a negative error. */
+int64_t fzb_merge_groups(const int64_t *rows, uint64_t n, int64_t *out_start, int64_t *out_end,
+                         int32_t *out_dist);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -10,7 +10,8 @@ import pytest
 
 import oracle
 from corpus import ASCII, make_corpus
-from fuzzysearch_b200.sharding import gather_rows, merge_raw_streams, shard_bounds
+from fuzzysearch_b200 import _native
+from fuzzysearch_b200.sharding import gather_and_merge_groups, gather_rows, merge_raw_streams, shard_bounds
 from parity import tup
 
 
@@ -56,6 +57,9 @@ def _worker(rank, world, port, n, m, k, q):
         allrows = gather_rows(rows)
         merged, final = merge_raw_streams(allrows)
         ok = (tup(merged[:, :3]) == tup(raw)) and (final == tup(oracle.consolidate(raw)))
+        # the production reduction: per-rank local groups -> one all-gather -> linear merge
+        groups = _native.consolidate_groups(rows[:, 0], rows[:, 1], rows[:, 2].astype(np.int32))
+        ok = ok and (gather_and_merge_groups(groups) == final)
         q.put((rank, bool(ok), int(rows.shape[0]), len(final)))
     finally:
         dist.destroy_process_group()
