@@ -324,7 +324,7 @@ def main():
         res = one_search(h or hs)
         st = res.stats()
         if world > 1:
-            nfinal = len(gather_and_merge_groups(res.group_rows()))
+            nfinal = len(gather_and_merge_groups(result=res, as_arrays=True)[0])
         else:
             nfinal = res.count(F.FINAL)
         res.close()

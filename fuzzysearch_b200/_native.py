@@ -75,6 +75,7 @@ SYMBOLS = {
     "fzb_result_count": (_u64, [_vp, _i32]),
     "fzb_result_copy": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "fzb_result_hulls": (_i32, [_vp, _vp, _vp]),
+    "fzb_result_group_rows": (_i64, [_vp, _vp, _u64]),
     "fzb_merge_groups": (_i64, [_vp, _u64, _vp, _vp, _vp]),
     "fzb_consolidate_groups": (_i64, [_vp, _vp, _vp, _u64, _vp]),
     "fzb_result_stats": (_i32, [_vp, ctypes.POINTER(Stats)]),
@@ -169,14 +170,21 @@ class Result(object):
         check(lib().fzb_result_copy(self._h, which, ptr(start), ptr(end), ptr(dist), None, None))
         return start, end, dist
 
-    def group_rows(self):
+    def group_rows(self, out=None):
         """FINAL list as int64 rows (start, end, dist, hull_start, hull_end): what a shard
-        contributes to the multi-GPU merge (fzb_merge_groups)."""
-        s, e, d = self.arrays(FINAL)
-        hs = np.empty(s.size, dtype=np.int64)
-        he = np.empty(s.size, dtype=np.int64)
-        check(lib().fzb_result_hulls(self._h, ptr(hs), ptr(he)))
-        return np.column_stack([s, e, d.astype(np.int64), hs, he]).reshape(-1, 5)
+        contributes to the multi-GPU merge (fzb_merge_groups).  With `out` (int64 [cap,5], C
+        contiguous) the rows are written there and the TOTAL count is returned."""
+        if out is not None:
+            cnt = lib().fzb_result_group_rows(self._h, ptr(out), out.shape[0])
+            if cnt < 0:
+                check(int(cnt))
+            return int(cnt)
+        n = self.count(FINAL)
+        rows = np.empty((max(n, 1), 5), dtype=np.int64)
+        cnt = lib().fzb_result_group_rows(self._h, ptr(rows), n)
+        if cnt < 0:
+            check(int(cnt))
+        return rows[:n]
 
     def triples(self, which=FINAL):
         s, e, d = self.arrays(which)
@@ -339,14 +347,17 @@ def consolidate_groups(start, end, dist):
     return rows[:cnt]
 
 
-def merge_groups(rows):
-    """fzb_merge_groups: rows[n,5] (start,end,dist,hull_start,hull_end) -> global final triples."""
+def merge_groups(rows, as_arrays=False):
+    """fzb_merge_groups: rows[n,5] (start,end,dist,hull_start,hull_end) -> global final triples
+    (list of tuples, or the three numpy arrays with as_arrays=True)."""
     rows = np.ascontiguousarray(rows, dtype=np.int64).reshape(-1, 5)
     n = rows.shape[0]
     os_, oe, od = np.empty(n, np.int64), np.empty(n, np.int64), np.empty(n, np.int32)
     cnt = lib().fzb_merge_groups(ptr(rows), n, ptr(os_), ptr(oe), ptr(od))
     if cnt < 0:
         check(int(cnt))
+    if as_arrays:
+        return os_[:cnt], oe[:cnt], od[:cnt]
     return list(zip(os_[:cnt].tolist(), oe[:cnt].tolist(), od[:cnt].tolist()))
 
 

@@ -447,6 +447,22 @@ extern "C" int64_t fzb_consolidate_groups(const int64_t *start, const int64_t *e
     return (int64_t)o.size();
 }
 
+extern "C" int64_t fzb_result_group_rows(const fzb_result *r, int64_t *rows, uint64_t max_rows) {
+    if (!r || (!rows && max_rows)) return fail(FZB_E_INVALID, "NULL argument");
+    const std::vector<RawRec> &v = r->final_is_raw ? r->raw : r->fin;
+    if (!r->final_is_raw && r->hulls.size() != v.size() * 2)
+        return fail(FZB_E_INVALID, "result was produced with FZB_F_NO_FINAL");
+    const size_t n = std::min<size_t>(v.size(), max_rows);
+    for (size_t i = 0; i < n; i++) {
+        rows[5 * i + 0] = v[i].start;
+        rows[5 * i + 1] = v[i].end;
+        rows[5 * i + 2] = v[i].dist;
+        rows[5 * i + 3] = r->final_is_raw ? v[i].start : r->hulls[2 * i];
+        rows[5 * i + 4] = r->final_is_raw ? v[i].end : r->hulls[2 * i + 1];
+    }
+    return (int64_t)v.size();
+}
+
 extern "C" int fzb_result_hulls(const fzb_result *r, int64_t *hull_start, int64_t *hull_end) {
     if (!r) return fail(FZB_E_INVALID, "result is NULL");
     if (r->final_is_raw) {  // unconsolidated routes: every match is its own group

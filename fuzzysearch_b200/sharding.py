@@ -18,7 +18,7 @@ The reference's CPU analogue of this layout is the chunk + carry-over tail loop 
 """
 import numpy as np
 
-__all__ = ["shard_bounds", "gather_rows", "merge_raw_streams", "gather_and_merge_groups"]
+__all__ = ["shard_bounds", "gather_rows", "merge_raw_streams", "gather_and_merge_groups", "GroupReducer"]
 
 ALIGN = 16  # shard buffers start on 16-byte boundaries of the global sequence (uint4 loads)
 
@@ -74,43 +74,89 @@ def gather_rows(rows, group=None, device=None):
     return np.concatenate(parts, axis=0) if parts else rows
 
 
-_GATHER_CAP = {"rows": 4096}
+class GroupReducer(object):
+    """The multi-GPU reduction of one search, with its buffers allocated once.
 
+    Every rank contributes its locally consolidated groups (rows (start, end, dist, hull_start,
+    hull_end)); ONE fixed-size all-gather (slot = count row + padded rows; grown and retried if a
+    rank overflows it) and a linear merge of the almost-ordered shard lists (fzb_merge_groups) yield
+    the global final list on every rank."""
 
-def gather_and_merge_groups(group_rows, group=None, device=None):
-    """The multi-GPU reduction of one search: every rank contributes its locally consolidated groups
-    (rows (start, end, dist, hull_start, hull_end), Result.group_rows()); ONE fixed-size all-gather
-    (slot = count + padded rows; grown and retried if a rank overflows it) and a linear merge of the
-    almost-ordered shard lists (fzb_merge_groups) yield the global final list on every rank."""
-    from . import _native
-    rows = np.ascontiguousarray(group_rows, dtype=np.int64).reshape(-1, 5)
-    try:
+    def __init__(self, group=None, device=None, cap=4096):
         import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group = torch, dist, group
+        self.world = dist.get_world_size(group)
+        self.nccl = dist.get_backend(group) == "nccl"
+        self.dev = torch.device("cpu")
+        if self.nccl:
+            self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self._alloc(cap)
+
+    def _alloc(self, cap):
+        torch = self.torch
+        self.cap = cap
+        self.send_host = torch.zeros((cap + 1, 5), dtype=torch.int64, pin_memory=self.nccl)
+        self.recv_host = torch.zeros((self.world, cap + 1, 5), dtype=torch.int64, pin_memory=self.nccl)
+        self.send_np = self.send_host.numpy()
+        self.recv_np = self.recv_host.numpy()
+        if self.nccl:
+            self.send_dev = torch.empty_like(self.send_host, device=self.dev)
+            self.recv_dev = torch.empty_like(self.recv_host, device=self.dev)
+
+    def reduce(self, result=None, rows=None, as_arrays=False):
+        """`result`: a _native.Result (rows are pulled straight into the pinned send buffer), or
+        `rows`: an int64 [n,5] array.  Returns the global final list."""
+        from . import _native
+        while True:
+            if result is not None:
+                n = result.group_rows(out=self.send_np[1:])
+            else:
+                rows = np.asarray(rows, dtype=np.int64).reshape(-1, 5)
+                n = rows.shape[0]
+                self.send_np[1:1 + min(n, self.cap)] = rows[:self.cap]
+            self.send_np[0, 0] = n
+            if self.nccl:
+                self.send_dev.copy_(self.send_host, non_blocking=True)
+                self.dist.all_gather_into_tensor(self.recv_dev.view(-1), self.send_dev.view(-1), group=self.group)
+                self.recv_host.copy_(self.recv_dev, non_blocking=True)
+                self.torch.cuda.current_stream().synchronize()
+            else:
+                parts = [self.torch.empty_like(self.send_host) for _ in range(self.world)]
+                self.dist.all_gather(parts, self.send_host, group=self.group)
+                for r in range(self.world):
+                    self.recv_host[r].copy_(parts[r])
+            counts = self.recv_np[:, 0, 0]
+            top = int(counts.max())
+            if top <= self.cap:
+                parts = [self.recv_np[r, 1:1 + int(counts[r])] for r in range(self.world)]
+                return _native.merge_groups(np.concatenate(parts, axis=0), as_arrays=as_arrays)
+            cap = self.cap
+            while cap < top:
+                cap *= 2
+            self._alloc(cap)
+
+
+_REDUCERS = {}
+
+
+def gather_and_merge_groups(group_rows=None, group=None, device=None, result=None, as_arrays=False):
+    """Global final list from every rank's local groups (see GroupReducer); single-process when
+    torch.distributed is not initialised."""
+    from . import _native
+    try:
         import torch.distributed as dist
         ready = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
     except ImportError:  # pragma: no cover
         ready = False
     if not ready:
-        return _native.merge_groups(rows)
-    world = dist.get_world_size(group)
-    dev = torch.device("cpu")
-    if dist.get_backend(group) == "nccl":
-        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-    while True:
-        cap = _GATHER_CAP["rows"]
-        slot = np.zeros((cap + 1, 5), dtype=np.int64)
-        slot[0, 0] = rows.shape[0]
-        slot[1:1 + min(cap, rows.shape[0])] = rows[:cap]
-        mine = torch.from_numpy(slot).to(dev, non_blocking=False)
-        out = torch.empty((world, cap + 1, 5), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(out.view(-1), mine.view(-1), group=group)
-        allr = out.cpu().numpy()
-        counts = allr[:, 0, 0]
-        if int(counts.max()) <= cap:
-            parts = [allr[r, 1:1 + int(counts[r])] for r in range(world)]
-            return _native.merge_groups(np.concatenate(parts, axis=0))
-        while _GATHER_CAP["rows"] < int(counts.max()):
-            _GATHER_CAP["rows"] *= 2
+        rows = result.group_rows() if result is not None else group_rows
+        return _native.merge_groups(rows, as_arrays=as_arrays)
+    key = (id(group), str(device))
+    red = _REDUCERS.get(key)
+    if red is None:
+        red = _REDUCERS[key] = GroupReducer(group, device)
+    return red.reduce(result=result, rows=group_rows, as_arrays=as_arrays)
 
 
 def merge_raw_streams(rows, ngram_route=True):

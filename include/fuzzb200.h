@@ -177,6 +177,11 @@ int fzb_result_copy(const fzb_result *r, int which, int64_t *start, int64_t *end
  * final match won (for the unconsolidated routes: the match itself). */
 int fzb_result_hulls(const fzb_result *r, int64_t *hull_start, int64_t *hull_end);
 
+/* FINAL list as rows (start, end, dist, hull_start, hull_end), at most max_rows of them, straight
+ * into a caller buffer (e.g. the pinned send buffer of the multi-GPU all-gather).  Returns the total
+ * number of groups (which may exceed max_rows) or a negative error. */
+int64_t fzb_result_group_rows(const fzb_result *r, int64_t *rows, uint64_t max_rows);
+
 typedef struct {
     double gpu_ms;          /* CUDA-event time of all kernels of the search */
     double filter_ms;       /* ... of the haystack scan (filter) kernel alone */
