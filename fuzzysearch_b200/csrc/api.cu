@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "ham_kernels.cuh"
 #include "lp_kernels.cuh"
 #include "post_kernels.cuh"
 
@@ -134,7 +135,7 @@ static int check_shard(uint64_t buf_len, uint64_t buf_lo, uint64_t global_len, u
 }
 
 static int alloc_buffer(fzb_haystack *h) {
-    h->padded_len = round_up(h->buf_len, 16) + 64;
+    h->padded_len = round_up(h->buf_len, 128) + 128;
     CK(cudaSetDevice(h->device));
     CK(cudaMalloc(&h->d, h->padded_len));
     h->capacity = h->padded_len;
@@ -221,7 +222,7 @@ extern "C" int fzb_haystack_adopt_device(const void *dev_ptr, uint64_t buf_len, 
     h->global_len = global_len;
     h->own_lo = own_lo;
     h->own_hi = own_hi;
-    h->padded_len = round_up(buf_len, 16) + 64;
+    h->padded_len = round_up(buf_len, 128) + 128;
     rc = haystack_common_init(h);
     if (rc) {
         fzb_haystack_destroy(h);
@@ -312,11 +313,11 @@ extern "C" uint64_t fzb_haystack_len(const fzb_haystack *h) { return h ? h->glob
 extern "C" int fzb_haystack_upload(fzb_haystack *h, const uint8_t *host, uint64_t n) {
     if (!h || (!host && n)) return fail(FZB_E_INVALID, "bad arguments");
     if (!h->owned || h->buf_lo != 0) return fail(FZB_E_INVALID, "upload needs an owned whole-sequence handle");
-    if (round_up(n, 16) + 64 > h->capacity) return fail(FZB_E_INVALID, "upload larger than the handle's capacity");
+    if (round_up(n, 128) + 128 > h->capacity) return fail(FZB_E_INVALID, "upload larger than the handle's capacity");
     CK(cudaSetDevice(h->device));
     h->buf_len = h->global_len = h->own_hi = n;
     h->own_lo = 0;
-    h->padded_len = round_up(n, 16) + 64;
+    h->padded_len = round_up(n, 128) + 128;
     if (n) CK(cudaMemcpyAsync(h->d, host, n, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemsetAsync(h->d + n, 0, h->padded_len - n, h->stream));
     CK(cudaStreamSynchronize(h->stream));  // the caller may reuse `host` as soon as we return
@@ -911,9 +912,37 @@ extern "C" int fzb_search_exact(fzb_haystack *h, const uint8_t *pattern, uint32_
     return FZB_OK;
 }
 
+// TMA descriptors of the buffer viewed as rows of 128 bytes (k_hamming_count): box 256 rows / 8 rows,
+// SWIZZLE_128B, out-of-bounds rows (the halo before row 0, the tail) read as zeros.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_row_maps(fzb_haystack *h, CUtensorMap *map256, CUtensorMap *map8) {
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (!fn || q != cudaDriverEntryPointSuccess) return fail(FZB_E_CUDA, "cuTensorMapEncodeTiled not available");
+        encode = (EncodeTiledFn)fn;
+    }
+    const cuuint64_t rows = h->padded_len / kHcRowBytes;  // whole rows inside the allocation
+    const cuuint64_t dims[2] = {(cuuint64_t)kHcRowBytes, rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)kHcRowBytes};
+    const cuuint32_t estr[2] = {1, 1};
+    for (int which = 0; which < 2; which++) {
+        const cuuint32_t box[2] = {(cuuint32_t)kHcRowBytes, which == 0 ? 256u : (cuuint32_t)kHcHaloRows};
+        CUresult r = encode(which == 0 ? map256 : map8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, h->d, dims, strides, box,
+                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(FZB_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    }
+    return FZB_OK;
+}
+
 extern "C" int fzb_search_hamming(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint32_t k,
                                   uint32_t flags, fzb_result **out) {
-    (void)flags;
     fzb_result *res;
     int rc = make_result(out, &res);
     if (rc) return rc;
@@ -927,9 +956,28 @@ extern "C" int fzb_search_hamming(fzb_haystack *h, const uint8_t *pattern, uint3
             CK(cudaSetDevice(h->device));
             res->stats.route = 4;
             res->stats.bytes_scanned = h->buf_len;
+            // counting q-sample filter needs W = floor((m-3)/4) >= k+1 aligned words and 4-bit fields (k <= 7)
+            const bool counting = !(flags & FZB_F_FORCE_DENSE) && (int)m >= 4 * p.k + 7 && p.k <= 7 && h->buf_len > 0;
+            HamCountParams hp{};
+            CUtensorMap map256, map8;
+            if (counting) {
+                hp.Wc = std::min<int>((int)(m - 3) / 4, 8);
+                hp.bias = 8 - (hp.Wc - p.k);
+                hp.nrows = (int64_t)(round_up(h->buf_len, kHcRowBytes) / kHcRowBytes);
+                int r3 = make_row_maps(h, &map256, &map8);
+                if (r3) return r3;
+                CK(cudaFuncSetAttribute(k_hamming_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHcSmem));
+            }
             int r2 = run_emitting(h, res, [&]() -> int {
-                k_hamming_scan<<<h->sm_count * 8, kHamThreads, 0, h->stream>>>(p, h->d_out, h->out_cap,
-                                                                               h->d_counters);
+                if (counting) {
+                    const int64_t ntiles = (hp.nrows + kHcThreads - 1) / kHcThreads;
+                    const int grid = (int)std::min<int64_t>(ntiles, h->sm_count);
+                    k_hamming_count<<<grid, kHcThreads, kHcSmem, h->stream>>>(p, hp, map256, map8, h->d_out,
+                                                                              h->out_cap, h->d_counters);
+                } else {
+                    k_hamming_scan<<<h->sm_count * 8, kHamThreads, 0, h->stream>>>(p, h->d_out, h->out_cap,
+                                                                                   h->d_counters);
+                }
                 res->stats.n_launches++;
                 return FZB_OK;
             }, PostPlan{true, 1, 0});
@@ -1000,7 +1048,7 @@ extern "C" int fzb_find_near_matches(const uint8_t *pattern, uint32_t m, const u
         return fail(FZB_E_CUDA, "CUDA device %d not available (%d devices)", device, fzb_device_count());
     std::lock_guard<std::mutex> lock(g_ws_mutex);
     fzb_haystack *&h = g_ws[device];
-    if (!h || round_up(n, 16) + 64 > h->capacity) {
+    if (!h || round_up(n, 128) + 128 > h->capacity) {
         if (h) fzb_haystack_destroy(h);
         h = nullptr;
         const uint64_t cap = std::max<uint64_t>(n + n / 8, 1u << 20);  // head-room: repeated calls with growing inputs

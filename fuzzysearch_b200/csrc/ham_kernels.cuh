@@ -1,0 +1,202 @@
+// ham_kernels.cuh -- substitutions-only (Hamming) search: every start p in [0, N-m] with
+// Hamming(P, H[p:p+m]) <= k  (substitutions_only.py:37-215 == brute force).
+//
+// k_hamming_count -- the HBM-streaming kernel (used when m >= 4k+7 and k <= 7):
+//   Counting q-sample filter.  An occurrence at p contains W = floor((m-3)/4) four-byte-aligned words
+//   (at ANY alignment of p); a substitution spoils at most one of them, so at least Wc-k of the first
+//   Wc = min(W, 8) aligned words inside it equal the pattern 4-gram at their own offset.  Unlike the
+//   Levenshtein filter a single q-gram hit is not selective on small alphabets (DNA: 29 grams among
+//   256 possible words), so the kernel COUNTS: per alignment class o0 = (first aligned word) - p in
+//   {0,1,2,3} it keeps a shift-add register S_o0 of Wc 4-bit fields; for every aligned text word w
+//        S_o0 = (S_o0 << 4) + T_o0[hash(w)]          (one IMAD per class)
+//   where T_o0[.] has a 1 in field i iff w == P[o0+4i : o0+4i+4)  (+ a bias of 8-(Wc-k) in field 0),
+//   so field Wc-1 reaches 8 (bit 3 set) exactly when >= Wc-k of the Wc words of the occurrence that
+//   ENDS its counted prefix at this word matched.  The table lives in shared memory, 16 B per bucket
+//   (the four classes: ONE LDS.128 per text word), replicated 8x so that the 8 lanes of a
+//   quarter-warp always hit distinct 16-byte bank groups (conflict-free).
+//   The recurrence runs ALONG the text, so each thread owns one 128-byte row of a tile; tiles are
+//   staged global -> shared by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B so that the per-thread
+//   row reads are bank-conflict free, mbarrier complete_tx, 2-stage ring), one elected thread issuing.
+//   Flagged rows (rare: true near-matches) are re-checked exactly, position by position.
+// k_hamming_scan  -- brute-force fallback for short patterns / large k.
+#pragma once
+#include <cuda.h>
+
+#include "kernels.cuh"
+
+namespace fzb {
+
+constexpr int kHamThreads = 256;
+
+__global__ void __launch_bounds__(kHamThreads)
+k_hamming_scan(const ScanParams p, RawRec *out, uint32_t cap, uint32_t *counters) {
+    __shared__ uint8_t sP[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sP[i] = p.P[i];
+    __syncthreads();
+    const int m = p.m, k = p.k;
+    const int64_t last = min(p.own_hi, p.N - m + 1);  // exclusive bound on starts
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t pos = p.own_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pos < last; pos += stride) {
+        const uint8_t *h = p.H + (pos - p.buf_lo);
+        int nd = 0;
+        for (int i = 0; i < m; i++) {
+            nd += (__ldg(h + i) != sP[i]);
+            if (nd > k) break;
+        }
+        if (nd <= k) emit(out, cap, counters, pos, pos + m, pos, nd, 0);
+    }
+}
+
+// ---- TMA / mbarrier primitives (sm_90+ PTX) ------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// ---- counting filter --------------------------------------------------------------------------------
+constexpr int kHcThreads = 512;               // one 128-byte row per thread
+constexpr int kHcRowBytes = 128;
+constexpr int kHcHaloRows = 8;                // one swizzle atom; only its last row is read
+constexpr int kHcTileRows = kHcHaloRows + kHcThreads;            // 520
+constexpr int kHcStageBytes = kHcTileRows * kHcRowBytes;         // 66560 (multiple of 1024)
+constexpr int kHcStages = 2;
+constexpr int kHcBuckets = 256;
+constexpr int kHcTableBytes = kHcBuckets * 8 * 16;               // 32 KiB
+constexpr size_t kHcSmem = 1024 + (size_t)kHcStages * kHcStageBytes + kHcTableBytes + 64;
+constexpr uint32_t kHcHashMul = 0x9E3779B1u;
+
+__device__ __forceinline__ uint32_t hc_bucket(uint32_t w) { return (w * kHcHashMul) >> 24; }
+
+struct HamCountParams {
+    int Wc;        // counted words per occurrence (<= 8)
+    int bias;      // 8 - (Wc - k)
+    int64_t nrows; // rows of the buffer that hold data: ceil(buf_len / 128)
+};
+
+// swizzled address of 16-byte chunk j of local row r (SWIZZLE_128B: chunk index ^= row % 8)
+__device__ __forceinline__ const uint4 *hc_chunk(const uint8_t *stage, int r, int j) {
+    return reinterpret_cast<const uint4 *>(stage + r * kHcRowBytes + ((j ^ (r & 7)) << 4));
+}
+
+__global__ void __launch_bounds__(kHcThreads, 1)
+k_hamming_count(const ScanParams p, const HamCountParams hp, const __grid_constant__ CUtensorMap map256,
+                const __grid_constant__ CUtensorMap map8, RawRec *out, uint32_t cap, uint32_t *counters) {
+    extern __shared__ uint8_t hc_smem_raw[];
+    uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(hc_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint4 *table = reinterpret_cast<uint4 *>(base + kHcStages * kHcStageBytes);
+    uint64_t *full = reinterpret_cast<uint64_t *>(base + kHcStages * kHcStageBytes + kHcTableBytes);
+    __shared__ uint8_t sP[256];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int m = p.m, k = p.k, Wc = hp.Wc;
+
+    for (int i = tid; i < 256; i += kHcThreads) sP[i] = p.P[i];
+    // table: every bucket starts with the bias in field 0 of all four classes
+    for (int i = tid; i < kHcBuckets * 8; i += kHcThreads)
+        table[i] = make_uint4((uint32_t)hp.bias, (uint32_t)hp.bias, (uint32_t)hp.bias, (uint32_t)hp.bias);
+    if (tid == 0) {
+        for (int s = 0; s < kHcStages; s++) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid < 8) {  // replica `tid` of the table: add the pattern's 4-grams (serial per replica: no races)
+        for (int o0 = 0; o0 < 4; o0++)
+            for (int i = 0; i < Wc; i++) {  // each (class, field) pair exactly once -> plain add
+                const int o = o0 + 4 * i;
+                const uint32_t w = (uint32_t)p.P[o] | ((uint32_t)p.P[o + 1] << 8) | ((uint32_t)p.P[o + 2] << 16) |
+                                   ((uint32_t)p.P[o + 3] << 24);
+                uint32_t *e = reinterpret_cast<uint32_t *>(&table[hc_bucket(w) * 8 + tid]);
+                e[o0] += 1u << (4 * i);
+            }
+    }
+    __syncthreads();
+
+    const int64_t ntiles = (hp.nrows + kHcThreads - 1) / kHcThreads;
+    const uint32_t flag_bit = 8u << (4 * (Wc - 1));
+    auto issue = [&](int64_t tile, int s) {  // one elected thread: 520 rows = 8 + 256 + 256
+        const int r0 = (int)(tile * kHcThreads) - kHcHaloRows;
+        uint8_t *dst = base + s * kHcStageBytes;
+        mbar_expect_tx(&full[s], kHcStageBytes);
+        tma_load_2d(dst, &map8, 0, r0, &full[s]);
+        tma_load_2d(dst + kHcHaloRows * kHcRowBytes, &map256, 0, r0 + kHcHaloRows, &full[s]);
+        tma_load_2d(dst + (kHcHaloRows + 256) * kHcRowBytes, &map256, 0, r0 + kHcHaloRows + 256, &full[s]);
+    };
+    int64_t tile = blockIdx.x;
+    if (tid == 0) {
+        if (tile < ntiles) issue(tile, 0);
+        if (tile + gridDim.x < ntiles) issue(tile + gridDim.x, 1);
+    }
+    const uint4 *my_table = table + (lane & 7);
+    uint32_t phases = 0;  // bit s = parity to wait for on stage s
+    for (int it = 0; tile < ntiles; tile += gridDim.x, it++) {
+        const int s = it & 1;
+        mbar_wait(&full[s], (phases >> s) & 1u);
+        phases ^= 1u << s;
+        const uint8_t *st = base + s * kHcStageBytes;
+        const int r = kHcHaloRows + tid;
+        uint32_t S0 = 0, S1 = 0, S2 = 0, S3 = 0, acc = 0;
+#define HC_STEP(WORD, track)                                               \
+    {                                                                      \
+        const uint4 T = my_table[hc_bucket(WORD) * 8];                     \
+        S0 = S0 * 16u + T.x;                                               \
+        S1 = S1 * 16u + T.y;                                               \
+        S2 = S2 * 16u + T.z;                                               \
+        S3 = S3 * 16u + T.w;                                               \
+        if (track) acc |= S0 | S1 | S2 | S3;                               \
+    }
+        {  // warm-up: the last 7 words of the previous row (no flags: they belong to that row's thread)
+            const uint4 a = *hc_chunk(st, r - 1, 6), b = *hc_chunk(st, r - 1, 7);
+            HC_STEP(a.y, false) HC_STEP(a.z, false) HC_STEP(a.w, false)
+            HC_STEP(b.x, false) HC_STEP(b.y, false) HC_STEP(b.z, false) HC_STEP(b.w, false)
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const uint4 d = *hc_chunk(st, r, j);
+            HC_STEP(d.x, true) HC_STEP(d.y, true) HC_STEP(d.z, true) HC_STEP(d.w, true)
+        }
+#undef HC_STEP
+        if (acc & flag_bit) {
+            // exact re-check of every start whose last counted word lies in my row (rare)
+            const int64_t grow = tile * kHcThreads + tid;  // buffer row index
+            const int64_t pr_lo = 4 * (grow * 32 - Wc + 1) - 3, pr_hi = 4 * (grow * 32 + 31 - Wc + 1);
+            for (int64_t pr = max(pr_lo, (int64_t)0); pr <= pr_hi; pr++) {
+                const int64_t pos = p.buf_lo + pr;
+                if (pos < p.own_lo || pos >= p.own_hi || pos + m > p.N) continue;
+                const uint8_t *h = p.H + pr;
+                int nd = 0;
+                for (int i = 0; i < m; i++) {
+                    nd += (__ldg(h + i) != sP[i]);
+                    if (nd > k) break;
+                }
+                if (nd <= k) emit(out, cap, counters, pos, pos + m, pos, nd, 0);
+            }
+        }
+        __syncthreads();  // everyone is done with stage s
+        if (tid == 0 && tile + 2 * (int64_t)gridDim.x < ntiles) issue(tile + 2 * (int64_t)gridDim.x, s);
+    }
+}
+
+}  // namespace fzb

@@ -466,33 +466,6 @@ k_verify_lev(const ScanParams p, uint64_t bitmap_words, const uint32_t *glist, u
 }
 
 // ------------------------------------------------------------------------------------------------
-// Hamming (substitutions only): every start p in [0, N-m] with Hamming(P, H[p:p+m]) <= k
-// (substitutions_only.py:37-215 == brute force).  v1: direct per-position count with
-// early exit at k+1 mismatches, 4 bytes per step.
-// ------------------------------------------------------------------------------------------------
-constexpr int kHamThreads = 256;
-
-__global__ void __launch_bounds__(kHamThreads)
-k_hamming_scan(const ScanParams p, RawRec *out, uint32_t cap, uint32_t *counters) {
-    __shared__ uint8_t sP[256];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) sP[i] = p.P[i];
-    __syncthreads();
-    const int m = p.m, k = p.k;
-    const int64_t last = min(p.own_hi, p.N - m + 1);  // exclusive bound on starts
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t pos = p.own_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pos < last;
-         pos += stride) {
-        const uint8_t *h = p.H + (pos - p.buf_lo);
-        int nd = 0;
-        for (int i = 0; i < m; i++) {
-            nd += (__ldg(h + i) != sP[i]);
-            if (nd > k) break;
-        }
-        if (nd <= k) emit(out, cap, counters, pos, pos + m, pos, nd, 0);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // Synthetic corpus fill (bench / tests): byte i = alphabet[hash(seed, i)], counter based.
 // ------------------------------------------------------------------------------------------------
 __global__ void k_fill_synth(uint8_t *H, int64_t buf_lo, int64_t nwords, uint64_t seed,

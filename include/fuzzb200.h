@@ -83,7 +83,7 @@ int fzb_haystack_create_shard(const uint8_t *host, uint64_t buf_len, uint64_t bu
                               fzb_haystack **out);
 
 /* Adopt an existing device allocation (not freed by destroy).  `dev_ptr` must be 16-byte aligned
- * and readable for buf_len rounded up to a multiple of 16 bytes plus 64. Used by bench.py to scan
+ * and readable for buf_len rounded up to a multiple of 128 bytes plus 128. Used by bench.py to scan
  * corpora generated on the device. */
 int fzb_haystack_adopt_device(const void *dev_ptr, uint64_t buf_len, uint64_t buf_lo,
                               uint64_t global_len, uint64_t own_lo, uint64_t own_hi, int device,

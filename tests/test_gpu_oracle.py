@@ -43,18 +43,24 @@ def test_levenshtein_ngrams_matches_oracle(cuda_device, alphabet, n, m, k, flags
     hs.close()
 
 
-@pytest.mark.parametrize("alphabet,n,m,k", [
-    (DNA, 1 << 20, 32, 3),   # config 3 of BASELINE.json (scaled)
-    (ASCII, 1 << 20, 32, 3),
-    (DNA, 1 << 16, 8, 2),
-    (b"ab", 1 << 12, 6, 5),
-    (ASCII, 1 << 12, 5, 7),  # k >= m: every start matches
+@pytest.mark.parametrize("alphabet,n,m,k,flags", [
+    (DNA, 1 << 20, 32, 3, 0),   # config 3 of BASELINE.json (scaled): counting filter (TMA tiles)
+    (DNA, (1 << 20) + 77, 32, 3, 0),
+    (DNA, 1 << 18, 32, 3, F.F_FORCE_DENSE),   # brute-force fallback kernel
+    (ASCII, 1 << 20, 32, 3, 0),
+    (b"ab", 1 << 16, 40, 5, 0),  # tiny alphabet, repeated grams, Wc = 8 < W
+    (b"ab", 1 << 14, 64, 7, 0),
+    (DNA, 300, 32, 3, 0),        # shorter than one tile
+    (DNA, 1 << 16, 11, 1, 0),    # smallest m for k = 1 (W = 2)
+    (DNA, 1 << 16, 8, 2, 0),     # lemma does not apply -> fallback
+    (b"ab", 1 << 12, 6, 5, 0),
+    (ASCII, 1 << 12, 5, 7, 0),   # k >= m: every start matches
 ])
-def test_hamming_matches_oracle(cuda_device, alphabet, n, m, k):
+def test_hamming_matches_oracle(cuda_device, alphabet, n, m, k, flags):
     pat, hay, _ = make_corpus(5, n, alphabet, m, 64, k + 1, subs_only=True)
     cpu = oracle.substitutions(pat, hay, k)
     hs = F.Haystack.from_host(hay)
-    res = hs.search_hamming(pat, k)
+    res = hs.search_hamming(pat, k, flags)
     assert res.triples(F.RAW) == tup(cpu)
     assert res.triples(F.FINAL) == tup(cpu)
     res.close()
