@@ -417,11 +417,11 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
             "matches_per_step": int(nfinal), "wall_ms_per_step": wall_ms / args.steps,
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_filter_sampled" if kind == "lev" else "k_hamming_scan",
+            "roofline": {"bound": "hbm", "kernel": "k_filter_sampled" if kind == "lev" else "k_hamming_count",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "kernel_ms": filt,
                          "algorithmic_bytes_per_launch": bhi - blo,
-                         "traffic": (traffic or {}).get("dram_bytes_per_launch")},
+                         "traffic": (traffic or {}).get("dram_bytes_per_launch") if kind == "lev" else None},
             "clocks": clocks}
     if e2e is not None:
         line["e2e"] = e2e

@@ -971,9 +971,17 @@ extern "C" int fzb_search_hamming(fzb_haystack *h, const uint8_t *pattern, uint3
             int r2 = run_emitting(h, res, [&]() -> int {
                 if (counting) {
                     const int64_t ntiles = (hp.nrows + kHcThreads - 1) / kHcThreads;
-                    const int grid = (int)std::min<int64_t>(ntiles, h->sm_count);
-                    k_hamming_count<<<grid, kHcThreads, kHcSmem, h->stream>>>(p, hp, map256, map8, h->d_out,
-                                                                              h->out_cap, h->d_counters);
+                    const int grid = (int)std::min<int64_t>(ntiles, (int64_t)h->sm_count * 2);
+                    k_hamming_count<<<grid, kHcThreads, kHcSmem, h->stream>>>(p, hp, map256, map8);
+                    CK(cudaEventRecord(h->ev[1], h->stream));
+                    h->ev1_recorded = true;
+                    k_compact_granules<<<h->sm_count * 4, 256, 0, h->stream>>>(h->d_bitmap, h->bitmap_words,
+                                                                               h->d_glist, h->glist_cap, h->d_counters);
+                    for (int scan_mode = 0; scan_mode < 2; scan_mode++)
+                        k_verify_ham<<<h->sm_count * 4, kVerifyThreads, 0, h->stream>>>(
+                            p, h->bitmap_words, h->d_glist, h->glist_cap, scan_mode, h->d_out, h->out_cap,
+                            h->d_counters);
+                    res->stats.n_launches += 3;
                 } else {
                     k_hamming_scan<<<h->sm_count * 8, kHamThreads, 0, h->stream>>>(p, h->d_out, h->out_cap,
                                                                                    h->d_counters);

@@ -78,11 +78,11 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
 }
 
 // ---- counting filter --------------------------------------------------------------------------------
-constexpr int kHcThreads = 512;               // one 128-byte row per thread
+constexpr int kHcThreads = 256;               // one 128-byte row per thread; 2 CTAs per SM
 constexpr int kHcRowBytes = 128;
 constexpr int kHcHaloRows = 8;                // one swizzle atom; only its last row is read
-constexpr int kHcTileRows = kHcHaloRows + kHcThreads;            // 520
-constexpr int kHcStageBytes = kHcTileRows * kHcRowBytes;         // 66560 (multiple of 1024)
+constexpr int kHcTileRows = kHcHaloRows + kHcThreads;            // 264
+constexpr int kHcStageBytes = kHcTileRows * kHcRowBytes;         // 33792 (multiple of 1024)
 constexpr int kHcStages = 2;
 constexpr int kHcBuckets = 256;
 constexpr int kHcTableBytes = kHcBuckets * 8 * 16;               // 32 KiB
@@ -102,18 +102,16 @@ __device__ __forceinline__ const uint4 *hc_chunk(const uint8_t *stage, int r, in
     return reinterpret_cast<const uint4 *>(stage + r * kHcRowBytes + ((j ^ (r & 7)) << 4));
 }
 
-__global__ void __launch_bounds__(kHcThreads, 1)
+__global__ void __launch_bounds__(kHcThreads, 2)
 k_hamming_count(const ScanParams p, const HamCountParams hp, const __grid_constant__ CUtensorMap map256,
-                const __grid_constant__ CUtensorMap map8, RawRec *out, uint32_t cap, uint32_t *counters) {
+                const __grid_constant__ CUtensorMap map8) {
     extern __shared__ uint8_t hc_smem_raw[];
     uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(hc_smem_raw) + 1023) & ~(uintptr_t)1023);
     uint4 *table = reinterpret_cast<uint4 *>(base + kHcStages * kHcStageBytes);
     uint64_t *full = reinterpret_cast<uint64_t *>(base + kHcStages * kHcStageBytes + kHcTableBytes);
-    __shared__ uint8_t sP[256];
     const int tid = threadIdx.x, lane = tid & 31;
-    const int m = p.m, k = p.k, Wc = hp.Wc;
+    const int Wc = hp.Wc;
 
-    for (int i = tid; i < 256; i += kHcThreads) sP[i] = p.P[i];
     // table: every bucket starts with the bias in field 0 of all four classes
     for (int i = tid; i < kHcBuckets * 8; i += kHcThreads)
         table[i] = make_uint4((uint32_t)hp.bias, (uint32_t)hp.bias, (uint32_t)hp.bias, (uint32_t)hp.bias);
@@ -136,13 +134,12 @@ k_hamming_count(const ScanParams p, const HamCountParams hp, const __grid_consta
 
     const int64_t ntiles = (hp.nrows + kHcThreads - 1) / kHcThreads;
     const uint32_t flag_bit = 8u << (4 * (Wc - 1));
-    auto issue = [&](int64_t tile, int s) {  // one elected thread: 520 rows = 8 + 256 + 256
+    auto issue = [&](int64_t tile, int s) {  // one elected thread: 264 rows = 8 (halo atom) + 256
         const int r0 = (int)(tile * kHcThreads) - kHcHaloRows;
         uint8_t *dst = base + s * kHcStageBytes;
         mbar_expect_tx(&full[s], kHcStageBytes);
         tma_load_2d(dst, &map8, 0, r0, &full[s]);
         tma_load_2d(dst + kHcHaloRows * kHcRowBytes, &map256, 0, r0 + kHcHaloRows, &full[s]);
-        tma_load_2d(dst + (kHcHaloRows + 256) * kHcRowBytes, &map256, 0, r0 + kHcHaloRows + 256, &full[s]);
     };
     int64_t tile = blockIdx.x;
     if (tid == 0) {
@@ -179,23 +176,81 @@ k_hamming_count(const ScanParams p, const HamCountParams hp, const __grid_consta
         }
 #undef HC_STEP
         if (acc & flag_bit) {
-            // exact re-check of every start whose last counted word lies in my row (rare)
+            // some start whose last counted word lies in my row passed the filter (rare: true
+            // near-matches): mark its granules; k_verify_ham re-checks them exactly
             const int64_t grow = tile * kHcThreads + tid;  // buffer row index
             const int64_t pr_lo = 4 * (grow * 32 - Wc + 1) - 3, pr_hi = 4 * (grow * 32 + 31 - Wc + 1);
-            for (int64_t pr = max(pr_lo, (int64_t)0); pr <= pr_hi; pr++) {
-                const int64_t pos = p.buf_lo + pr;
-                if (pos < p.own_lo || pos >= p.own_hi || pos + m > p.N) continue;
-                const uint8_t *h = p.H + pr;
-                int nd = 0;
-                for (int i = 0; i < m; i++) {
-                    nd += (__ldg(h + i) != sP[i]);
-                    if (nd > k) break;
-                }
-                if (nd <= k) emit(out, cap, counters, pos, pos + m, pos, nd, 0);
-            }
+            mark_range(p, p.buf_lo + max(pr_lo, (int64_t)0), p.buf_lo + pr_hi);
         }
         __syncthreads();  // everyone is done with stage s
         if (tid == 0 && tile + 2 * (int64_t)gridDim.x < ntiles) issue(tile + 2 * (int64_t)gridDim.x, s);
+    }
+}
+
+// ---- exact verification of the marked granules (same work-list scheme as k_verify_lev) -------------
+__device__ __forceinline__ void verify_granule_ham(const ScanParams &p, const uint8_t *sP, uint32_t *sWin,
+                                                   int64_t granule, int lane, RawRec *out, uint32_t cap,
+                                                   uint32_t *counters) {
+    const int m = p.m, k = p.k;
+    const int64_t gbase = p.buf_lo + (granule << kGranuleShift);
+    const int64_t alo = stage_window(p, gbase, m, lane, sWin);
+    const uint8_t *W = reinterpret_cast<const uint8_t *>(sWin) - alo;
+#pragma unroll 1
+    for (int half = 0; half < kGranule / 32; half++) {
+        const int64_t pos = gbase + half * 32 + lane;
+        if (pos < p.own_lo || pos >= p.own_hi || pos + m > p.N) continue;
+        int nd = 0;
+        for (int i = 0; i < m; i++) {
+            nd += (W[pos + i] != sP[i]);
+            if (nd > k) break;
+        }
+        if (nd <= k) emit(out, cap, counters, pos, pos + m, pos, nd, 0);
+    }
+}
+
+__global__ void __launch_bounds__(kVerifyThreads)
+k_verify_ham(const ScanParams p, uint64_t bitmap_words, const uint32_t *glist, uint32_t glist_cap, int scan_mode,
+             RawRec *out, uint32_t cap, uint32_t *counters) {
+    __shared__ uint8_t sP[256];
+    __shared__ uint32_t sWinAll[kVerifyThreads / 32][kWinWords];
+    const uint32_t ngran = counters[CNT_GRAN];
+    if (scan_mode && ngran <= glist_cap) return;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sP[i] = p.P[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    uint32_t *sWin = sWinAll[threadIdx.x >> 5];
+    if (!scan_mode) {
+        const uint32_t nitems = min(ngran, glist_cap);
+        for (;;) {
+            uint32_t item = 0;
+            if (lane == 0) item = atomicAdd(&counters[CNT_WORK], 1u);
+            item = __shfl_sync(0xFFFFFFFFu, item, 0);
+            if (item >= nitems) break;
+            const uint32_t g = glist[item];
+            verify_granule_ham(p, sP, sWin, (int64_t)g, lane, out, cap, counters);
+            if (lane == 0) atomicAnd(&p.bitmap[g >> 5], ~(1u << (g & 31)));
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counters[CNT_CAND], nitems);
+        return;
+    }
+    const uint64_t gwarp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t wbase = gwarp * 32; wbase < bitmap_words; wbase += nwarps * 32) {
+        const uint64_t wi = wbase + lane;
+        uint32_t bits = wi < bitmap_words ? p.bitmap[wi] : 0u;
+        if (bits) p.bitmap[wi] = 0u;
+        unsigned active = __ballot_sync(0xFFFFFFFFu, bits != 0);
+        while (active) {
+            const int src = __ffs(active) - 1;
+            active &= active - 1;
+            uint32_t b = __shfl_sync(0xFFFFFFFFu, bits, src);
+            if (lane == 0) atomicAdd(&counters[CNT_CAND], (uint32_t)__popc(b));
+            while (b) {
+                const int bit = __ffs(b) - 1;
+                b &= b - 1;
+                verify_granule_ham(p, sP, sWin, (int64_t)(wbase + src) * 32 + bit, lane, out, cap, counters);
+            }
+        }
     }
 }
 
