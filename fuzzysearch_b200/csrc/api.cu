@@ -79,6 +79,7 @@ struct fzb_haystack {
     uint64_t *d_keys_sorted = nullptr;
     int64_t *h_fin = nullptr;        // pinned
     bool ev1_recorded = false;
+    bool filter_attrs_set = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     int sm_count = 148;
     uint32_t *d_glist = nullptr;    // compacted list of marked granules
@@ -92,7 +93,10 @@ struct fzb_result {
     std::vector<RawRec> fin;
     std::vector<int64_t> hulls;  // (hull_start, hull_end) of the group behind each final match
     bool final_is_raw = false;
-    bool device_post = false;  // raw already ordered (and fin filled) by k_post_small
+    bool device_post = false;  // final list (and, unless raw_order_pending, the raw order) came from the device
+    bool raw_ordered = false;  // raw is already in its reference order
+    int raw_order = 0;         // 0 generation (ngram, idx) / 1 canonical / 2 generic n-grams (5 fields)
+    void order_raw();
     fzb_stats stats{};
 };
 
@@ -450,6 +454,7 @@ extern "C" int64_t fzb_consolidate_groups(const int64_t *start, const int64_t *e
 
 extern "C" int64_t fzb_result_group_rows(const fzb_result *r, int64_t *rows, uint64_t max_rows) {
     if (!r || (!rows && max_rows)) return fail(FZB_E_INVALID, "NULL argument");
+    if (r->final_is_raw) const_cast<fzb_result *>(r)->order_raw();
     const std::vector<RawRec> &v = r->final_is_raw ? r->raw : r->fin;
     if (!r->final_is_raw && r->hulls.size() != v.size() * 2)
         return fail(FZB_E_INVALID, "result was produced with FZB_F_NO_FINAL");
@@ -466,6 +471,7 @@ extern "C" int64_t fzb_result_group_rows(const fzb_result *r, int64_t *rows, uin
 
 extern "C" int fzb_result_hulls(const fzb_result *r, int64_t *hull_start, int64_t *hull_end) {
     if (!r) return fail(FZB_E_INVALID, "result is NULL");
+    if (r->final_is_raw) const_cast<fzb_result *>(r)->order_raw();
     if (r->final_is_raw) {  // unconsolidated routes: every match is its own group
         for (size_t i = 0; i < r->raw.size(); i++) {
             if (hull_start) hull_start[i] = r->raw[i].start;
@@ -575,7 +581,7 @@ constexpr uint32_t kSpecRecs = 4096;
 // What k_post_small should do behind the emitting kernels (post.enable == false: host does it).
 struct PostPlan {
     bool enable = false;
-    int raw_canonical = 0;
+    int raw_mode = 0;  // 0 generation order, 1 canonical order, 2 arrival order (ordered lazily on the host)
     int do_consolidate = 0;
 };
 
@@ -593,9 +599,9 @@ static int run_emitting(fzb_haystack *h, fzb_result *res, F enqueue, PostPlan po
         if (post.enable) {
             uint32_t *ranks = h->d_counters + CNT_COUNT;
             k_rank<<<dim3(kPostMax / kRankThreads, kPostMax / kRankChunk), kRankThreads, 0, h->stream>>>(
-                h->d_out, h->out_cap, post.raw_canonical, ranks, h->d_counters);
+                h->d_out, h->out_cap, post.raw_mode, ranks, h->d_counters);
             k_consolidate<<<1, kConsThreads, kConsSmem, h->stream>>>(h->d_out, ranks, h->d_raw_sorted,
-                                                                     h->d_keys_sorted, h->out_cap,
+                                                                     h->d_keys_sorted, h->out_cap, post.raw_mode,
                                                                      post.do_consolidate, h->d_fin, h->d_counters);
             CK(cudaGetLastError());
             res->stats.n_launches += 2;
@@ -603,7 +609,8 @@ static int run_emitting(fzb_haystack *h, fzb_result *res, F enqueue, PostPlan po
         CK(cudaEventRecord(h->ev[2], h->stream));
         CK(cudaMemcpyAsync(h->h_counters, h->d_counters, CNT_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                            h->stream));
-        CK(cudaMemcpyAsync(h->h_stage, post.enable ? h->d_raw_sorted : h->d_out, (size_t)spec * sizeof(RawRec),
+        const bool raw_from_sorted = post.enable && post.raw_mode != 2;
+        CK(cudaMemcpyAsync(h->h_stage, raw_from_sorted ? h->d_raw_sorted : h->d_out, (size_t)spec * sizeof(RawRec),
                            cudaMemcpyDeviceToHost, h->stream));
         if (post.enable && post.do_consolidate)
             CK(cudaMemcpyAsync(h->h_fin, h->d_fin, (size_t)spec * kFinCols * sizeof(int64_t), cudaMemcpyDeviceToHost,
@@ -617,10 +624,11 @@ static int run_emitting(fzb_haystack *h, fzb_result *res, F enqueue, PostPlan po
             continue;
         }
         const bool posted = post.enable && h->h_counters[CNT_POST_DONE] != 0;
-        const RawRec *dsrc = posted ? h->d_raw_sorted : h->d_out;
+        const RawRec *dsrc = (posted && raw_from_sorted) ? h->d_raw_sorted : h->d_out;
+        const bool stage_ok = !raw_from_sorted || posted;  // staging holds what we want
         res->raw.resize(n);
-        if (n && (posted || !post.enable)) memcpy(res->raw.data(), h->h_stage, (size_t)std::min(n, spec) * sizeof(RawRec));
-        const uint32_t have = (posted || !post.enable) ? std::min(n, spec) : 0;
+        if (n && stage_ok) memcpy(res->raw.data(), h->h_stage, (size_t)std::min(n, spec) * sizeof(RawRec));
+        const uint32_t have = stage_ok ? std::min(n, spec) : 0;
         if (n > have)
             CK(cudaMemcpyAsync(res->raw.data() + have, dsrc + have, (size_t)(n - have) * sizeof(RawRec),
                                cudaMemcpyDeviceToHost, h->stream));
@@ -646,6 +654,7 @@ static int run_emitting(fzb_haystack *h, fzb_result *res, F enqueue, PostPlan po
             CK(cudaStreamSynchronize(h->stream));
         }
         res->device_post = posted;
+        res->raw_ordered = posted && raw_from_sorted;
         float ms = 0.f;
         cudaEventElapsedTime(&ms, h->ev[0], h->ev[2]);
         res->stats.gpu_ms = ms;
@@ -664,6 +673,26 @@ static void sort_generation_order(std::vector<RawRec> &v) {
         if (a.ngram != b.ngram) return a.ngram < b.ngram;
         return a.idx < b.idx;
     });
+}
+
+static void sort_generation_order(std::vector<RawRec> &v);
+static void sort_canonical(std::vector<RawRec> &v);
+
+void fzb_result::order_raw() {
+    if (raw_ordered) return;
+    if (raw_order == 0)
+        sort_generation_order(raw);
+    else if (raw_order == 1)
+        sort_canonical(raw);
+    else
+        std::sort(raw.begin(), raw.end(), [](const RawRec &a, const RawRec &b) {
+            if (a.ngram != b.ngram) return a.ngram < b.ngram;
+            if (a.idx != b.idx) return a.idx < b.idx;
+            if (a.start != b.start) return a.start < b.start;
+            if (a.end != b.end) return a.end < b.end;
+            return a.dist < b.dist;
+        });
+    raw_ordered = true;
 }
 
 static void sort_canonical(std::vector<RawRec> &v) {
@@ -724,8 +753,11 @@ static int search_lev_ngrams(fzb_haystack *h, const uint8_t *pattern, uint32_t m
     res->stats.route = k == 0 ? 0 : (sampled ? 1 : 2);
     res->stats.bytes_scanned = h->buf_len;
     CK(cudaSetDevice(h->device));
-    rc = set_filter_attrs(kFilterSmem);
-    if (rc) return rc;
+    if (!h->filter_attrs_set) {
+        rc = set_filter_attrs(kFilterSmem);
+        if (rc) return rc;
+        h->filter_attrs_set = true;
+    }
     rc = run_emitting(h, res, [&]() -> int {
         int r2 = enqueue_filter(h, p, sampled, res);
         if (r2) return r2;
@@ -737,9 +769,9 @@ static int search_lev_ngrams(fzb_haystack *h, const uint8_t *pattern, uint32_t m
                 p, h->bitmap_words, h->d_glist, gcap, scan_mode, h->d_out, h->out_cap, h->d_counters);
         res->stats.n_launches += 3;
         return FZB_OK;
-    }, PostPlan{true, 0, want_final ? 1 : 0});
+    }, PostPlan{true, 2, want_final ? 1 : 0});  // raw order (n-gram, hit index) is produced lazily
     if (rc) return rc;
-    if (!res->device_post) sort_generation_order(res->raw);
+    res->raw_order = 0;
     return FZB_OK;
 }
 
@@ -789,7 +821,7 @@ static int search_lev_lp(fzb_haystack *h, const uint8_t *pattern, uint32_t m, ui
         return FZB_OK;
     }, PostPlan{true, 1, want_final ? 1 : 0});
     if (rc) return rc;
-    if (!res->device_post) sort_canonical(res->raw);
+    res->raw_order = 1;
     return FZB_OK;
 }
 
@@ -822,7 +854,7 @@ static int search_generic(fzb_haystack *h, const uint8_t *pattern, uint32_t m, u
             return FZB_OK;
         }, PostPlan{true, 1, want_final ? 1 : 0});
         if (rc) return rc;
-        if (!res->device_post) sort_canonical(res->raw);
+        res->raw_order = 1;
         return FZB_OK;
     }
     p.L = (int)(m / (max_l + 1));
@@ -842,14 +874,7 @@ static int search_generic(fzb_haystack *h, const uint8_t *pattern, uint32_t m, u
         return FZB_OK;
     });
     if (rc) return rc;
-    // generation order: n-gram major, hit index, then the window's matches in canonical order
-    std::sort(res->raw.begin(), res->raw.end(), [](const RawRec &a, const RawRec &b) {
-        if (a.ngram != b.ngram) return a.ngram < b.ngram;
-        if (a.idx != b.idx) return a.idx < b.idx;
-        if (a.start != b.start) return a.start < b.start;
-        if (a.end != b.end) return a.end < b.end;
-        return a.dist < b.dist;
-    });
+    res->raw_order = 2;  // n-gram major, hit index, then the window's matches in canonical order
     return FZB_OK;
 }
 
@@ -990,7 +1015,8 @@ extern "C" int fzb_search_hamming(fzb_haystack *h, const uint8_t *pattern, uint3
                 return FZB_OK;
             }, PostPlan{true, 1, 0});
             if (r2) return r2;
-            if (!res->device_post) sort_canonical(res->raw);
+            res->raw_order = 1;
+            res->order_raw();  // FINAL == RAW for this route: order now
             for (auto &r : res->raw) r.ngram = -1;
             return FZB_OK;
         }();
@@ -1089,6 +1115,7 @@ extern "C" uint64_t fzb_result_count(const fzb_result *r, int which) {
 extern "C" int fzb_result_copy(const fzb_result *r, int which, int64_t *start, int64_t *end, int32_t *dist,
                                int32_t *anchor_ngram, int64_t *anchor_idx) {
     if (!r) return fail(FZB_E_INVALID, "result is NULL");
+    if (which == FZB_RAW || r->final_is_raw) const_cast<fzb_result *>(r)->order_raw();
     const std::vector<RawRec> &v = (which == FZB_RAW || r->final_is_raw) ? r->raw : r->fin;
     const bool anchors = (which == FZB_RAW) && (r->stats.route <= 2);
     for (size_t i = 0; i < v.size(); i++) {

@@ -38,11 +38,14 @@ __device__ __forceinline__ uint64_t generation_key(const RawRec &r) {
 // All-pairs ranking.  Grid (i-tiles, j-chunks): block (bi, bj) ranks records i in [256 bi, 256 bi+256)
 // against records j in [kRankChunk bj, kRankChunk (bj+1)) and adds its partial counts to ranks[] (zeroed
 // by the host's counter memset).  ranks[i] = generation-order rank, ranks[kPostMax + i] = canonical rank.
-// raw_canonical: 0 -> raw order (ngram, idx); 1 -> raw order (start, end, dist).
+// raw_mode: 0 -> raw order (ngram, idx); 1 -> raw order (start, end, dist); 2 -> the raw stream is left in
+// arrival order (the host orders it lazily, only if somebody asks for it) and only canonical ranks
+// are computed.
 constexpr int kRankChunk = 1024;
 
 __global__ void __launch_bounds__(kRankThreads)
-k_rank(const RawRec *recs, uint32_t cap, int raw_canonical, uint32_t *ranks, const uint32_t *counters) {
+k_rank(const RawRec *recs, uint32_t cap, int raw_mode, uint32_t *ranks, const uint32_t *counters) {
+    const bool two_keys = raw_mode == 0;
     __shared__ uint64_t s1[kRankThreads], s2[kRankThreads];
     const uint32_t n = counters[CNT_OUT];
     if (n > (uint32_t)kPostMax || n > cap) return;
@@ -52,7 +55,7 @@ k_rank(const RawRec *recs, uint32_t cap, int raw_canonical, uint32_t *ranks, con
     if (i < n) {
         const RawRec me = recs[i];
         k2 = canonical_key(me);
-        k1 = raw_canonical ? k2 : generation_key(me);
+        k1 = two_keys ? generation_key(me) : k2;
     }
     uint32_t r1 = 0, r2 = 0;
     const uint32_t t0 = blockIdx.y * (kRankChunk / kRankThreads);
@@ -62,7 +65,7 @@ k_rank(const RawRec *recs, uint32_t cap, int raw_canonical, uint32_t *ranks, con
         if (j < n) {
             const RawRec o = recs[j];
             b = canonical_key(o);
-            a = raw_canonical ? b : generation_key(o);
+            a = two_keys ? generation_key(o) : b;
         }
         __syncthreads();
         s1[threadIdx.x] = a;
@@ -70,15 +73,17 @@ k_rank(const RawRec *recs, uint32_t cap, int raw_canonical, uint32_t *ranks, con
         __syncthreads();
         if (t < blockIdx.x) {  // every j of the tile is < i: ties rank before me
 #pragma unroll 8
-            for (int jj = 0; jj < kRankThreads; jj++) {
-                r1 += (s1[jj] <= k1);
-                r2 += (s2[jj] <= k2);
+            for (int jj = 0; jj < kRankThreads; jj++) r2 += (s2[jj] <= k2);
+            if (two_keys) {
+#pragma unroll 8
+                for (int jj = 0; jj < kRankThreads; jj++) r1 += (s1[jj] <= k1);
             }
         } else if (t > blockIdx.x) {
 #pragma unroll 8
-            for (int jj = 0; jj < kRankThreads; jj++) {
-                r1 += (s1[jj] < k1);
-                r2 += (s2[jj] < k2);
+            for (int jj = 0; jj < kRankThreads; jj++) r2 += (s2[jj] < k2);
+            if (two_keys) {
+#pragma unroll 8
+                for (int jj = 0; jj < kRankThreads; jj++) r1 += (s1[jj] < k1);
             }
         } else {
 #pragma unroll 8
@@ -90,7 +95,7 @@ k_rank(const RawRec *recs, uint32_t cap, int raw_canonical, uint32_t *ranks, con
         }
     }
     if (i < n) {
-        atomicAdd(&ranks[i], r1);
+        atomicAdd(&ranks[i], two_keys ? r1 : r2);
         atomicAdd(&ranks[kPostMax + i], r2);
     }
 }
@@ -137,7 +142,7 @@ __device__ __forceinline__ uint32_t block_excl_scan_sum(uint32_t v, uint32_t *wa
 // One CTA: scatter the records into rank order, then the consolidation sweep.
 __global__ void __launch_bounds__(kConsThreads)
 k_consolidate(const RawRec *recs, const uint32_t *ranks, RawRec *raw_sorted, uint64_t *keys, uint32_t cap,
-              int do_consolidate, int64_t *fin, uint32_t *counters) {
+              int raw_mode, int do_consolidate, int64_t *fin, uint32_t *counters) {
     extern __shared__ __align__(16) uint8_t post_smem[];
     uint32_t *segbest = reinterpret_cast<uint32_t *>(post_smem);
     __shared__ unsigned long long warp_max[32];
@@ -149,7 +154,7 @@ k_consolidate(const RawRec *recs, const uint32_t *ranks, RawRec *raw_sorted, uin
     }
     for (uint32_t i = threadIdx.x; i < n; i += kConsThreads) {
         const RawRec me = recs[i];
-        raw_sorted[ranks[i]] = me;
+        if (raw_mode != 2) raw_sorted[ranks[i]] = me;
         keys[ranks[kPostMax + i]] = canonical_key(me);
     }
     __syncthreads();  // keys[] was written by this CTA: visible after the barrier
