@@ -234,6 +234,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-mib", type=int, default=0, help="0 = auto (about 10-20 s of CPU work)")
+    ap.add_argument("--reduce", default="nccl", choices=["nccl", "torch"],
+                    help="multi-GPU reduction: NCCL inside the library (default) or via torch.distributed")
     ap.add_argument("--ref-cores", type=int, default=0, help="reference arm: processes to use (0 = all cores)")
     args = ap.parse_args()
 
@@ -293,7 +295,7 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from fuzzysearch_b200.sharding import gather_and_merge_groups, shard_bounds
+    from fuzzysearch_b200.sharding import gather_and_merge_groups, init_shard_comm, shard_bounds
 
     global_len = per_gpu * world
     halo = m + k
@@ -313,17 +315,23 @@ def main():
         if pos >= blo and pos + len(b) <= bhi:
             hs.write(pos, b)
 
+    in_library = world > 1 and args.reduce == "nccl"
+    if in_library:
+        init_shard_comm(hs)
+    gflag = F.F_GLOBAL if in_library else 0
+
     def one_search(h):
         if kind == "lev":
-            return h.search_levenshtein(pat, k)
-        return h.search_hamming(pat, k)
+            return h.search_levenshtein(pat, k, gflag)
+        return h.search_hamming(pat, k, gflag)
 
     def step(h=None):
-        # one search of this rank's shard (local consolidation on the device), then -- multi-GPU only --
-        # ONE all-gather of the per-shard groups and the linear merge into the global final list
+        # one search of this rank's shard (local consolidation on the device); multi-GPU: the per-shard
+        # groups are all-gathered by NCCL inside the library, on the search's stream, and merged
+        # (--reduce torch: the same reduction through torch.distributed, for comparison)
         res = one_search(h or hs)
         st = res.stats()
-        if world > 1:
+        if world > 1 and not in_library:
             nfinal = len(gather_and_merge_groups(result=res, as_arrays=True)[0])
         else:
             nfinal = res.count(F.FINAL)
@@ -372,6 +380,13 @@ def main():
             pinned.array[off:off + nb] = np.frombuffer(hs.read(blo + off, nb), dtype=np.uint8)
         subs, ins, dels, l = (k, k, k, k) if kind == "lev" else (k, 0, 0, k)
 
+        h2 = None
+        if world > 1:  # persistent shard handle: a step re-uploads the shard from pinned host memory
+            h2 = F.Haystack.alloc(bhi - blo, device=local_rank, buf_lo=blo, global_len=global_len, own_lo=own_lo,
+                                  own_hi=own_hi)
+            if in_library:
+                init_shard_comm(h2)
+
         def e2e_step():
             if world == 1:
                 r = F.find_near_matches_host(pat, pinned.array, subs, ins, dels, l, device=local_rank)
@@ -379,10 +394,8 @@ def main():
                 d2h = cnt * 20
                 r.close()
                 return cnt, d2h
-            h2 = F.Haystack.from_host(pinned.array, device=local_rank, buf_lo=blo, global_len=global_len,
-                                      own_lo=own_lo, own_hi=own_hi)
+            h2.upload(pinned.array)
             _, nf = step(h2)
-            h2.close()
             return nf, nf * 40
 
         e2e_step()

@@ -19,7 +19,7 @@ FZB_E_NGRAM_ZERO = -4
 FZB_MAX_PATTERN = 255
 
 RAW, FINAL = 0, 1
-F_NO_FINAL, F_FORCE_DENSE, F_FORCE_LP, F_FORCE_NGRAMS, F_TINY_LIST = 1, 2, 4, 8, 16
+F_NO_FINAL, F_FORCE_DENSE, F_FORCE_LP, F_FORCE_NGRAMS, F_TINY_LIST, F_GLOBAL = 1, 2, 4, 8, 16, 32
 
 ROUTE_NAMES = {0: "exact", 1: "ngrams/sampled-filter", 2: "ngrams/dense-filter", 3: "lp",
                4: "hamming", 5: "generic-ngrams", 6: "generic-lp"}
@@ -59,6 +59,9 @@ SYMBOLS = {
     "fzb_synth_host": (None, [_u8p, _u64, _u64, _u8p, _u32, _u64]),
     "fzb_haystack_write": (_i32, [_vp, _u64, _u8p, _u64]),
     "fzb_haystack_read": (_i32, [_vp, _u64, _u8p, _u64]),
+    "fzb_nccl_set_library": (None, [ctypes.c_char_p]),
+    "fzb_nccl_unique_id": (_i32, [_vp]),
+    "fzb_haystack_comm_init": (_i32, [_vp, _vp, _i32, _i32]),
     "fzb_haystack_upload": (_i32, [_vp, _u8p, _u64]),
     "fzb_host_alloc": (_vp, [_u64]),
     "fzb_host_free": (None, [_vp]),
@@ -245,6 +248,12 @@ class Haystack(object):
     def __len__(self):
         return int(lib().fzb_haystack_len(self._h))
 
+    def comm_init(self, unique_id, rank, world_size):
+        """Collective: bind this shard handle to an NCCL communicator (FZB_F_GLOBAL searches)."""
+        _prefer_bundled_nccl()
+        buf = (ctypes.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+        check(lib().fzb_haystack_comm_init(self._h, buf, rank, world_size))
+
     def upload(self, data):
         a = as_u8(data)
         check(lib().fzb_haystack_upload(self._h, ptr(a), a.size))
@@ -316,6 +325,34 @@ class PinnedBuffer(object):
             self._p = None
 
     __del__ = close
+
+
+_nccl_path_set = False
+
+
+def _prefer_bundled_nccl():
+    """If the PyTorch wheel's NCCL is installed, make the library load THAT libnccl.so.2: the SONAME
+    is shared process-wide, and torch (imported before or after) needs its own, newer build."""
+    global _nccl_path_set
+    if _nccl_path_set:
+        return
+    _nccl_path_set = True
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        if spec and spec.submodule_search_locations:
+            path = os.path.join(list(spec.submodule_search_locations)[0], "lib", "libnccl.so.2")
+            if os.path.exists(path):
+                lib().fzb_nccl_set_library(path.encode())
+    except Exception:  # noqa: BLE001 -- fall back to the default search path
+        pass
+
+
+def nccl_unique_id():
+    _prefer_bundled_nccl()
+    buf = (ctypes.c_uint8 * 128)()
+    check(lib().fzb_nccl_unique_id(buf))
+    return bytes(buf)
 
 
 def synth_host(global_offset, n, alphabet, seed):

@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <dlfcn.h>
 #include <mutex>
 #include <new>
 #include <string>
@@ -56,6 +57,54 @@ extern "C" int fzb_device_count(void) {
 extern "C" const char *fzb_last_error(void) { return g_err.c_str(); }
 
 // ------------------------------------------------------------------------------------------------
+// NCCL, resolved at run time (the process usually has torch's libnccl.so.2 loaded already)
+// ------------------------------------------------------------------------------------------------
+struct NcclId {
+    char b[FZB_NCCL_ID_BYTES];
+};
+struct NcclApi {
+    int (*GetUniqueId)(NcclId *id) = nullptr;
+    int (*CommInitRank)(void **comm, int nranks, NcclId id, int rank) = nullptr;  // ncclUniqueId is passed by value
+    int (*AllGather)(const void *send, void *recv, size_t count, int dtype, void *comm, cudaStream_t s) = nullptr;
+    int (*CommDestroy)(void *comm) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+static NcclApi g_nccl;
+static std::string g_nccl_path;  // optional explicit library path (fzb_nccl_set_library)
+
+extern "C" void fzb_nccl_set_library(const char *path) { g_nccl_path = path ? path : ""; }
+
+static int nccl_load() {
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *lib = nullptr;
+        if (!g_nccl_path.empty()) lib = dlopen(g_nccl_path.c_str(), RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) return;
+        *(void **)&g_nccl.GetUniqueId = dlsym(lib, "ncclGetUniqueId");
+        *(void **)&g_nccl.CommInitRank = dlsym(lib, "ncclCommInitRank");
+        *(void **)&g_nccl.AllGather = dlsym(lib, "ncclAllGather");
+        *(void **)&g_nccl.CommDestroy = dlsym(lib, "ncclCommDestroy");
+        *(void **)&g_nccl.GetErrorString = dlsym(lib, "ncclGetErrorString");
+        g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllGather && g_nccl.CommDestroy;
+    });
+    return g_nccl.ok ? FZB_OK : fail(FZB_E_CUDA, "libnccl.so.2 not available: %s", dlerror() ? dlerror() : "missing symbols");
+}
+
+static void nccl_comm_destroy(void *comm) {
+    if (g_nccl.ok && comm) g_nccl.CommDestroy(comm);
+}
+
+#define NCCLCK(call)                                                                                      \
+    do {                                                                                                  \
+        int r_ = (call);                                                                                  \
+        if (r_ != 0)                                                                                      \
+            return fail(FZB_E_CUDA, "%s failed: %s", #call, g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?"); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
 // handles
 // ------------------------------------------------------------------------------------------------
 struct fzb_haystack {
@@ -80,6 +129,13 @@ struct fzb_haystack {
     int64_t *h_fin = nullptr;        // pinned
     bool ev1_recorded = false;
     bool filter_attrs_set = false;
+    // multi-GPU reduction (FZB_F_GLOBAL)
+    void *comm = nullptr;  // ncclComm_t
+    int rank = 0, world = 1;
+    uint32_t gather_cap = 4096;     // rows per rank in one all-gather slot
+    int64_t *d_send = nullptr, *d_recv = nullptr;
+    int64_t *h_send = nullptr, *h_recv = nullptr;  // pinned
+    uint32_t gather_alloc = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     int sm_count = 148;
     uint32_t *d_glist = nullptr;    // compacted list of marked granules
@@ -95,6 +151,11 @@ struct fzb_result {
     bool final_is_raw = false;
     bool device_post = false;  // final list (and, unless raw_order_pending, the raw order) came from the device
     bool raw_ordered = false;  // raw is already in its reference order
+    bool has_global = false;   // FZB_F_GLOBAL: gfin is the global consolidated list of all shards
+    bool gather_valid = false;
+    bool fused_issued = false;
+    std::vector<int64_t> gathered;  // group rows of all shards (rank major)
+    std::vector<RawRec> gfin;
     int raw_order = 0;         // 0 generation (ngram, idx) / 1 canonical / 2 generic n-grams (5 fields)
     void order_raw();
     fzb_stats stats{};
@@ -157,6 +218,11 @@ extern "C" void fzb_haystack_destroy(fzb_haystack *h) {
     if (h->d_counters) cudaFree(h->d_counters);
     if (h->d_scratch) cudaFree(h->d_scratch);
     if (h->d_glist) cudaFree(h->d_glist);
+    if (h->d_send) cudaFree(h->d_send);
+    if (h->d_recv) cudaFree(h->d_recv);
+    if (h->h_send) cudaFreeHost(h->h_send);
+    if (h->h_recv) cudaFreeHost(h->h_recv);
+    if (h->comm) nccl_comm_destroy(h->comm);
     if (h->h_counters) cudaFreeHost(h->h_counters);
     if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->h_fin) cudaFreeHost(h->h_fin);
@@ -316,11 +382,16 @@ extern "C" uint64_t fzb_haystack_len(const fzb_haystack *h) { return h ? h->glob
 
 extern "C" int fzb_haystack_upload(fzb_haystack *h, const uint8_t *host, uint64_t n) {
     if (!h || (!host && n)) return fail(FZB_E_INVALID, "bad arguments");
-    if (!h->owned || h->buf_lo != 0) return fail(FZB_E_INVALID, "upload needs an owned whole-sequence handle");
+    if (!h->owned) return fail(FZB_E_INVALID, "upload needs an owned handle");
     if (round_up(n, 128) + 128 > h->capacity) return fail(FZB_E_INVALID, "upload larger than the handle's capacity");
     CK(cudaSetDevice(h->device));
-    h->buf_len = h->global_len = h->own_hi = n;
-    h->own_lo = 0;
+    const bool shard = h->buf_lo != 0 || h->global_len != h->buf_len || h->own_lo != 0 || h->own_hi != h->buf_len;
+    if (shard) {  // a shard keeps its geometry: the new bytes replace the same window of the global sequence
+        if (n != h->buf_len) return fail(FZB_E_INVALID, "a shard upload must supply exactly buf_len bytes");
+    } else {
+        h->buf_len = h->global_len = h->own_hi = n;
+        h->own_lo = 0;
+    }
     h->padded_len = round_up(n, 128) + 128;
     if (n) CK(cudaMemcpyAsync(h->d, host, n, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemsetAsync(h->d + n, 0, h->padded_len - n, h->stream));
@@ -358,6 +429,49 @@ extern "C" int fzb_timer_stop(fzb_haystack *h, double *ms) {
     CK(cudaEventElapsedTime(&f, h->ev[3], h->ev_stop));
     *ms = f;
     return FZB_OK;
+}
+
+extern "C" int fzb_nccl_unique_id(uint8_t id[FZB_NCCL_ID_BYTES]) {
+    if (!id) return fail(FZB_E_INVALID, "NULL argument");
+    int rc = nccl_load();
+    if (rc) return rc;
+    NcclId nid;
+    NCCLCK(g_nccl.GetUniqueId(&nid));
+    memcpy(id, nid.b, FZB_NCCL_ID_BYTES);
+    return FZB_OK;
+}
+
+static int ensure_gather_buffers(fzb_haystack *h, uint32_t cap) {
+    if (cap <= h->gather_alloc) return FZB_OK;
+    if (h->d_send) cudaFree(h->d_send);
+    if (h->d_recv) cudaFree(h->d_recv);
+    if (h->h_send) cudaFreeHost(h->h_send);
+    if (h->h_recv) cudaFreeHost(h->h_recv);
+    h->d_send = h->d_recv = h->h_send = h->h_recv = nullptr;
+    h->gather_alloc = 0;
+    const size_t slot = (size_t)(cap + 1) * kFinCols * sizeof(int64_t);
+    CK(cudaMalloc(&h->d_send, slot));
+    CK(cudaMalloc(&h->d_recv, slot * h->world));
+    CK(cudaMallocHost(&h->h_send, slot));
+    CK(cudaMallocHost(&h->h_recv, slot * h->world));
+    h->gather_alloc = cap;
+    return FZB_OK;
+}
+
+extern "C" int fzb_haystack_comm_init(fzb_haystack *h, const uint8_t id[FZB_NCCL_ID_BYTES], int rank,
+                                      int world_size) {
+    if (!h || !id || world_size < 1 || rank < 0 || rank >= world_size) return fail(FZB_E_INVALID, "bad arguments");
+    int rc = nccl_load();
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    if (h->comm) nccl_comm_destroy(h->comm);
+    h->comm = nullptr;
+    NcclId nid;
+    memcpy(nid.b, id, FZB_NCCL_ID_BYTES);
+    NCCLCK(g_nccl.CommInitRank(&h->comm, world_size, nid, rank));
+    h->rank = rank;
+    h->world = world_size;
+    return ensure_gather_buffers(h, h->gather_cap);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -493,9 +607,7 @@ extern "C" int fzb_result_hulls(const fzb_result *r, int64_t *hull_start, int64_
 // members, so hulls overlap iff members do), and the winner of a union is the better of the two
 // winners -- so the global consolidate_overlapping_matches (common.py:185-189) is the same sweep run
 // over the groups instead of the raw matches.
-extern "C" int64_t fzb_merge_groups(const int64_t *rows, uint64_t n, int64_t *out_start, int64_t *out_end,
-                                    int32_t *out_dist) {
-    if (n && !rows) return fail(FZB_E_INVALID, "NULL input");
+static void merge_group_rows(const int64_t *rows, uint64_t n, std::vector<RawRec> &out) {
     struct G { int64_t s, e, d, hs, he; };
     std::vector<G> g(n);
     for (uint64_t i = 0; i < n; i++) g[i] = G{rows[5 * i], rows[5 * i + 1], rows[5 * i + 2], rows[5 * i + 3], rows[5 * i + 4]};
@@ -514,7 +626,7 @@ extern "C" int64_t fzb_merge_groups(const int64_t *rows, uint64_t n, int64_t *ou
         if (a.s != b.s) return a.s < b.s;
         return a.e < b.e;
     };
-    uint64_t w = 0;
+    out.clear();
     for (uint64_t i = 0; i < n;) {
         G best = g[i];
         int64_t hull_end = g[i].he;
@@ -524,13 +636,61 @@ extern "C" int64_t fzb_merge_groups(const int64_t *rows, uint64_t n, int64_t *ou
             hull_end = std::max(hull_end, g[j].he);
             j++;
         }
-        if (out_start) out_start[w] = best.s;
-        if (out_end) out_end[w] = best.e;
-        if (out_dist) out_dist[w] = (int32_t)best.d;
-        w++;
+        RawRec r;
+        r.start = best.s;
+        r.end = best.e;
+        r.dist = (int32_t)best.d;
+        r.idx = -1;
+        r.ngram = -1;
+        out.push_back(r);
         i = j;
     }
-    return (int64_t)w;
+}
+
+extern "C" int64_t fzb_merge_groups(const int64_t *rows, uint64_t n, int64_t *out_start, int64_t *out_end,
+                                    int32_t *out_dist) {
+    if (n && !rows) return fail(FZB_E_INVALID, "NULL input");
+    std::vector<RawRec> o;
+    merge_group_rows(rows, n, o);
+    for (size_t i = 0; i < o.size(); i++) {
+        if (out_start) out_start[i] = o[i].start;
+        if (out_end) out_end[i] = o[i].end;
+        if (out_dist) out_dist[i] = o[i].dist;
+    }
+    return (int64_t)o.size();
+}
+
+// The staged (host-buffer) all-gather of group rows: used when the fused one behind the kernels could
+// not be trusted on every rank (a rank overflowed a buffer and retried, or its list was too long for
+// the on-device consolidation).  Collective: every rank calls it the same number of times.
+static int allgather_groups_staged(fzb_haystack *h, const std::vector<int64_t> &rows, std::vector<int64_t> &all) {
+    const uint64_t n = rows.size() / kFinCols;
+    for (;;) {
+        const uint32_t cap = h->gather_cap;
+        int rc = ensure_gather_buffers(h, cap);
+        if (rc) return rc;
+        const size_t slot_rows = (size_t)cap + 1, slot = slot_rows * kFinCols * sizeof(int64_t);
+        h->h_send[0] = (int64_t)n;
+        h->h_send[1] = n <= cap;
+        h->h_send[2] = h->h_send[3] = h->h_send[4] = 0;
+        if (n <= cap && n) memcpy(h->h_send + kFinCols, rows.data(), n * kFinCols * sizeof(int64_t));
+        CK(cudaMemcpyAsync(h->d_send, h->h_send, (1 + (n <= cap ? n : 0)) * kFinCols * sizeof(int64_t),
+                           cudaMemcpyHostToDevice, h->stream));
+        NCCLCK(g_nccl.AllGather(h->d_send, h->d_recv, slot, /*ncclInt8*/ 0, h->comm, h->stream));
+        CK(cudaMemcpyAsync(h->h_recv, h->d_recv, slot * h->world, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        uint64_t top = 0;
+        for (int r = 0; r < h->world; r++) top = std::max<uint64_t>(top, (uint64_t)h->h_recv[(size_t)r * slot_rows * kFinCols]);
+        if (top <= cap) {
+            all.clear();
+            for (int r = 0; r < h->world; r++) {
+                const int64_t *base = h->h_recv + (size_t)r * slot_rows * kFinCols;
+                all.insert(all.end(), base + kFinCols, base + kFinCols + (size_t)base[0] * kFinCols);
+            }
+            return FZB_OK;
+        }
+        while (h->gather_cap < top) h->gather_cap *= 2;  // every rank sees the same `top`
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -583,6 +743,7 @@ struct PostPlan {
     bool enable = false;
     int raw_mode = 0;  // 0 generation order, 1 canonical order, 2 arrival order (ordered lazily on the host)
     int do_consolidate = 0;
+    bool global = false;  // FZB_F_GLOBAL: all-gather the groups of every shard behind the kernels
 };
 
 template <class F>
@@ -606,6 +767,17 @@ static int run_emitting(fzb_haystack *h, fzb_result *res, F enqueue, PostPlan po
             CK(cudaGetLastError());
             res->stats.n_launches += 2;
         }
+        // fused multi-GPU reduction: exactly one all-gather per search, in the FIRST attempt (so that
+        // a rank that has to retry locally never issues a collective the others do not)
+        const bool fused_gather = post.global && attempt == 0;
+        const size_t slot_rows = (size_t)h->gather_cap + 1, slot_bytes = slot_rows * kFinCols * sizeof(int64_t);
+        if (fused_gather) {
+            k_pack_groups<<<32, 256, 0, h->stream>>>(h->d_fin, h->d_counters, h->d_send, h->gather_cap);
+            CK(cudaGetLastError());
+            NCCLCK(g_nccl.AllGather(h->d_send, h->d_recv, slot_bytes, /*ncclInt8*/ 0, h->comm, h->stream));
+            CK(cudaMemcpyAsync(h->h_recv, h->d_recv, slot_bytes * h->world, cudaMemcpyDeviceToHost, h->stream));
+            res->stats.n_launches += 2;
+        }
         CK(cudaEventRecord(h->ev[2], h->stream));
         CK(cudaMemcpyAsync(h->h_counters, h->d_counters, CNT_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                            h->stream));
@@ -618,6 +790,20 @@ static int run_emitting(fzb_haystack *h, fzb_result *res, F enqueue, PostPlan po
         CK(cudaStreamSynchronize(h->stream));
         const uint32_t n = h->h_counters[CNT_OUT];
         res->stats.n_candidates = h->h_counters[CNT_CAND];
+        if (fused_gather) {  // every rank sees every header: all agree on whether the fused gather is usable
+            res->fused_issued = true;
+            res->gather_valid = true;
+            res->gathered.clear();
+            for (int r = 0; r < h->world; r++) {
+                const int64_t *base = h->h_recv + (size_t)r * slot_rows * kFinCols;
+                if (!base[1]) res->gather_valid = false;
+            }
+            if (res->gather_valid)
+                for (int r = 0; r < h->world; r++) {
+                    const int64_t *base = h->h_recv + (size_t)r * slot_rows * kFinCols;
+                    res->gathered.insert(res->gathered.end(), base + kFinCols, base + kFinCols + (size_t)base[0] * kFinCols);
+                }
+        }
         if (n > h->out_cap) {  // output buffer too small: grow and redo the whole attempt
             rc = ensure_out_cap(h, n);
             if (rc) return rc;
@@ -769,7 +955,7 @@ static int search_lev_ngrams(fzb_haystack *h, const uint8_t *pattern, uint32_t m
                 p, h->bitmap_words, h->d_glist, gcap, scan_mode, h->d_out, h->out_cap, h->d_counters);
         res->stats.n_launches += 3;
         return FZB_OK;
-    }, PostPlan{true, 2, want_final ? 1 : 0});  // raw order (n-gram, hit index) is produced lazily
+    }, PostPlan{true, 2, want_final ? 1 : 0, want_final && (flags & FZB_F_GLOBAL) != 0});  // raw order: lazily
     if (rc) return rc;
     res->raw_order = 0;
     return FZB_OK;
@@ -878,6 +1064,43 @@ static int search_generic(fzb_haystack *h, const uint8_t *pattern, uint32_t m, u
     return FZB_OK;
 }
 
+// FZB_F_GLOBAL epilogue of every search entry point: turn the per-shard groups into the global final list.
+static int finish_global(fzb_haystack *h, fzb_result *res) {
+    if (!h->comm) return fail(FZB_E_INVALID, "FZB_F_GLOBAL needs fzb_haystack_comm_init");
+    std::vector<int64_t> all;
+    if (res->fused_issued && res->gather_valid) {
+        all.swap(res->gathered);
+    } else {  // staged: the local result is complete now, whatever it took
+        if (res->final_is_raw) res->order_raw();
+        const std::vector<RawRec> &v = res->final_is_raw ? res->raw : res->fin;
+        std::vector<int64_t> rows(v.size() * kFinCols);
+        for (size_t i = 0; i < v.size(); i++) {
+            rows[kFinCols * i + 0] = v[i].start;
+            rows[kFinCols * i + 1] = v[i].end;
+            rows[kFinCols * i + 2] = v[i].dist;
+            rows[kFinCols * i + 3] = res->final_is_raw ? v[i].start : res->hulls[2 * i];
+            rows[kFinCols * i + 4] = res->final_is_raw ? v[i].end : res->hulls[2 * i + 1];
+        }
+        int rc = allgather_groups_staged(h, rows, all);
+        if (rc) return rc;
+    }
+    if (res->final_is_raw) {  // unconsolidated routes (exact, Hamming): the global list is the sorted union
+        res->gfin.resize(all.size() / kFinCols);
+        for (size_t i = 0; i < res->gfin.size(); i++) {
+            res->gfin[i].start = all[kFinCols * i];
+            res->gfin[i].end = all[kFinCols * i + 1];
+            res->gfin[i].dist = (int32_t)all[kFinCols * i + 2];
+            res->gfin[i].idx = -1;
+            res->gfin[i].ngram = -1;
+        }
+        sort_canonical(res->gfin);
+    } else {
+        merge_group_rows(all.data(), all.size() / kFinCols, res->gfin);
+    }
+    res->has_global = true;
+    return FZB_OK;
+}
+
 static int make_result(fzb_result **out, fzb_result **res) {
     if (!out) return fail(FZB_E_INVALID, "out is NULL");
     *out = nullptr;
@@ -886,8 +1109,10 @@ static int make_result(fzb_result **out, fzb_result **res) {
     return FZB_OK;
 }
 
-static int check_pattern(const fzb_haystack *h, const uint8_t *pattern, uint32_t m) {
+static int check_pattern(const fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint32_t flags = 0) {
     if (!h) return fail(FZB_E_INVALID, "haystack handle is NULL");
+    if ((flags & FZB_F_GLOBAL) && !h->comm)
+        return fail(FZB_E_INVALID, "FZB_F_GLOBAL needs fzb_haystack_comm_init on this handle");
     if (!pattern || m == 0) return fail(FZB_E_INVALID, "Given subsequence is empty!");
     if (m > FZB_MAX_PATTERN) return fail(FZB_E_UNSUPPORTED, "pattern longer than %d bytes", FZB_MAX_PATTERN);
     return FZB_OK;
@@ -898,7 +1123,7 @@ extern "C" int fzb_search_levenshtein(fzb_haystack *h, const uint8_t *pattern, u
     fzb_result *res;
     int rc = make_result(out, &res);
     if (rc) return rc;
-    rc = check_pattern(h, pattern, m);
+    rc = check_pattern(h, pattern, m, flags);
     if (rc == FZB_OK) {
         // find_near_matches_levenshtein (levenshtein.py:9-38)
         bool ngrams = (k == 0) || (m / (k + 1) >= 3);
@@ -911,6 +1136,7 @@ extern "C" int fzb_search_levenshtein(fzb_haystack *h, const uint8_t *pattern, u
         else
             rc = search_lev_lp(h, pattern, m, k, res, want_final);
         if (rc == FZB_OK && want_final && !res->device_post) consolidate_recs(res->raw, res->fin, &res->hulls);
+        if (rc == FZB_OK && want_final && (flags & FZB_F_GLOBAL)) rc = finish_global(h, res);
     }
     if (rc) {
         delete res;
@@ -925,7 +1151,7 @@ extern "C" int fzb_search_exact(fzb_haystack *h, const uint8_t *pattern, uint32_
     fzb_result *res;
     int rc = make_result(out, &res);
     if (rc) return rc;
-    rc = check_pattern(h, pattern, m);
+    rc = check_pattern(h, pattern, m, flags);
     if (rc == FZB_E_INVALID && h) rc = fail(FZB_E_INVALID, "subsequence must not be empty");
     if (rc == FZB_OK) rc = search_lev_ngrams(h, pattern, m, 0, flags, res, false);
     if (rc) {
@@ -933,6 +1159,13 @@ extern "C" int fzb_search_exact(fzb_haystack *h, const uint8_t *pattern, uint32_
         return rc;
     }
     res->final_is_raw = true;  // ExactSearch.consolidate_matches is the base no-op (common.py:198-205)
+    if (flags & FZB_F_GLOBAL) {
+        rc = finish_global(h, res);
+        if (rc) {
+            delete res;
+            return rc;
+        }
+    }
     *out = res;
     return FZB_OK;
 }
@@ -971,7 +1204,7 @@ extern "C" int fzb_search_hamming(fzb_haystack *h, const uint8_t *pattern, uint3
     fzb_result *res;
     int rc = make_result(out, &res);
     if (rc) return rc;
-    rc = check_pattern(h, pattern, m);
+    rc = check_pattern(h, pattern, m, flags);
     if (rc == FZB_OK) rc = check_halo(h, m);
     if (rc == FZB_OK) {
         rc = [&]() -> int {
@@ -1026,6 +1259,13 @@ extern "C" int fzb_search_hamming(fzb_haystack *h, const uint8_t *pattern, uint3
         return rc;
     }
     res->final_is_raw = true;
+    if (flags & FZB_F_GLOBAL) {
+        rc = finish_global(h, res);
+        if (rc) {
+            delete res;
+            return rc;
+        }
+    }
     *out = res;
     return FZB_OK;
 }
@@ -1036,7 +1276,7 @@ extern "C" int fzb_search_generic(fzb_haystack *h, const uint8_t *pattern, uint3
     fzb_result *res;
     int rc = make_result(out, &res);
     if (rc) return rc;
-    rc = check_pattern(h, pattern, m);
+    rc = check_pattern(h, pattern, m, flags);
     if (rc == FZB_OK) {
         // find_near_matches_generic (generic_search.py:25-54)
         const bool want_final = !(flags & FZB_F_NO_FINAL);
@@ -1050,6 +1290,7 @@ extern "C" int fzb_search_generic(fzb_haystack *h, const uint8_t *pattern, uint3
         }
         if (rc == FZB_OK && want_final && !(res->device_post && res->stats.route != 5))
             consolidate_recs(res->raw, res->fin, &res->hulls);
+        if (rc == FZB_OK && want_final && (flags & FZB_F_GLOBAL)) rc = finish_global(h, res);
     }
     if (rc) {
         delete res;
@@ -1108,6 +1349,7 @@ extern "C" int fzb_find_near_matches(const uint8_t *pattern, uint32_t m, const u
 // ------------------------------------------------------------------------------------------------
 extern "C" uint64_t fzb_result_count(const fzb_result *r, int which) {
     if (!r) return 0;
+    if (which != FZB_RAW && r->has_global) return r->gfin.size();
     if (which == FZB_RAW || r->final_is_raw) return r->raw.size();
     return r->fin.size();
 }
@@ -1116,7 +1358,9 @@ extern "C" int fzb_result_copy(const fzb_result *r, int which, int64_t *start, i
                                int32_t *anchor_ngram, int64_t *anchor_idx) {
     if (!r) return fail(FZB_E_INVALID, "result is NULL");
     if (which == FZB_RAW || r->final_is_raw) const_cast<fzb_result *>(r)->order_raw();
-    const std::vector<RawRec> &v = (which == FZB_RAW || r->final_is_raw) ? r->raw : r->fin;
+    const std::vector<RawRec> &v = (which != FZB_RAW && r->has_global)
+                                       ? r->gfin
+                                       : ((which == FZB_RAW || r->final_is_raw) ? r->raw : r->fin);
     const bool anchors = (which == FZB_RAW) && (r->stats.route <= 2);
     for (size_t i = 0; i < v.size(); i++) {
         if (start) start[i] = v[i].start;

@@ -18,7 +18,7 @@ The reference's CPU analogue of this layout is the chunk + carry-over tail loop 
 """
 import numpy as np
 
-__all__ = ["shard_bounds", "gather_rows", "merge_raw_streams", "gather_and_merge_groups", "GroupReducer"]
+__all__ = ["shard_bounds", "gather_rows", "merge_raw_streams", "gather_and_merge_groups", "GroupReducer", "init_shard_comm"]
 
 ALIGN = 16  # shard buffers start on 16-byte boundaries of the global sequence (uint4 loads)
 
@@ -72,6 +72,18 @@ def gather_rows(rows, group=None, device=None):
     dist.all_gather(out, padded, group=group)
     parts = [out[r][:counts[r]].cpu().numpy() for r in range(world)]
     return np.concatenate(parts, axis=0) if parts else rows
+
+
+def init_shard_comm(haystack, group=None):
+    """Give a shard handle its own NCCL communicator so that searches flagged F_GLOBAL all-gather the
+    per-shard groups inside the library, on the search's stream (no Python or torch in the timed path).
+    The unique id travels over torch.distributed (plumbing only)."""
+    import torch.distributed as dist
+    from . import _native
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    box = [_native.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    haystack.comm_init(box[0], rank, world)
 
 
 class GroupReducer(object):

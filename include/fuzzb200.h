@@ -57,6 +57,10 @@ extern "C" {
 #define FZB_F_FORCE_LP 4u     /* Levenshtein/generic: force the "linear programming" route */
 #define FZB_F_FORCE_NGRAMS 8u /* Levenshtein/generic/Hamming: force the n-gram route */
 #define FZB_F_TINY_LIST 16u   /* testing: cap the granule work list at 8 entries (overflow path) */
+#define FZB_F_GLOBAL 32u      /* multi-GPU: FINAL becomes the GLOBAL consolidated list of all shards: the
+                                 per-shard groups are all-gathered with NCCL on the search's own stream,
+                                 right behind the kernels (needs fzb_haystack_comm_init on every rank;
+                                 collective: every rank must issue the same searches in the same order) */
 
 typedef struct fzb_haystack fzb_haystack; /* a device-resident sequence (or one shard of it) */
 typedef struct fzb_result fzb_result;     /* the matches of one search */
@@ -106,6 +110,18 @@ void fzb_synth_host(uint8_t *dst, uint64_t global_offset, uint64_t n, const uint
 int fzb_haystack_write(fzb_haystack *h, uint64_t global_offset, const uint8_t *src, uint64_t n);
 /* Read bytes back (for Match.matched and tests). */
 int fzb_haystack_read(fzb_haystack *h, uint64_t global_offset, uint8_t *dst, uint64_t n);
+
+/* NCCL plumbing for FZB_F_GLOBAL (one process per GPU).  Rank 0 obtains a unique id and ships it to
+ * the other ranks by any means (bench.py: torch.distributed broadcast); then every rank calls
+ * fzb_haystack_comm_init with its shard handle (collective, blocking).  libnccl.so.2 is resolved at
+ * run time (dlopen), so the library has no link-time NCCL dependency. */
+#define FZB_NCCL_ID_BYTES 128
+/* Optional, before the first NCCL use: load this libnccl.so.2 instead of the default search path.  A
+ * process that will also import torch must load torch's bundled NCCL (the same SONAME is shared), which
+ * the Python binding arranges automatically. */
+void fzb_nccl_set_library(const char *path);
+int fzb_nccl_unique_id(uint8_t id[FZB_NCCL_ID_BYTES]);
+int fzb_haystack_comm_init(fzb_haystack *h, const uint8_t id[FZB_NCCL_ID_BYTES], int rank, int world_size);
 
 /* Replace the contents of a whole-sequence handle with `n` new host bytes (n <= the capacity the
  * handle was created with); the device allocations are reused -- the analogue of the reference's
