@@ -86,7 +86,7 @@ constexpr int kHcStageBytes = kHcTileRows * kHcRowBytes;         // 33792 (multi
 constexpr int kHcStages = 2;
 constexpr int kHcBuckets = 256;
 constexpr int kHcTableBytes = kHcBuckets * 8 * 16;               // 32 KiB
-constexpr size_t kHcSmem = 1024 + (size_t)kHcStages * kHcStageBytes + kHcTableBytes + 64;
+constexpr size_t kHcSmem = (size_t)kHcStages * kHcStageBytes + kHcTableBytes + 64;
 constexpr uint32_t kHcHashMul = 0x9E3779B1u;
 
 __device__ __forceinline__ uint32_t hc_bucket(uint32_t w) { return (w * kHcHashMul) >> 24; }
@@ -97,16 +97,23 @@ struct HamCountParams {
     int64_t nrows; // rows of the buffer that hold data: ceil(buf_len / 128)
 };
 
-// swizzled address of 16-byte chunk j of local row r (SWIZZLE_128B: chunk index ^= row % 8)
-__device__ __forceinline__ const uint4 *hc_chunk(const uint8_t *stage, int r, int j) {
-    return reinterpret_cast<const uint4 *>(stage + r * kHcRowBytes + ((j ^ (r & 7)) << 4));
+// explicit shared-space 128-bit load (32-bit shared address: no generic-address arithmetic)
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr));
+    return r;
+}
+
+// swizzled shared address of 16-byte chunk j of local row r (SWIZZLE_128B: chunk index ^= row % 8)
+__device__ __forceinline__ uint32_t hc_chunk(uint32_t stage, int r, int j) {
+    return stage + r * kHcRowBytes + ((j ^ (r & 7)) << 4);
 }
 
 __global__ void __launch_bounds__(kHcThreads, 2)
 k_hamming_count(const ScanParams p, const HamCountParams hp, const __grid_constant__ CUtensorMap map256,
                 const __grid_constant__ CUtensorMap map8) {
-    extern __shared__ uint8_t hc_smem_raw[];
-    uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(hc_smem_raw) + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) uint8_t hc_smem[];  // SWIZZLE_128B tiles need 1024-byte alignment
+    uint8_t *base = hc_smem;
     uint4 *table = reinterpret_cast<uint4 *>(base + kHcStages * kHcStageBytes);
     uint64_t *full = reinterpret_cast<uint64_t *>(base + kHcStages * kHcStageBytes + kHcTableBytes);
     const int tid = threadIdx.x, lane = tid & 31;
@@ -146,18 +153,19 @@ k_hamming_count(const ScanParams p, const HamCountParams hp, const __grid_consta
         if (tile < ntiles) issue(tile, 0);
         if (tile + gridDim.x < ntiles) issue(tile + gridDim.x, 1);
     }
-    const uint4 *my_table = table + (lane & 7);
+    const uint32_t my_table = smem_u32(table) + ((lane & 7) << 4);  // my replica: bank group = lane % 8
+    const uint32_t stage0 = smem_u32(base);
     uint32_t phases = 0;  // bit s = parity to wait for on stage s
     for (int it = 0; tile < ntiles; tile += gridDim.x, it++) {
         const int s = it & 1;
         mbar_wait(&full[s], (phases >> s) & 1u);
         phases ^= 1u << s;
-        const uint8_t *st = base + s * kHcStageBytes;
+        const uint32_t st = stage0 + s * kHcStageBytes;
         const int r = kHcHaloRows + tid;
         uint32_t S0 = 0, S1 = 0, S2 = 0, S3 = 0, acc = 0;
 #define HC_STEP(WORD, track)                                               \
     {                                                                      \
-        const uint4 T = my_table[hc_bucket(WORD) * 8];                     \
+        const uint4 T = lds128(my_table + (hc_bucket(WORD) << 7));         \
         S0 = S0 * 16u + T.x;                                               \
         S1 = S1 * 16u + T.y;                                               \
         S2 = S2 * 16u + T.z;                                               \
@@ -165,13 +173,13 @@ k_hamming_count(const ScanParams p, const HamCountParams hp, const __grid_consta
         if (track) acc |= S0 | S1 | S2 | S3;                               \
     }
         {  // warm-up: the last 7 words of the previous row (no flags: they belong to that row's thread)
-            const uint4 a = *hc_chunk(st, r - 1, 6), b = *hc_chunk(st, r - 1, 7);
+            const uint4 a = lds128(hc_chunk(st, r - 1, 6)), b = lds128(hc_chunk(st, r - 1, 7));
             HC_STEP(a.y, false) HC_STEP(a.z, false) HC_STEP(a.w, false)
             HC_STEP(b.x, false) HC_STEP(b.y, false) HC_STEP(b.z, false) HC_STEP(b.w, false)
         }
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            const uint4 d = *hc_chunk(st, r, j);
+            const uint4 d = lds128(hc_chunk(st, r, j));
             HC_STEP(d.x, true) HC_STEP(d.y, true) HC_STEP(d.z, true) HC_STEP(d.w, true)
         }
 #undef HC_STEP
