@@ -19,7 +19,7 @@ FZB_E_NGRAM_ZERO = -4
 FZB_MAX_PATTERN = 255
 
 RAW, FINAL = 0, 1
-F_NO_FINAL, F_FORCE_DENSE, F_FORCE_LP, F_FORCE_NGRAMS, F_TINY_LIST, F_GLOBAL = 1, 2, 4, 8, 16, 32
+F_NO_FINAL, F_FORCE_DENSE, F_FORCE_LP, F_FORCE_NGRAMS, F_TINY_LIST, F_GLOBAL, F_FORCE_SAMPLED = 1, 2, 4, 8, 16, 32, 64
 
 ROUTE_NAMES = {0: "exact", 1: "ngrams/sampled-filter", 2: "ngrams/dense-filter", 3: "lp",
                4: "hamming", 5: "generic-ngrams", 6: "generic-lp"}

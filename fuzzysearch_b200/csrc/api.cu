@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include <dlfcn.h>
 #include <mutex>
@@ -129,6 +130,7 @@ struct fzb_haystack {
     int64_t *h_fin = nullptr;        // pinned
     bool ev1_recorded = false;
     bool filter_attrs_set = false;
+    double coll_prob = -1.0;  // sum_c p_c^2 of the byte distribution (sampled lazily; < 0 = unknown)
     // multi-GPU reduction (FZB_F_GLOBAL)
     void *comm = nullptr;  // ncclComm_t
     int rank = 0, world = 1;
@@ -355,6 +357,7 @@ extern "C" int fzb_haystack_fill_synthetic(fzb_haystack *h, const uint8_t *alpha
         CK(cudaMemsetAsync(h->d + h->buf_len, 0, 4 - h->buf_len % 4, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaFree(d_alpha));
+    h->coll_prob = -1.0;
     return FZB_OK;
 }
 
@@ -393,6 +396,7 @@ extern "C" int fzb_haystack_upload(fzb_haystack *h, const uint8_t *host, uint64_
         h->own_lo = 0;
     }
     h->padded_len = round_up(n, 128) + 128;
+    h->coll_prob = -1.0;
     if (n) CK(cudaMemcpyAsync(h->d, host, n, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemsetAsync(h->d + n, 0, h->padded_len - n, h->stream));
     CK(cudaStreamSynchronize(h->stream));  // the caller may reuse `host` as soon as we return
@@ -892,7 +896,7 @@ static void sort_canonical(std::vector<RawRec> &v) {
 static int set_filter_attrs(size_t smem) {
     // per device: the attribute belongs to the function on the current device
     CK(cudaFuncSetAttribute(k_filter_sampled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaFuncSetAttribute(k_filter_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k_filter_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDenseSmem));
     return FZB_OK;
 }
 
@@ -905,6 +909,45 @@ static bool sampled_filter_applies(uint32_t m, uint32_t k, uint32_t flags) {
     return (m - k - 3) / 4 >= k + 1;
 }
 
+// Byte statistics of the haystack from 16 sampled 4 KiB blocks (once per handle content): the
+// collision probability sum_c p_c^2 tells how selective a q-gram test is (1/4 on DNA, ~1/95 on text).
+static int sample_collision_prob(fzb_haystack *h) {
+    if (h->coll_prob >= 0.0) return FZB_OK;
+    const uint64_t blk = 4096, nblk = 16;
+    std::vector<uint8_t> buf;
+    uint64_t hist[256] = {0}, total = 0;
+    if (h->buf_len <= blk * nblk) {
+        buf.resize(h->buf_len);
+        if (h->buf_len) CK(cudaMemcpy(buf.data(), h->d, h->buf_len, cudaMemcpyDeviceToHost));
+    } else {
+        buf.resize(blk * nblk);
+        for (uint64_t i = 0; i < nblk; i++) {
+            const uint64_t off = ((h->buf_len - blk) / (nblk - 1) * i) & ~(uint64_t)15;
+            CK(cudaMemcpyAsync(buf.data() + i * blk, h->d + off, blk, cudaMemcpyDeviceToHost, h->stream));
+        }
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    for (uint8_t c : buf) hist[c]++;
+    total = buf.size();
+    double s = 0.0;
+    if (total)
+        for (int c = 0; c < 256; c++) s += ((double)hist[c] / total) * ((double)hist[c] / total);
+    h->coll_prob = total ? s : 1.0;
+    return FZB_OK;
+}
+
+// The sampled filter is sound whenever the lemma holds, but only SELECTIVE if an aligned word rarely
+// equals a pattern 4-gram; otherwise (small alphabets) the dense filter, which finds the n-gram hits
+// themselves, marks far fewer granules.  Expected marked-granule fractions decide.
+static bool sampled_is_selective(fzb_haystack *h, uint32_t m, uint32_t k, int L, int n_ngrams) {
+    if (sample_collision_prob(h) != FZB_OK) return true;
+    const double c = h->coll_prob;
+    const double span = (2.0 * m + 2.0 * k - L - 3.0) / kGranule + 1.0;       // granules marked per word hit
+    const double sampled = std::min(1.0, (m - 3.0) * c * c * c * c * (kGranule / 4.0) * span);
+    const double dense = std::min(1.0, n_ngrams * std::pow(c, std::min(L, 8)) * kGranule);
+    return sampled <= 0.02 || sampled <= dense;
+}
+
 // Enqueue the one pass over the haystack that marks candidate granules; records ev[1] behind it.
 static int enqueue_filter(fzb_haystack *h, const ScanParams &p, bool sampled, fzb_result *res) {
     const int64_t nvec = (int64_t)(round_up(h->buf_len, 16) / 16);
@@ -914,7 +957,7 @@ static int enqueue_filter(fzb_haystack *h, const ScanParams &p, bool sampled, fz
         if (sampled)
             k_filter_sampled<<<grid, kFilterThreads, kFilterSmem, h->stream>>>(p, nvec, ntiles);
         else
-            k_filter_dense<<<grid, kFilterThreads, kFilterSmem, h->stream>>>(p, nvec, ntiles);
+            k_filter_dense<<<grid, kFilterThreads, kDenseSmem, h->stream>>>(p, nvec, ntiles);
         CK(cudaGetLastError());
         res->stats.n_launches++;
     }
@@ -934,8 +977,10 @@ static int search_lev_ngrams(fzb_haystack *h, const uint8_t *pattern, uint32_t m
     p.n_ngrams = (int)m / p.L;  // range(0, m-L+1, L)
     int rc = check_halo(h, (uint64_t)m + k);
     if (rc) return rc;
-    const bool sampled = sampled_filter_applies(m, k, flags);
-    p.q = sampled ? 4 : std::min(p.L, 4);
+    CK(cudaSetDevice(h->device));
+    const bool sampled = sampled_filter_applies(m, k, flags) &&
+                         ((flags & FZB_F_FORCE_SAMPLED) || sampled_is_selective(h, m, k, p.L, p.n_ngrams));
+    p.q = sampled ? 4 : std::min(p.L, 8);
     res->stats.route = k == 0 ? 0 : (sampled ? 1 : 2);
     res->stats.bytes_scanned = h->buf_len;
     CK(cudaSetDevice(h->device));
@@ -1046,8 +1091,9 @@ static int search_generic(fzb_haystack *h, const uint8_t *pattern, uint32_t m, u
     p.L = (int)(m / (max_l + 1));
     if (p.L == 0) return fail(FZB_E_NGRAM_ZERO, "the subsequence length must be greater than max_l_dist");
     p.n_ngrams = (int)m / p.L;
-    const bool sampled = sampled_filter_applies(m, max_l, flags);
-    p.q = sampled ? 4 : std::min(p.L, 4);
+    const bool sampled = sampled_filter_applies(m, max_l, flags) &&
+                         ((flags & FZB_F_FORCE_SAMPLED) || sampled_is_selective(h, m, max_l, p.L, p.n_ngrams));
+    p.q = sampled ? 4 : std::min(p.L, 8);
     res->stats.route = 5;
     rc = set_filter_attrs(kFilterSmem);
     if (rc) return rc;

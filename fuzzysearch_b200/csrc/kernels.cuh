@@ -126,59 +126,100 @@ k_filter_sampled(const ScanParams p, int64_t nvec, int64_t ntiles) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Dense filter (every position): the fallback when the q-sample lemma does not apply (short
-// patterns / large k).  Tests the first q=min(L,4) bytes at EVERY position against the n-gram
-// prefixes (hashed byte table + exact re-check); a hit marks the granule of that position.
+// Dense filter (every position): used when the q-sample lemma does not apply (short patterns / large
+// k) or when it is not selective (small alphabets: on DNA an aligned 4-byte word carries 8 bits and
+// almost every granule would be marked).  It tests the first q = min(L, 8) bytes at EVERY position
+// against the n-grams themselves, i.e. it finds the n-gram hits of levenshtein_ngram.py:176 directly:
+//   per position: two funnel shifts build the 8-byte window (lo, hi), a 2-multiply hash picks one bit
+//   of a 16 Kibit table, replicated once per shared-memory bank so that lane l always reads bank l
+//   (address = row * 128 + 4 l: every lookup is one conflict-free wavefront).
+// Hits are confirmed warp-cooperatively (ballot, broadcast the window, lane j compares with n-gram j)
+// and mark the granule of that anchor position only.
 // ------------------------------------------------------------------------------------------------
-__device__ __noinline__ void dense_slow_path(const ScanParams &p, const uint32_t *grams,
-                                             int64_t off, uint32_t w) {
+constexpr int kDenseBits = 14;                       // 16 Kibit table ...
+constexpr int kDenseRows = (1 << kDenseBits) / 32;   // ... = 512 rows of 32 bits, one copy per bank
+constexpr size_t kDenseSmem = (size_t)kDenseRows * 128 + 256 * 8;  // 64 KiB + the n-gram windows
+constexpr uint32_t kHashMul2 = 0x85EBCA77u;
+
+__device__ __forceinline__ uint32_t dense_key(uint32_t lo, uint32_t hi) {
+    return (lo * kHashMul + hi * kHashMul2) >> (32 - kDenseBits);
+}
+
+__device__ __forceinline__ void dense_confirm(const ScanParams &p, const uint2 *grams, int lane, uint32_t lo,
+                                              uint32_t hi, int64_t off) {
     bool real = false;
-    for (int j = 0; j < p.n_ngrams; j++) real |= (grams[j] == w);
-    if (!real) return;
-    int64_t g = p.buf_lo + off;
-    mark_range(p, g, g);
+    for (int j = lane; j < p.n_ngrams; j += 32) real |= (grams[j].x == lo && grams[j].y == hi);
+    if (__ballot_sync(0xFFFFFFFFu, real) != 0 && lane == 0) mark_range(p, p.buf_lo + off, p.buf_lo + off);
 }
 
 __global__ void __launch_bounds__(kFilterThreads)
 k_filter_dense(const ScanParams p, int64_t nvec, int64_t ntiles) {
     extern __shared__ __align__(16) uint8_t smem[];
-    uint8_t *tbl = smem;
-    uint32_t *grams = reinterpret_cast<uint32_t *>(smem + kTblSize);
-    for (int i = threadIdx.x; i < kTblSize / 16; i += blockDim.x)
+    uint32_t *tbl = reinterpret_cast<uint32_t *>(smem);                        // [kDenseRows][32 banks]
+    uint2 *grams = reinterpret_cast<uint2 *>(smem + (size_t)kDenseRows * 128);  // (lo, hi) per n-gram (<= 255)
+    for (int i = threadIdx.x; i < kDenseRows * 32 / 4; i += blockDim.x)
         reinterpret_cast<uint4 *>(tbl)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
-    const uint32_t qmask = p.q >= 4 ? 0xFFFFFFFFu : ((1u << (8 * p.q)) - 1u);
-    for (int j = threadIdx.x; j < p.n_ngrams; j += blockDim.x) {
-        uint32_t w = 0;
-        for (int b = 0; b < p.q; b++) w |= (uint32_t)p.P[j * p.L + b] << (8 * b);
-        grams[j] = w;
-        tbl[hash_word(w)] = 1;
+    const int q = p.q;  // 1..8
+    const uint32_t mlo = q >= 4 ? 0xFFFFFFFFu : ((1u << (8 * q)) - 1u);
+    const uint32_t mhi = q <= 4 ? 0u : (q >= 8 ? 0xFFFFFFFFu : ((1u << (8 * (q - 4))) - 1u));
+    if (threadIdx.x < 32) {  // lane l fills its own bank's copy (the n-gram count is small)
+        for (int j = 0; j < p.n_ngrams; j++) {
+            uint32_t lo = 0, hi = 0;
+            for (int b = 0; b < q; b++) {
+                const uint32_t c = p.P[j * p.L + b];
+                if (b < 4) lo |= c << (8 * b); else hi |= c << (8 * (b - 4));
+            }
+            if (threadIdx.x == 0) grams[j] = make_uint2(lo, hi);
+            const uint32_t key = dense_key(lo, hi);
+            tbl[(key >> 5) * 32 + threadIdx.x] |= 1u << (key & 31);
+        }
     }
     __syncthreads();
 
+    const int lane = threadIdx.x & 31;
+    const uint32_t my_bank = (uint32_t)__cvta_generic_to_shared(tbl) + 4u * lane;
     const uint4 *base = reinterpret_cast<const uint4 *>(p.H);
-    const uint32_t *words = reinterpret_cast<const uint32_t *>(p.H);
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int64_t v0 = t * kTileVecs + threadIdx.x;
-#pragma unroll 1
+#pragma unroll 2
         for (int u = 0; u < kFilterUnroll; u++) {
-            int64_t v = v0 + (int64_t)u * kFilterThreads;
-            if (v >= nvec) continue;
-            uint4 d = __ldg(base + v);
-            uint32_t nx = __ldg(words + (v + 1) * 4);  // buffer is padded by >= 64 bytes
-            const uint32_t ws[5] = {d.x, d.y, d.z, d.w, nx};
+            const int64_t v = v0 + (int64_t)u * kFilterThreads;
+            const bool live = v < nvec;
+            uint4 d = live ? ldg_stream(base + v) : make_uint4(0, 0, 0, 0);
+            // the next 8 bytes: the neighbour lane has them; the last lane reads them itself
+            uint32_t n0 = __shfl_down_sync(0xFFFFFFFFu, d.x, 1), n1 = __shfl_down_sync(0xFFFFFFFFu, d.y, 1);
+            if (lane == 31 && live) {  // the buffer is padded: v + 1 is always readable
+                const uint2 nx = __ldg(reinterpret_cast<const uint2 *>(base + v + 1));
+                n0 = nx.x;
+                n1 = nx.y;
+            }
+            const uint32_t ws[6] = {d.x, d.y, d.z, d.w, n0, n1};
             uint32_t acc = 0;
 #pragma unroll
             for (int b = 0; b < 16; b++) {
-                uint32_t w = __funnelshift_r(ws[b >> 2], ws[(b >> 2) + 1], 8 * (b & 3)) & qmask;
-                acc = acc * 2u + tbl[hash_word(w)];
+                const uint32_t lo = __funnelshift_r(ws[b >> 2], ws[(b >> 2) + 1], 8 * (b & 3)) & mlo;
+                const uint32_t hi = __funnelshift_r(ws[(b >> 2) + 1], ws[(b >> 2) + 2], 8 * (b & 3)) & mhi;
+                const uint32_t key = dense_key(lo, hi);
+                uint32_t row;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(row) : "r"(my_bank + ((key >> 5) << 7)));
+                acc = acc * 2u + (__funnelshift_r(row, 0u, key) & 1u);  // bit (key & 31) of the row
             }
-            if (acc) {
+            unsigned flagged = __ballot_sync(0xFFFFFFFFu, acc != 0);
+            while (flagged) {  // warp-uniform
+                const int src = __ffs(flagged) - 1;
+                flagged &= flagged - 1;
+                const uint32_t a = __shfl_sync(0xFFFFFFFFu, acc, src);
+                uint32_t sw[6];
+#pragma unroll
+                for (int i = 0; i < 6; i++) sw[i] = __shfl_sync(0xFFFFFFFFu, ws[i], src);
+                const int64_t off0 = (t * kTileVecs + (threadIdx.x - lane + src) + (int64_t)u * kFilterThreads) * 16;
 #pragma unroll
                 for (int b = 0; b < 16; b++) {
-                    if (acc & (1u << (15 - b))) {
-                        uint32_t w = __funnelshift_r(ws[b >> 2], ws[(b >> 2) + 1], 8 * (b & 3)) & qmask;
-                        dense_slow_path(p, grams, v * 16 + b, w);
+                    if (a & (1u << (15 - b))) {  // uniform
+                        const uint32_t lo = __funnelshift_r(sw[b >> 2], sw[(b >> 2) + 1], 8 * (b & 3)) & mlo;
+                        const uint32_t hi = __funnelshift_r(sw[(b >> 2) + 1], sw[(b >> 2) + 2], 8 * (b & 3)) & mhi;
+                        dense_confirm(p, grams, lane, lo, hi, off0 + b);
                     }
                 }
             }

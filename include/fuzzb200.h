@@ -57,6 +57,8 @@ extern "C" {
 #define FZB_F_FORCE_LP 4u     /* Levenshtein/generic: force the "linear programming" route */
 #define FZB_F_FORCE_NGRAMS 8u /* Levenshtein/generic/Hamming: force the n-gram route */
 #define FZB_F_TINY_LIST 16u   /* testing: cap the granule work list at 8 entries (overflow path) */
+#define FZB_F_FORCE_SAMPLED 64u /* testing: use the sampled filter whenever its lemma holds, even if the
+                                 byte statistics say it is not selective */
 #define FZB_F_GLOBAL 32u      /* multi-GPU: FINAL becomes the GLOBAL consolidated list of all shards: the
                                  per-shard groups are all-gathered with NCCL on the search's own stream,
                                  right behind the kernels (needs fzb_haystack_comm_init on every rank;

@@ -20,7 +20,10 @@ def _raw(res):
     (ASCII, 1 << 22, 20, 2, 0),
     (ASCII, 1 << 22, 20, 2, F.F_FORCE_DENSE),
     (ASCII, 1 << 22, 20, 2, F.F_TINY_LIST),   # granule work list overflows -> bitmap sweep
-    (DNA, 1 << 18, 20, 2, F.F_TINY_LIST),
+    (DNA, 1 << 18, 20, 2, F.F_TINY_LIST | F.F_FORCE_SAMPLED),
+    (DNA, 1 << 20, 20, 2, F.F_FORCE_SAMPLED),  # non-selective sampled filter: nearly every granule marked
+    (DNA, 1 << 16, 30, 3, 0),                  # L = 7: dense filter hashes 7-byte n-grams
+    (b"ab", 1 << 14, 50, 4, 0),                # L = 10 > 8: dense filter on an 8-byte prefix
     (ASCII, (1 << 20) + 13, 32, 3, 0),
     (ASCII, 1 << 20, 9, 2, 0),          # L = 3: dense filter, q = 3
     (ASCII, 1 << 20, 64, 4, 0),
