@@ -953,7 +953,7 @@ static int enqueue_filter(fzb_haystack *h, const ScanParams &p, bool sampled, fz
     const int64_t nvec = (int64_t)(round_up(h->buf_len, 16) / 16);
     const int64_t ntiles = (nvec + kTileVecs - 1) / kTileVecs;
     if (ntiles > 0) {
-        int grid = (int)std::min<int64_t>(ntiles, (int64_t)h->sm_count * 4);
+        int grid = (int)std::min<int64_t>(ntiles, (int64_t)h->sm_count * (sampled ? 4 : 6));
         if (sampled)
             k_filter_sampled<<<grid, kFilterThreads, kFilterSmem, h->stream>>>(p, nvec, ntiles);
         else

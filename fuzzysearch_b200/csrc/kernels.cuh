@@ -131,25 +131,64 @@ k_filter_sampled(const ScanParams p, int64_t nvec, int64_t ntiles) {
 // almost every granule would be marked).  It tests the first q = min(L, 8) bytes at EVERY position
 // against the n-grams themselves, i.e. it finds the n-gram hits of levenshtein_ngram.py:176 directly:
 //   per position: two funnel shifts build the 8-byte window (lo, hi), a 2-multiply hash picks one bit
-//   of a 16 Kibit table, replicated once per shared-memory bank so that lane l always reads bank l
+//   of an 8 Kibit table, replicated once per shared-memory bank so that lane l always reads bank l
 //   (address = row * 128 + 4 l: every lookup is one conflict-free wavefront).
 // Hits are confirmed warp-cooperatively (ballot, broadcast the window, lane j compares with n-gram j)
 // and mark the granule of that anchor position only.
 // ------------------------------------------------------------------------------------------------
-constexpr int kDenseBits = 14;                       // 16 Kibit table ...
-constexpr int kDenseRows = (1 << kDenseBits) / 32;   // ... = 512 rows of 32 bits, one copy per bank
-constexpr size_t kDenseSmem = (size_t)kDenseRows * 128 + 256 * 8;  // 64 KiB + the n-gram windows
+constexpr int kDenseBits = 13;                       // 8 Kibit table ...
+constexpr int kDenseRows = (1 << kDenseBits) / 32;   // ... = 256 rows of 32 bits, one copy per bank
+constexpr size_t kDenseSmem = (size_t)kDenseRows * 128 + 256 * 8 + 8 * 32;  // 32 KiB + n-gram windows + scratch
 constexpr uint32_t kHashMul2 = 0x85EBCA77u;
 
 __device__ __forceinline__ uint32_t dense_key(uint32_t lo, uint32_t hi) {
     return (lo * kHashMul + hi * kHashMul2) >> (32 - kDenseBits);
 }
 
-__device__ __forceinline__ void dense_confirm(const ScanParams &p, const uint2 *grams, int lane, uint32_t lo,
-                                              uint32_t hi, int64_t off) {
-    bool real = false;
-    for (int j = lane; j < p.n_ngrams; j += 32) real |= (grams[j].x == lo && grams[j].y == hi);
-    if (__ballot_sync(0xFFFFFFFFu, real) != 0 && lane == 0) mark_range(p, p.buf_lo + off, p.buf_lo + off);
+// Slow path of the dense filter, for the whole warp: every flagged lane in turn parks its six words in
+// a per-warp scratch line, then all lanes walk its set bits, rebuild the 8-byte window at that byte
+// offset from the scratch and lane j compares it with n-gram j.
+struct MarkCtx {  // the few scalars mark_range needs, passed by value (a reference to the kernel's
+    int64_t buf_lo, own_lo, own_hi;  // ScanParams would force a local-memory copy of the whole block)
+    uint32_t *bitmap;
+};
+
+__device__ __noinline__ void dense_confirm_warp(MarkCtx mc, int n_ngrams, const uint2 *grams, uint32_t *scratch,
+                                                int lane, unsigned flagged, uint32_t acc, uint32_t w0_, uint32_t w1_,
+                                                uint32_t w2_, uint32_t w3_, uint32_t w4_, uint32_t w5_,
+                                                int64_t off_warp, uint32_t mlo, uint32_t mhi) {
+    while (flagged) {
+        const int src = __ffs(flagged) - 1;
+        flagged &= flagged - 1;
+        uint32_t a = __shfl_sync(0xFFFFFFFFu, acc, src);
+        __syncwarp();
+        if (lane == src) {
+            scratch[0] = w0_;
+            scratch[1] = w1_;
+            scratch[2] = w2_;
+            scratch[3] = w3_;
+            scratch[4] = w4_;
+            scratch[5] = w5_;
+        }
+        __syncwarp();
+        while (a) {
+            const int bit = 31 - __clz(a);  // bit 15 <-> byte 0
+            a &= ~(1u << bit);
+            const int b = 15 - bit;
+            const uint32_t w0 = scratch[b >> 2], w1 = scratch[(b >> 2) + 1], w2 = scratch[(b >> 2) + 2];
+            const uint32_t lo = __funnelshift_r(w0, w1, 8 * (b & 3)) & mlo;
+            const uint32_t hi = __funnelshift_r(w1, w2, 8 * (b & 3)) & mhi;
+            bool real = false;
+            for (int j = lane; j < n_ngrams; j += 32) real |= (grams[j].x == lo && grams[j].y == hi);
+            if (__ballot_sync(0xFFFFFFFFu, real) != 0 && lane == 0) {
+                const int64_t g = mc.buf_lo + off_warp + (int64_t)src * 16 + b;
+                if (g >= mc.own_lo && g < mc.own_hi) {
+                    const int64_t gr = (g - mc.buf_lo) >> kGranuleShift;
+                    atomicOr(&mc.bitmap[gr >> 5], 1u << (gr & 31));
+                }
+            }
+        }
+    }
 }
 
 __global__ void __launch_bounds__(kFilterThreads)
@@ -157,6 +196,7 @@ k_filter_dense(const ScanParams p, int64_t nvec, int64_t ntiles) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint32_t *tbl = reinterpret_cast<uint32_t *>(smem);                        // [kDenseRows][32 banks]
     uint2 *grams = reinterpret_cast<uint2 *>(smem + (size_t)kDenseRows * 128);  // (lo, hi) per n-gram (<= 255)
+    uint32_t *scratch = reinterpret_cast<uint32_t *>(smem + (size_t)kDenseRows * 128 + 256 * 8);  // 8 words per warp
     for (int i = threadIdx.x; i < kDenseRows * 32 / 4; i += blockDim.x)
         reinterpret_cast<uint4 *>(tbl)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
@@ -206,22 +246,11 @@ k_filter_dense(const ScanParams p, int64_t nvec, int64_t ntiles) {
                 acc = acc * 2u + (__funnelshift_r(row, 0u, key) & 1u);  // bit (key & 31) of the row
             }
             unsigned flagged = __ballot_sync(0xFFFFFFFFu, acc != 0);
-            while (flagged) {  // warp-uniform
-                const int src = __ffs(flagged) - 1;
-                flagged &= flagged - 1;
-                const uint32_t a = __shfl_sync(0xFFFFFFFFu, acc, src);
-                uint32_t sw[6];
-#pragma unroll
-                for (int i = 0; i < 6; i++) sw[i] = __shfl_sync(0xFFFFFFFFu, ws[i], src);
-                const int64_t off0 = (t * kTileVecs + (threadIdx.x - lane + src) + (int64_t)u * kFilterThreads) * 16;
-#pragma unroll
-                for (int b = 0; b < 16; b++) {
-                    if (a & (1u << (15 - b))) {  // uniform
-                        const uint32_t lo = __funnelshift_r(sw[b >> 2], sw[(b >> 2) + 1], 8 * (b & 3)) & mlo;
-                        const uint32_t hi = __funnelshift_r(sw[(b >> 2) + 1], sw[(b >> 2) + 2], 8 * (b & 3)) & mhi;
-                        dense_confirm(p, grams, lane, lo, hi, off0 + b);
-                    }
-                }
+            if (flagged) {  // warp-uniform, kept out of line and compact (instruction cache)
+                const int64_t off_warp = (t * kTileVecs + (threadIdx.x - lane) + (int64_t)u * kFilterThreads) * 16;
+                dense_confirm_warp(MarkCtx{p.buf_lo, p.own_lo, p.own_hi, p.bitmap}, p.n_ngrams, grams,
+                                   scratch + (threadIdx.x >> 5) * 8, lane, flagged, acc, ws[0], ws[1], ws[2], ws[3],
+                                   ws[4], ws[5], off_warp, mlo, mhi);
             }
         }
     }
