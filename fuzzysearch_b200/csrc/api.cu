@@ -140,6 +140,8 @@ struct fzb_haystack {
     uint32_t gather_alloc = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     int sm_count = 148;
+    uint64_t *d_hits = nullptr;     // dense route: list of confirmed n-gram hits
+    uint32_t hits_cap = 0;
     uint32_t *d_glist = nullptr;    // compacted list of marked granules
     uint32_t glist_cap = 0;
     uint32_t *d_scratch = nullptr;  // candidate lists of the LP / generic kernels
@@ -220,6 +222,7 @@ extern "C" void fzb_haystack_destroy(fzb_haystack *h) {
     if (h->d_counters) cudaFree(h->d_counters);
     if (h->d_scratch) cudaFree(h->d_scratch);
     if (h->d_glist) cudaFree(h->d_glist);
+    if (h->d_hits) cudaFree(h->d_hits);
     if (h->d_send) cudaFree(h->d_send);
     if (h->d_recv) cudaFree(h->d_recv);
     if (h->h_send) cudaFreeHost(h->h_send);
@@ -957,7 +960,7 @@ static int enqueue_filter(fzb_haystack *h, const ScanParams &p, bool sampled, fz
         if (sampled)
             k_filter_sampled<<<grid, kFilterThreads, kFilterSmem, h->stream>>>(p, nvec, ntiles);
         else
-            k_filter_dense<<<grid, kFilterThreads, kDenseSmem, h->stream>>>(p, nvec, ntiles);
+            k_filter_dense<<<grid, kFilterThreads, kDenseSmem, h->stream>>>(p, nvec, ntiles, h->d_counters);
         CK(cudaGetLastError());
         res->stats.n_launches++;
     }
@@ -989,9 +992,25 @@ static int search_lev_ngrams(fzb_haystack *h, const uint8_t *pattern, uint32_t m
         if (rc) return rc;
         h->filter_attrs_set = true;
     }
+    // dense route: confirmed n-gram hits go to a list and are verified one lane per hit (the window of a
+    // hit must fit a lane's shared-memory slot); the list overflowing triggers one retry in granule mode
+    bool use_hits = !sampled && k > 0 && (m + 2 * k + 8 <= (uint32_t)kHitSlotBytes);
+    if (use_hits && !h->d_hits) {
+        h->hits_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1u << 20, h->capacity / 256), 1u << 28);
+        CK(cudaMalloc(&h->d_hits, (size_t)h->hits_cap * sizeof(uint64_t)));
+    }
+    bool fuse_gather = want_final && (flags & FZB_F_GLOBAL) != 0;
+retry_without_hits:
+    p.hits = use_hits ? h->d_hits : nullptr;
+    p.hits_cap = use_hits ? ((flags & FZB_F_TINY_LIST) ? std::min(h->hits_cap, 8u) : h->hits_cap) : 0;
     rc = run_emitting(h, res, [&]() -> int {
         int r2 = enqueue_filter(h, p, sampled, res);
         if (r2) return r2;
+        if (use_hits) {
+            k_verify_hits<<<h->sm_count * 8, kHitThreads, 0, h->stream>>>(p, h->d_out, h->out_cap, h->d_counters);
+            res->stats.n_launches++;
+            return FZB_OK;
+        }
         const uint32_t gcap = (flags & FZB_F_TINY_LIST) ? std::min(h->glist_cap, 8u) : h->glist_cap;
         k_compact_granules<<<h->sm_count * 4, 256, 0, h->stream>>>(h->d_bitmap, h->bitmap_words, h->d_glist, gcap,
                                                                    h->d_counters);
@@ -1000,8 +1019,17 @@ static int search_lev_ngrams(fzb_haystack *h, const uint8_t *pattern, uint32_t m
                 p, h->bitmap_words, h->d_glist, gcap, scan_mode, h->d_out, h->out_cap, h->d_counters);
         res->stats.n_launches += 3;
         return FZB_OK;
-    }, PostPlan{true, 2, want_final ? 1 : 0, want_final && (flags & FZB_F_GLOBAL) != 0});  // raw order: lazily
+    }, PostPlan{true, 2, want_final ? 1 : 0, fuse_gather});  // raw order (n-gram, hit index): lazily
     if (rc) return rc;
+    if (use_hits && h->h_counters[CNT_HITS] > p.hits_cap) {
+        // the fused all-gather (if any) went out with valid = 0 (k_verify_hits raised CNT_OVERFLOW), so every
+        // rank will take finish_global's staged round; the retry itself must not issue another collective
+        fuse_gather = false;
+        use_hits = false;
+        res->raw.clear();
+        res->fin.clear();
+        goto retry_without_hits;
+    }
     res->raw_order = 0;
     return FZB_OK;
 }

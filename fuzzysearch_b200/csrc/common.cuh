@@ -29,6 +29,8 @@ struct ScanParams {
     int64_t own_lo;     // anchors owned by this shard: [own_lo, own_hi)
     int64_t own_hi;
     uint32_t *bitmap;   // dirty-granule bitmap, bit g <-> buffer offsets [64g, 64g+64)
+    uint64_t *hits;     // dense filter, hit-list mode: confirmed n-gram hits (idx << 8 | n-gram ordinal)
+    uint32_t hits_cap;  // 0 = mark granules instead
     int32_t m, k, L, n_ngrams;
     int32_t q;          // bytes per hashed sample (4 sampled filter; min(L,4) dense filter)
     int32_t max_subs, max_ins, max_dels;  // generic route only
@@ -36,7 +38,8 @@ struct ScanParams {
 };
 
 // counters[] slots (device, uint32 each unless noted)
-enum { CNT_OUT = 0, CNT_CAND = 1, CNT_OVERFLOW = 2, CNT_GRAN = 3, CNT_WORK = 4, CNT_COUNT = 8 };
+enum { CNT_OUT = 0, CNT_CAND = 1, CNT_OVERFLOW = 2, CNT_GRAN = 3, CNT_WORK = 4, /* 5,6: post_kernels.cuh */
+       CNT_HITS = 7, CNT_HITWORK = 8, CNT_COUNT = 16 };
 
 __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
     x += 0x9E3779B97F4A7C15ull;

@@ -151,6 +151,9 @@ __device__ __forceinline__ uint32_t dense_key(uint32_t lo, uint32_t hi) {
 struct MarkCtx {  // the few scalars mark_range needs, passed by value (a reference to the kernel's
     int64_t buf_lo, own_lo, own_hi;  // ScanParams would force a local-memory copy of the whole block)
     uint32_t *bitmap;
+    uint64_t *hits;
+    uint32_t hits_cap;
+    uint32_t *counters;
 };
 
 __device__ __noinline__ void dense_confirm_warp(MarkCtx mc, int n_ngrams, const uint2 *grams, uint32_t *scratch,
@@ -178,11 +181,18 @@ __device__ __noinline__ void dense_confirm_warp(MarkCtx mc, int n_ngrams, const 
             const uint32_t w0 = scratch[b >> 2], w1 = scratch[(b >> 2) + 1], w2 = scratch[(b >> 2) + 2];
             const uint32_t lo = __funnelshift_r(w0, w1, 8 * (b & 3)) & mlo;
             const uint32_t hi = __funnelshift_r(w1, w2, 8 * (b & 3)) & mhi;
-            bool real = false;
-            for (int j = lane; j < n_ngrams; j += 32) real |= (grams[j].x == lo && grams[j].y == hi);
-            if (__ballot_sync(0xFFFFFFFFu, real) != 0 && lane == 0) {
-                const int64_t g = mc.buf_lo + off_warp + (int64_t)src * 16 + b;
-                if (g >= mc.own_lo && g < mc.own_hi) {
+            const int64_t g = mc.buf_lo + off_warp + (int64_t)src * 16 + b;
+            const bool owned = g >= mc.own_lo && g < mc.own_hi;
+            if (mc.hits_cap) {  // hit-list mode: one entry per (n-gram, position); verified lane-parallel later
+                for (int j = lane; j < n_ngrams; j += 32)
+                    if (owned && grams[j].x == lo && grams[j].y == hi) {
+                        const uint32_t slot = atomicAdd(&mc.counters[CNT_HITS], 1u);
+                        if (slot < mc.hits_cap) mc.hits[slot] = ((uint64_t)g << 8) | (uint64_t)j;
+                    }
+            } else {
+                bool real = false;
+                for (int j = lane; j < n_ngrams; j += 32) real |= (grams[j].x == lo && grams[j].y == hi);
+                if (__ballot_sync(0xFFFFFFFFu, real) != 0 && lane == 0 && owned) {
                     const int64_t gr = (g - mc.buf_lo) >> kGranuleShift;
                     atomicOr(&mc.bitmap[gr >> 5], 1u << (gr & 31));
                 }
@@ -192,7 +202,7 @@ __device__ __noinline__ void dense_confirm_warp(MarkCtx mc, int n_ngrams, const 
 }
 
 __global__ void __launch_bounds__(kFilterThreads)
-k_filter_dense(const ScanParams p, int64_t nvec, int64_t ntiles) {
+k_filter_dense(const ScanParams p, int64_t nvec, int64_t ntiles, uint32_t *counters) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint32_t *tbl = reinterpret_cast<uint32_t *>(smem);                        // [kDenseRows][32 banks]
     uint2 *grams = reinterpret_cast<uint2 *>(smem + (size_t)kDenseRows * 128);  // (lo, hi) per n-gram (<= 255)
@@ -248,7 +258,8 @@ k_filter_dense(const ScanParams p, int64_t nvec, int64_t ntiles) {
             unsigned flagged = __ballot_sync(0xFFFFFFFFu, acc != 0);
             if (flagged) {  // warp-uniform, kept out of line and compact (instruction cache)
                 const int64_t off_warp = (t * kTileVecs + (threadIdx.x - lane) + (int64_t)u * kFilterThreads) * 16;
-                dense_confirm_warp(MarkCtx{p.buf_lo, p.own_lo, p.own_hi, p.bitmap}, p.n_ngrams, grams,
+                dense_confirm_warp(MarkCtx{p.buf_lo, p.own_lo, p.own_hi, p.bitmap, p.hits, p.hits_cap, counters},
+                                   p.n_ngrams, grams,
                                    scratch + (threadIdx.x >> 5) * 8, lane, flagged, acc, ws[0], ws[1], ws[2], ws[3],
                                    ws[4], ws[5], off_warp, mlo, mhi);
             }
@@ -413,12 +424,12 @@ __device__ __forceinline__ int64_t stage_window(const ScanParams &p, int64_t gba
 }
 
 __device__ void verify_anchor_lev(const ScanParams &p, const uint8_t *sP, const uint8_t *W, int64_t idx,
-                                  DpScratch &S, RawRec *out, uint32_t cap, uint32_t *counters) {
-    // W[g] is the haystack byte at global position g (shared-memory window)
+                                  DpScratch &S, RawRec *out, uint32_t cap, uint32_t *counters, int j_lo, int j_hi) {
+    // W[g] is the haystack byte at global position g (shared-memory window); n-grams j_lo..j_hi-1
     const int m = p.m, k = p.k, L = p.L;
     const int64_t N = p.N;
     const uint8_t *h = W + idx;
-    for (int j = 0; j < p.n_ngrams; j++) {
+    for (int j = j_lo; j < j_hi; j++) {
         const int s = j * L;  // :170
         // search window of n-gram j, clamped like search_exact.py:29-30   (:174-176)
         int64_t ws = max((int64_t)0, (int64_t)(s - k));
@@ -482,7 +493,7 @@ __device__ __forceinline__ void verify_granule_lev(const ScanParams &p, const ui
 #pragma unroll 1
     for (int half = 0; half < kGranule / 32; half++) {
         const int64_t idx = gbase + half * 32 + lane;
-        if (idx >= p.own_lo && idx < p.own_hi) verify_anchor_lev(p, sP, W, idx, S, out, cap, counters);
+        if (idx >= p.own_lo && idx < p.own_hi) verify_anchor_lev(p, sP, W, idx, S, out, cap, counters, 0, p.n_ngrams);
     }
 }
 
@@ -533,6 +544,53 @@ k_verify_lev(const ScanParams p, uint64_t bitmap_words, const uint32_t *glist, u
             }
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Hit-list verification (dense route on low-entropy data, where hits are many): ONE LANE PER HIT.
+// Each lane copies the window of its own hit, H[p0-k : p0+m+k), into its private slot of shared
+// memory (one round trip, independent loads), then runs the n-gram compare and both expansions from
+// there -- 32 hits verified in parallel per warp instead of one hit per granule per warp.
+// ------------------------------------------------------------------------------------------------
+constexpr int kHitSlotBytes = 144;  // per-lane window slot: m + 2k + alignment slack must fit
+constexpr int kHitThreads = 128;
+
+__global__ void __launch_bounds__(kHitThreads)
+k_verify_hits(const ScanParams p, RawRec *out, uint32_t cap, uint32_t *counters) {
+    __shared__ uint8_t sP[256];
+    __shared__ __align__(16) uint8_t slots[kHitThreads][kHitSlotBytes];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sP[i] = p.P[i];
+    __syncthreads();
+    const uint32_t nhits = counters[CNT_HITS];
+    if (nhits > p.hits_cap) {  // list overflowed: the host repeats the search in granule mode
+        if (blockIdx.x == 0 && threadIdx.x == 0) counters[CNT_OVERFLOW] = 1;
+        return;
+    }
+    DpScratch S;
+    const int lane = threadIdx.x & 31;
+    uint8_t *slot = slots[threadIdx.x];
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&counters[CNT_HITWORK], 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= nhits) break;
+        const uint32_t item = base + lane;
+        if (item < nhits) {
+            const uint64_t hv = p.hits[item];
+            const int64_t idx = (int64_t)(hv >> 8);
+            const int j = (int)(hv & 0xFFu);
+            const int64_t p0 = idx - (int64_t)j * p.L;
+            const int64_t wlo = max(max(p0 - p.k, (int64_t)0), p.buf_lo);
+            const int64_t whi = min(min(p0 + p.m + p.k, p.N), p.buf_lo + p.buf_len);
+            const int64_t alo = wlo & ~(int64_t)3;
+            const int nwords = (int)((whi - alo + 3) >> 2);
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(p.H + (alo - p.buf_lo));
+            uint32_t *dst = reinterpret_cast<uint32_t *>(slot);
+            for (int w = 0; w < nwords; w++) dst[w] = __ldg(src + w);
+            verify_anchor_lev(p, sP, slot - alo, idx, S, out, cap, counters, j, j + 1);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counters[CNT_CAND], nhits);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -226,7 +226,7 @@ k_consolidate(const RawRec *recs, const uint32_t *ranks, RawRec *raw_sorted, uin
 __global__ void __launch_bounds__(256)
 k_pack_groups(const int64_t *fin, const uint32_t *counters, int64_t *slot, uint32_t cap) {
     const uint32_t nf = counters[CNT_NFINAL];
-    const bool valid = counters[CNT_POST_DONE] != 0 && nf <= cap;
+    const bool valid = counters[CNT_POST_DONE] != 0 && nf <= cap && counters[CNT_OVERFLOW] == 0;
     if (blockIdx.x == 0 && threadIdx.x < kFinCols)
         slot[threadIdx.x] = threadIdx.x == 0 ? (int64_t)nf : (threadIdx.x == 1 ? (int64_t)valid : 0);
     if (!valid) return;

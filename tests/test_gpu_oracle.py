@@ -23,6 +23,7 @@ def _raw(res):
     (DNA, 1 << 18, 20, 2, F.F_TINY_LIST | F.F_FORCE_SAMPLED),
     (DNA, 1 << 20, 20, 2, F.F_FORCE_SAMPLED),  # non-selective sampled filter: nearly every granule marked
     (DNA, 1 << 16, 30, 3, 0),                  # L = 7: dense filter hashes 7-byte n-grams
+    (DNA, 1 << 18, 20, 2, F.F_TINY_LIST),      # hit list overflows -> retry in granule mode (tiny work list)
     (b"ab", 1 << 14, 50, 4, 0),                # L = 10 > 8: dense filter on an 8-byte prefix
     (ASCII, (1 << 20) + 13, 32, 3, 0),
     (ASCII, 1 << 20, 9, 2, 0),          # L = 3: dense filter, q = 3
