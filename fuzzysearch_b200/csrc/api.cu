@@ -743,7 +743,8 @@ static int ensure_out_cap(fzb_haystack *h, uint64_t need) {
 // bitmap as they consume it, so a retry has to re-mark it) and may record h->ev[1] after its scan
 // kernel.  One attempt = one stream synchronisation: the counters and the first kSpecRecs records
 // are copied speculatively into pinned staging memory behind the kernels.
-constexpr uint32_t kSpecRecs = 4096;
+constexpr uint32_t kSpecRecs = 16384;  // raw records copied speculatively (512 KiB, ~10 us of PCIe)
+constexpr uint32_t kSpecFin = 4096;    // final rows copied speculatively
 
 // What k_post_small should do behind the emitting kernels (post.enable == false: host does it).
 struct PostPlan {
@@ -792,8 +793,8 @@ static int run_emitting(fzb_haystack *h, fzb_result *res, F enqueue, PostPlan po
         CK(cudaMemcpyAsync(h->h_stage, raw_from_sorted ? h->d_raw_sorted : h->d_out, (size_t)spec * sizeof(RawRec),
                            cudaMemcpyDeviceToHost, h->stream));
         if (post.enable && post.do_consolidate)
-            CK(cudaMemcpyAsync(h->h_fin, h->d_fin, (size_t)spec * kFinCols * sizeof(int64_t), cudaMemcpyDeviceToHost,
-                               h->stream));
+            CK(cudaMemcpyAsync(h->h_fin, h->d_fin, (size_t)kSpecFin * kFinCols * sizeof(int64_t),
+                               cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         const uint32_t n = h->h_counters[CNT_OUT];
         res->stats.n_candidates = h->h_counters[CNT_CAND];
@@ -827,11 +828,11 @@ static int run_emitting(fzb_haystack *h, fzb_result *res, F enqueue, PostPlan po
                                cudaMemcpyDeviceToHost, h->stream));
         if (posted && post.do_consolidate) {
             const uint32_t nf = h->h_counters[CNT_NFINAL];
-            if (nf > spec)
-                CK(cudaMemcpyAsync(h->h_fin + (size_t)spec * kFinCols, h->d_fin + (size_t)spec * kFinCols,
-                                   (size_t)(nf - spec) * kFinCols * sizeof(int64_t), cudaMemcpyDeviceToHost,
+            if (nf > kSpecFin)
+                CK(cudaMemcpyAsync(h->h_fin + (size_t)kSpecFin * kFinCols, h->d_fin + (size_t)kSpecFin * kFinCols,
+                                   (size_t)(nf - kSpecFin) * kFinCols * sizeof(int64_t), cudaMemcpyDeviceToHost,
                                    h->stream));
-            if (n > have || nf > spec) CK(cudaStreamSynchronize(h->stream));
+            if (n > have || nf > kSpecFin) CK(cudaStreamSynchronize(h->stream));
             res->fin.resize(nf);
             res->hulls.resize((size_t)nf * 2);
             for (uint32_t i = 0; i < nf; i++) {
