@@ -159,6 +159,7 @@ struct fzb_result {
     bool gather_valid = false;
     bool fused_issued = false;
     std::vector<int64_t> gathered;  // group rows of all shards (rank major)
+    std::vector<uint64_t> gathered_counts;  // rows per shard
     std::vector<RawRec> gfin;
     int raw_order = 0;         // 0 generation (ngram, idx) / 1 canonical / 2 generic n-grams (5 fields)
     void order_raw();
@@ -614,19 +615,40 @@ extern "C" int fzb_result_hulls(const fzb_result *r, int64_t *hull_start, int64_
 // members, so hulls overlap iff members do), and the winner of a union is the better of the two
 // winners -- so the global consolidate_overlapping_matches (common.py:185-189) is the same sweep run
 // over the groups instead of the raw matches.
-static void merge_group_rows(const int64_t *rows, uint64_t n, std::vector<RawRec> &out) {
-    struct G { int64_t s, e, d, hs, he; };
-    std::vector<G> g(n);
-    for (uint64_t i = 0; i < n; i++) g[i] = G{rows[5 * i], rows[5 * i + 1], rows[5 * i + 2], rows[5 * i + 3], rows[5 * i + 4]};
-    auto less = [](const G &a, const G &b) {
+// Global consolidation over per-shard groups.  `runs` = (pointer, count) of each shard's rows, in shard
+// order; every run is sorted by hull start and runs only interleave within a halo of their seams, so
+// instead of sorting, each seam is fixed with an inplace_merge of the few out-of-order rows around it.
+struct GroupRow {
+    int64_t s, e, d, hs, he;
+};
+
+static void merge_group_runs(const std::vector<std::pair<const int64_t *, uint64_t>> &runs, std::vector<RawRec> &out) {
+    uint64_t n = 0;
+    for (auto &r : runs) n += r.second;
+    std::vector<GroupRow> g;
+    g.reserve(n);
+    auto less = [](const GroupRow &a, const GroupRow &b) {
         if (a.hs != b.hs) return a.hs < b.hs;
         if (a.he != b.he) return a.he < b.he;
         if (a.s != b.s) return a.s < b.s;
         if (a.e != b.e) return a.e < b.e;
         return a.d < b.d;
     };
-    if (!std::is_sorted(g.begin(), g.end(), less)) std::sort(g.begin(), g.end(), less);  // shards arrive almost ordered
-    auto better = [](const G &a, const G &b) {
+    for (auto &r : runs) {
+        const size_t seam = g.size();
+        for (uint64_t i = 0; i < r.second; i++) {
+            const int64_t *q = r.first + 5 * i;
+            g.push_back(GroupRow{q[0], q[1], q[2], q[3], q[4]});
+        }
+        if (!std::is_sorted(g.begin() + seam, g.end(), less)) std::sort(g.begin() + seam, g.end(), less);  // defensive
+        if (seam > 0 && seam < g.size() && less(g[seam], g[seam - 1])) {
+            auto lo = std::upper_bound(g.begin(), g.begin() + seam, g[seam], less);
+            auto hi = std::lower_bound(g.begin() + seam, g.end(), g[seam - 1], less);
+            std::inplace_merge(lo, g.begin() + seam, hi, less);
+        }
+    }
+    if (!std::is_sorted(g.begin(), g.end(), less)) std::sort(g.begin(), g.end(), less);  // shards smaller than a halo
+    auto better = [](const GroupRow &a, const GroupRow &b) {
         if (a.d != b.d) return a.d < b.d;
         int64_t la = a.e - a.s, lb = b.e - b.s;
         if (la != lb) return la > lb;
@@ -634,8 +656,9 @@ static void merge_group_rows(const int64_t *rows, uint64_t n, std::vector<RawRec
         return a.e < b.e;
     };
     out.clear();
+    out.reserve(n);
     for (uint64_t i = 0; i < n;) {
-        G best = g[i];
+        GroupRow best = g[i];
         int64_t hull_end = g[i].he;
         uint64_t j = i + 1;
         while (j < n && g[j].hs < hull_end) {
@@ -654,6 +677,12 @@ static void merge_group_rows(const int64_t *rows, uint64_t n, std::vector<RawRec
     }
 }
 
+static void merge_group_rows(const int64_t *rows, uint64_t n, std::vector<RawRec> &out) {
+    // one run per maximal sorted stretch is not known here: treat the input as a single run (sorted if needed)
+    std::vector<std::pair<const int64_t *, uint64_t>> runs{{rows, n}};
+    merge_group_runs(runs, out);
+}
+
 extern "C" int64_t fzb_merge_groups(const int64_t *rows, uint64_t n, int64_t *out_start, int64_t *out_end,
                                     int32_t *out_dist) {
     if (n && !rows) return fail(FZB_E_INVALID, "NULL input");
@@ -670,7 +699,8 @@ extern "C" int64_t fzb_merge_groups(const int64_t *rows, uint64_t n, int64_t *ou
 // The staged (host-buffer) all-gather of group rows: used when the fused one behind the kernels could
 // not be trusted on every rank (a rank overflowed a buffer and retried, or its list was too long for
 // the on-device consolidation).  Collective: every rank calls it the same number of times.
-static int allgather_groups_staged(fzb_haystack *h, const std::vector<int64_t> &rows, std::vector<int64_t> &all) {
+static int allgather_groups_staged(fzb_haystack *h, const std::vector<int64_t> &rows, std::vector<int64_t> &all,
+                                   std::vector<uint64_t> &counts) {
     const uint64_t n = rows.size() / kFinCols;
     for (;;) {
         const uint32_t cap = h->gather_cap;
@@ -690,9 +720,11 @@ static int allgather_groups_staged(fzb_haystack *h, const std::vector<int64_t> &
         for (int r = 0; r < h->world; r++) top = std::max<uint64_t>(top, (uint64_t)h->h_recv[(size_t)r * slot_rows * kFinCols]);
         if (top <= cap) {
             all.clear();
+            counts.clear();
             for (int r = 0; r < h->world; r++) {
                 const int64_t *base = h->h_recv + (size_t)r * slot_rows * kFinCols;
                 all.insert(all.end(), base + kFinCols, base + kFinCols + (size_t)base[0] * kFinCols);
+                counts.push_back((uint64_t)base[0]);
             }
             return FZB_OK;
         }
@@ -806,10 +838,12 @@ static int run_emitting(fzb_haystack *h, fzb_result *res, F enqueue, PostPlan po
                 const int64_t *base = h->h_recv + (size_t)r * slot_rows * kFinCols;
                 if (!base[1]) res->gather_valid = false;
             }
+            res->gathered_counts.clear();
             if (res->gather_valid)
                 for (int r = 0; r < h->world; r++) {
                     const int64_t *base = h->h_recv + (size_t)r * slot_rows * kFinCols;
                     res->gathered.insert(res->gathered.end(), base + kFinCols, base + kFinCols + (size_t)base[0] * kFinCols);
+                    res->gathered_counts.push_back((uint64_t)base[0]);
                 }
         }
         if (n > h->out_cap) {  // output buffer too small: grow and redo the whole attempt
@@ -1143,8 +1177,10 @@ static int search_generic(fzb_haystack *h, const uint8_t *pattern, uint32_t m, u
 static int finish_global(fzb_haystack *h, fzb_result *res) {
     if (!h->comm) return fail(FZB_E_INVALID, "FZB_F_GLOBAL needs fzb_haystack_comm_init");
     std::vector<int64_t> all;
+    std::vector<uint64_t> counts;
     if (res->fused_issued && res->gather_valid) {
         all.swap(res->gathered);
+        counts.swap(res->gathered_counts);
     } else {  // staged: the local result is complete now, whatever it took
         if (res->final_is_raw) res->order_raw();
         const std::vector<RawRec> &v = res->final_is_raw ? res->raw : res->fin;
@@ -1156,7 +1192,7 @@ static int finish_global(fzb_haystack *h, fzb_result *res) {
             rows[kFinCols * i + 3] = res->final_is_raw ? v[i].start : res->hulls[2 * i];
             rows[kFinCols * i + 4] = res->final_is_raw ? v[i].end : res->hulls[2 * i + 1];
         }
-        int rc = allgather_groups_staged(h, rows, all);
+        int rc = allgather_groups_staged(h, rows, all, counts);
         if (rc) return rc;
     }
     if (res->final_is_raw) {  // unconsolidated routes (exact, Hamming): the global list is the sorted union
@@ -1170,7 +1206,13 @@ static int finish_global(fzb_haystack *h, fzb_result *res) {
         }
         sort_canonical(res->gfin);
     } else {
-        merge_group_rows(all.data(), all.size() / kFinCols, res->gfin);
+        std::vector<std::pair<const int64_t *, uint64_t>> runs;
+        uint64_t off = 0;
+        for (uint64_t c : counts) {
+            runs.push_back({all.data() + off * kFinCols, c});
+            off += c;
+        }
+        merge_group_runs(runs, res->gfin);
     }
     res->has_global = true;
     return FZB_OK;
