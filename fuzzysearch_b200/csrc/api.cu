@@ -762,7 +762,7 @@ static int ensure_out_cap(fzb_haystack *h, uint64_t need) {
     if (need <= h->out_cap) return FZB_OK;
     uint64_t cap = h->out_cap;
     while (cap < need) cap *= 2;
-    if (cap > (1ull << 31)) return fail(FZB_E_UNSUPPORTED, "more than 2^31 raw matches");
+    if (cap > (1ull << 27)) return fail(FZB_E_UNSUPPORTED, "more than 2^27 raw matches in one search");
     CK(cudaFree(h->d_out));
     h->d_out = nullptr;
     CK(cudaMalloc(&h->d_out, (size_t)cap * sizeof(RawRec)));
