@@ -744,6 +744,9 @@ static void fill_params(const fzb_haystack *h, const uint8_t *pattern, uint32_t 
     p.own_lo = (int64_t)h->own_lo;
     p.own_hi = (int64_t)h->own_hi;
     p.bitmap = h->d_bitmap;
+    p.glist = h->d_glist;
+    p.glist_cap = h->glist_cap;
+    p.counters = h->d_counters;
     p.m = (int)m;
     memcpy(p.P, pattern, m);
 }
@@ -995,7 +998,7 @@ static int enqueue_filter(fzb_haystack *h, const ScanParams &p, bool sampled, fz
         if (sampled)
             k_filter_sampled<<<grid, kFilterThreads, kFilterSmem, h->stream>>>(p, nvec, ntiles);
         else
-            k_filter_dense<<<grid, kFilterThreads, kDenseSmem, h->stream>>>(p, nvec, ntiles, h->d_counters);
+            k_filter_dense<<<grid, kFilterThreads, kDenseSmem, h->stream>>>(p, nvec, ntiles);
         CK(cudaGetLastError());
         res->stats.n_launches++;
     }
@@ -1035,6 +1038,7 @@ static int search_lev_ngrams(fzb_haystack *h, const uint8_t *pattern, uint32_t m
         CK(cudaMalloc(&h->d_hits, (size_t)h->hits_cap * sizeof(uint64_t)));
     }
     bool fuse_gather = want_final && (flags & FZB_F_GLOBAL) != 0;
+    if (flags & FZB_F_TINY_LIST) p.glist_cap = std::min(h->glist_cap, 8u);
 retry_without_hits:
     p.hits = use_hits ? h->d_hits : nullptr;
     p.hits_cap = use_hits ? ((flags & FZB_F_TINY_LIST) ? std::min(h->hits_cap, 8u) : h->hits_cap) : 0;
@@ -1046,13 +1050,10 @@ retry_without_hits:
             res->stats.n_launches++;
             return FZB_OK;
         }
-        const uint32_t gcap = (flags & FZB_F_TINY_LIST) ? std::min(h->glist_cap, 8u) : h->glist_cap;
-        k_compact_granules<<<h->sm_count * 4, 256, 0, h->stream>>>(h->d_bitmap, h->bitmap_words, h->d_glist, gcap,
-                                                                   h->d_counters);
         for (int scan_mode = 0; scan_mode < 2; scan_mode++)
             k_verify_lev<<<h->sm_count * 4, kVerifyThreads, 0, h->stream>>>(
-                p, h->bitmap_words, h->d_glist, gcap, scan_mode, h->d_out, h->out_cap, h->d_counters);
-        res->stats.n_launches += 3;
+                p, h->bitmap_words, h->d_glist, p.glist_cap, scan_mode, h->d_out, h->out_cap, h->d_counters);
+        res->stats.n_launches += 2;
         return FZB_OK;
     }, PostPlan{true, 2, want_final ? 1 : 0, fuse_gather});  // raw order (n-gram, hit index): lazily
     if (rc) return rc;
@@ -1350,13 +1351,11 @@ extern "C" int fzb_search_hamming(fzb_haystack *h, const uint8_t *pattern, uint3
                     k_hamming_count<<<grid, kHcThreads, kHcSmem, h->stream>>>(p, hp, map256, map8);
                     CK(cudaEventRecord(h->ev[1], h->stream));
                     h->ev1_recorded = true;
-                    k_compact_granules<<<h->sm_count * 4, 256, 0, h->stream>>>(h->d_bitmap, h->bitmap_words,
-                                                                               h->d_glist, h->glist_cap, h->d_counters);
                     for (int scan_mode = 0; scan_mode < 2; scan_mode++)
                         k_verify_ham<<<h->sm_count * 4, kVerifyThreads, 0, h->stream>>>(
                             p, h->bitmap_words, h->d_glist, h->glist_cap, scan_mode, h->d_out, h->out_cap,
                             h->d_counters);
-                    res->stats.n_launches += 3;
+                    res->stats.n_launches += 2;
                 } else {
                     k_hamming_scan<<<h->sm_count * 8, kHamThreads, 0, h->stream>>>(p, h->d_out, h->out_cap,
                                                                                    h->d_counters);

@@ -29,6 +29,9 @@ struct ScanParams {
     int64_t own_lo;     // anchors owned by this shard: [own_lo, own_hi)
     int64_t own_hi;
     uint32_t *bitmap;   // dirty-granule bitmap, bit g <-> buffer offsets [64g, 64g+64)
+    uint32_t *glist;    // work list of marked granules, appended by whoever flips a bitmap bit 0 -> 1
+    uint32_t glist_cap;
+    uint32_t *counters; // CNT_* slots
     uint64_t *hits;     // dense filter, hit-list mode: confirmed n-gram hits (idx << 8 | n-gram ordinal)
     uint32_t hits_cap;  // 0 = mark granules instead
     int32_t m, k, L, n_ngrams;

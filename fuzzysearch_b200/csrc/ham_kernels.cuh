@@ -188,7 +188,7 @@ k_hamming_count(const ScanParams p, const HamCountParams hp, const __grid_consta
             // near-matches): mark its granules; k_verify_ham re-checks them exactly
             const int64_t grow = tile * kHcThreads + tid;  // buffer row index
             const int64_t pr_lo = 4 * (grow * 32 - Wc + 1) - 3, pr_hi = 4 * (grow * 32 + 31 - Wc + 1);
-            mark_range(p, p.buf_lo + max(pr_lo, (int64_t)0), p.buf_lo + pr_hi);
+            mark_range_inline(p, p.buf_lo + max(pr_lo, (int64_t)0), p.buf_lo + pr_hi);
         }
         __syncthreads();  // everyone is done with stage s
         if (tid == 0 && tile + 2 * (int64_t)gridDim.x < ntiles) issue(tile + 2 * (int64_t)gridDim.x, s);

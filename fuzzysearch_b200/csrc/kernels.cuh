@@ -30,13 +30,56 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
     return r;
 }
 
+// Mark granule g.  The bitmap de-duplicates; the thread that flips the bit 0 -> 1 also appends the
+// granule to the verify kernel's work list (no separate compaction pass over the bitmap).  If the list
+// is full the bit simply stays set and the verify kernel's bitmap sweep picks it up.
+__device__ __forceinline__ void mark_granule(uint32_t *bitmap, uint32_t *glist, uint32_t glist_cap,
+                                             uint32_t *counters, int64_t g) {
+    const uint32_t bit = 1u << (g & 31);
+    const uint32_t old = atomicOr(&bitmap[g >> 5], bit);
+    if (!(old & bit)) {
+        const uint32_t slot = atomicAdd(&counters[CNT_GRAN], 1u);
+        if (slot < glist_cap) glist[slot] = (uint32_t)g;
+    }
+}
+
+// The few scalars marking needs, passed BY VALUE to the out-of-line slow paths (a reference to the
+// kernel's ScanParams would force a local-memory copy of the whole parameter block, and inlining the
+// atomics into the streaming loops upsets their register allocation).
+struct MarkCtx {
+    int64_t buf_lo, own_lo, own_hi;
+    uint32_t *bitmap;
+    uint32_t *glist;
+    uint32_t glist_cap;
+    uint64_t *hits;
+    uint32_t hits_cap;
+    uint32_t *counters;
+};
+
+__device__ __forceinline__ MarkCtx mark_ctx(const ScanParams &p) {
+    return MarkCtx{p.buf_lo, p.own_lo, p.own_hi, p.bitmap, p.glist, p.glist_cap, p.hits, p.hits_cap, p.counters};
+}
+
+// mark the granules covering anchors [lo, hi] (global coords), clipped to the owned range
+__device__ __noinline__ void mark_range_ctx(MarkCtx mc, int64_t lo, int64_t hi) {
+    if (lo < mc.own_lo) lo = mc.own_lo;
+    if (hi > mc.own_hi - 1) hi = mc.own_hi - 1;
+    if (lo > hi) return;
+    int64_t g0 = (lo - mc.buf_lo) >> kGranuleShift, g1 = (hi - mc.buf_lo) >> kGranuleShift;
+    for (int64_t g = g0; g <= g1; g++) mark_granule(mc.bitmap, mc.glist, mc.glist_cap, mc.counters, g);
+}
+
 __device__ __forceinline__ void mark_range(const ScanParams &p, int64_t lo, int64_t hi) {
-    // mark the granules covering anchors [lo, hi] (global coords), clipped to the owned range
+    mark_range_ctx(mark_ctx(p), lo, hi);
+}
+
+// inlined variant for kernels whose register budget is pinned anyway (k_hamming_count)
+__device__ __forceinline__ void mark_range_inline(const ScanParams &p, int64_t lo, int64_t hi) {
     if (lo < p.own_lo) lo = p.own_lo;
     if (hi > p.own_hi - 1) hi = p.own_hi - 1;
     if (lo > hi) return;
     int64_t g0 = (lo - p.buf_lo) >> kGranuleShift, g1 = (hi - p.buf_lo) >> kGranuleShift;
-    for (int64_t g = g0; g <= g1; g++) atomicOr(&p.bitmap[g >> 5], 1u << (g & 31));
+    for (int64_t g = g0; g <= g1; g++) mark_granule(p.bitmap, p.glist, p.glist_cap, p.counters, g);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -148,14 +191,6 @@ __device__ __forceinline__ uint32_t dense_key(uint32_t lo, uint32_t hi) {
 // Slow path of the dense filter, for the whole warp: every flagged lane in turn parks its six words in
 // a per-warp scratch line, then all lanes walk its set bits, rebuild the 8-byte window at that byte
 // offset from the scratch and lane j compares it with n-gram j.
-struct MarkCtx {  // the few scalars mark_range needs, passed by value (a reference to the kernel's
-    int64_t buf_lo, own_lo, own_hi;  // ScanParams would force a local-memory copy of the whole block)
-    uint32_t *bitmap;
-    uint64_t *hits;
-    uint32_t hits_cap;
-    uint32_t *counters;
-};
-
 __device__ __noinline__ void dense_confirm_warp(MarkCtx mc, int n_ngrams, const uint2 *grams, uint32_t *scratch,
                                                 int lane, unsigned flagged, uint32_t acc, uint32_t w0_, uint32_t w1_,
                                                 uint32_t w2_, uint32_t w3_, uint32_t w4_, uint32_t w5_,
@@ -193,8 +228,7 @@ __device__ __noinline__ void dense_confirm_warp(MarkCtx mc, int n_ngrams, const 
                 bool real = false;
                 for (int j = lane; j < n_ngrams; j += 32) real |= (grams[j].x == lo && grams[j].y == hi);
                 if (__ballot_sync(0xFFFFFFFFu, real) != 0 && lane == 0 && owned) {
-                    const int64_t gr = (g - mc.buf_lo) >> kGranuleShift;
-                    atomicOr(&mc.bitmap[gr >> 5], 1u << (gr & 31));
+                    mark_granule(mc.bitmap, mc.glist, mc.glist_cap, mc.counters, (g - mc.buf_lo) >> kGranuleShift);
                 }
             }
         }
@@ -202,7 +236,7 @@ __device__ __noinline__ void dense_confirm_warp(MarkCtx mc, int n_ngrams, const 
 }
 
 __global__ void __launch_bounds__(kFilterThreads)
-k_filter_dense(const ScanParams p, int64_t nvec, int64_t ntiles, uint32_t *counters) {
+k_filter_dense(const ScanParams p, int64_t nvec, int64_t ntiles) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint32_t *tbl = reinterpret_cast<uint32_t *>(smem);                        // [kDenseRows][32 banks]
     uint2 *grams = reinterpret_cast<uint2 *>(smem + (size_t)kDenseRows * 128);  // (lo, hi) per n-gram (<= 255)
@@ -258,7 +292,7 @@ k_filter_dense(const ScanParams p, int64_t nvec, int64_t ntiles, uint32_t *count
             unsigned flagged = __ballot_sync(0xFFFFFFFFu, acc != 0);
             if (flagged) {  // warp-uniform, kept out of line and compact (instruction cache)
                 const int64_t off_warp = (t * kTileVecs + (threadIdx.x - lane) + (int64_t)u * kFilterThreads) * 16;
-                dense_confirm_warp(MarkCtx{p.buf_lo, p.own_lo, p.own_hi, p.bitmap, p.hits, p.hits_cap, counters},
+                dense_confirm_warp(mark_ctx(p),
                                    p.n_ngrams, grams,
                                    scratch + (threadIdx.x >> 5) * 8, lane, flagged, acc, ws[0], ws[1], ws[2], ws[3],
                                    ws[4], ws[5], off_warp, mlo, mhi);
@@ -460,30 +494,11 @@ __device__ void verify_anchor_lev(const ScanParams &p, const uint8_t *sP, const 
     }
 }
 
-// Work distribution.  The marked granules are first compacted into a list (k_compact_granules: one
-// thread per bitmap word, ~8 MB for a 4 GiB haystack) and the verify kernel hands ONE GRANULE TO ONE
-// WARP through an atomic work counter, so clustered matches (the realistic case) spread over the
+// Work distribution.  The filters append every newly marked granule to a work list (mark_granule) and
+// the verify kernel hands ONE GRANULE TO ONE WARP through an atomic work counter, so clustered matches (the realistic case) spread over the
 // whole GPU instead of serialising on the warp that owns their bitmap words.  Each processed granule
 // clears its own bit; if the list overflows (dense candidates, e.g. small alphabets) the bits left
 // set are swept by the bitmap-scanning fallback loop of the same kernel launched in "scan" mode.
-__global__ void __launch_bounds__(256)
-k_compact_granules(const uint32_t *bitmap, uint64_t bitmap_words, uint32_t *glist, uint32_t glist_cap,
-                   uint32_t *counters) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t wi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; wi < bitmap_words; wi += stride) {
-        uint32_t bits = bitmap[wi];
-        if (!bits) continue;
-        const uint32_t n = (uint32_t)__popc(bits);
-        uint32_t slot = atomicAdd(&counters[CNT_GRAN], n);
-        while (bits) {
-            const int bit = __ffs(bits) - 1;
-            bits &= bits - 1;
-            if (slot < glist_cap) glist[slot] = (uint32_t)(wi * 32 + bit);
-            slot++;
-        }
-    }
-}
-
 __device__ __forceinline__ void verify_granule_lev(const ScanParams &p, const uint8_t *sP, uint32_t *sWin,
                                                    int64_t granule, int lane, DpScratch &S, RawRec *out,
                                                    uint32_t cap, uint32_t *counters) {
