@@ -41,6 +41,9 @@ WORKLOADS = {
     "ascii4g_lev_m20_k2": (ASCII, 4 * GiB, 20, "lev", 2),
     "dna4g_ham_m32_k3": (DNA, 4 * GiB, 32, "ham", 3),
     "ascii64m_lev_m20_k2": (ASCII, 64 << 20, 20, "lev", 2),  # quick self-test size
+    # BASELINE.json configs[4]: 1024 patterns |p| in [8,64], k in [1,4] over one 4 GiB haystack; a step is
+    # the whole batch (round 1: one pass per pattern); m and k below are only used for the halo
+    "ascii4g_batch1024": (ASCII, 4 * GiB, 64, "batch", 4),
 }
 
 
@@ -320,6 +323,19 @@ def main():
         init_shard_comm(hs)
     gflag = F.F_GLOBAL if in_library else 0
 
+    batch_pats, batch_ks = [], []
+    if kind == "batch":
+        brng = np.random.default_rng(seed + 99)
+        alpha = np.frombuffer(alphabet, dtype=np.uint8)
+        for i in range(1024):
+            bm, bk = int(brng.integers(8, 65)), int(brng.integers(1, 5))
+            bp = bytes(alpha[brng.integers(0, len(alpha), size=bm)])
+            batch_pats.append(bp)
+            batch_ks.append(bk)
+            for _ in range(8):
+                pos = own_lo + 1000 + int(brng.integers(0, own_hi - own_lo - 2000))
+                hs.write(pos, mutate(brng, bp, alphabet, int(brng.integers(0, bk + 2)), False))
+
     def one_search(h):
         if kind == "lev":
             return h.search_levenshtein(pat, k, gflag)
@@ -329,6 +345,12 @@ def main():
         # one search of this rank's shard (local consolidation on the device); multi-GPU: the per-shard
         # groups are all-gathered by NCCL inside the library, on the search's stream, and merged
         # (--reduce torch: the same reduction through torch.distributed, for comparison)
+        if kind == "batch":
+            results, st = (h or hs).search_levenshtein_batch(batch_pats, batch_ks)
+            nfinal = sum(r.count(F.FINAL) for r in results)
+            for r in results:
+                r.close()
+            return st, nfinal
         res = one_search(h or hs)
         st = res.stats()
         if world > 1 and not in_library:
@@ -372,7 +394,7 @@ def main():
 
     # ---- end to end through the one-shot C-ABI call with pinned HOST buffers -----------------------
     e2e = None
-    if args.e2e_steps > 0:
+    if args.e2e_steps > 0 and kind != "batch":
         pinned = F.PinnedBuffer(bhi - blo)
         chunk = 256 << 20
         for off in range(0, bhi - blo, chunk):  # host copy of the shard (setup, untimed)
@@ -430,7 +452,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
             "matches_per_step": int(nfinal), "wall_ms_per_step": wall_ms / args.steps,
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_filter_sampled" if kind == "lev" else "k_hamming_count",
+            "roofline": {"bound": "hbm", "kernel": {"lev": "k_filter_sampled", "ham": "k_hamming_count"}.get(kind, "all scans of the batch"),
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "kernel_ms": filt,
                          "algorithmic_bytes_per_launch": bhi - blo,
@@ -438,7 +460,10 @@ def main():
             "clocks": clocks}
     if e2e is not None:
         line["e2e"] = e2e
-    if not args.no_cpu_baseline and world == 1 and reference_available():
+    if kind == "batch":
+        line["config"]["patterns"] = 1024
+        line["pattern_GB_per_s"] = value * 1024
+    if not args.no_cpu_baseline and world == 1 and reference_available() and kind != "batch":
         # run in a fresh process: the reference arm forks worker processes, which must not inherit
         # this process's CUDA context
         def ref_run(extra):

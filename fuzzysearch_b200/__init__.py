@@ -10,7 +10,7 @@ Every search runs as hand-written CUDA kernels behind the C-ABI of libfuzzb200.s
 """
 __version__ = "0.1.0"
 
-__all__ = ["find_near_matches", "find_near_matches_in_file", "Match", "LevenshteinSearchParams",
+__all__ = ["find_near_matches", "find_near_matches_batch", "find_near_matches_in_file", "Match", "LevenshteinSearchParams",
            "DeviceSequence", "ExactSearch", "SubstitutionsOnlySearch", "LevenshteinSearch",
            "GenericSearch", "choose_search_class"]
 
@@ -30,6 +30,33 @@ def find_near_matches(subsequence, sequence, max_substitutions=None, max_inserti
     search_class = choose_search_class(search_params)
     matches = search_class.search(subsequence, sequence, search_params)
     return search_class.consolidate_matches(matches)
+
+
+def find_near_matches_batch(subsequences, sequence, max_l_dist):
+    """Many patterns over one sequence (uploaded once): -> list of find_near_matches(...) results.
+
+    `max_l_dist` is one int or one per pattern.  Equivalent to
+    ``[find_near_matches(p, sequence, max_l_dist=k) for p, k in zip(subsequences, ks)]``."""
+    from . import _native
+    from .search import _coerce, _prepare
+    subsequences = list(subsequences)
+    ks = [max_l_dist] * len(subsequences) if isinstance(max_l_dist, int) else list(max_l_dist)
+    if len(ks) != len(subsequences):
+        raise ValueError("one max_l_dist per subsequence expected")
+    for p, k in zip(subsequences, ks):
+        LevenshteinSearchParams(None, None, None, k)  # same validation as find_near_matches
+        if len(p) == 0:
+            raise ValueError("Given subsequence is empty!")
+    if not subsequences:
+        return []
+    _, hay, slicer, _ = _prepare(subsequences[0], sequence)
+    results, _ = hay.search_levenshtein_batch([_coerce(p)[0] for p in subsequences], ks)
+    out = []
+    for res in results:
+        s, e, d = res.arrays(_native.FINAL)
+        out.append([Match(a, b, c, matched=slicer(a, b)) for a, b, c in zip(s.tolist(), e.tolist(), d.tolist())])
+        res.close()
+    return out
 
 
 def choose_search_class(search_params):

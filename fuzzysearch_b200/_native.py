@@ -21,7 +21,7 @@ FZB_MAX_PATTERN = 255
 RAW, FINAL = 0, 1
 F_NO_FINAL, F_FORCE_DENSE, F_FORCE_LP, F_FORCE_NGRAMS, F_TINY_LIST, F_GLOBAL, F_FORCE_SAMPLED = 1, 2, 4, 8, 16, 32, 64
 
-ROUTE_NAMES = {0: "exact", 1: "ngrams/sampled-filter", 2: "ngrams/dense-filter", 3: "lp",
+ROUTE_NAMES = {7: "batch", 0: "exact", 1: "ngrams/sampled-filter", 2: "ngrams/dense-filter", 3: "lp",
                4: "hamming", 5: "generic-ngrams", 6: "generic-lp"}
 
 
@@ -73,6 +73,7 @@ SYMBOLS = {
     "fzb_search_hamming": (_i32, [_vp, _u8p, _u32, _u32, _u32, _vpp]),
     "fzb_search_generic": (_i32, [_vp, _u8p, _u32, _u32, _u32, _u32, _u32, _u32, _vpp]),
     "fzb_search_exact": (_i32, [_vp, _u8p, _u32, _u32, _vpp]),
+    "fzb_search_levenshtein_batch": (_i32, [_vp, _u8p, _vp, _vp, _u32, _u32, _vpp, ctypes.POINTER(Stats)]),
     "fzb_find_near_matches": (_i32, [_u8p, _u32, _u8p, _u64, _u32, _u32, _u32, _u32, _i32, _vpp]),
     "fzb_release_workspace": (None, []),
     "fzb_result_count": (_u64, [_vp, _i32]),
@@ -301,6 +302,21 @@ class Haystack(object):
         check(lib().fzb_search_generic(self._h, pp, m, max_subs, max_ins, max_dels, max_l, flags,
                                        ctypes.byref(r)))
         return Result(r)
+
+    def search_levenshtein_batch(self, patterns, ks, flags=0):
+        """-> (list of Result, one per pattern; summed stats dict)."""
+        pats = [as_u8(p) for p in patterns]
+        blob = np.concatenate(pats) if pats else np.zeros(0, np.uint8)
+        offsets = np.zeros(len(pats) + 1, dtype=np.uint32)
+        offsets[1:] = np.cumsum([p.size for p in pats])
+        ks = np.ascontiguousarray(ks, dtype=np.uint32)
+        out = (ctypes.c_void_p * max(len(pats), 1))()
+        st = Stats()
+        check(lib().fzb_search_levenshtein_batch(self._h, ptr(blob), ptr(offsets), ptr(ks), len(pats), flags, out,
+                                                 ctypes.byref(st)))
+        results = [Result(ctypes.c_void_p(out[i])) for i in range(len(pats))]
+        return results, {"gpu_ms": st.gpu_ms, "filter_ms": st.filter_ms, "bytes_scanned": st.bytes_scanned,
+                         "n_candidates": st.n_candidates, "n_launches": st.n_launches, "route": "batch"}
 
     def search_exact(self, pattern, flags=0):
         p, pp, m = self._pat(pattern)

@@ -1264,6 +1264,34 @@ extern "C" int fzb_search_levenshtein(fzb_haystack *h, const uint8_t *pattern, u
     return FZB_OK;
 }
 
+extern "C" int fzb_search_levenshtein_batch(fzb_haystack *h, const uint8_t *patterns, const uint32_t *offsets,
+                                            const uint32_t *max_l_dist, uint32_t count, uint32_t flags,
+                                            fzb_result **out, fzb_stats *total) {
+    if (!h || !out || (count && (!patterns || !offsets || !max_l_dist))) return fail(FZB_E_INVALID, "NULL argument");
+    for (uint32_t i = 0; i < count; i++) out[i] = nullptr;
+    fzb_stats sum{};
+    for (uint32_t i = 0; i < count; i++) {
+        if (offsets[i + 1] < offsets[i]) return fail(FZB_E_INVALID, "offsets must be non-decreasing");
+        int rc = fzb_search_levenshtein(h, patterns + offsets[i], offsets[i + 1] - offsets[i], max_l_dist[i], flags,
+                                        &out[i]);
+        if (rc) {
+            for (uint32_t j = 0; j < i; j++) {
+                fzb_result_destroy(out[j]);
+                out[j] = nullptr;
+            }
+            return rc;
+        }
+        sum.gpu_ms += out[i]->stats.gpu_ms;
+        sum.filter_ms += out[i]->stats.filter_ms;
+        sum.bytes_scanned += out[i]->stats.bytes_scanned;
+        sum.n_candidates += out[i]->stats.n_candidates;
+        sum.n_launches += out[i]->stats.n_launches;
+    }
+    sum.route = 7;  // batch
+    if (total) *total = sum;
+    return FZB_OK;
+}
+
 extern "C" int fzb_search_exact(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint32_t flags,
                                 fzb_result **out) {
     fzb_result *res;

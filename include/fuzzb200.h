@@ -64,6 +64,7 @@ extern "C" {
                                  right behind the kernels (needs fzb_haystack_comm_init on every rank;
                                  collective: every rank must issue the same searches in the same order) */
 
+struct fzb_stats_s;
 typedef struct fzb_haystack fzb_haystack; /* a device-resident sequence (or one shard of it) */
 typedef struct fzb_result fzb_result;     /* the matches of one search */
 
@@ -169,6 +170,18 @@ int fzb_search_generic(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint
                        uint32_t max_ins, uint32_t max_dels, uint32_t max_l_dist, uint32_t flags,
                        fzb_result **out);
 
+/*
+ * Batch of Levenshtein searches over ONE resident haystack (BASELINE.json configs[4]): `count` patterns
+ * concatenated in `patterns` (pattern i = patterns[offsets[i] : offsets[i+1]]), each with its own
+ * max_l_dist[i].  out[i] receives an ordinary fzb_result for pattern i (the caller destroys each).
+ * Round 1: the patterns are searched one after another on the handle's stream (the haystack is read
+ * once per pattern); the single-pass multi-pattern filter is described in DESIGN.md section 8.
+ * `total` (optional) sums the statistics.  On error nothing is returned.
+ */
+int fzb_search_levenshtein_batch(fzb_haystack *h, const uint8_t *patterns, const uint32_t *offsets,
+                                 const uint32_t *max_l_dist, uint32_t count, uint32_t flags,
+                                 fzb_result **out, struct fzb_stats_s *total);
+
 /* ExactSearch.search (search_exact.py:80-85): all (overlapping) occurrences. FINAL == RAW. */
 int fzb_search_exact(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint32_t flags,
                      fzb_result **out);
@@ -200,7 +213,7 @@ int fzb_result_hulls(const fzb_result *r, int64_t *hull_start, int64_t *hull_end
  * number of groups (which may exceed max_rows) or a negative error. */
 int64_t fzb_result_group_rows(const fzb_result *r, int64_t *rows, uint64_t max_rows);
 
-typedef struct {
+typedef struct fzb_stats_s {
     double gpu_ms;          /* CUDA-event time of all kernels of the search */
     double filter_ms;       /* ... of the haystack scan (filter) kernel alone */
     uint64_t bytes_scanned; /* haystack bytes the scan kernel read (algorithmic bytes) */
