@@ -160,6 +160,7 @@ struct fzb_result {
     bool fused_issued = false;
     std::vector<int64_t> gathered;  // group rows of all shards (rank major)
     std::vector<uint64_t> gathered_counts;  // rows per shard
+    size_t gather_slot_rows = 0;
     std::vector<RawRec> gfin;
     int raw_order = 0;         // 0 generation (ngram, idx) / 1 canonical / 2 generic n-grams (5 fields)
     void order_raw();
@@ -841,13 +842,7 @@ static int run_emitting(fzb_haystack *h, fzb_result *res, F enqueue, PostPlan po
                 const int64_t *base = h->h_recv + (size_t)r * slot_rows * kFinCols;
                 if (!base[1]) res->gather_valid = false;
             }
-            res->gathered_counts.clear();
-            if (res->gather_valid)
-                for (int r = 0; r < h->world; r++) {
-                    const int64_t *base = h->h_recv + (size_t)r * slot_rows * kFinCols;
-                    res->gathered.insert(res->gathered.end(), base + kFinCols, base + kFinCols + (size_t)base[0] * kFinCols);
-                    res->gathered_counts.push_back((uint64_t)base[0]);
-                }
+            res->gather_slot_rows = slot_rows;  // the rows stay in h->h_recv until finish_global merges them
         }
         if (n > h->out_cap) {  // output buffer too small: grow and redo the whole attempt
             rc = ensure_out_cap(h, n);
@@ -1180,8 +1175,15 @@ static int finish_global(fzb_haystack *h, fzb_result *res) {
     std::vector<int64_t> all;
     std::vector<uint64_t> counts;
     if (res->fused_issued && res->gather_valid) {
-        all.swap(res->gathered);
-        counts.swap(res->gathered_counts);
+        // merge straight out of the pinned receive buffer (one run per rank)
+        std::vector<std::pair<const int64_t *, uint64_t>> runs;
+        for (int r = 0; r < h->world; r++) {
+            const int64_t *base = h->h_recv + (size_t)r * res->gather_slot_rows * kFinCols;
+            runs.push_back({base + kFinCols, (uint64_t)base[0]});
+        }
+        merge_group_runs(runs, res->gfin);
+        res->has_global = true;
+        return FZB_OK;
     } else {  // staged: the local result is complete now, whatever it took
         if (res->final_is_raw) res->order_raw();
         const std::vector<RawRec> &v = res->final_is_raw ? res->raw : res->fin;
