@@ -26,14 +26,14 @@ __device__ __forceinline__ bool lp_push(uint32_t *list, int &n, int cap, int j, 
 }
 
 // Simulates the candidates whose start is `start` (global).  Returns false on list overflow.
-__device__ bool sim_lev_lp(const ScanParams &p, const uint8_t *sP, int64_t start, uint32_t *A, uint32_t *B,
-                           int cap, RawRec *out, uint32_t ocap, uint32_t *counters) {
+// H[g] must be the haystack byte at global position g (global memory or a staged tile).
+__device__ bool sim_lev_lp(const ScanParams &p, const uint8_t *sP, const uint8_t *H, int64_t start, uint32_t *A,
+                           uint32_t *B, int cap, RawRec *out, uint32_t ocap, uint32_t *counters) {
     const int m = p.m, k = p.k;
     const int64_t N = p.N;
-    const uint8_t *H = p.H - p.buf_lo;  // index with global positions
     int nA = 0;
     {
-        const uint8_t ch = __ldg(H + start);
+        const uint8_t ch = H[start];
         // make_char2first_subseq_index (levenshtein.py:44-49): first index of ch in P[:k+1]
         int j0 = -1;
         const int lim = min(k, m - 1);
@@ -52,7 +52,7 @@ __device__ bool sim_lev_lp(const ScanParams &p, const uint8_t *sP, int64_t start
     }
     int64_t i = start + 1;
     for (; i < N && nA > 0; i++) {  // :73
-        const uint8_t ch = __ldg(H + i);
+        const uint8_t ch = H[i];
         int nB = 0;
         for (int c = 0; c < nA; c++) {  // :83
             const int j = (int)(A[c] & 0xFFFFu), d = (int)(A[c] >> 16);
@@ -97,11 +97,28 @@ __device__ bool sim_lev_lp(const ScanParams &p, const uint8_t *sP, int64_t start
 
 constexpr int kLpThreads = 128;
 
+// One CTA works on tiles of kLpTile start positions: the tile (+ the m+k bytes a candidate can run
+// ahead) is staged in shared memory with coalesced loads; phase 1 tests every start against the
+// first-character table (levenshtein.py:44-49,75-80: only a character of P[:k+1] opens a candidate --
+// ~5 % of the starts on text) and queues the survivors; phase 2 hands the queued starts to the threads
+// one by one, so the expensive candidate simulation runs with every lane busy.
+constexpr int kLpTile = 8192;
+constexpr int kLpHalo = 2 * kMaxPattern + 16;
+
 __global__ void __launch_bounds__(kLpThreads)
 k_lev_lp(const ScanParams p, uint32_t *scratch, int cap, RawRec *out, uint32_t ocap, uint32_t *counters) {
     __shared__ uint8_t sP[256];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) sP[i] = p.P[i];
+    __shared__ int16_t sFirst[256];
+    __shared__ __align__(16) uint8_t sH[kLpTile + kLpHalo];
+    __shared__ uint16_t sQueue[kLpTile];
+    __shared__ uint32_t sQn;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        sP[i] = p.P[i];
+        sFirst[i] = -1;
+    }
     __syncthreads();
+    if (threadIdx.x == 0)  // make_char2first_subseq_index: first index of each char within P[:k+1]
+        for (int j = min(p.k, p.m - 1); j >= 0; j--) sFirst[p.P[j]] = (int16_t)j;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     uint32_t *A = scratch + tid * 2 * (int64_t)cap, *B = A + cap;
@@ -111,8 +128,25 @@ k_lev_lp(const ScanParams p, uint32_t *scratch, int cap, RawRec *out, uint32_t o
         return;
     }
     const int64_t hi = min(p.own_hi, p.N);
-    for (int64_t s = p.own_lo + tid; s < hi; s += stride)
-        if (!sim_lev_lp(p, sP, s, A, B, cap, out, ocap, counters)) atomicExch(&counters[CNT_OVERFLOW], 1u);
+    const int ahead = p.m + p.k + 1;
+    for (int64_t tile_lo = p.own_lo + (int64_t)blockIdx.x * kLpTile; tile_lo < hi; tile_lo += (int64_t)gridDim.x * kLpTile) {
+        const int tile_n = (int)min((int64_t)kLpTile, hi - tile_lo);
+        const int64_t load_hi = min(min(tile_lo + tile_n + ahead, p.N), p.buf_lo + p.buf_len);
+        const int nwords = (int)((load_hi - tile_lo + 3) >> 2);  // tile_lo is a multiple of 16: aligned words
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(p.H + (tile_lo - p.buf_lo));
+        __syncthreads();  // previous tile fully consumed (also orders sFirst on the first pass)
+        for (int w = threadIdx.x; w < nwords; w += blockDim.x) reinterpret_cast<uint32_t *>(sH)[w] = __ldg(src + w);
+        if (threadIdx.x == 0) sQn = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < tile_n; i += blockDim.x)
+            if (sFirst[sH[i]] >= 0) sQueue[atomicAdd(&sQn, 1u)] = (uint16_t)i;
+        __syncthreads();
+        const uint32_t qn = sQn;
+        const uint8_t *W = sH - tile_lo;  // W[g]: byte at global position g
+        for (uint32_t q = threadIdx.x; q < qn; q += blockDim.x)
+            if (!sim_lev_lp(p, sP, W, tile_lo + sQueue[q], A, B, cap, out, ocap, counters))
+                atomicExch(&counters[CNT_OVERFLOW], 1u);
+    }
 }
 
 // ---- generic NFA ---------------------------------------------------------------------------------
