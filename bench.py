@@ -40,6 +40,7 @@ WORKLOADS = {
     # name: (alphabet, bytes per GPU, m, search kind, k)
     "ascii4g_lev_m20_k2": (ASCII, 4 * GiB, 20, "lev", 2),
     "dna4g_ham_m32_k3": (DNA, 4 * GiB, 32, "ham", 3),
+    "dna4g_lev_m20_k2": (DNA, 4 * GiB, 20, "lev", 2),       # configs[0]'s corpus at scale (dense filter route)
     "ascii64m_lev_m20_k2": (ASCII, 64 << 20, 20, "lev", 2),  # quick self-test size
     # BASELINE.json configs[4]: 1024 patterns |p| in [8,64], k in [1,4] over one 4 GiB haystack; a step is
     # the whole batch (round 1: one pass per pattern); m and k below are only used for the halo
@@ -452,11 +453,12 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
             "matches_per_step": int(nfinal), "wall_ms_per_step": wall_ms / args.steps,
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": {"lev": "k_filter_sampled", "ham": "k_hamming_count"}.get(kind, "all scans of the batch"),
+            "roofline": {"bound": "hbm", "kernel": ({"lev": "k_filter_sampled" if len(alphabet) > 16 else "k_filter_dense",
+                                     "ham": "k_hamming_count"}.get(kind, "all scans of the batch")),
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "kernel_ms": filt,
                          "algorithmic_bytes_per_launch": bhi - blo,
-                         "traffic": (traffic or {}).get("dram_bytes_per_launch") if kind == "lev" else None},
+                         "traffic": (traffic or {}).get("dram_bytes_per_launch") if (kind == "lev" and len(alphabet) > 16) else None},
             "clocks": clocks}
     if e2e is not None:
         line["e2e"] = e2e

@@ -26,6 +26,18 @@ def test_library_exports_every_declared_symbol():
     assert lib.fzb_version() == 100
 
 
+def test_header_is_plain_c(tmp_path):
+    """include/fuzzb200.h must be consumable from C (the boundary is a C-ABI)."""
+    import subprocess
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "fuzzb200.h"\nint main(void) { fzb_stats s; (void)s; return fzb_version() == FZB_VERSION ? 0 : 1; }\n')
+    exe = tmp_path / "use_header"
+    lib_dir = os.path.join(ROOT, "fuzzysearch_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                           "-o", str(exe), "-L", lib_dir, "-l:libfuzzb200.so", "-Wl,-rpath," + lib_dir])
+    assert subprocess.call([str(exe)]) == 0
+
+
 def test_match_semantics():
     # common.py:15-32: eq/hash/order on (start,end,dist); matched excluded; frozen
     a, b = Match(1, 3, 0, matched=b"xy"), Match(1, 3, 0, matched=b"zz")
