@@ -932,7 +932,10 @@ static void sort_canonical(std::vector<RawRec> &v) {
 static int set_filter_attrs(size_t smem) {
     // per device: the attribute belongs to the function on the current device
     CK(cudaFuncSetAttribute(k_filter_sampled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaFuncSetAttribute(k_filter_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDenseSmem));
+    CK(cudaFuncSetAttribute(k_filter_dense<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDenseSmem));
+    CK(cudaFuncSetAttribute(k_filter_dense<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDenseSmem));
+    CK(cudaFuncSetAttribute(k_filter_dense<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDenseSmem));
+    CK(cudaFuncSetAttribute(k_filter_dense<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDenseSmem));
     return FZB_OK;
 }
 
@@ -992,8 +995,14 @@ static int enqueue_filter(fzb_haystack *h, const ScanParams &p, bool sampled, fz
         int grid = (int)std::min<int64_t>(ntiles, (int64_t)h->sm_count * (sampled ? 4 : 6));
         if (sampled)
             k_filter_sampled<<<grid, kFilterThreads, kFilterSmem, h->stream>>>(p, nvec, ntiles);
+        else if (p.q < 4)
+            k_filter_dense<0><<<grid, kFilterThreads, kDenseSmem, h->stream>>>(p, nvec, ntiles);
+        else if (p.q == 4)
+            k_filter_dense<1><<<grid, kFilterThreads, kDenseSmem, h->stream>>>(p, nvec, ntiles);
+        else if (p.q < 8)
+            k_filter_dense<2><<<grid, kFilterThreads, kDenseSmem, h->stream>>>(p, nvec, ntiles);
         else
-            k_filter_dense<<<grid, kFilterThreads, kDenseSmem, h->stream>>>(p, nvec, ntiles);
+            k_filter_dense<3><<<grid, kFilterThreads, kDenseSmem, h->stream>>>(p, nvec, ntiles);
         CK(cudaGetLastError());
         res->stats.n_launches++;
     }

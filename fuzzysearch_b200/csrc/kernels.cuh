@@ -235,6 +235,9 @@ __device__ __noinline__ void dense_confirm_warp(MarkCtx mc, int n_ngrams, const 
     }
 }
 
+// MODE: 0 = q < 4 (lo masked), 1 = q == 4, 2 = 4 < q < 8 (hi masked), 3 = q == 8 -- compile-time so that the
+// short-n-gram cases do not pay for the second funnel shift, the masks and the second multiply.
+template <int MODE>
 __global__ void __launch_bounds__(kFilterThreads)
 k_filter_dense(const ScanParams p, int64_t nvec, int64_t ntiles) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -282,9 +285,16 @@ k_filter_dense(const ScanParams p, int64_t nvec, int64_t ntiles) {
             uint32_t acc = 0;
 #pragma unroll
             for (int b = 0; b < 16; b++) {
-                const uint32_t lo = __funnelshift_r(ws[b >> 2], ws[(b >> 2) + 1], 8 * (b & 3)) & mlo;
-                const uint32_t hi = __funnelshift_r(ws[(b >> 2) + 1], ws[(b >> 2) + 2], 8 * (b & 3)) & mhi;
-                const uint32_t key = dense_key(lo, hi);
+                uint32_t lo = __funnelshift_r(ws[b >> 2], ws[(b >> 2) + 1], 8 * (b & 3));
+                if (MODE == 0) lo &= mlo;
+                uint32_t key;
+                if (MODE <= 1) {
+                    key = (lo * kHashMul) >> (32 - kDenseBits);  // == dense_key(lo, 0)
+                } else {
+                    uint32_t hi = __funnelshift_r(ws[(b >> 2) + 1], ws[(b >> 2) + 2], 8 * (b & 3));
+                    if (MODE == 2) hi &= mhi;
+                    key = dense_key(lo, hi);
+                }
                 uint32_t row;
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(row) : "r"(my_bank + ((key >> 5) << 7)));
                 acc = acc * 2u + (__funnelshift_r(row, 0u, key) & 1u);  // bit (key & 31) of the row
