@@ -992,7 +992,16 @@ static int enqueue_filter(fzb_haystack *h, const ScanParams &p, bool sampled, fz
     const int64_t nvec = (int64_t)(round_up(h->buf_len, 16) / 16);
     const int64_t ntiles = (nvec + kTileVecs - 1) / kTileVecs;
     if (ntiles > 0) {
-        int grid = (int)std::min<int64_t>(ntiles, (int64_t)h->sm_count * (sampled ? 4 : 6));
+        int per_sm = 4;
+        if (!sampled) {  // persistent grid = exactly the resident CTAs of the chosen instantiation
+            const void *fn = p.q < 4    ? (const void *)k_filter_dense<0>
+                             : p.q == 4 ? (const void *)k_filter_dense<1>
+                             : p.q < 8  ? (const void *)k_filter_dense<2>
+                                        : (const void *)k_filter_dense<3>;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kFilterThreads, kDenseSmem));
+            per_sm = std::max(per_sm, 1);
+        }
+        int grid = (int)std::min<int64_t>(ntiles, (int64_t)h->sm_count * per_sm);
         if (sampled)
             k_filter_sampled<<<grid, kFilterThreads, kFilterSmem, h->stream>>>(p, nvec, ntiles);
         else if (p.q < 4)

@@ -181,11 +181,27 @@ k_filter_sampled(const ScanParams p, int64_t nvec, int64_t ntiles) {
 // ------------------------------------------------------------------------------------------------
 constexpr int kDenseBits = 13;                       // 8 Kibit table ...
 constexpr int kDenseRows = (1 << kDenseBits) / 32;   // ... = 256 rows of 32 bits, one copy per bank
-constexpr size_t kDenseSmem = (size_t)kDenseRows * 128 + 256 * 8 + 8 * 32;  // 32 KiB + n-gram windows + scratch
+constexpr int kDenseWarpScratch = 8 + 2 + 64;      // words per warp: 6-word window, count, 32 buffered hits (u64)
+constexpr size_t kDenseSmem = (size_t)kDenseRows * 128 + 256 * 8 + 8 * kDenseWarpScratch * 4;  // 32 KiB + windows + scratch
 constexpr uint32_t kHashMul2 = 0x85EBCA77u;
 
 __device__ __forceinline__ uint32_t dense_key(uint32_t lo, uint32_t hi) {
     return (lo * kHashMul + hi * kHashMul2) >> (32 - kDenseBits);
+}
+
+// Flush the warp's buffered hits to the global hit list (one atomicAdd for all of them).
+__device__ __forceinline__ void dense_flush_hits(const MarkCtx &mc, uint32_t *scratch, int lane) {
+    __syncwarp();
+    const uint32_t n = scratch[8];
+    if (n == 0) return;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&mc.counters[CNT_HITS], n);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    const uint64_t *buf = reinterpret_cast<const uint64_t *>(scratch + 10);
+    if ((uint32_t)lane < n && base + lane < mc.hits_cap) mc.hits[base + lane] = buf[lane];
+    __syncwarp();
+    if (lane == 0) scratch[8] = 0;
+    __syncwarp();
 }
 
 // Slow path of the dense filter, for the whole warp: every flagged lane in turn parks its six words in
@@ -219,11 +235,25 @@ __device__ __noinline__ void dense_confirm_warp(MarkCtx mc, int n_ngrams, const 
             const int64_t g = mc.buf_lo + off_warp + (int64_t)src * 16 + b;
             const bool owned = g >= mc.own_lo && g < mc.own_hi;
             if (mc.hits_cap) {  // hit-list mode: one entry per (n-gram, position); verified lane-parallel later
-                for (int j = lane; j < n_ngrams; j += 32)
-                    if (owned && grams[j].x == lo && grams[j].y == hi) {
-                        const uint32_t slot = atomicAdd(&mc.counters[CNT_HITS], 1u);
-                        if (slot < mc.hits_cap) mc.hits[slot] = ((uint64_t)g << 8) | (uint64_t)j;
+                // hits are buffered per warp in shared memory and flushed 24+ at a time: one global
+                // atomic per flush instead of one per hit (millions of hits on low-entropy data)
+                uint32_t &cnt = scratch[8];
+                uint64_t *buf = reinterpret_cast<uint64_t *>(scratch + 10);
+                for (int j0 = 0; j0 < n_ngrams; j0 += 32) {
+                    const int j = j0 + lane;
+                    const bool mt = owned && j < n_ngrams && grams[j].x == lo && grams[j].y == hi;
+                    const unsigned bm = __ballot_sync(0xFFFFFFFFu, mt);
+                    if (!bm) continue;
+                    uint32_t c0 = cnt;
+                    if (c0 + __popc(bm) > 32) {  // make room first
+                        dense_flush_hits(mc, scratch, lane);
+                        c0 = 0;
                     }
+                    if (mt) buf[c0 + __popc(bm & ((1u << lane) - 1u))] = ((uint64_t)g << 8) | (uint64_t)j;
+                    __syncwarp();
+                    if (lane == 0) cnt = c0 + __popc(bm);
+                    __syncwarp();
+                }
             } else {
                 bool real = false;
                 for (int j = lane; j < n_ngrams; j += 32) real |= (grams[j].x == lo && grams[j].y == hi);
@@ -233,6 +263,7 @@ __device__ __noinline__ void dense_confirm_warp(MarkCtx mc, int n_ngrams, const 
             }
         }
     }
+    if (mc.hits_cap && scratch[8] >= 24) dense_flush_hits(mc, scratch, lane);
 }
 
 // MODE: 0 = q < 4 (lo masked), 1 = q == 4, 2 = 4 < q < 8 (hi masked), 3 = q == 8 -- compile-time so that the
@@ -243,7 +274,9 @@ k_filter_dense(const ScanParams p, int64_t nvec, int64_t ntiles) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint32_t *tbl = reinterpret_cast<uint32_t *>(smem);                        // [kDenseRows][32 banks]
     uint2 *grams = reinterpret_cast<uint2 *>(smem + (size_t)kDenseRows * 128);  // (lo, hi) per n-gram (<= 255)
-    uint32_t *scratch = reinterpret_cast<uint32_t *>(smem + (size_t)kDenseRows * 128 + 256 * 8);  // 8 words per warp
+    uint32_t *scratch = reinterpret_cast<uint32_t *>(smem + (size_t)kDenseRows * 128 + 256 * 8) +
+                        (threadIdx.x >> 5) * kDenseWarpScratch;  // this warp's window / hit buffer
+    if ((threadIdx.x & 31) == 0) scratch[8] = 0;
     for (int i = threadIdx.x; i < kDenseRows * 32 / 4; i += blockDim.x)
         reinterpret_cast<uint4 *>(tbl)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
@@ -269,17 +302,27 @@ k_filter_dense(const ScanParams p, int64_t nvec, int64_t ntiles) {
     const uint4 *base = reinterpret_cast<const uint4 *>(p.H);
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int64_t v0 = t * kTileVecs + threadIdx.x;
-#pragma unroll 2
-        for (int u = 0; u < kFilterUnroll; u++) {
-            const int64_t v = v0 + (int64_t)u * kFilterThreads;
-            const bool live = v < nvec;
-            uint4 d = live ? ldg_stream(base + v) : make_uint4(0, 0, 0, 0);
-            // the next 8 bytes: the neighbour lane has them; the last lane reads them itself
+        // two loads in flight per thread (memory-level parallelism), then the per-position work
+#pragma unroll 1
+        for (int uh = 0; uh < kFilterUnroll; uh += 2) {
+        uint4 dd[2];
+        uint2 nn[2];
+#pragma unroll
+        for (int u2 = 0; u2 < 2; u2++) {
+            const int64_t v = v0 + (int64_t)(uh + u2) * kFilterThreads;
+            dd[u2] = (v < nvec) ? ldg_stream(base + v) : make_uint4(0, 0, 0, 0);
+            nn[u2] = make_uint2(0, 0);
+            // the 8 bytes after my 16: the neighbour lane has them, the last lane reads them itself
+            if (lane == 31 && v < nvec) nn[u2] = __ldg(reinterpret_cast<const uint2 *>(base + v + 1));  // padded buffer
+        }
+#pragma unroll
+        for (int u2 = 0; u2 < 2; u2++) {
+            const int u = uh + u2;
+            const uint4 d = dd[u2];
             uint32_t n0 = __shfl_down_sync(0xFFFFFFFFu, d.x, 1), n1 = __shfl_down_sync(0xFFFFFFFFu, d.y, 1);
-            if (lane == 31 && live) {  // the buffer is padded: v + 1 is always readable
-                const uint2 nx = __ldg(reinterpret_cast<const uint2 *>(base + v + 1));
-                n0 = nx.x;
-                n1 = nx.y;
+            if (lane == 31) {
+                n0 = nn[u2].x;
+                n1 = nn[u2].y;
             }
             const uint32_t ws[6] = {d.x, d.y, d.z, d.w, n0, n1};
             uint32_t acc = 0;
@@ -304,11 +347,13 @@ k_filter_dense(const ScanParams p, int64_t nvec, int64_t ntiles) {
                 const int64_t off_warp = (t * kTileVecs + (threadIdx.x - lane) + (int64_t)u * kFilterThreads) * 16;
                 dense_confirm_warp(mark_ctx(p),
                                    p.n_ngrams, grams,
-                                   scratch + (threadIdx.x >> 5) * 8, lane, flagged, acc, ws[0], ws[1], ws[2], ws[3],
+                                   scratch, lane, flagged, acc, ws[0], ws[1], ws[2], ws[3],
                                    ws[4], ws[5], off_warp, mlo, mhi);
             }
         }
+        }
     }
+    if (p.hits_cap) dense_flush_hits(mark_ctx(p), scratch, lane);  // what is still buffered
 }
 
 // ------------------------------------------------------------------------------------------------
