@@ -357,8 +357,8 @@ k_filter_dense(const ScanParams p, int64_t nvec, int64_t ntiles) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Expansion DP -- literal device restatement of levenshtein_ngram.py:8-143 (see oracle/fzoracle.c
-// for the same statements on the CPU).  `sub` lives in shared memory, `seq` in global memory; both
+// Expansion DP -- literal device restatement of levenshtein_ngram.py:8-143 (the CPU test oracle restates
+// the same statements independently).  `sub` lives in shared memory, `seq` in global memory; both
 // are walked with a stride of +1 (right expansion) or -1 (left expansion, reversed slices of
 // levenshtein_ngram.py:186-188).  Returns true and (dist,len), or false for (None, None).
 // ------------------------------------------------------------------------------------------------

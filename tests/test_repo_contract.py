@@ -1,0 +1,44 @@
+"""Repository-level contracts checked on the CPU: the product never touches the oracle, the bench's
+reference arm prints a well-formed line, the build hook works."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "fuzzysearch_b200")
+    offenders = []
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                if re.search(r"^\s*(import|from)\s+oracle\b|fzoracle|libfzoracle|oracle/_ref", text, re.M):
+                    offenders.append(os.path.join(dirpath, f))
+    assert not offenders, offenders
+    header = open(os.path.join(ROOT, "include", "fuzzb200.h")).read()
+    assert "oracle" not in header
+
+
+def test_reference_arm_prints_the_contract_line():
+    if not os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "fuzzysearch")):
+        import pytest
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload",
+                          "ascii64m_lev_m20_k2", "--steps", "1", "--warmup", "0", "--cpu-sample-mib", "16",
+                          "--ref-cores", "2"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "GB/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] == 2
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    assert line["config"]["workload"] == "ascii64m_lev_m20_k2" and line["metric"] == "haystack_GB_per_s_scanned"
+
+
+def test_graft_entry_exposes_build_and_smoke():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as g
+    assert callable(g.build) and callable(g.smoke)
