@@ -461,11 +461,133 @@ __device__ bool expand_long(const uint8_t *sub, int sublen, const uint8_t *seq, 
     return false;
 }
 
+// Register-resident variants for sub-sequences of at most kRegSub characters (the common case: the
+// expansions of a 20-byte pattern are 2..14 characters long).  Same statements as above, but the DP
+// row lives in registers (fully unrolled, predicated on j < sublen) instead of local memory, whose
+// store->load round trip per cell dominated the verify kernel.
+constexpr int kRegSub = 16;
+
+template <int DIR>
+__device__ bool expand_short_reg(const uint8_t *sub, int sublen, const uint8_t *seq, int seqlen, int max_l, int &dist,
+                                 int &len) {
+    if (sublen == 0) {
+        dist = 0;
+        len = 0;
+        return true;
+    }
+    int sc[kRegSub];
+    uint8_t pc[kRegSub];
+#pragma unroll
+    for (int j = 0; j < kRegSub; j++) {
+        sc[j] = j + 1;
+        pc[j] = j < sublen ? sub[DIR * j] : 0;
+    }
+    int min_score = sublen, min_idx = -1;
+    for (int si = 0; si < seqlen; si++) {
+        const uint8_t ch = seq[DIR * si];
+        int a = si, c = si + 1;
+        int row_min = 1 << 30;
+#pragma unroll
+        for (int j = 0; j < kRegSub; j++) {
+            if (j < sublen) {
+                const int b = sc[j];
+                int v = a + (ch != pc[j]);
+                v = min(v, min(b + 1, c + 1));
+                c = v;
+                sc[j] = v;
+                row_min = min(row_min, v);
+                a = b;
+            }
+        }
+        if (c <= min_score) {
+            min_score = c;
+            min_idx = si;
+        } else if (row_min >= min_score) {
+            break;
+        }
+    }
+    if (min_score <= max_l) {
+        dist = min_score;
+        len = min_idx + 1;
+        return true;
+    }
+    return false;
+}
+
+template <int DIR>
+__device__ bool expand_long_reg(const uint8_t *sub, int sublen, const uint8_t *seq, int seqlen, int max_l, int &dist,
+                                int &len) {
+    if (sublen == 0) {
+        dist = 0;
+        len = 0;
+        return true;
+    }
+    int sc[kRegSub];
+    uint8_t pc[kRegSub];
+#pragma unroll
+    for (int j = 0; j < kRegSub; j++) {
+        sc[j] = j + 1;
+        pc[j] = j < sublen ? sub[DIR * j] : 0;
+    }
+    int min_score = sublen, min_idx = -1;
+    int max_good = max_l;
+    int new_start = 0, new_end = sublen - 1;
+    bool ns_none = false;
+    for (int si = 0; si < seqlen; si++) {
+        const uint8_t ch = seq[DIR * si];
+        const int rstart = new_start;
+        const int rend = min(sublen, new_end + 1);
+        int a = si, c = si + 1;
+        if (c <= max_good) {
+            new_start = 0;
+            ns_none = false;
+            new_end = 0;
+        } else {
+            new_start = 0;
+            ns_none = true;
+            new_end = -1;
+        }
+#pragma unroll
+        for (int j = 0; j < kRegSub; j++) {
+            if (j >= rstart && j < rend) {
+                const int b = sc[j];
+                int v = a + (ch != pc[j]);
+                v = min(v, min(b + 1, c + 1));
+                c = v;
+                sc[j] = v;
+                a = b;
+                if (c <= max_good) {
+                    if (ns_none) {
+                        ns_none = false;
+                        new_start = j;
+                    }
+                    new_end = max(new_end, j + 1 + (max_good - c));
+                }
+            }
+        }
+        if (ns_none) break;
+        if (rend == sublen && c <= min_score) {
+            min_score = c;
+            min_idx = si;
+            if (min_score < max_good) max_good = min_score;
+        }
+    }
+    if (min_score <= max_l) {
+        dist = min_score;
+        len = min_idx + 1;
+        return true;
+    }
+    return false;
+}
+
 template <int DIR>
 __device__ __forceinline__ bool expand_any(const uint8_t *sub, int sublen, const uint8_t *seq,
                                            int seqlen, int max_l, DpScratch &S, int &dist, int &len) {
-    if (sublen > max(2 * max_l, 10))  // levenshtein_ngram.py:16
+    if (sublen > max(2 * max_l, 10)) {  // levenshtein_ngram.py:16
+        if (sublen <= kRegSub) return expand_long_reg<DIR>(sub, sublen, seq, seqlen, max_l, dist, len);
         return expand_long<DIR>(sub, sublen, seq, seqlen, max_l, S, dist, len);
+    }
+    if (sublen <= kRegSub) return expand_short_reg<DIR>(sub, sublen, seq, seqlen, max_l, dist, len);
     return expand_short<DIR>(sub, sublen, seq, seqlen, max_l, S, dist, len);
 }
 
