@@ -461,67 +461,24 @@ __device__ bool expand_long(const uint8_t *sub, int sublen, const uint8_t *seq, 
     return false;
 }
 
-// Register-resident variants for sub-sequences of at most kRegSub characters (the common case: the
-// expansions of a 20-byte pattern are 2..14 characters long).  Same statements as above, but the DP
-// row lives in registers (fully unrolled, predicated on j < sublen) instead of local memory, whose
-// store->load round trip per cell dominated the verify kernel.
+// Register-resident variant for sub-sequences of at most kRegSub characters (the common case: the
+// expansions of a 20-byte pattern are 2..14 characters long): same statements as above, but the DP
+// row lives in registers (fully unrolled, predicated) instead of local memory.
 constexpr int kRegSub = 16;
 
+// One routine for both reference variants (levenshtein_ngram.py:22-74 and :77-143) when the row fits
+// the registers: the variant is a per-lane FLAG, not a different function, so the lanes of a warp that
+// expand different hits (different lengths, different variants) stay converged and the warp pays for
+// the longest expansion instead of the sum of all of them.
 template <int DIR>
-__device__ bool expand_short_reg(const uint8_t *sub, int sublen, const uint8_t *seq, int seqlen, int max_l, int &dist,
-                                 int &len) {
+__device__ bool expand_uni_reg(const uint8_t *sub, int sublen, const uint8_t *seq, int seqlen, int max_l, int &dist,
+                               int &len) {
     if (sublen == 0) {
         dist = 0;
         len = 0;
         return true;
     }
-    int sc[kRegSub];
-    uint8_t pc[kRegSub];
-#pragma unroll
-    for (int j = 0; j < kRegSub; j++) {
-        sc[j] = j + 1;
-        pc[j] = j < sublen ? sub[DIR * j] : 0;
-    }
-    int min_score = sublen, min_idx = -1;
-    for (int si = 0; si < seqlen; si++) {
-        const uint8_t ch = seq[DIR * si];
-        int a = si, c = si + 1;
-        int row_min = 1 << 30;
-#pragma unroll
-        for (int j = 0; j < kRegSub; j++) {
-            if (j < sublen) {
-                const int b = sc[j];
-                int v = a + (ch != pc[j]);
-                v = min(v, min(b + 1, c + 1));
-                c = v;
-                sc[j] = v;
-                row_min = min(row_min, v);
-                a = b;
-            }
-        }
-        if (c <= min_score) {
-            min_score = c;
-            min_idx = si;
-        } else if (row_min >= min_score) {
-            break;
-        }
-    }
-    if (min_score <= max_l) {
-        dist = min_score;
-        len = min_idx + 1;
-        return true;
-    }
-    return false;
-}
-
-template <int DIR>
-__device__ bool expand_long_reg(const uint8_t *sub, int sublen, const uint8_t *seq, int seqlen, int max_l, int &dist,
-                                int &len) {
-    if (sublen == 0) {
-        dist = 0;
-        len = 0;
-        return true;
-    }
+    const bool is_long = sublen > max(2 * max_l, 10);  // levenshtein_ngram.py:16
     int sc[kRegSub];
     uint8_t pc[kRegSub];
 #pragma unroll
@@ -535,18 +492,15 @@ __device__ bool expand_long_reg(const uint8_t *sub, int sublen, const uint8_t *s
     bool ns_none = false;
     for (int si = 0; si < seqlen; si++) {
         const uint8_t ch = seq[DIR * si];
-        const int rstart = new_start;
-        const int rend = min(sublen, new_end + 1);
+        const int rstart = is_long ? new_start : 0;
+        const int rend = is_long ? min(sublen, new_end + 1) : sublen;
         int a = si, c = si + 1;
-        if (c <= max_good) {
+        if (is_long) {
             new_start = 0;
-            ns_none = false;
-            new_end = 0;
-        } else {
-            new_start = 0;
-            ns_none = true;
-            new_end = -1;
+            ns_none = !(c <= max_good);
+            new_end = ns_none ? -1 : 0;
         }
+        int row_min = 1 << 30;
 #pragma unroll
         for (int j = 0; j < kRegSub; j++) {
             if (j >= rstart && j < rend) {
@@ -555,8 +509,9 @@ __device__ bool expand_long_reg(const uint8_t *sub, int sublen, const uint8_t *s
                 v = min(v, min(b + 1, c + 1));
                 c = v;
                 sc[j] = v;
+                row_min = min(row_min, v);
                 a = b;
-                if (c <= max_good) {
+                if (is_long && c <= max_good) {
                     if (ns_none) {
                         ns_none = false;
                         new_start = j;
@@ -565,11 +520,20 @@ __device__ bool expand_long_reg(const uint8_t *sub, int sublen, const uint8_t *s
                 }
             }
         }
-        if (ns_none) break;
-        if (rend == sublen && c <= min_score) {
-            min_score = c;
-            min_idx = si;
-            if (min_score < max_good) max_good = min_score;
+        if (is_long) {
+            if (ns_none) break;
+            if (rend == sublen && c <= min_score) {
+                min_score = c;
+                min_idx = si;
+                if (min_score < max_good) max_good = min_score;
+            }
+        } else {
+            if (c <= min_score) {
+                min_score = c;
+                min_idx = si;
+            } else if (row_min >= min_score) {
+                break;
+            }
         }
     }
     if (min_score <= max_l) {
@@ -583,11 +547,9 @@ __device__ bool expand_long_reg(const uint8_t *sub, int sublen, const uint8_t *s
 template <int DIR>
 __device__ __forceinline__ bool expand_any(const uint8_t *sub, int sublen, const uint8_t *seq,
                                            int seqlen, int max_l, DpScratch &S, int &dist, int &len) {
-    if (sublen > max(2 * max_l, 10)) {  // levenshtein_ngram.py:16
-        if (sublen <= kRegSub) return expand_long_reg<DIR>(sub, sublen, seq, seqlen, max_l, dist, len);
+    if (sublen <= kRegSub) return expand_uni_reg<DIR>(sub, sublen, seq, seqlen, max_l, dist, len);
+    if (sublen > max(2 * max_l, 10))  // levenshtein_ngram.py:16
         return expand_long<DIR>(sub, sublen, seq, seqlen, max_l, S, dist, len);
-    }
-    if (sublen <= kRegSub) return expand_short_reg<DIR>(sub, sublen, seq, seqlen, max_l, dist, len);
     return expand_short<DIR>(sub, sublen, seq, seqlen, max_l, S, dist, len);
 }
 
@@ -634,40 +596,54 @@ __device__ __forceinline__ int64_t stage_window(const ScanParams &p, int64_t gba
     return alo;
 }
 
-__device__ void verify_anchor_lev(const ScanParams &p, const uint8_t *sP, const uint8_t *W, int64_t idx,
+// All lanes of the warp call this together (lanes without an anchor pass valid = false).  Each lane
+// first finds the next n-gram that really occurs at its anchor (cheap), THEN the lanes that found one
+// run the two expansions side by side (converged), and the search for further n-grams resumes.
+__device__ void verify_anchor_lev(const ScanParams &p, const uint8_t *sP, const uint8_t *W, int64_t idx, bool valid,
                                   DpScratch &S, RawRec *out, uint32_t cap, uint32_t *counters, int j_lo, int j_hi) {
     // W[g] is the haystack byte at global position g (shared-memory window); n-grams j_lo..j_hi-1
     const int m = p.m, k = p.k, L = p.L;
     const int64_t N = p.N;
     const uint8_t *h = W + idx;
-    for (int j = j_lo; j < j_hi; j++) {
-        const int s = j * L;  // :170
-        // search window of n-gram j, clamped like search_exact.py:29-30   (:174-176)
-        int64_t ws = max((int64_t)0, (int64_t)(s - k));
-        int64_t we = min(N, N - m + s + L + k);
-        ws = max((int64_t)0, min(ws, N));
-        we = max(ws, min(we, N));
-        if (idx < ws || idx + L > we) continue;
-        bool eq = true;
-        for (int i = 0; i < L; i++) {
-            if (h[i] != sP[s + i]) {
-                eq = false;
-                break;
+    int j = valid ? j_lo : j_hi;
+    for (;;) {
+        for (; j < j_hi; j++) {  // next n-gram hit at this anchor
+            const int s = j * L;  // :170
+            // search window of n-gram j, clamped like search_exact.py:29-30   (:174-176)
+            int64_t ws = max((int64_t)0, (int64_t)(s - k));
+            int64_t we = min(N, N - m + s + L + k);
+            ws = max((int64_t)0, min(ws, N));
+            we = max(ws, min(we, N));
+            if (idx < ws || idx + L > we) continue;
+            bool eq = true;
+            for (int i = 0; i < L; i++) {
+                if (h[i] != sP[s + i]) {
+                    eq = false;
+                    break;
+                }
             }
+            if (eq) break;
         }
-        if (!eq) continue;
+        const bool have = j < j_hi;
+        if (!__any_sync(0xFFFFFFFFu, have)) return;
+        const int s = have ? j * L : 0;
         const int64_t p0 = idx - s;
         // right: _expand(P[s+L:], H[idx+L : p0+m+k], k)   (:178-182)
-        int64_t rhi = min(N, p0 + m + k);
-        int rlen = (int)max((int64_t)0, rhi - (idx + L));
-        int dr, rs;
-        if (!expand_any<1>(sP + s + L, m - s - L, h + L, rlen, k, S, dr, rs)) continue;
+        int dr = 0, rs = 0, dl = 0, ls = 0;
+        bool ok = have;
+        if (ok) {
+            const int64_t rhi = min(N, p0 + m + k);
+            const int rlen = (int)max((int64_t)0, rhi - (idx + L));
+            ok = expand_any<1>(sP + s + L, m - s - L, h + L, rlen, k, S, dr, rs);
+        }
         // left: _expand(P[:s][::-1], H[max(0,p0-(k-dr)) : idx][::-1], k-dr)   (:185-189)
-        int64_t llo = max((int64_t)0, p0 - (k - dr));
-        int llen = (int)max((int64_t)0, idx - llo);
-        int dl, ls;
-        if (!expand_any<-1>(sP + s - 1, s, h - 1, llen, k - dr, S, dl, ls)) continue;
-        emit(out, cap, counters, idx - ls, idx + L + rs, idx, dl + dr, j);  // :194-198
+        if (ok) {
+            const int64_t llo = max((int64_t)0, p0 - (k - dr));
+            const int llen = (int)max((int64_t)0, idx - llo);
+            ok = expand_any<-1>(sP + s - 1, s, h - 1, llen, k - dr, S, dl, ls);
+        }
+        if (ok) emit(out, cap, counters, idx - ls, idx + L + rs, idx, dl + dr, j);  // :194-198
+        j++;
     }
 }
 
@@ -685,7 +661,7 @@ __device__ __forceinline__ void verify_granule_lev(const ScanParams &p, const ui
 #pragma unroll 1
     for (int half = 0; half < kGranule / 32; half++) {
         const int64_t idx = gbase + half * 32 + lane;
-        if (idx >= p.own_lo && idx < p.own_hi) verify_anchor_lev(p, sP, W, idx, S, out, cap, counters, 0, p.n_ngrams);
+        verify_anchor_lev(p, sP, W, idx, idx >= p.own_lo && idx < p.own_hi, S, out, cap, counters, 0, p.n_ngrams);
     }
 }
 
@@ -767,20 +743,23 @@ k_verify_hits(const ScanParams p, RawRec *out, uint32_t cap, uint32_t *counters)
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         if (base >= nhits) break;
         const uint32_t item = base + lane;
-        if (item < nhits) {
+        const bool valid = item < nhits;
+        int64_t idx = 0, alo = 0;
+        int j = 0;
+        if (valid) {
             const uint64_t hv = p.hits[item];
-            const int64_t idx = (int64_t)(hv >> 8);
-            const int j = (int)(hv & 0xFFu);
+            idx = (int64_t)(hv >> 8);
+            j = (int)(hv & 0xFFu);
             const int64_t p0 = idx - (int64_t)j * p.L;
             const int64_t wlo = max(max(p0 - p.k, (int64_t)0), p.buf_lo);
             const int64_t whi = min(min(p0 + p.m + p.k, p.N), p.buf_lo + p.buf_len);
-            const int64_t alo = wlo & ~(int64_t)3;
+            alo = wlo & ~(int64_t)3;
             const int nwords = (int)((whi - alo + 3) >> 2);
             const uint32_t *src = reinterpret_cast<const uint32_t *>(p.H + (alo - p.buf_lo));
             uint32_t *dst = reinterpret_cast<uint32_t *>(slot);
             for (int w = 0; w < nwords; w++) dst[w] = __ldg(src + w);
-            verify_anchor_lev(p, sP, slot - alo, idx, S, out, cap, counters, j, j + 1);
         }
+        verify_anchor_lev(p, sP, slot - alo, idx, valid, S, out, cap, counters, j, j + 1);  // whole warp
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counters[CNT_CAND], nhits);
 }
