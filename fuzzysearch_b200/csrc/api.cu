@@ -1264,6 +1264,7 @@ extern "C" int fzb_search_levenshtein(fzb_haystack *h, const uint8_t *pattern, u
     rc = check_pattern(h, pattern, m, flags);
     if (rc == FZB_OK) {
         // find_near_matches_levenshtein (levenshtein.py:9-38)
+        if (k >= m) k = m;  // every k >= len(pattern) takes the same branch (levenshtein.py:62-65): (i, i, m) for all i
         bool ngrams = (k == 0) || (m / (k + 1) >= 3);
         if (flags & FZB_F_FORCE_NGRAMS) ngrams = true;
         if (flags & FZB_F_FORCE_LP) ngrams = false;

@@ -157,6 +157,7 @@ def test_edge_cases(cuda_device):
     t = lambda ms: [(m.start, m.end, m.dist) for m in ms]  # noqa: E731
     assert t(find_near_matches(b"abc", b"", max_l_dist=1)) == []
     assert t(find_near_matches(b"ab", b"xyz", max_l_dist=2)) == [(0, 0, 2), (1, 1, 2), (2, 2, 2), (3, 3, 2)]
+    assert t(find_near_matches(b"ab", b"xyz", max_l_dist=10 ** 6)) == [(0, 0, 2), (1, 1, 2), (2, 2, 2), (3, 3, 2)]
     assert t(find_near_matches(b"abc", b"ab", max_l_dist=1)) == [(0, 2, 1)]
     assert t(find_near_matches(b"abc", b"xbz", max_substitutions=5, max_insertions=0, max_deletions=0)) == \
         [(0, 3, 2)]
