@@ -383,8 +383,16 @@ def main():
     dev_ms = hs.timer_stop()
     wall_ms = (time.perf_counter() - t0) * 1e3
     sync_all()
-    time.sleep(0.3)
+    # the timed region of a default run lasts ~20 ms, shorter than one nvidia-smi sampling period: keep
+    # the SAME searches running (untimed, same count on every rank) so the clock monitor sees the load
+    soak = 0 if kind == "batch" else max(0, 400 - args.steps)
+    for _ in range(soak):
+        step()
+    sync_all()
+    time.sleep(0.2)
     clocks = clocks_monitor_stop(mon, clock_path)
+    if clocks is not None:
+        clocks["note"] = "sampled every 100 ms over the timed region plus %d identical untimed searches" % soak
     ms_per_step = dev_ms / args.steps
     if dist is not None:
         import torch

@@ -10,7 +10,7 @@ Every search runs as hand-written CUDA kernels behind the C-ABI of libfuzzb200.s
 """
 __version__ = "0.1.0"
 
-__all__ = ["find_near_matches", "find_near_matches_batch", "find_near_matches_in_file", "Match", "LevenshteinSearchParams",
+__all__ = ["find_near_matches", "find_near_matches_batch", "find_near_matches_in_file", "has_near_match", "Match", "LevenshteinSearchParams",
            "DeviceSequence", "ExactSearch", "SubstitutionsOnlySearch", "LevenshteinSearch",
            "GenericSearch", "choose_search_class"]
 
@@ -30,6 +30,16 @@ def find_near_matches(subsequence, sequence, max_substitutions=None, max_inserti
     search_class = choose_search_class(search_params)
     matches = search_class.search(subsequence, sequence, search_params)
     return search_class.consolidate_matches(matches)
+
+
+def has_near_match(subsequence, sequence, max_substitutions=None, max_insertions=None, max_deletions=None,
+                   max_l_dist=None):
+    """True iff find_near_matches(...) would return at least one match -- the public-API form of the
+    reference's internal has_near_match_* helpers (substitutions_only.py:18-34,139-145,218-233;
+    generic_search.py:240-253).  Round 1: runs the full search (no grid-wide early exit yet)."""
+    search_params = LevenshteinSearchParams(max_substitutions, max_insertions, max_deletions, max_l_dist)
+    search_class = choose_search_class(search_params)
+    return len(search_class.search(subsequence, sequence, search_params)) > 0
 
 
 def find_near_matches_batch(subsequences, sequence, max_l_dist):

@@ -162,6 +162,10 @@ def test_edge_cases(cuda_device):
     assert t(find_near_matches(b"abc", b"xbz", max_substitutions=5, max_insertions=0, max_deletions=0)) == \
         [(0, 3, 2)]
     assert t(find_near_matches(b"abcd", b"ab", max_substitutions=1, max_insertions=0, max_deletions=0)) == []
+    from fuzzysearch_b200 import has_near_match
+    assert has_near_match(b"PATTERN", b"---PATERN---", max_l_dist=1) is True
+    assert has_near_match(b"PATTERN", b"---PATERN---", max_l_dist=0) is False
+    assert has_near_match(b"abc", b"xbz", max_substitutions=1, max_insertions=0, max_deletions=0) is False
     ms = find_near_matches(b"PATTERN", b"---PATERN---", max_l_dist=1)
     assert t(ms) == [(3, 9, 1)] and ms[0].matched == b"PATERN"
     ms = find_near_matches("PATTERN", "---PATERN---", max_l_dist=1)
