@@ -178,3 +178,28 @@ def test_edge_cases(cuda_device):
         find_near_matches(b"a", b"a", max_l_dist=-1)
     with pytest.raises(TypeError):
         find_near_matches(["a"], ["a"], max_l_dist=1)
+
+
+def test_python_surface_variants(cuda_device):
+    """bytes / bytearray / memoryview / numpy / latin-1 str / DeviceSequence all take the same path."""
+    from fuzzysearch_b200 import DeviceSequence, Match, find_near_matches
+    pat, hay, _ = make_corpus(8, 1 << 16, ASCII, 12, 16, 2)
+    exp = oracle.find_near_matches(pat, hay, max_l_dist=1)
+    raw = hay.tobytes()
+    for seq in (raw, bytearray(raw), memoryview(raw), hay, raw.decode("latin-1")):
+        p = pat.decode("latin-1") if isinstance(seq, str) else pat
+        ms = find_near_matches(p, seq, max_l_dist=1)
+        assert [(m.start, m.end, m.dist) for m in ms] == exp
+        assert all(isinstance(m, Match) for m in ms)
+        want = seq[ms[0].start:ms[0].end]
+        assert ms[0].matched == (bytes(want) if not isinstance(seq, str) else want)
+    dev = DeviceSequence(raw)
+    for k in (0, 1, 2):
+        ms = find_near_matches(pat, dev, max_l_dist=k)
+        assert [(m.start, m.end, m.dist) for m in ms] == oracle.find_near_matches(pat, hay, max_l_dist=k)
+    ms = find_near_matches(pat, dev, max_substitutions=2, max_insertions=0, max_deletions=0)
+    assert [(m.start, m.end, m.dist) for m in ms] == oracle.find_near_matches(pat, hay, 2, 0, 0)
+    assert len(dev) == len(raw)
+    dev.close()
+    with pytest.raises(TypeError):
+        find_near_matches(pat, raw.decode("latin-1"), max_l_dist=1)   # bytes pattern vs str sequence
