@@ -148,3 +148,25 @@ def test_synth_host_is_counter_based():
     assert a[333:433].tobytes() == b.tobytes()
     assert set(a.tolist()) == set(b"ACGT")
     assert _native.synth_host(0, 64, b"ACGT", 43).tobytes() != a[:64].tobytes()
+
+
+def test_merge_groups_equals_whole_consolidation():
+    """fzb_consolidate_groups per shard + fzb_merge_groups == consolidation of the whole raw list
+    (random intervals incl. empty ones, random anchor partitions into 3 shards)."""
+    rng = np.random.default_rng(5)
+    for trial in range(400):
+        n = int(rng.integers(0, 60))
+        span = int(rng.integers(10, 200))
+        raw = []
+        for _ in range(n):
+            s = int(rng.integers(0, span))
+            ln = int(rng.integers(0 if trial % 2 else 1, 9))
+            raw.append((s, s + ln, int(rng.integers(0, 4))))
+        raw = np.array(raw, dtype=np.int64).reshape(-1, 3)
+        whole = tup(oracle.consolidate(raw))
+        cuts = sorted(rng.integers(0, span + 1, size=2).tolist())
+        parts = []
+        for lo, hi in zip([0] + cuts, cuts + [span + 10]):
+            sub = raw[(raw[:, 0] >= lo) & (raw[:, 0] < hi)]
+            parts.append(_native.consolidate_groups(sub[:, 0], sub[:, 1], sub[:, 2].astype(np.int32)))
+        assert _native.merge_groups(np.concatenate(parts, axis=0)) == whole, (raw.tolist(), cuts)
