@@ -59,13 +59,21 @@ def find_near_matches_batch(subsequences, sequence, max_l_dist):
             raise ValueError("Given subsequence is empty!")
     if not subsequences:
         return []
-    _, hay, slicer, _ = _prepare(subsequences[0], sequence)
-    results, _ = hay.search_levenshtein_batch([_coerce(p)[0] for p in subsequences], ks)
-    out = []
-    for res in results:
-        s, e, d = res.arrays(_native.FINAL)
-        out.append([Match(a, b, c, matched=slicer(a, b)) for a, b, c in zip(s.tolist(), e.tolist(), d.tolist())])
-        res.close()
+    from .search import _WORKSPACE_LOCK, DeviceSequence
+    pats = [_coerce(p) for p in subsequences]
+    seq_is_str = sequence._is_str if isinstance(sequence, DeviceSequence) else isinstance(sequence, str)
+    if any(is_str != seq_is_str for _, is_str in pats):
+        raise TypeError("subsequence and sequence must both be str or both be byte-like")
+    with _WORKSPACE_LOCK:
+        _, hay, slicer, _ = _prepare(subsequences[0], sequence)
+        results, _ = hay.search_levenshtein_batch([p for p, _ in pats], ks)
+        out = []
+        for res, k in zip(results, ks):
+            # max_l_dist == 0 selects ExactSearch in find_near_matches (__init__.py:65-66), whose result is
+            # the unconsolidated occurrence list (search_exact.py:80-89): the RAW stream of the k == 0 route
+            s, e, d = res.arrays(_native.RAW if k == 0 else _native.FINAL)
+            out.append([Match(a, b, c, matched=slicer(a, b)) for a, b, c in zip(s.tolist(), e.tolist(), d.tolist())])
+            res.close()
     return out
 
 

@@ -152,6 +152,9 @@ class FuzzySearchBase(object):
 
     @classmethod
     def consolidate_matches(cls, matches):
+        materialize = getattr(matches, "materialize", None)  # search.RawMatches -> a plain list
+        if materialize is not None:
+            return materialize()
         try:
             len(matches)
         except TypeError:
@@ -172,12 +175,12 @@ def consolidate_overlapping_matches(matches):
     smallest (start, end).  Returns a list sorted by (start, end, dist)."""
     from . import _native
     import numpy as np
+    precomputed = getattr(matches, "final", None)  # RawMatches: the device already consolidated
+    if precomputed is not None:
+        return list(precomputed)
     matches = list(matches)
     if not matches:
         return []
-    precomputed = getattr(matches, "final", None)
-    if precomputed is not None:
-        return list(precomputed)
     start = np.fromiter((m.start for m in matches), dtype=np.int64, count=len(matches))
     end = np.fromiter((m.end for m in matches), dtype=np.int64, count=len(matches))
     dist = np.fromiter((m.dist for m in matches), dtype=np.int32, count=len(matches))

@@ -6,6 +6,9 @@ SubstitutionsOnlySearch / LevenshteinSearch / GenericSearch, each a ``FuzzySearc
 (common.py:192-209).  Here each ``search`` is ONE call into libfuzzb200.so (sm_100a kernels);
 there is no CPU implementation behind them.
 """
+import threading
+from collections.abc import Sequence
+
 import numpy as np
 
 from . import _native
@@ -56,11 +59,53 @@ def _coerce(seq):
     return _native.as_u8(seq), False
 
 
-class RawMatches(list):
-    """The raw match stream of one search; carries the device-side consolidated list so that
-    ``consolidate_matches`` does not have to recompute it."""
-    final = None
-    stats = None
+class RawMatches(Sequence):
+    """The raw match stream of one search, materialised LAZILY: ``find_near_matches`` only needs the
+    consolidated list (``.final``, built from the device-side consolidation), so the raw ``Match``
+    objects -- one Python object and one slice per raw record -- are only built if somebody iterates,
+    indexes or compares this object (the search-class ``search()`` contract of the reference,
+    common.py:192-197, is "an iterable of Match")."""
+
+    def __init__(self, result, slicer, consolidated):
+        self._result = result
+        self._slicer = slicer
+        self._list = None
+        self.stats = result.stats()
+        self.final = _to_matches(result, _native.FINAL, slicer) if consolidated else None
+        self._n = result.count(_native.RAW)
+
+    def materialize(self):
+        if self._list is None:
+            self._list = _to_matches(self._result, _native.RAW, self._slicer)
+            self._result.close()
+            self._result = None
+        return self._list
+
+    def __len__(self):
+        return self._n
+
+    def __iter__(self):
+        return iter(self.materialize())
+
+    def __getitem__(self, i):
+        return self.materialize()[i]
+
+    def __eq__(self, other):
+        if isinstance(other, RawMatches):
+            other = other.materialize()
+        return self.materialize() == other
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
+
+    __hash__ = None
+
+    def __repr__(self):
+        return repr(self.materialize())
+
+    def __del__(self):
+        if getattr(self, "_result", None) is not None:
+            self._result.close()
 
 
 def _prepare(subsequence, sequence):
@@ -90,6 +135,11 @@ def _prepare(subsequence, sequence):
 
 
 _WORKSPACE = {}
+# One lock per process around upload + search + copy-out of the SHARED workspace: ctypes drops the GIL
+# during the native calls, so without it two threads calling find_near_matches() would overwrite each
+# other's haystack mid-search.  (The reference is serialised by the GIL; DeviceSequence handles are
+# serialised per handle inside the library.)
+_WORKSPACE_LOCK = threading.RLock()
 
 
 def _workspace(nbytes, device=0):
@@ -118,20 +168,20 @@ def _to_matches(result, which, slicer):
 
 
 def _run(subsequence, sequence, call, consolidated):
-    pat, hay, slicer, owns = _prepare(subsequence, sequence)
+    shared = not isinstance(sequence, DeviceSequence)
+    if shared:
+        _WORKSPACE_LOCK.acquire()
     try:
+        pat, hay, slicer, _ = _prepare(subsequence, sequence)
         res = call(hay, pat)
         try:
-            out = RawMatches(_to_matches(res, _native.RAW, slicer))
-            out.stats = res.stats()
-            if consolidated:
-                out.final = _to_matches(res, _native.FINAL, slicer)
-            return out
-        finally:
+            return RawMatches(res, slicer, consolidated)
+        except BaseException:
             res.close()
+            raise
     finally:
-        if owns:
-            hay.close()
+        if shared:
+            _WORKSPACE_LOCK.release()
 
 
 class ExactSearch(FuzzySearchBase):

@@ -93,6 +93,18 @@ def _as_tuples(arr):
     return [tuple(int(x) for x in row) for row in arr]
 
 
+def synth(global_offset, n, alphabet, seed):
+    """Bytes [global_offset, global_offset+n) of the counter-based synthetic benchmark corpus
+    (fzo_synth; same definition as the device generator) -> numpy uint8."""
+    lib = _load()
+    ka, pa, la = _buf(alphabet)
+    out = np.empty(n, dtype=np.uint8)
+    lib.fzo_synth.restype = None
+    lib.fzo_synth(ctypes.c_void_p(out.ctypes.data), ctypes.c_uint64(global_offset), ctypes.c_uint64(n), pa,
+                  ctypes.c_uint32(la), ctypes.c_uint64(seed))
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 # expansion DP (levenshtein_ngram.py:8-143)
 # ---------------------------------------------------------------------------------------------

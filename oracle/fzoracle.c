@@ -744,3 +744,30 @@ FZO_API int64_t fzo_consolidate(const fzo_match *raw, int64_t n, fzo_match **out
     *out = res;
     return w;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Synthetic benchmark corpus (NOT a restatement of the reference, which has no corpus generator:
+ * SURVEY F9/F10).  Counter-based: bytes 4q..4q+3 of the global sequence come from one splitmix64
+ * hash of (seed, q), 16 bits per byte -- the same definition as the device generator
+ * (fuzzysearch_b200/csrc/common.cuh: synth_word), restated here so that bench.py's reference arm
+ * and the parity checks can rebuild any slice of the corpus WITHOUT loading the product library.
+ * ------------------------------------------------------------------------------------------------ */
+static uint64_t fzo_splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+FZO_API void fzo_synth(uint8_t *dst, uint64_t global_offset, uint64_t n, const uint8_t *alphabet,
+                       uint32_t alen, uint64_t seed) {
+    uint64_t i = 0;
+    while (i < n) {
+        uint64_t g = global_offset + i, q = g / 4;
+        uint64_t x = fzo_splitmix64(seed ^ (q * 0xD1342543DE82EF95ull));
+        for (uint64_t b = g % 4; b < 4 && i < n; b++, i++) {
+            uint32_t r = (uint32_t)(x >> (16 * b)) & 0xFFFFu;
+            dst[i] = alphabet[(r * alen) >> 16];
+        }
+    }
+}

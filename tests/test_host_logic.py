@@ -170,3 +170,17 @@ def test_merge_groups_equals_whole_consolidation():
             sub = raw[(raw[:, 0] >= lo) & (raw[:, 0] < hi)]
             parts.append(_native.consolidate_groups(sub[:, 0], sub[:, 1], sub[:, 2].astype(np.int32)))
         assert _native.merge_groups(np.concatenate(parts, axis=0)) == whole, (raw.tolist(), cuts)
+
+
+def test_consolidate_uses_the_device_side_final_list():
+    """A RawMatches-like object carrying `.final` short-circuits the host consolidation."""
+    from fuzzysearch_b200.common import consolidate_overlapping_matches
+
+    class Carrier(list):
+        final = None
+
+    c = Carrier([Match(0, 3, 1, b"abc"), Match(1, 4, 0, b"bcd")])
+    sentinel = [Match(7, 9, 0, b"zz")]
+    c.final = sentinel
+    assert consolidate_overlapping_matches(c) == sentinel
+    assert consolidate_overlapping_matches(list(c)) == [Match(1, 4, 0, b"bcd")]

@@ -36,6 +36,28 @@ def test_reference_arm_prints_the_contract_line():
     assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] == 2
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
     assert line["config"]["workload"] == "ascii64m_lev_m20_k2" and line["metric"] == "haystack_GB_per_s_scanned"
+    assert line["steps"] >= 5 and line["cpu_baseline"]["single_core_value"] > 0
+
+
+def test_reference_arm_never_loads_the_product_library(tmp_path):
+    """`bench.py --impl reference` must time the reference alone: no fuzzysearch_b200 import, no
+    libfuzzb200.so mapped (the driver lists the shared objects each arm loaded)."""
+    if not os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "fuzzysearch")):
+        import pytest
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    probe = tmp_path / "probe.py"
+    probe.write_text(
+        "import runpy, sys, atexit\n"
+        "def report():\n"
+        "    maps = open('/proc/self/maps').read()\n"
+        "    sys.stderr.write('PRODUCT_LIB_MAPPED=%d\\n' % ('libfuzzb200' in maps))\n"
+        "    sys.stderr.write('PRODUCT_PKG_IMPORTED=%d\\n' % any(m.startswith('fuzzysearch_b200') for m in sys.modules))\n"
+        "atexit.register(report)\n"
+        "sys.argv = ['bench.py', '--impl', 'reference', '--workload', 'ascii64m_lev_m20_k2', '--steps', '1',\n"
+        "            '--warmup', '0', '--cpu-sample-mib', '4', '--ref-cores', '1']\n"
+        "runpy.run_path(BENCH, run_name='__main__')\n".replace("BENCH", repr(os.path.join(ROOT, "bench.py"))))
+    out = subprocess.run([sys.executable, str(probe)], capture_output=True, text=True, timeout=600)
+    assert "PRODUCT_LIB_MAPPED=0" in out.stderr and "PRODUCT_PKG_IMPORTED=0" in out.stderr, out.stderr[-2000:]
 
 
 def test_graft_entry_exposes_build_and_smoke():
