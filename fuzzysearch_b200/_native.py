@@ -85,6 +85,8 @@ SYMBOLS = {
     "fzb_result_stats": (_i32, [_vp, ctypes.POINTER(Stats)]),
     "fzb_result_destroy": (None, [_vp]),
     "fzb_consolidate": (_i64, [_vp, _vp, _vp, _u64, _vp, _vp, _vp]),
+    "fzb_debug_counters": (_i32, [_vp, _vp]),
+    "fzb_debug_expand": (_i32, [_u8p, _vp, _u8p, _vp, _vp, _vp, _u32, _i32, _vp]),
 }
 
 _lib = None
@@ -259,6 +261,11 @@ class Haystack(object):
         a = as_u8(data)
         check(lib().fzb_haystack_upload(self._h, ptr(a), a.size))
 
+    def debug_counters(self):
+        out = np.zeros(16, dtype=np.uint32)
+        check(lib().fzb_debug_counters(self._h, ptr(out)))
+        return out.tolist()
+
     def timer_start(self):
         check(lib().fzb_timer_start(self._h))
 
@@ -386,6 +393,23 @@ def find_near_matches_host(pattern, haystack, max_subs, max_ins, max_dels, max_l
     check(lib().fzb_find_near_matches(ptr(p), p.size, ptr(a), a.size, max_subs, max_ins, max_dels, max_l,
                                       device, ctypes.byref(r)))
     return Result(r)
+
+
+def debug_expand(cases, device=0):
+    """Test hook: cases = [(sub, seq, max_l, variant)], variant 0 auto / 1 short / 2 long ->
+    int32 array [n, 8] (see fzb_debug_expand in include/fuzzb200.h)."""
+    n = len(cases)
+    subs = np.frombuffer(b"".join(bytes(c[0]) for c in cases), dtype=np.uint8)
+    seqs = np.frombuffer(b"".join(bytes(c[1]) for c in cases), dtype=np.uint8)
+    so = np.zeros(n + 1, dtype=np.uint32)
+    qo = np.zeros(n + 1, dtype=np.uint32)
+    so[1:] = np.cumsum([len(c[0]) for c in cases])
+    qo[1:] = np.cumsum([len(c[1]) for c in cases])
+    ks = np.ascontiguousarray([c[2] for c in cases], dtype=np.int32)
+    vs = np.ascontiguousarray([c[3] for c in cases], dtype=np.int32)
+    out = np.zeros((max(n, 1), 8), dtype=np.int32)
+    check(lib().fzb_debug_expand(ptr(subs), ptr(so), ptr(seqs), ptr(qo), ptr(ks), ptr(vs), n, device, ptr(out)))
+    return out[:n]
 
 
 def consolidate_groups(start, end, dist):

@@ -19,6 +19,7 @@
 #include "ham_kernels.cuh"
 #include "lp_kernels.cuh"
 #include "post_kernels.cuh"
+#include "debug_kernels.cuh"
 
 using namespace fzb;
 
@@ -122,12 +123,13 @@ struct fzb_haystack {
     RawRec *d_out = nullptr;
     uint32_t out_cap = 0;
     uint32_t *d_counters = nullptr;
-    uint32_t *h_counters = nullptr;  // pinned
-    RawRec *h_stage = nullptr;       // pinned staging for the first kSpecRecs records
-    RawRec *d_raw_sorted = nullptr;  // k_post_small outputs (kPostMax entries each)
-    int64_t *d_fin = nullptr;
-    uint64_t *d_keys_sorted = nullptr;
-    int64_t *h_fin = nullptr;        // pinned
+    // k_post writes these three straight into MAPPED pinned host memory (no copy operations per search)
+    uint32_t *h_counters = nullptr;  // CNT_COUNT counters
+    RawRec *h_stage = nullptr;       // raw records, arrival order (kPostMax entries)
+    int64_t *h_fin = nullptr;        // final rows (kPostMax x kFinCols)
+    int64_t *d_fin = nullptr;        // device copy of the final rows (input of the multi-GPU reduction)
+    uint64_t *d_sorted = nullptr;    // k_post scratch: the sorted canonical keys
+    fzb_result *pending = nullptr;   // the last result, while its raw records still sit in h_stage only
     bool ev1_recorded = false;
     bool filter_attrs_set = false;
     double coll_prob = -1.0;  // sum_c p_c^2 of the byte distribution (sampled lazily; < 0 = unknown)
@@ -149,11 +151,15 @@ struct fzb_haystack {
 };
 
 struct fzb_result {
-    std::vector<RawRec> raw;
+    std::vector<RawRec> raw;      // filled lazily from the owner's mapped staging buffer (fetch_raw)
+    uint32_t raw_n = 0;           // number of raw records
+    fzb_haystack *owner = nullptr;  // non-null while the raw records still sit in owner->h_stage only
+    void fetch_raw();
     std::vector<RawRec> fin;
     std::vector<int64_t> hulls;  // (hull_start, hull_end) of the group behind each final match
-    bool final_is_raw = false;
-    bool device_post = false;  // final list (and, unless raw_order_pending, the raw order) came from the device
+    bool unconsolidated = false;  // exact / Hamming routes: FINAL is the whole raw list in (start, end, dist) order
+    bool have_fin = false;        // fin / hulls are filled
+    bool device_post = false;  // the final list came from the device (k_post)
     bool raw_ordered = false;  // raw is already in its reference order
     bool has_global = false;   // FZB_F_GLOBAL: gfin is the global consolidated list of all shards
     bool gather_valid = false;
@@ -169,6 +175,30 @@ struct fzb_result {
 
 static uint64_t round_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 
+// The raw records of the LAST search of a handle stay in its mapped staging buffer until somebody asks for
+// them (fzb_result_copy(FZB_RAW)), the next search on the handle is about to overwrite the buffer, or the
+// handle / the result dies: find_near_matches() only needs the consolidated list, and a 200 KB host
+// memcpy per search is 1 % of a 4 GiB scan.  One process-wide mutex guards the result <-> handle link.
+static std::mutex g_pending_mutex;
+
+void fzb_result::fetch_raw() {
+    std::lock_guard<std::mutex> lock(g_pending_mutex);
+    if (!owner) return;
+    raw.resize(raw_n);
+    if (raw_n) memcpy(raw.data(), owner->h_stage, (size_t)raw_n * sizeof(RawRec));
+    owner->pending = nullptr;
+    owner = nullptr;
+}
+
+static void detach_pending(fzb_haystack *h) {  // before h->h_stage is overwritten or freed
+    fzb_result *r;
+    {
+        std::lock_guard<std::mutex> lock(g_pending_mutex);
+        r = h->pending;
+    }
+    if (r) r->fetch_raw();
+}
+
 static int haystack_common_init(fzb_haystack *h) {
     CK(cudaSetDevice(h->device));
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -180,19 +210,19 @@ static int haystack_common_init(fzb_haystack *h) {
     uint64_t granules = (h->padded_len >> kGranuleShift) + 2;
     h->bitmap_words = round_up((granules + 31) / 32, 32);
     CK(cudaMalloc(&h->d_bitmap, h->bitmap_words * sizeof(uint32_t)));
-    CK(cudaMalloc(&h->d_counters, (CNT_COUNT + 2 * (size_t)kPostMax) * sizeof(uint32_t)));  // + k_rank's ranks
-    CK(cudaMallocHost(&h->h_counters, CNT_COUNT * sizeof(uint32_t)));
-    CK(cudaMallocHost(&h->h_stage, (size_t)kPostMax * sizeof(RawRec)));
-    CK(cudaMallocHost(&h->h_fin, (size_t)kPostMax * kFinCols * sizeof(int64_t)));
-    CK(cudaMalloc(&h->d_raw_sorted, (size_t)kPostMax * sizeof(RawRec)));
+    CK(cudaMalloc(&h->d_counters, CNT_COUNT * sizeof(uint32_t)));
+    const unsigned hflags = cudaHostAllocMapped | cudaHostAllocPortable;
+    CK(cudaHostAlloc(&h->h_counters, CNT_COUNT * sizeof(uint32_t), hflags));
+    CK(cudaHostAlloc(&h->h_stage, (size_t)kPostMax * sizeof(RawRec), hflags));
+    CK(cudaHostAlloc(&h->h_fin, (size_t)kPostMax * kFinCols * sizeof(int64_t), hflags));
     CK(cudaMalloc(&h->d_fin, (size_t)kPostMax * kFinCols * sizeof(int64_t)));
-    CK(cudaMalloc(&h->d_keys_sorted, (size_t)kPostMax * sizeof(uint64_t)));
-    CK(cudaFuncSetAttribute(k_consolidate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConsSmem));
+    CK(cudaMalloc(&h->d_sorted, (size_t)kPostMax * sizeof(uint64_t)));
+    CK(cudaFuncSetAttribute(k_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPostSmem));
     CK(cudaMemset(h->d_bitmap, 0, h->bitmap_words * sizeof(uint32_t)));  // stays all-zero between searches
     h->glist_cap = (uint32_t)std::min<uint64_t>(granules, 1u << 20);
     CK(cudaMalloc(&h->d_glist, (size_t)std::max<uint32_t>(h->glist_cap, 1) * sizeof(uint32_t)));
     h->out_cap = 1u << 16;
-    CK(cudaMalloc(&h->d_out, (size_t)h->out_cap * sizeof(RawRec)));
+    CK(cudaMalloc(&h->d_out, (size_t)h->out_cap * (sizeof(RawRec) + sizeof(uint64_t))));  // records + their keys
     return FZB_OK;
 }
 
@@ -218,6 +248,7 @@ extern "C" void fzb_haystack_destroy(fzb_haystack *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    detach_pending(h);
     if (h->owned && h->d) cudaFree(h->d);
     if (h->d_bitmap) cudaFree(h->d_bitmap);
     if (h->d_out) cudaFree(h->d_out);
@@ -233,9 +264,8 @@ extern "C" void fzb_haystack_destroy(fzb_haystack *h) {
     if (h->h_counters) cudaFreeHost(h->h_counters);
     if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->h_fin) cudaFreeHost(h->h_fin);
-    if (h->d_raw_sorted) cudaFree(h->d_raw_sorted);
     if (h->d_fin) cudaFree(h->d_fin);
-    if (h->d_keys_sorted) cudaFree(h->d_keys_sorted);
+    if (h->d_sorted) cudaFree(h->d_sorted);
     for (auto &e : h->ev)
         if (e) cudaEventDestroy(e);
     if (h->ev_stop) cudaEventDestroy(h->ev_stop);
@@ -577,32 +607,25 @@ extern "C" int64_t fzb_consolidate_groups(const int64_t *start, const int64_t *e
 
 extern "C" int64_t fzb_result_group_rows(const fzb_result *r, int64_t *rows, uint64_t max_rows) {
     if (!r || (!rows && max_rows)) return fail(FZB_E_INVALID, "NULL argument");
-    if (r->final_is_raw) const_cast<fzb_result *>(r)->order_raw();
-    const std::vector<RawRec> &v = r->final_is_raw ? r->raw : r->fin;
-    if (!r->final_is_raw && r->hulls.size() != v.size() * 2)
+    const std::vector<RawRec> &v = r->fin;
+    if (!r->have_fin || r->hulls.size() != v.size() * 2)
         return fail(FZB_E_INVALID, "result was produced with FZB_F_NO_FINAL");
     const size_t n = std::min<size_t>(v.size(), max_rows);
     for (size_t i = 0; i < n; i++) {
         rows[5 * i + 0] = v[i].start;
         rows[5 * i + 1] = v[i].end;
         rows[5 * i + 2] = v[i].dist;
-        rows[5 * i + 3] = r->final_is_raw ? v[i].start : r->hulls[2 * i];
-        rows[5 * i + 4] = r->final_is_raw ? v[i].end : r->hulls[2 * i + 1];
+        rows[5 * i + 3] = r->hulls[2 * i];
+        rows[5 * i + 4] = r->hulls[2 * i + 1];
     }
     return (int64_t)v.size();
 }
 
 extern "C" int fzb_result_hulls(const fzb_result *r, int64_t *hull_start, int64_t *hull_end) {
     if (!r) return fail(FZB_E_INVALID, "result is NULL");
-    if (r->final_is_raw) const_cast<fzb_result *>(r)->order_raw();
-    if (r->final_is_raw) {  // unconsolidated routes: every match is its own group
-        for (size_t i = 0; i < r->raw.size(); i++) {
-            if (hull_start) hull_start[i] = r->raw[i].start;
-            if (hull_end) hull_end[i] = r->raw[i].end;
-        }
-        return FZB_OK;
-    }
-    if (r->hulls.size() != r->fin.size() * 2) return fail(FZB_E_INVALID, "result was produced with FZB_F_NO_FINAL");
+    // (unconsolidated routes: every match is its own group, hull == the match)
+    if (!r->have_fin || r->hulls.size() != r->fin.size() * 2)
+        return fail(FZB_E_INVALID, "result was produced with FZB_F_NO_FINAL");
     for (size_t i = 0; i < r->fin.size(); i++) {
         if (hull_start) hull_start[i] = r->hulls[2 * i];
         if (hull_end) hull_end[i] = r->hulls[2 * i + 1];
@@ -769,7 +792,7 @@ static int ensure_out_cap(fzb_haystack *h, uint64_t need) {
     if (cap > (1ull << 27)) return fail(FZB_E_UNSUPPORTED, "more than 2^27 raw matches in one search");
     CK(cudaFree(h->d_out));
     h->d_out = nullptr;
-    CK(cudaMalloc(&h->d_out, (size_t)cap * sizeof(RawRec)));
+    CK(cudaMalloc(&h->d_out, (size_t)cap * (sizeof(RawRec) + sizeof(uint64_t))));
     h->out_cap = (uint32_t)cap;
     return FZB_OK;
 }
@@ -777,40 +800,33 @@ static int ensure_out_cap(fzb_haystack *h, uint64_t need) {
 // Runs one search attempt after another until the output buffer was large enough.  `enqueue` must
 // put EVERY kernel of the search on h->stream (filter included: the verify kernels clear the dirty
 // bitmap as they consume it, so a retry has to re-mark it) and may record h->ev[1] after its scan
-// kernel.  One attempt = one stream synchronisation: the counters and the first kSpecRecs records
-// are copied speculatively into pinned staging memory behind the kernels.
-constexpr uint32_t kSpecRecs = 16384;  // raw records copied speculatively (512 KiB, ~10 us of PCIe)
-constexpr uint32_t kSpecFin = 4096;    // final rows copied speculatively
+// kernel.  One attempt = one stream synchronisation and NO copy operation: k_post, enqueued behind the
+// emitting kernels, writes the counters, the raw records and the final rows into mapped pinned host
+// memory, which the host reads as soon as the stream has drained.
 
-// What k_post_small should do behind the emitting kernels (post.enable == false: host does it).
+// What k_post should do behind the emitting kernels.
 struct PostPlan {
-    bool enable = false;
-    int raw_mode = 0;  // 0 generation order, 1 canonical order, 2 arrival order (ordered lazily on the host)
-    int do_consolidate = 0;
-    bool global = false;  // FZB_F_GLOBAL: all-gather the groups of every shard behind the kernels
+    int mode = 1;         // 0 raw stream only; 1 consolidate_overlapping_matches; 2 final = sorted raw list
+    bool global = false;  // FZB_F_GLOBAL: reduce the groups of every shard behind the kernels
 };
+
+static void finalize_on_host(fzb_result *res, int mode);
 
 template <class F>
 static int run_emitting(fzb_haystack *h, fzb_result *res, F enqueue, PostPlan post = PostPlan()) {
+    detach_pending(h);  // k_post is about to overwrite the staging buffer an earlier result may still point at
     for (int attempt = 0; attempt < 8; attempt++) {
-        CK(cudaMemsetAsync(h->d_counters, 0,
-                           (CNT_COUNT + (post.enable ? 2 * (size_t)kPostMax : 0)) * sizeof(uint32_t), h->stream));
+        CK(cudaMemsetAsync(h->d_counters, 0, CNT_COUNT * sizeof(uint32_t), h->stream));
         CK(cudaEventRecord(h->ev[0], h->stream));
         h->ev1_recorded = false;
         int rc = enqueue();
         if (rc) return rc;
         CK(cudaGetLastError());
-        const uint32_t spec = std::min(kSpecRecs, h->out_cap);
-        if (post.enable) {
-            uint32_t *ranks = h->d_counters + CNT_COUNT;
-            k_rank<<<dim3(kPostMax / kRankThreads, kPostMax / kRankChunk), kRankThreads, 0, h->stream>>>(
-                h->d_out, h->out_cap, post.raw_mode, ranks, h->d_counters);
-            k_consolidate<<<1, kConsThreads, kConsSmem, h->stream>>>(h->d_out, ranks, h->d_raw_sorted,
-                                                                     h->d_keys_sorted, h->out_cap, post.raw_mode,
-                                                                     post.do_consolidate, h->d_fin, h->d_counters);
-            CK(cudaGetLastError());
-            res->stats.n_launches += 2;
-        }
+        PostArgs pa{h->d_out, reinterpret_cast<const uint64_t *>(h->d_out + h->out_cap), h->out_cap, post.mode, 1,
+                    h->d_sorted, h->d_fin, h->h_fin, h->h_stage, h->h_counters, h->d_counters};
+        k_post<<<h->sm_count, kPostThreads, kPostSmem, h->stream>>>(pa);
+        CK(cudaGetLastError());
+        res->stats.n_launches++;
         // fused multi-GPU reduction: exactly one all-gather per search, in the FIRST attempt (so that
         // a rank that has to retry locally never issues a collective the others do not)
         const bool fused_gather = post.global && attempt == 0;
@@ -823,14 +839,6 @@ static int run_emitting(fzb_haystack *h, fzb_result *res, F enqueue, PostPlan po
             res->stats.n_launches += 2;
         }
         CK(cudaEventRecord(h->ev[2], h->stream));
-        CK(cudaMemcpyAsync(h->h_counters, h->d_counters, CNT_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost,
-                           h->stream));
-        const bool raw_from_sorted = post.enable && post.raw_mode != 2;
-        CK(cudaMemcpyAsync(h->h_stage, raw_from_sorted ? h->d_raw_sorted : h->d_out, (size_t)spec * sizeof(RawRec),
-                           cudaMemcpyDeviceToHost, h->stream));
-        if (post.enable && post.do_consolidate)
-            CK(cudaMemcpyAsync(h->h_fin, h->d_fin, (size_t)kSpecFin * kFinCols * sizeof(int64_t),
-                               cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         const uint32_t n = h->h_counters[CNT_OUT];
         res->stats.n_candidates = h->h_counters[CNT_CAND];
@@ -849,38 +857,43 @@ static int run_emitting(fzb_haystack *h, fzb_result *res, F enqueue, PostPlan po
             if (rc) return rc;
             continue;
         }
-        const bool posted = post.enable && h->h_counters[CNT_POST_DONE] != 0;
-        const RawRec *dsrc = (posted && raw_from_sorted) ? h->d_raw_sorted : h->d_out;
-        const bool stage_ok = !raw_from_sorted || posted;  // staging holds what we want
-        res->raw.resize(n);
-        if (n && stage_ok) memcpy(res->raw.data(), h->h_stage, (size_t)std::min(n, spec) * sizeof(RawRec));
-        const uint32_t have = stage_ok ? std::min(n, spec) : 0;
-        if (n > have)
-            CK(cudaMemcpyAsync(res->raw.data() + have, dsrc + have, (size_t)(n - have) * sizeof(RawRec),
-                               cudaMemcpyDeviceToHost, h->stream));
-        if (posted && post.do_consolidate) {
-            const uint32_t nf = h->h_counters[CNT_NFINAL];
-            if (nf > kSpecFin)
-                CK(cudaMemcpyAsync(h->h_fin + (size_t)kSpecFin * kFinCols, h->d_fin + (size_t)kSpecFin * kFinCols,
-                                   (size_t)(nf - kSpecFin) * kFinCols * sizeof(int64_t), cudaMemcpyDeviceToHost,
-                                   h->stream));
-            if (n > have || nf > kSpecFin) CK(cudaStreamSynchronize(h->stream));
-            res->fin.resize(nf);
-            res->hulls.resize((size_t)nf * 2);
-            for (uint32_t i = 0; i < nf; i++) {
-                res->fin[i].start = h->h_fin[kFinCols * i];
-                res->fin[i].end = h->h_fin[kFinCols * i + 1];
-                res->fin[i].dist = (int32_t)h->h_fin[kFinCols * i + 2];
-                res->fin[i].idx = -1;
-                res->fin[i].ngram = -1;
-                res->hulls[2 * i] = h->h_fin[kFinCols * i + 3];
-                res->hulls[2 * i + 1] = h->h_fin[kFinCols * i + 4];
-            }
-        } else if (n > have) {
+        const bool posted = h->h_counters[CNT_POST_DONE] != 0;
+        res->raw.clear();
+        res->raw_n = n;
+        res->raw_ordered = false;
+        if (posted) {  // the records are in h->h_stage: copied out lazily (fetch_raw)
+            std::lock_guard<std::mutex> lock(g_pending_mutex);
+            res->owner = h;
+            h->pending = res;
+        } else if (n) {  // list too long for k_post: fetch it, the host orders and consolidates
+            res->raw.resize(n);
+            CK(cudaMemcpyAsync(res->raw.data(), h->d_out, (size_t)n * sizeof(RawRec), cudaMemcpyDeviceToHost, h->stream));
             CK(cudaStreamSynchronize(h->stream));
         }
-        res->device_post = posted;
-        res->raw_ordered = posted && raw_from_sorted;
+        res->fin.clear();
+        res->hulls.clear();
+        res->have_fin = false;
+        res->device_post = false;
+        if (post.mode != 0) {
+            if (posted) {
+                const uint32_t nf = h->h_counters[CNT_NFINAL];
+                res->fin.resize(nf);
+                res->hulls.resize((size_t)nf * 2);
+                for (uint32_t i = 0; i < nf; i++) {
+                    res->fin[i].start = h->h_fin[kFinCols * i];
+                    res->fin[i].end = h->h_fin[kFinCols * i + 1];
+                    res->fin[i].dist = (int32_t)h->h_fin[kFinCols * i + 2];
+                    res->fin[i].idx = -1;
+                    res->fin[i].ngram = -1;
+                    res->hulls[2 * i] = h->h_fin[kFinCols * i + 3];
+                    res->hulls[2 * i + 1] = h->h_fin[kFinCols * i + 4];
+                }
+                res->device_post = true;
+            } else {
+                finalize_on_host(res, post.mode);
+            }
+            res->have_fin = true;
+        }
         float ms = 0.f;
         cudaEventElapsedTime(&ms, h->ev[0], h->ev[2]);
         res->stats.gpu_ms = ms;
@@ -905,6 +918,7 @@ static void sort_generation_order(std::vector<RawRec> &v);
 static void sort_canonical(std::vector<RawRec> &v);
 
 void fzb_result::order_raw() {
+    fetch_raw();
     if (raw_ordered) return;
     if (raw_order == 0)
         sort_generation_order(raw);
@@ -929,6 +943,23 @@ static void sort_canonical(std::vector<RawRec> &v) {
     });
 }
 
+// Host twin of k_post for lists it does not take (more than kPostMax records).
+static void finalize_on_host(fzb_result *res, int mode) {
+    if (mode == 1) {
+        consolidate_recs(res->raw, res->fin, &res->hulls);
+        return;
+    }
+    res->fin = res->raw;
+    sort_canonical(res->fin);
+    res->hulls.resize(res->fin.size() * 2);
+    for (size_t i = 0; i < res->fin.size(); i++) {
+        res->fin[i].idx = -1;
+        res->fin[i].ngram = -1;
+        res->hulls[2 * i] = res->fin[i].start;
+        res->hulls[2 * i + 1] = res->fin[i].end;
+    }
+}
+
 static int set_filter_attrs(size_t smem) {
     // per device: the attribute belongs to the function on the current device
     CK(cudaFuncSetAttribute(k_filter_sampled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -940,6 +971,7 @@ static int set_filter_attrs(size_t smem) {
 }
 
 constexpr size_t kFilterSmem = kTblSize + 256 * sizeof(uint32_t);
+constexpr int kVerifyCtasPerSm = 8;  // k_verify_lev is latency bound (one DRAM round trip + a dependent chain per granule)
 
 // The q-sample lemma of k_filter_sampled needs floor((m-k-3)/4) >= k+1 aligned words per occurrence.
 static bool sampled_filter_applies(uint32_t m, uint32_t k, uint32_t flags) {
@@ -1022,7 +1054,7 @@ static int enqueue_filter(fzb_haystack *h, const ScanParams &p, bool sampled, fz
 
 // n-gram Levenshtein search (also serves exact search as k == 0, L == m)
 static int search_lev_ngrams(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint32_t k, uint32_t flags,
-                             fzb_result *res, bool want_final) {
+                             fzb_result *res, int post_mode) {
     ScanParams p;
     fill_params(h, pattern, m, p);
     p.k = (int)k;
@@ -1045,12 +1077,13 @@ static int search_lev_ngrams(fzb_haystack *h, const uint8_t *pattern, uint32_t m
     }
     // dense route: confirmed n-gram hits go to a list and are verified one lane per hit (the window of a
     // hit must fit a lane's shared-memory slot); the list overflowing triggers one retry in granule mode
+    const int vm = verify_mode((int)m, p.L);
     bool use_hits = !sampled && k > 0 && (m + 2 * k + 8 <= (uint32_t)kHitSlotBytes);
     if (use_hits && !h->d_hits) {
         h->hits_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1u << 20, h->capacity / 256), 1u << 28);
         CK(cudaMalloc(&h->d_hits, (size_t)h->hits_cap * sizeof(uint64_t)));
     }
-    bool fuse_gather = want_final && (flags & FZB_F_GLOBAL) != 0;
+    bool fuse_gather = post_mode == 1 && (flags & FZB_F_GLOBAL) != 0;
     if (flags & FZB_F_TINY_LIST) p.glist_cap = std::min(h->glist_cap, 8u);
 retry_without_hits:
     p.hits = use_hits ? h->d_hits : nullptr;
@@ -1059,23 +1092,39 @@ retry_without_hits:
         int r2 = enqueue_filter(h, p, sampled, res);
         if (r2) return r2;
         if (use_hits) {
-            k_verify_hits<<<h->sm_count * 8, kHitThreads, 0, h->stream>>>(p, h->d_out, h->out_cap, h->d_counters);
+            if (vm == 0)
+                k_verify_hits<0><<<h->sm_count * 8, kHitThreads, 0, h->stream>>>(p, h->d_out, h->out_cap, h->d_counters);
+            else if (vm == 1)
+                k_verify_hits<1><<<h->sm_count * 8, kHitThreads, 0, h->stream>>>(p, h->d_out, h->out_cap, h->d_counters);
+            else
+                k_verify_hits<2><<<h->sm_count * 8, kHitThreads, 0, h->stream>>>(p, h->d_out, h->out_cap, h->d_counters);
             res->stats.n_launches++;
             return FZB_OK;
         }
-        for (int scan_mode = 0; scan_mode < 2; scan_mode++)
-            k_verify_lev<<<h->sm_count * 4, kVerifyThreads, 0, h->stream>>>(
-                p, h->bitmap_words, h->d_glist, p.glist_cap, scan_mode, h->d_out, h->out_cap, h->d_counters);
+        for (int scan_mode = 0; scan_mode < 2; scan_mode++) {
+            const int grid = h->sm_count * kVerifyCtasPerSm;
+            if (vm == 0)
+                k_verify_lev<0><<<grid, kVerifyThreads, 0, h->stream>>>(p, h->bitmap_words, h->d_glist, p.glist_cap,
+                                                                        scan_mode, h->d_out, h->out_cap, h->d_counters);
+            else if (vm == 1)
+                k_verify_lev<1><<<grid, kVerifyThreads, 0, h->stream>>>(p, h->bitmap_words, h->d_glist, p.glist_cap,
+                                                                        scan_mode, h->d_out, h->out_cap, h->d_counters);
+            else
+                k_verify_lev<2><<<grid, kVerifyThreads, 0, h->stream>>>(p, h->bitmap_words, h->d_glist, p.glist_cap,
+                                                                        scan_mode, h->d_out, h->out_cap, h->d_counters);
+        }
         res->stats.n_launches += 2;
         return FZB_OK;
-    }, PostPlan{true, 2, want_final ? 1 : 0, fuse_gather});  // raw order (n-gram, hit index): lazily
+    }, PostPlan{post_mode, fuse_gather});  // the raw stream's order (n-gram, hit index) is restored lazily
     if (rc) return rc;
     if (use_hits && h->h_counters[CNT_HITS] > p.hits_cap) {
         // the fused all-gather (if any) went out with valid = 0 (k_verify_hits raised CNT_OVERFLOW), so every
         // rank will take finish_global's staged round; the retry itself must not issue another collective
         fuse_gather = false;
         use_hits = false;
+        res->fetch_raw();  // unlink from the staging buffer
         res->raw.clear();
+        res->raw_n = 0;
         res->fin.clear();
         goto retry_without_hits;
     }
@@ -1113,7 +1162,7 @@ static int run_lp(fzb_haystack *h, fzb_result *res, F enqueue, PostPlan post = P
 }
 
 static int search_lev_lp(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint32_t k, fzb_result *res,
-                         bool want_final) {
+                         int post_mode) {
     if (k > 0xFFFF) return fail(FZB_E_UNSUPPORTED, "max_l_dist too large");
     ScanParams p;
     fill_params(h, pattern, m, p);
@@ -1127,7 +1176,7 @@ static int search_lev_lp(fzb_haystack *h, const uint8_t *pattern, uint32_t m, ui
         k_lev_lp<<<grid, kLpThreads, 0, h->stream>>>(p, h->d_scratch, cap, h->d_out, h->out_cap, h->d_counters);
         res->stats.n_launches++;
         return FZB_OK;
-    }, PostPlan{true, 1, want_final ? 1 : 0});
+    }, PostPlan{post_mode, false});
     if (rc) return rc;
     res->raw_order = 1;
     return FZB_OK;
@@ -1135,7 +1184,7 @@ static int search_lev_lp(fzb_haystack *h, const uint8_t *pattern, uint32_t m, ui
 
 static int search_generic(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint32_t max_subs, uint32_t max_ins,
                           uint32_t max_dels, uint32_t max_l, bool ngrams, uint32_t flags, fzb_result *res,
-                          bool want_final) {
+                          int post_mode) {
     // the packed candidate of sim_generic keeps 6 bits per counter
     if (max_l > 63) return fail(FZB_E_UNSUPPORTED, "max_l_dist > 63 is not supported by the generic search");
     // no counter can exceed max_l (every operation that increments one costs >= 1), so clamping the
@@ -1160,7 +1209,7 @@ static int search_generic(fzb_haystack *h, const uint8_t *pattern, uint32_t m, u
                                                              h->d_counters);
             res->stats.n_launches++;
             return FZB_OK;
-        }, PostPlan{true, 1, want_final ? 1 : 0});
+        }, PostPlan{post_mode, false});
         if (rc) return rc;
         res->raw_order = 1;
         return FZB_OK;
@@ -1181,7 +1230,7 @@ static int search_generic(fzb_haystack *h, const uint8_t *pattern, uint32_t m, u
                                                              h->out_cap, h->d_counters);
         res->stats.n_launches++;
         return FZB_OK;
-    });
+    }, PostPlan{post_mode, false});
     if (rc) return rc;
     res->raw_order = 2;  // n-gram major, hit index, then the window's matches in canonical order
     return FZB_OK;
@@ -1203,20 +1252,19 @@ static int finish_global(fzb_haystack *h, fzb_result *res) {
         res->has_global = true;
         return FZB_OK;
     } else {  // staged: the local result is complete now, whatever it took
-        if (res->final_is_raw) res->order_raw();
-        const std::vector<RawRec> &v = res->final_is_raw ? res->raw : res->fin;
+        const std::vector<RawRec> &v = res->fin;
         std::vector<int64_t> rows(v.size() * kFinCols);
         for (size_t i = 0; i < v.size(); i++) {
             rows[kFinCols * i + 0] = v[i].start;
             rows[kFinCols * i + 1] = v[i].end;
             rows[kFinCols * i + 2] = v[i].dist;
-            rows[kFinCols * i + 3] = res->final_is_raw ? v[i].start : res->hulls[2 * i];
-            rows[kFinCols * i + 4] = res->final_is_raw ? v[i].end : res->hulls[2 * i + 1];
+            rows[kFinCols * i + 3] = res->hulls[2 * i];
+            rows[kFinCols * i + 4] = res->hulls[2 * i + 1];
         }
         int rc = allgather_groups_staged(h, rows, all, counts);
         if (rc) return rc;
     }
-    if (res->final_is_raw) {  // unconsolidated routes (exact, Hamming): the global list is the sorted union
+    if (res->unconsolidated) {  // unconsolidated routes (exact, Hamming): the global list is the sorted union
         res->gfin.resize(all.size() / kFinCols);
         for (size_t i = 0; i < res->gfin.size(); i++) {
             res->gfin[i].start = all[kFinCols * i];
@@ -1271,14 +1319,13 @@ extern "C" int fzb_search_levenshtein(fzb_haystack *h, const uint8_t *pattern, u
         // LevenshteinSearch.consolidate_matches (levenshtein.py:158-160) also applies when k == 0
         const bool want_final = !(flags & FZB_F_NO_FINAL);
         if (ngrams)
-            rc = search_lev_ngrams(h, pattern, m, k, flags, res, want_final);
+            rc = search_lev_ngrams(h, pattern, m, k, flags, res, want_final ? 1 : 0);
         else
-            rc = search_lev_lp(h, pattern, m, k, res, want_final);
-        if (rc == FZB_OK && want_final && !res->device_post) consolidate_recs(res->raw, res->fin, &res->hulls);
+            rc = search_lev_lp(h, pattern, m, k, res, want_final ? 1 : 0);
         if (rc == FZB_OK && want_final && (flags & FZB_F_GLOBAL)) rc = finish_global(h, res);
     }
     if (rc) {
-        delete res;
+        fzb_result_destroy(res);
         return rc;
     }
     *out = res;
@@ -1320,16 +1367,16 @@ extern "C" int fzb_search_exact(fzb_haystack *h, const uint8_t *pattern, uint32_
     if (rc) return rc;
     rc = check_pattern(h, pattern, m, flags);
     if (rc == FZB_E_INVALID && h) rc = fail(FZB_E_INVALID, "subsequence must not be empty");
-    if (rc == FZB_OK) rc = search_lev_ngrams(h, pattern, m, 0, flags, res, false);
+    if (rc == FZB_OK) rc = search_lev_ngrams(h, pattern, m, 0, flags, res, 2);
     if (rc) {
-        delete res;
+        fzb_result_destroy(res);
         return rc;
     }
-    res->final_is_raw = true;  // ExactSearch.consolidate_matches is the base no-op (common.py:198-205)
+    res->unconsolidated = true;  // ExactSearch.consolidate_matches is the base no-op (common.py:198-205)
     if (flags & FZB_F_GLOBAL) {
         rc = finish_global(h, res);
         if (rc) {
-            delete res;
+            fzb_result_destroy(res);
             return rc;
         }
     }
@@ -1411,23 +1458,21 @@ extern "C" int fzb_search_hamming(fzb_haystack *h, const uint8_t *pattern, uint3
                 }
                 res->stats.n_launches++;
                 return FZB_OK;
-            }, PostPlan{true, 1, 0});
+            }, PostPlan{2, false});  // FINAL == RAW in (start, end, dist) order, ordered by k_post
             if (r2) return r2;
             res->raw_order = 1;
-            res->order_raw();  // FINAL == RAW for this route: order now
-            for (auto &r : res->raw) r.ngram = -1;
             return FZB_OK;
         }();
     }
     if (rc) {
-        delete res;
+        fzb_result_destroy(res);
         return rc;
     }
-    res->final_is_raw = true;
+    res->unconsolidated = true;
     if (flags & FZB_F_GLOBAL) {
         rc = finish_global(h, res);
         if (rc) {
-            delete res;
+            fzb_result_destroy(res);
             return rc;
         }
     }
@@ -1446,19 +1491,18 @@ extern "C" int fzb_search_generic(fzb_haystack *h, const uint8_t *pattern, uint3
         // find_near_matches_generic (generic_search.py:25-54)
         const bool want_final = !(flags & FZB_F_NO_FINAL);
         if (max_l == 0 && !(flags & (FZB_F_FORCE_LP | FZB_F_FORCE_NGRAMS))) {
-            rc = search_lev_ngrams(h, pattern, m, 0, flags, res, want_final);
+            rc = search_lev_ngrams(h, pattern, m, 0, flags, res, want_final ? 1 : 0);
         } else {
             bool ngrams = m / (max_l + 1) >= 3;
             if (flags & FZB_F_FORCE_NGRAMS) ngrams = true;
             if (flags & FZB_F_FORCE_LP) ngrams = false;
-            rc = search_generic(h, pattern, m, max_subs, max_ins, max_dels, max_l, ngrams, flags, res, want_final);
+            rc = search_generic(h, pattern, m, max_subs, max_ins, max_dels, max_l, ngrams, flags, res,
+                                want_final ? 1 : 0);
         }
-        if (rc == FZB_OK && want_final && !(res->device_post && res->stats.route != 5))
-            consolidate_recs(res->raw, res->fin, &res->hulls);
         if (rc == FZB_OK && want_final && (flags & FZB_F_GLOBAL)) rc = finish_global(h, res);
     }
     if (rc) {
-        delete res;
+        fzb_result_destroy(res);
         return rc;
     }
     *out = res;
@@ -1509,23 +1553,77 @@ extern "C" int fzb_find_near_matches(const uint8_t *pattern, uint32_t m, const u
     return rc;
 }
 
+extern "C" int fzb_debug_counters(const fzb_haystack *h, uint32_t out[16]) {
+    if (!h || !out) return fail(FZB_E_INVALID, "NULL argument");
+    memcpy(out, h->h_counters, CNT_COUNT * sizeof(uint32_t));
+    return FZB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// test hook: the expansion routines of the verify kernels on caller-supplied (sub, seq, budget) cases
+// ------------------------------------------------------------------------------------------------
+extern "C" int fzb_debug_expand(const uint8_t *subs, const uint32_t *sub_off, const uint8_t *seqs,
+                                const uint32_t *seq_off, const int32_t *max_l, const int32_t *variant, uint32_t count,
+                                int device, int32_t *out) {
+    if (count && (!subs || !sub_off || !seqs || !seq_off || !max_l || !variant || !out))
+        return fail(FZB_E_INVALID, "NULL argument");
+    if (device < 0 || device >= fzb_device_count()) return fail(FZB_E_CUDA, "CUDA device %d not available", device);
+    if (count == 0) return FZB_OK;
+    for (uint32_t i = 0; i < count; i++) {
+        if (sub_off[i + 1] < sub_off[i] || seq_off[i + 1] < seq_off[i]) return fail(FZB_E_INVALID, "bad offsets");
+        if (sub_off[i + 1] - sub_off[i] >= (uint32_t)kDbgMax || seq_off[i + 1] - seq_off[i] >= 2u * kDbgMax)
+            return fail(FZB_E_UNSUPPORTED, "case %u too long for the debug entry", i);
+        if (variant[i] < 0 || variant[i] > 2 || max_l[i] < 0) return fail(FZB_E_INVALID, "bad variant / budget");
+    }
+    CK(cudaSetDevice(device));
+    uint8_t *d_subs = nullptr, *d_seqs = nullptr;
+    uint32_t *d_so = nullptr, *d_qo = nullptr;
+    int32_t *d_k = nullptr, *d_v = nullptr, *d_out = nullptr;
+    const size_t nsub = std::max<size_t>(sub_off[count], 1), nseq = std::max<size_t>(seq_off[count], 1);
+    int rc = [&]() -> int {
+        CK(cudaMalloc(&d_subs, nsub));
+        CK(cudaMalloc(&d_seqs, nseq));
+        CK(cudaMalloc(&d_so, (count + 1) * sizeof(uint32_t)));
+        CK(cudaMalloc(&d_qo, (count + 1) * sizeof(uint32_t)));
+        CK(cudaMalloc(&d_k, count * sizeof(int32_t)));
+        CK(cudaMalloc(&d_v, count * sizeof(int32_t)));
+        CK(cudaMalloc(&d_out, (size_t)count * 8 * sizeof(int32_t)));
+        CK(cudaMemcpy(d_subs, subs, sub_off[count], cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d_seqs, seqs, seq_off[count], cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d_so, sub_off, (count + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d_qo, seq_off, (count + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d_k, max_l, count * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d_v, variant, count * sizeof(int32_t), cudaMemcpyHostToDevice));
+        k_debug_expand<<<count, 32>>>(d_subs, d_so, d_seqs, d_qo, d_k, d_v, d_out);
+        CK(cudaGetLastError());
+        CK(cudaMemcpy(out, d_out, (size_t)count * 8 * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        return FZB_OK;
+    }();
+    cudaFree(d_subs);
+    cudaFree(d_seqs);
+    cudaFree(d_so);
+    cudaFree(d_qo);
+    cudaFree(d_k);
+    cudaFree(d_v);
+    cudaFree(d_out);
+    return rc;
+}
+
 // ------------------------------------------------------------------------------------------------
 // results
 // ------------------------------------------------------------------------------------------------
 extern "C" uint64_t fzb_result_count(const fzb_result *r, int which) {
     if (!r) return 0;
     if (which != FZB_RAW && r->has_global) return r->gfin.size();
-    if (which == FZB_RAW || r->final_is_raw) return r->raw.size();
+    if (which == FZB_RAW) return r->raw_n;
     return r->fin.size();
 }
 
 extern "C" int fzb_result_copy(const fzb_result *r, int which, int64_t *start, int64_t *end, int32_t *dist,
                                int32_t *anchor_ngram, int64_t *anchor_idx) {
     if (!r) return fail(FZB_E_INVALID, "result is NULL");
-    if (which == FZB_RAW || r->final_is_raw) const_cast<fzb_result *>(r)->order_raw();
-    const std::vector<RawRec> &v = (which != FZB_RAW && r->has_global)
-                                       ? r->gfin
-                                       : ((which == FZB_RAW || r->final_is_raw) ? r->raw : r->fin);
+    if (which == FZB_RAW) const_cast<fzb_result *>(r)->order_raw();
+    const std::vector<RawRec> &v = (which != FZB_RAW && r->has_global) ? r->gfin : (which == FZB_RAW ? r->raw : r->fin);
     const bool anchors = (which == FZB_RAW) && (r->stats.route <= 2);
     for (size_t i = 0; i < v.size(); i++) {
         if (start) start[i] = v[i].start;
@@ -1543,4 +1641,14 @@ extern "C" int fzb_result_stats(const fzb_result *r, fzb_stats *out) {
     return FZB_OK;
 }
 
-extern "C" void fzb_result_destroy(fzb_result *r) { delete r; }
+extern "C" void fzb_result_destroy(fzb_result *r) {
+    if (!r) return;
+    {
+        std::lock_guard<std::mutex> lock(g_pending_mutex);
+        if (r->owner) {
+            r->owner->pending = nullptr;
+            r->owner = nullptr;
+        }
+    }
+    delete r;
+}

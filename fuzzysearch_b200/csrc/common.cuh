@@ -42,7 +42,7 @@ struct ScanParams {
 
 // counters[] slots (device, uint32 each unless noted)
 enum { CNT_OUT = 0, CNT_CAND = 1, CNT_OVERFLOW = 2, CNT_GRAN = 3, CNT_WORK = 4, /* 5,6: post_kernels.cuh */
-       CNT_HITS = 7, CNT_HITWORK = 8, CNT_COUNT = 16 };
+       CNT_HITS = 7, CNT_HITWORK = 8, /* 9: post_kernels.cuh */ CNT_KEYS = 14, CNT_COUNT = 16 };
 
 __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
     x += 0x9E3779B97F4A7C15ull;

@@ -554,23 +554,122 @@ __device__ __forceinline__ bool expand_any(const uint8_t *sub, int sublen, const
 }
 
 // ------------------------------------------------------------------------------------------------
+// Bit-parallel expansion (patterns of at most 64 bytes): the same function _expand computes
+// (levenshtein_ngram.py:8-143), evaluated with the Myers / Hyyro bit-vector recurrence instead of the
+// reference's cell-by-cell lists.  One machine word holds the vertical deltas of one DP row of the
+// reference (= one haystack character); D[len(sub)][l] is tracked from the horizontal delta at the last
+// pattern position, with +1 shifted in at position 0 because D[0][l] = l (prefix-anchored distance).
+//   * "long" variant (_py_expand_long, :77-143): the exact rule -- minimise over prefix lengths l, ties to
+//     the largest l.  Its Ukkonen band only prunes cells that cannot matter, so the full
+//     recurrence returns the same (dist, len).
+//   * "short" variant (_py_expand_short, :22-74): same scan plus the reference's early break
+//     `elif min(row) >= min_score: break` (:71-72); the row minimum is recovered from the
+//     vertical deltas (a running sum over the <= max(2k,10) positions), only on rows that do not improve.
+// Both were checked against the oracle on 600 000 random cases on the CPU before being written here;
+// tests/test_gpu_oracle.py / test_gpu_expand.py pin the device code.
+// The Eq masks come from ONE table per pattern, PM[c] = {i : P[i] == c}: the right sub-pattern
+// P[s+L:] is PM >> (s+L); the left one, reversed P[:s], is the bit reversal of PM shifted down.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void build_pm(unsigned long long *sPM, const uint8_t *P, int m, int tid, int nthreads) {
+    for (int c = tid; c < 256; c += nthreads) {
+        unsigned long long v = 0;
+        for (int i = 0; i < m && i < 64; i++) v |= (unsigned long long)(P[i] == c) << i;
+        sPM[c] = v;
+    }
+}
+
+template <typename Wt, int DIR>
+__device__ __forceinline__ bool expand_bp(const unsigned long long *sPM, int s_off, int sublen, const uint8_t *seq,
+                                          int seqlen, int max_l, int &dist, int &len, int variant = 0) {
+    // DIR = +1: sub = P[s_off : s_off+sublen];  DIR = -1: sub = reversed P[:s_off] (sublen == s_off)
+    if (sublen == 0) {  // :42-43, :86-88
+        dist = 0;
+        len = 0;
+        return true;
+    }
+    // levenshtein_ngram.py:16 (variant 1 / 2 force _py_expand_short / _py_expand_long: fzb_debug_expand only)
+    const bool is_long = variant == 0 ? sublen > max(2 * max_l, 10) : variant == 2;
+    Wt VP = ~(Wt)0, VN = 0;
+    const Wt top = (Wt)1 << (sublen - 1);
+    int score = sublen, min_score = sublen, min_idx = -1;  // :49-50, :94-95
+    for (int si = 0; si < seqlen; si++) {
+        const unsigned long long pm = sPM[seq[DIR * si]];
+        const Wt Eq = DIR > 0 ? (Wt)(pm >> s_off) : (Wt)(__brevll(pm) >> (64 - s_off));
+        const Wt Xv = Eq | VN;
+        const Wt Xh = (((Eq & VP) + VP) ^ VP) | Eq;
+        Wt HP = VN | ~(Xh | VP);
+        Wt HN = VP & Xh;
+        score += (HP & top) ? 1 : 0;
+        score -= (HN & top) ? 1 : 0;
+        HP = (HP << 1) | (Wt)1;  // D[0][l] = l: the top row steps by +1
+        HN <<= 1;
+        VP = HN | ~(Xv | HP);
+        VN = HP & Xv;
+        if (score <= min_score) {  // :66-68, :137-139 (ties -> the later row)
+            min_score = score;
+            min_idx = si;
+        } else if (!is_long) {  // :71-72: stop if no cell of this row is below the best so far
+            int v = si + 1, row_min = 1 << 30;
+            for (int j = 0; j < sublen; j++) {
+                v += (int)((VP >> j) & 1) - (int)((VN >> j) & 1);
+                row_min = min(row_min, v);
+            }
+            if (row_min >= min_score) break;
+        }
+    }
+    if (min_score <= max_l) {  // :74, :143
+        dist = min_score;
+        len = min_idx + 1;
+        return true;
+    }
+    return false;
+}
+
+// The cell-by-cell routines need a DP row in local memory; the bit-parallel modes must not carry it.
+template <int VM>
+struct DpHolder {
+    __device__ __forceinline__ DpScratch *get() { return nullptr; }
+};
+template <>
+struct DpHolder<2> {
+    DpScratch s;
+    __device__ __forceinline__ DpScratch *get() { return &s; }
+};
+
+// Verification mode of a pattern: 0 = bit-parallel, 32-bit words (m <= 64, m-L <= 32); 1 = bit-parallel, 64-bit
+// words (m <= 64); 2 = cell-by-cell DP with the row in registers / local memory (longer patterns).
+__host__ __device__ __forceinline__ int verify_mode(int m, int L) { return m > 64 ? 2 : (m - L <= 32 ? 0 : 1); }
+
+// ------------------------------------------------------------------------------------------------
 // Verify kernel for the Levenshtein n-gram route (levenshtein_ngram.py:159-198).  One warp per
 // marked granule; lane <-> anchor position.  Boundary rules are evaluated in GLOBAL coordinates
 // (0 and N), never at shard seams.
 // ------------------------------------------------------------------------------------------------
 constexpr int kVerifyThreads = 128;
 
+// canonical order (start, end, dist): start < 2^46, end-start < 2^10, dist < 2^8
+__device__ __forceinline__ uint64_t canonical_key(const RawRec &r) {
+    return ((uint64_t)r.start << 18) | ((uint64_t)(r.end - r.start) << 8) | (uint64_t)r.dist;
+}
+
+// Appends one raw match.  The packed canonical keys k_post orders and consolidates live in a parallel array
+// right behind the records, with their own counter: a caller that KNOWS another lane of its warp is emitting
+// the identical (start, end, dist) right now passes with_key = false for all but one of them -- duplicates
+// change neither the groups nor the winners of consolidate_overlapping_matches, and the n-gram search finds
+// most occurrences once per n-gram (levenshtein_ngram.py:194-198 yields them all; the raw stream keeps them).
 __device__ __forceinline__ void emit(RawRec *out, uint32_t cap, uint32_t *counters, int64_t start,
-                                     int64_t end, int64_t idx, int dist, int ngram) {
+                                     int64_t end, int64_t idx, int dist, int ngram, bool with_key = true) {
     uint32_t slot = atomicAdd(&counters[CNT_OUT], 1u);
-    if (slot < cap) {
-        RawRec r;
-        r.start = start;
-        r.end = end;
-        r.idx = idx;
-        r.dist = dist;
-        r.ngram = ngram;
-        out[slot] = r;
+    RawRec r;
+    r.start = start;
+    r.end = end;
+    r.idx = idx;
+    r.dist = dist;
+    r.ngram = ngram;
+    if (slot < cap) out[slot] = r;
+    if (with_key) {
+        slot = atomicAdd(&counters[CNT_KEYS], 1u);
+        if (slot < cap) reinterpret_cast<uint64_t *>(out + cap)[slot] = canonical_key(r);
     }
 }
 
@@ -599,8 +698,11 @@ __device__ __forceinline__ int64_t stage_window(const ScanParams &p, int64_t gba
 // All lanes of the warp call this together (lanes without an anchor pass valid = false).  Each lane
 // first finds the next n-gram that really occurs at its anchor (cheap), THEN the lanes that found one
 // run the two expansions side by side (converged), and the search for further n-grams resumes.
-__device__ void verify_anchor_lev(const ScanParams &p, const uint8_t *sP, const uint8_t *W, int64_t idx, bool valid,
-                                  DpScratch &S, RawRec *out, uint32_t cap, uint32_t *counters, int j_lo, int j_hi) {
+// VM = verify_mode(m, L); S is only used (and only non-null) in mode 2.
+template <int VM>
+__device__ void verify_anchor_lev(const ScanParams &p, const uint8_t *sP, const unsigned long long *sPM,
+                                  const uint8_t *W, int64_t idx, bool valid, DpScratch *S, RawRec *out, uint32_t cap,
+                                  uint32_t *counters, int j_lo, int j_hi) {
     // W[g] is the haystack byte at global position g (shared-memory window); n-grams j_lo..j_hi-1
     const int m = p.m, k = p.k, L = p.L;
     const int64_t N = p.N;
@@ -634,15 +736,32 @@ __device__ void verify_anchor_lev(const ScanParams &p, const uint8_t *sP, const 
         if (ok) {
             const int64_t rhi = min(N, p0 + m + k);
             const int rlen = (int)max((int64_t)0, rhi - (idx + L));
-            ok = expand_any<1>(sP + s + L, m - s - L, h + L, rlen, k, S, dr, rs);
+            if (VM == 0)
+                ok = expand_bp<uint32_t, 1>(sPM, s + L, m - s - L, h + L, rlen, k, dr, rs);
+            else if (VM == 1)
+                ok = expand_bp<unsigned long long, 1>(sPM, s + L, m - s - L, h + L, rlen, k, dr, rs);
+            else
+                ok = expand_any<1>(sP + s + L, m - s - L, h + L, rlen, k, *S, dr, rs);
         }
         // left: _expand(P[:s][::-1], H[max(0,p0-(k-dr)) : idx][::-1], k-dr)   (:185-189)
         if (ok) {
             const int64_t llo = max((int64_t)0, p0 - (k - dr));
             const int llen = (int)max((int64_t)0, idx - llo);
-            ok = expand_any<-1>(sP + s - 1, s, h - 1, llen, k - dr, S, dl, ls);
+            if (VM == 0)
+                ok = expand_bp<uint32_t, -1>(sPM, s, s, h - 1, llen, k - dr, dl, ls);
+            else if (VM == 1)
+                ok = expand_bp<unsigned long long, -1>(sPM, s, s, h - 1, llen, k - dr, dl, ls);
+            else
+                ok = expand_any<-1>(sP + s - 1, s, h - 1, llen, k - dr, *S, dl, ls);
         }
-        if (ok) emit(out, cap, counters, idx - ls, idx + L + rs, idx, dl + dr, j);  // :194-198
+        // :194-198.  Lanes of this warp that found the SAME match through different n-grams share one key.
+        const unsigned okm = __ballot_sync(0xFFFFFFFFu, ok);
+        if (ok) {
+            const unsigned long long ident = ((unsigned long long)(idx - ls) << 18) |
+                                             ((unsigned long long)(L + rs + ls) << 8) | (unsigned long long)(dl + dr);
+            const unsigned peers = __match_any_sync(okm, ident);
+            emit(out, cap, counters, idx - ls, idx + L + rs, idx, dl + dr, j, (__ffs(peers) - 1) == (int)(threadIdx.x & 31));
+        }
         j++;
     }
 }
@@ -652,31 +771,38 @@ __device__ void verify_anchor_lev(const ScanParams &p, const uint8_t *sP, const 
 // whole GPU instead of serialising on the warp that owns their bitmap words.  Each processed granule
 // clears its own bit; if the list overflows (dense candidates, e.g. small alphabets) the bits left
 // set are swept by the bitmap-scanning fallback loop of the same kernel launched in "scan" mode.
-__device__ __forceinline__ void verify_granule_lev(const ScanParams &p, const uint8_t *sP, uint32_t *sWin,
-                                                   int64_t granule, int lane, DpScratch &S, RawRec *out,
-                                                   uint32_t cap, uint32_t *counters) {
+template <int VM>
+__device__ __forceinline__ void verify_granule_lev(const ScanParams &p, const uint8_t *sP,
+                                                   const unsigned long long *sPM, uint32_t *sWin, int64_t granule,
+                                                   int lane, DpScratch *S, RawRec *out, uint32_t cap,
+                                                   uint32_t *counters) {
     const int64_t gbase = p.buf_lo + (granule << kGranuleShift);
     const int64_t alo = stage_window(p, gbase, p.m + p.k, lane, sWin);
     const uint8_t *W = reinterpret_cast<const uint8_t *>(sWin) - alo;
 #pragma unroll 1
     for (int half = 0; half < kGranule / 32; half++) {
         const int64_t idx = gbase + half * 32 + lane;
-        verify_anchor_lev(p, sP, W, idx, idx >= p.own_lo && idx < p.own_hi, S, out, cap, counters, 0, p.n_ngrams);
+        verify_anchor_lev<VM>(p, sP, sPM, W, idx, idx >= p.own_lo && idx < p.own_hi, S, out, cap, counters, 0,
+                              p.n_ngrams);
     }
 }
 
 // scan_mode == 0: process glist[0 .. min(CNT_GRAN, glist_cap)) one granule per warp.
 // scan_mode == 1: only if the list overflowed, sweep the bitmap for the bits still set.
+template <int VM>
 __global__ void __launch_bounds__(kVerifyThreads)
 k_verify_lev(const ScanParams p, uint64_t bitmap_words, const uint32_t *glist, uint32_t glist_cap, int scan_mode,
              RawRec *out, uint32_t cap, uint32_t *counters) {
     __shared__ uint8_t sP[256];
+    __shared__ unsigned long long sPM[VM < 2 ? 256 : 1];
     __shared__ uint32_t sWinAll[kVerifyThreads / 32][kWinWords];
     const uint32_t ngran = counters[CNT_GRAN];
     if (scan_mode && ngran <= glist_cap) return;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) sP[i] = p.P[i];
+    if (VM < 2) build_pm(sPM, p.P, p.m, threadIdx.x, blockDim.x);
     __syncthreads();
-    DpScratch S;
+    DpHolder<VM> dp_holder;
+    DpScratch *S = dp_holder.get();
     const int lane = threadIdx.x & 31;
     uint32_t *sWin = sWinAll[threadIdx.x >> 5];
     if (!scan_mode) {
@@ -687,7 +813,7 @@ k_verify_lev(const ScanParams p, uint64_t bitmap_words, const uint32_t *glist, u
             item = __shfl_sync(0xFFFFFFFFu, item, 0);
             if (item >= nitems) break;
             const uint32_t g = glist[item];
-            verify_granule_lev(p, sP, sWin, (int64_t)g, lane, S, out, cap, counters);
+            verify_granule_lev<VM>(p, sP, sPM, sWin, (int64_t)g, lane, S, out, cap, counters);
             if (lane == 0) atomicAnd(&p.bitmap[g >> 5], ~(1u << (g & 31)));
         }
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counters[CNT_CAND], nitems);
@@ -708,7 +834,8 @@ k_verify_lev(const ScanParams p, uint64_t bitmap_words, const uint32_t *glist, u
             while (b) {
                 const int bit = __ffs(b) - 1;
                 b &= b - 1;
-                verify_granule_lev(p, sP, sWin, (int64_t)(wbase + src) * 32 + bit, lane, S, out, cap, counters);
+                verify_granule_lev<VM>(p, sP, sPM, sWin, (int64_t)(wbase + src) * 32 + bit, lane, S, out, cap,
+                                       counters);
             }
         }
     }
@@ -723,18 +850,22 @@ k_verify_lev(const ScanParams p, uint64_t bitmap_words, const uint32_t *glist, u
 constexpr int kHitSlotBytes = 144;  // per-lane window slot: m + 2k + alignment slack must fit
 constexpr int kHitThreads = 128;
 
+template <int VM>
 __global__ void __launch_bounds__(kHitThreads)
 k_verify_hits(const ScanParams p, RawRec *out, uint32_t cap, uint32_t *counters) {
     __shared__ uint8_t sP[256];
+    __shared__ unsigned long long sPM[VM < 2 ? 256 : 1];
     __shared__ __align__(16) uint8_t slots[kHitThreads][kHitSlotBytes];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) sP[i] = p.P[i];
+    if (VM < 2) build_pm(sPM, p.P, p.m, threadIdx.x, blockDim.x);
     __syncthreads();
     const uint32_t nhits = counters[CNT_HITS];
     if (nhits > p.hits_cap) {  // list overflowed: the host repeats the search in granule mode
         if (blockIdx.x == 0 && threadIdx.x == 0) counters[CNT_OVERFLOW] = 1;
         return;
     }
-    DpScratch S;
+    DpHolder<VM> dp_holder;
+    DpScratch *S = dp_holder.get();
     const int lane = threadIdx.x & 31;
     uint8_t *slot = slots[threadIdx.x];
     for (;;) {
@@ -759,7 +890,7 @@ k_verify_hits(const ScanParams p, RawRec *out, uint32_t cap, uint32_t *counters)
             uint32_t *dst = reinterpret_cast<uint32_t *>(slot);
             for (int w = 0; w < nwords; w++) dst[w] = __ldg(src + w);
         }
-        verify_anchor_lev(p, sP, slot - alo, idx, valid, S, out, cap, counters, j, j + 1);  // whole warp
+        verify_anchor_lev<VM>(p, sP, sPM, slot - alo, idx, valid, S, out, cap, counters, j, j + 1);  // whole warp
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counters[CNT_CAND], nhits);
 }

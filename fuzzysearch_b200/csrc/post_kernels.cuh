@@ -1,224 +1,252 @@
 // post_kernels.cuh -- on-device ordering and consolidation of the raw match list (small lists).
 //
-// Two kernels run behind the verify kernel, on the same stream, and replace the host's sorts for
-// lists of up to kPostMax records (the common case: matches are sparse); nothing waits for the host:
-//   k_rank_scatter   orders the records by all-pairs ranking (rank = number of records with a smaller
-//                    key; O(n^2) compares spread over the whole GPU -- 64 CTAs, shared-memory tiles --
-//                    which for n <= 16K beats any multi-pass sort that has to synchronise):
-//                    * the raw stream in the reference's generation order (n-gram ordinal, hit index)
-//                      -- or canonical (start, end, dist) order for the unanchored routes;
-//                    * the packed canonical keys in (start, end, dist) order for the consolidation.
-//   k_consolidate    consolidate_overlapping_matches (common.py:145-189) on the sorted keys: running
-//                    maximum of `end` as the hull, a record opens a new group iff start >= hull
-//                    (connected components of interval overlap), winner per group =
-//                    min (dist, -(end-start)), ties -> first in (start, end) order.
+// ONE kernel runs behind the verify kernel, on the same stream, and replaces the host's sort + sweep for
+// lists of up to kPostMax records (the common case: matches are sparse); nothing waits for the host and
+// there is no device->host copy operation either: the kernel writes its outputs straight into MAPPED
+// pinned host memory, so a search ends with a single stream synchronisation.
+//   every CTA  (one per SM) copies its slice of the raw records (arrival order) to the host, loads the
+//              packed canonical keys (start, end-start, dist; written by emit() next to each record) of ALL
+//              records into shared memory and ranks its slice of them against all of them (rank = number of
+//              smaller keys; a warp ranks two records per pass over the list), scatters its keys to their
+//              sorted positions in global memory and takes a ticket.  Measured alternatives for 7 K records:
+//              a single-SM bitonic network 60 us, a single-SM sample sort 38 us, this all-pairs ranking
+//              spread over 148 SMs 20 us -- one SM issues 4 warp-instructions per clock whatever the algorithm.
+//   the last   CTA to finish (ticket == grid-1) runs consolidate_overlapping_matches (common.py:145-189) on
+//              the sorted keys, one element per thread per round (bank-conflict free): running maximum of
+//              `end` as the hull, a record opens a new group iff start >= hull (connected components of
+//              interval overlap), winner per group = min (dist, -(end-start)), ties -> first in
+//              (start, end) order.  Final rows (winner + hull) stay on the device (input of the multi-GPU
+//              reduction) and go to the host in coalesced 16-byte stores.
+// The host puts the raw stream into the reference's generation order lazily, only if a caller asks for it.
 // Larger lists fall back to the host implementation (consolidate_recs in api.cu), which computes
 // exactly the same thing.
 #pragma once
-#include "common.cuh"
+#include "kernels.cuh"
 
 namespace fzb {
 
 constexpr int kPostMax = 16384;
-constexpr int kRankThreads = 256;
-constexpr int kConsThreads = 1024;
-enum { CNT_POST_DONE = 5, CNT_NFINAL = 6 };
-constexpr size_t kConsSmem = (size_t)kPostMax * 4;  // segbest
+constexpr int kPostThreads = 1024;
+enum { CNT_POST_DONE = 5, CNT_NFINAL = 6, CNT_TICKET = 9 };
 constexpr int kFinCols = 5;  // start, end, dist, hull_start, hull_end of the group
+constexpr size_t kPostSmem = (size_t)kPostMax * 8 + (size_t)kPostMax * 4;  // keys + per-group best
 
-// canonical order (start, end, dist): start < 2^46, end-start < 2^10, dist < 2^8
-__device__ __forceinline__ uint64_t canonical_key(const RawRec &r) {
-    return ((uint64_t)r.start << 18) | ((uint64_t)(r.end - r.start) << 8) | (uint64_t)r.dist;
-}
-// generation order of the n-gram search: (n-gram ordinal, hit index)
-__device__ __forceinline__ uint64_t generation_key(const RawRec &r) {
-    return ((uint64_t)(uint32_t)r.ngram << 48) | (uint64_t)r.idx;
-}
+struct PostArgs {
+    const RawRec *recs;    // raw records, arrival order
+    const uint64_t *rkeys; // their canonical keys (same order)
+    uint32_t cap;          // capacity of recs / rkeys
+    int mode;              // 0 raw only; 1 consolidate; 2 final = the raw list in (start, end, dist) order
+    int copy_raw;          // copy the raw records to h_raw
+    uint64_t *sorted;      // device scratch: kPostMax sorted keys
+    int64_t *fin;          // device: final rows [kPostMax][kFinCols]
+    int64_t *h_fin;        // mapped host: the same rows
+    RawRec *h_raw;         // mapped host: raw records
+    uint32_t *h_counters;  // mapped host: CNT_COUNT counters
+    uint32_t *counters;
+};
 
-// All-pairs ranking.  Grid (i-tiles, j-chunks): block (bi, bj) ranks records i in [256 bi, 256 bi+256)
-// against records j in [kRankChunk bj, kRankChunk (bj+1)) and adds its partial counts to ranks[] (zeroed
-// by the host's counter memset).  ranks[i] = generation-order rank, ranks[kPostMax + i] = canonical rank.
-// raw_mode: 0 -> raw order (ngram, idx); 1 -> raw order (start, end, dist); 2 -> the raw stream is left in
-// arrival order (the host orders it lazily, only if somebody asks for it) and only canonical ranks
-// are computed.
-constexpr int kRankChunk = 1024;
-
-__global__ void __launch_bounds__(kRankThreads)
-k_rank(const RawRec *recs, uint32_t cap, int raw_mode, uint32_t *ranks, const uint32_t *counters) {
-    const bool two_keys = raw_mode == 0;
-    __shared__ uint64_t s1[kRankThreads], s2[kRankThreads];
-    const uint32_t n = counters[CNT_OUT];
-    if (n > (uint32_t)kPostMax || n > cap) return;
-    if (blockIdx.x * kRankThreads >= n || blockIdx.y * kRankChunk >= n) return;
-    const uint32_t i = blockIdx.x * kRankThreads + threadIdx.x;
-    uint64_t k1 = ~0ull, k2 = ~0ull;
-    if (i < n) {
-        const RawRec me = recs[i];
-        k2 = canonical_key(me);
-        k1 = two_keys ? generation_key(me) : k2;
-    }
-    uint32_t r1 = 0, r2 = 0;
-    const uint32_t t0 = blockIdx.y * (kRankChunk / kRankThreads);
-    for (uint32_t t = t0; t < t0 + kRankChunk / kRankThreads && t * kRankThreads < n; t++) {
-        const uint32_t j = t * kRankThreads + threadIdx.x;
-        uint64_t a = ~0ull, b = ~0ull;
-        if (j < n) {
-            const RawRec o = recs[j];
-            b = canonical_key(o);
-            a = two_keys ? generation_key(o) : b;
-        }
-        __syncthreads();
-        s1[threadIdx.x] = a;
-        s2[threadIdx.x] = b;
-        __syncthreads();
-        if (t < blockIdx.x) {  // every j of the tile is < i: ties rank before me
-#pragma unroll 8
-            for (int jj = 0; jj < kRankThreads; jj++) r2 += (s2[jj] <= k2);
-            if (two_keys) {
-#pragma unroll 8
-                for (int jj = 0; jj < kRankThreads; jj++) r1 += (s1[jj] <= k1);
-            }
-        } else if (t > blockIdx.x) {
-#pragma unroll 8
-            for (int jj = 0; jj < kRankThreads; jj++) r2 += (s2[jj] < k2);
-            if (two_keys) {
-#pragma unroll 8
-                for (int jj = 0; jj < kRankThreads; jj++) r1 += (s1[jj] < k1);
-            }
-        } else {
-#pragma unroll 8
-            for (int jj = 0; jj < kRankThreads; jj++) {
-                const bool before = jj < (int)threadIdx.x;
-                r1 += (s1[jj] < k1) || (before && s1[jj] == k1);
-                r2 += (s2[jj] < k2) || (before && s2[jj] == k2);
-            }
-        }
-    }
-    if (i < n) {
-        atomicAdd(&ranks[i], two_keys ? r1 : r2);
-        atomicAdd(&ranks[kPostMax + i], r2);
-    }
+__device__ __forceinline__ uint32_t gtimer_lo() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return (uint32_t)t;
 }
 
-// block-wide exclusive scans over one value per thread (1024 threads)
-__device__ __forceinline__ unsigned long long block_excl_scan_max(unsigned long long v, unsigned long long *warp_tot) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    unsigned long long inc = v;
-    for (int o = 1; o < 32; o <<= 1) {
-        unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-        if (lane >= o) inc = max(inc, t);
-    }
-    if (lane == 31) warp_tot[w] = inc;
-    __syncthreads();
-    unsigned long long pre = 0;
-    for (int i = 0; i < w; i++) pre = max(pre, warp_tot[i]);
-    unsigned long long exc = __shfl_up_sync(0xFFFFFFFFu, inc, 1);
-    if (lane == 0) exc = 0;
-    __syncthreads();
-    return max(pre, exc);
-}
-
-__device__ __forceinline__ uint32_t block_excl_scan_sum(uint32_t v, uint32_t *warp_tot, uint32_t *total) {
+// Block-wide exclusive scans of one value per thread (1024 threads = 32 warps); *total = sum / max of all.
+// scratch: 33 entries.
+__device__ __forceinline__ uint32_t block_scan_sum(uint32_t v, uint32_t *scratch, uint32_t *total) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     uint32_t inc = v;
+#pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
         if (lane >= o) inc += t;
     }
-    if (lane == 31) warp_tot[w] = inc;
+    if (lane == 31) scratch[w] = inc;
     __syncthreads();
-    uint32_t pre = 0, tot = 0;
-    for (int i = 0; i < 32; i++) {
-        if (i < w) pre += warp_tot[i];
-        tot += warp_tot[i];
+    if (w == 0) {
+        const uint32_t x = scratch[lane];
+        uint32_t xi = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, xi, o);
+            if (lane >= o) xi += t;
+        }
+        scratch[lane] = xi - x;  // exclusive
+        if (lane == 31) scratch[32] = xi;
     }
-    *total = tot;
-    uint32_t exc = __shfl_up_sync(0xFFFFFFFFu, inc, 1);
-    if (lane == 0) exc = 0;
     __syncthreads();
-    return pre + exc;
+    const uint32_t r = scratch[w] + inc - v;
+    *total = scratch[32];
+    __syncthreads();
+    return r;
 }
 
-// One CTA: scatter the records into rank order, then the consolidation sweep.
-__global__ void __launch_bounds__(kConsThreads)
-k_consolidate(const RawRec *recs, const uint32_t *ranks, RawRec *raw_sorted, uint64_t *keys, uint32_t cap,
-              int raw_mode, int do_consolidate, int64_t *fin, uint32_t *counters) {
+__device__ __forceinline__ unsigned long long block_scan_max(unsigned long long v, unsigned long long *scratch,
+                                                             unsigned long long *total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned long long inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= o) inc = max(inc, t);
+    }
+    unsigned long long exc = __shfl_up_sync(0xFFFFFFFFu, inc, 1);
+    if (lane == 0) exc = 0;
+    if (lane == 31) scratch[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        const unsigned long long x = scratch[lane];
+        unsigned long long xi = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, xi, o);
+            if (lane >= o) xi = max(xi, t);
+        }
+        unsigned long long xe = __shfl_up_sync(0xFFFFFFFFu, xi, 1);
+        if (lane == 0) xe = 0;
+        scratch[lane] = xe;  // exclusive
+        if (lane == 31) scratch[32] = xi;
+    }
+    __syncthreads();
+    const unsigned long long r = max(scratch[w], exc);
+    *total = scratch[32];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(kPostThreads, 1)
+k_post(const PostArgs a) {
     extern __shared__ __align__(16) uint8_t post_smem[];
-    uint32_t *segbest = reinterpret_cast<uint32_t *>(post_smem);
-    __shared__ unsigned long long warp_max[32];
-    __shared__ uint32_t warp_sum[32];
-    const uint32_t n = counters[CNT_OUT];
-    if (n > (uint32_t)kPostMax || n > cap) {
-        if (threadIdx.x == 0) counters[CNT_POST_DONE] = 0;
+    uint64_t *keys = reinterpret_cast<uint64_t *>(post_smem);
+    uint32_t *segbest = reinterpret_cast<uint32_t *>(post_smem + (size_t)kPostMax * 8);
+    __shared__ unsigned long long scr64[33];
+    __shared__ uint32_t scr32[33];
+    __shared__ uint32_t s_ticket;
+    const uint32_t nraw = a.counters[CNT_OUT];
+    const uint32_t n = a.counters[CNT_KEYS];  // distinct-ish keys (<= nraw): what gets ordered and consolidated
+    const bool fits = nraw <= (uint32_t)kPostMax && nraw <= a.cap;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t G = gridDim.x, b = blockIdx.x;
+    if (!fits) {  // the host fetches the list and does the rest
+        if (b == 0 && tid < CNT_COUNT) a.h_counters[tid] = a.counters[tid];  // POST_DONE stays 0
         return;
     }
-    for (uint32_t i = threadIdx.x; i < n; i += kConsThreads) {
-        const RawRec me = recs[i];
-        if (raw_mode != 2) raw_sorted[ranks[i]] = me;
-        keys[ranks[kPostMax + i]] = canonical_key(me);
+    const uint32_t t_start = gtimer_lo();
+    if (a.copy_raw) {  // my slice of the raw records -> host: 2 x 16 bytes per record, coalesced
+        const uint32_t rlo = (uint32_t)((uint64_t)nraw * b / G), rhi = (uint32_t)((uint64_t)nraw * (b + 1) / G);
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.recs);
+        uint4 *dst = reinterpret_cast<uint4 *>(a.h_raw);
+        for (uint32_t i = 2 * rlo + tid; i < 2 * rhi; i += kPostThreads) dst[i] = src[i];
     }
-    __syncthreads();  // keys[] was written by this CTA: visible after the barrier
+    const uint32_t lo = (uint32_t)((uint64_t)n * b / G), hi = (uint32_t)((uint64_t)n * (b + 1) / G);
+    if (a.mode != 0 && n > 0) {
+        for (uint32_t i = tid; i < n; i += kPostThreads) keys[i] = a.rkeys[i];
+        __syncthreads();
+        // rank: a warp takes two records of my slice per pass, its lanes split the list
+        for (uint32_t i0 = lo + 2 * warp; i0 < hi; i0 += 2 * (kPostThreads / 32)) {
+            const uint32_t i1 = min(i0 + 1, hi - 1);
+            const uint64_t key0 = keys[i0], key1 = keys[i1];
+            uint32_t c0 = 0, c1 = 0;
+            for (uint32_t j = lane; j < n; j += 32) {
+                const uint64_t kj = keys[j];
+                c0 += (kj < key0) || (kj == key0 && j < i0);
+                c1 += (kj < key1) || (kj == key1 && j < i1);
+            }
+            c0 = __reduce_add_sync(0xFFFFFFFFu, c0);
+            c1 = __reduce_add_sync(0xFFFFFFFFu, c1);
+            if (lane == 0) {
+                a.sorted[c0] = key0;
+                a.sorted[c1] = key1;  // (i1 == i0 for an odd tail: the same store twice)
+            }
+        }
+    }
+    const uint32_t t_ranked = gtimer_lo();
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_ticket = atomicAdd(&a.counters[CNT_TICKET], 1u);
+    __syncthreads();
+    if (s_ticket != G - 1) return;
+    __threadfence();  // every other CTA's scatter is visible now
+    const uint32_t t_ticket = gtimer_lo();
+    uint32_t t_sorted = t_ticket, t_swept = t_ticket;
     uint32_t nfinal = 0;
-    if (do_consolidate && n > 0) {
-        const int chunk = (int)((n + kConsThreads - 1) / kConsThreads);  // <= 16
-        const int lo = threadIdx.x * chunk;  // thread t owns sorted elements [t*chunk, (t+1)*chunk)
-        uint64_t mykeys[kPostMax / kConsThreads];
-        unsigned long long local_max = 0;
-#pragma unroll
-        for (int c = 0; c < kPostMax / kConsThreads; c++) {
-            const int i = lo + c;
-            mykeys[c] = (c < chunk && i < (int)n) ? keys[i] : ~0ull;
-            if (c < chunk && i < (int)n)
-                local_max = max(local_max, (unsigned long long)((mykeys[c] >> 18) + ((mykeys[c] >> 8) & 1023u)));
-        }
-        const unsigned long long hull0 = block_excl_scan_max(local_max, warp_max);
-        unsigned long long hull = hull0;
-        uint32_t nflags = 0;
-#pragma unroll
-        for (int c = 0; c < kPostMax / kConsThreads; c++) {  // group heads in my chunk
-            const int i = lo + c;
-            if (c < chunk && i < (int)n) {
-                const unsigned long long s = mykeys[c] >> 18, e = s + ((mykeys[c] >> 8) & 1023u);
-                if (i == 0 || s >= hull) nflags++;
-                hull = max(hull, e);
-            }
-        }
-        uint32_t total = 0;
-        uint32_t seg = block_excl_scan_sum(nflags, warp_sum, &total);  // groups opened before my chunk
-        nfinal = total;
-        for (int t = threadIdx.x; t < (int)nfinal; t += kConsThreads) segbest[t] = 0xFFFFFFFFu;
+    if (a.mode != 0 && n > 0) {
+        for (uint32_t i = tid; i < n; i += kPostThreads) keys[i] = __ldcg(a.sorted + i);
         __syncthreads();
-        hull = hull0;
-#pragma unroll
-        for (int c = 0; c < kPostMax / kConsThreads; c++) {
-            const int i = lo + c;
-            if (c < chunk && i < (int)n) {
-                const uint64_t kx = mykeys[c];
-                const unsigned long long s = kx >> 18, len = (kx >> 8) & 1023u, e = s + len;
-                if (i == 0 || s >= hull) {  // group head: hull_start of this group, hull_end of the previous
-                    seg++;
-                    fin[kFinCols * (seg - 1) + 3] = (int64_t)s;
-                    if (seg >= 2) fin[kFinCols * (seg - 2) + 4] = (int64_t)hull;
+        t_sorted = gtimer_lo();
+        // ---- final rows --------------------------------------------------------------------------
+        if (a.mode == 2) {  // unconsolidated routes: the final list is the sorted raw list
+            nfinal = n;
+            for (uint32_t i = tid; i < n; i += kPostThreads) {
+                const uint64_t kx = keys[i];
+                const int64_t s = (int64_t)(kx >> 18), e = s + (int64_t)((kx >> 8) & 1023u);
+                int64_t *row = a.fin + (size_t)kFinCols * i;
+                row[0] = s;
+                row[1] = e;
+                row[2] = (int64_t)(kx & 255u);
+                row[3] = s;
+                row[4] = e;
+            }
+        } else {
+            for (uint32_t i = tid; i < n; i += kPostThreads) segbest[i] = 0xFFFFFFFFu;
+            __syncthreads();
+            unsigned long long carry_hull = 0;  // max end of all earlier rounds
+            uint32_t carry_groups = 0;          // groups opened in earlier rounds
+            for (uint32_t base = 0; base < n; base += kPostThreads) {
+                const uint32_t i = base + tid;
+                const bool live = i < n;
+                const uint64_t kx = live ? keys[i] : 0;
+                const unsigned long long s = kx >> 18, len = (kx >> 8) & 1023u, e = live ? s + len : 0;
+                unsigned long long round_max;
+                const unsigned long long hull = max(carry_hull, block_scan_max(e, scr64, &round_max));  // exclusive
+                const bool head = live && (i == 0 || s >= hull);
+                uint32_t round_heads;
+                const uint32_t before = block_scan_sum(head ? 1u : 0u, scr32, &round_heads);
+                if (live) {
+                    const uint32_t g = carry_groups + before + (head ? 1u : 0u) - 1u;  // my group
+                    if (head) {
+                        a.fin[(size_t)kFinCols * g + 3] = (int64_t)s;                       // hull start of my group
+                        if (g >= 1) a.fin[(size_t)kFinCols * (g - 1) + 4] = (int64_t)hull;  // hull end of the previous
+                    }
+                    if (i == n - 1) a.fin[(size_t)kFinCols * g + 4] = (int64_t)max(hull, e);  // last group
+                    const uint32_t score = ((uint32_t)(kx & 255u) << 24) | ((uint32_t)(1023u - len) << 14) | i;
+                    atomicMin(&segbest[g], score);
                 }
-                hull = max(hull, e);
-                if (i == (int)n - 1) fin[kFinCols * (seg - 1) + 4] = (int64_t)hull;  // last group
-                const uint32_t score = ((uint32_t)(kx & 255u) << 24) | ((uint32_t)(1023u - len) << 14) | (uint32_t)i;
-                atomicMin(&segbest[seg - 1], score);
+                carry_hull = max(carry_hull, round_max);
+                carry_groups += round_heads;
+            }
+            nfinal = carry_groups;
+            __syncthreads();
+            for (uint32_t g = tid; g < nfinal; g += kPostThreads) {
+                const uint64_t kx = keys[segbest[g] & 16383u];
+                const int64_t s = (int64_t)(kx >> 18);
+                int64_t *row = a.fin + (size_t)kFinCols * g;
+                row[0] = s;
+                row[1] = s + (int64_t)((kx >> 8) & 1023u);
+                row[2] = (int64_t)(kx & 255u);
             }
         }
+        // device rows -> host, coalesced 16-byte stores (rows are 40 bytes: copy the whole block as uint4)
+        __threadfence_block();
         __syncthreads();
-        for (int g = threadIdx.x; g < (int)nfinal; g += kConsThreads) {
-            const uint64_t kx = keys[segbest[g] & 16383u];
-            const int64_t s = (int64_t)(kx >> 18);
-            fin[kFinCols * g + 0] = s;
-            fin[kFinCols * g + 1] = s + (int64_t)((kx >> 8) & 1023u);
-            fin[kFinCols * g + 2] = (int64_t)(kx & 255u);
-        }
+        t_swept = gtimer_lo();
+        const uint32_t nvec = (uint32_t)(((size_t)nfinal * kFinCols * 8 + 15) / 16);
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.fin);
+        uint4 *dst = reinterpret_cast<uint4 *>(a.h_fin);
+        for (uint32_t i = tid; i < nvec; i += kPostThreads) dst[i] = __ldcg(src + i);
     }
-    if (threadIdx.x == 0) {
-        counters[CNT_NFINAL] = nfinal;
-        counters[CNT_POST_DONE] = 1;
+    __syncthreads();
+    if (tid == 0) {
+        a.counters[CNT_NFINAL] = nfinal;
+        a.counters[CNT_POST_DONE] = 1u;
+        // phase times of the last CTA in ns (fzb_debug_counters): copy + rank, ticket + reload, sweep, copy-out
+        a.counters[10] = t_ranked - t_start;
+        a.counters[11] = t_sorted - t_ranked;
+        a.counters[12] = t_swept - t_sorted;
+        a.counters[13] = gtimer_lo() - t_swept;
     }
+    __syncthreads();
+    if (tid < CNT_COUNT) a.h_counters[tid] = a.counters[tid];
 }
 
 // Pack this shard's groups for the all-gather: slot = header row {count, valid, 0, 0, 0} + up to `cap`

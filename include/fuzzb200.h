@@ -242,6 +242,23 @@ int64_t fzb_consolidate_groups(const int64_t *start, const int64_t *end, const i
 int64_t fzb_merge_groups(const int64_t *rows, uint64_t n, int64_t *out_start, int64_t *out_end,
                          int32_t *out_dist);
 
+/*
+ * TEST HOOK (not part of the search API): runs the expansion routines of the verify kernels -- the device
+ * restatement of _expand / _py_expand_short / _py_expand_long (levenshtein_ngram.py:8-143; the Cython
+ * seams c_expand_short / c_expand_long, _levenshtein_ngrams.pyx:9-154, are what a per-candidate FFI would
+ * bind) -- on `count` caller-supplied cases: case i is (subs[sub_off[i]:sub_off[i+1]],
+ * seqs[seq_off[i]:seq_off[i+1]], max_l[i]); variant[i] = 0 (_expand's own choice), 1 (short), 2 (long).
+ * out[8*i..8*i+7] = (dist, len) from four device code paths: bit-parallel forwards / backwards (the right- and
+ * left-expansion forms), cell-by-cell forwards / backwards; (-1,-1) = (None, None), (-2,-2) = path not applicable.
+ */
+int fzb_debug_expand(const uint8_t *subs, const uint32_t *sub_off, const uint8_t *seqs,
+                     const uint32_t *seq_off, const int32_t *max_l, const int32_t *variant, uint32_t count,
+                     int device, int32_t *out);
+
+/* TEST / PROFILING HOOK: the 16 device counters of the handle's last search (candidates, raw records, final
+ * groups, and in slots 10-13 the phase times of k_post's last CTA in nanoseconds). */
+int fzb_debug_counters(const fzb_haystack *h, uint32_t out[16]);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif
