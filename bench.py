@@ -305,8 +305,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the full-shard oracle comparison")
     ap.add_argument("--cpu-sample-mib", type=int, default=0, help="0 = auto (about 10-20 s of CPU work)")
-    ap.add_argument("--reduce", default="nccl", choices=["nccl", "torch"],
-                    help="multi-GPU reduction: NCCL inside the library (default) or via torch.distributed")
+    ap.add_argument("--reduce", default="p2p", choices=["p2p", "nccl", "torch"],
+                    help="multi-GPU reduction: inside the library over NVLink peer memory (default; 'nccl' is an "
+                         "alias), or through torch.distributed (tools/torch_reduce.py, comparison only)")
     ap.add_argument("--ref-cores", type=int, default=0, help="reference arm: processes to use (0 = all cores)")
     args = ap.parse_args()
 
@@ -373,7 +374,10 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from fuzzysearch_b200.sharding import gather_and_merge_groups, init_shard_comm, shard_bounds
+    from fuzzysearch_b200.sharding import init_shard_comm, shard_bounds
+    if args.reduce == "torch":  # comparison arm only: the same reduction through torch.distributed
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        from torch_reduce import gather_and_merge_groups
 
     global_len = per_gpu * world
     halo = m + k
@@ -393,9 +397,13 @@ def main():
         if pos >= blo and pos + len(b) <= bhi:
             hs.write(pos, b)
 
-    in_library = world > 1 and args.reduce == "nccl"
+    in_library = world > 1 and args.reduce in ("p2p", "nccl")
     if in_library:
         init_shard_comm(hs)
+        config["reduction"] = ("in-library, NVLink peer memory (k_push + k_merge on the search stream)"
+                               if hs.p2p_enabled() else "in-library, staged NCCL all-gather + host merge")
+    elif world > 1:
+        config["reduction"] = "torch.distributed (tools/torch_reduce.py)"
     gflag = F.F_GLOBAL if in_library else 0
 
     batch_pats, batch_ks = [], []

@@ -62,6 +62,8 @@ SYMBOLS = {
     "fzb_nccl_set_library": (None, [ctypes.c_char_p]),
     "fzb_nccl_unique_id": (_i32, [_vp]),
     "fzb_haystack_comm_init": (_i32, [_vp, _vp, _i32, _i32]),
+    "fzb_comm_init_local": (_i32, [_vp, _i32]),
+    "fzb_haystack_p2p_enabled": (_i32, [_vp]),
     "fzb_haystack_upload": (_i32, [_vp, _u8p, _u64]),
     "fzb_host_alloc": (_vp, [_u64]),
     "fzb_host_free": (None, [_vp]),
@@ -257,6 +259,9 @@ class Haystack(object):
         buf = (ctypes.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
         check(lib().fzb_haystack_comm_init(self._h, buf, rank, world_size))
 
+    def p2p_enabled(self):
+        return bool(lib().fzb_haystack_p2p_enabled(self._h))
+
     def upload(self, data):
         a = as_u8(data)
         check(lib().fzb_haystack_upload(self._h, ptr(a), a.size))
@@ -330,6 +335,12 @@ class Haystack(object):
         r = ctypes.c_void_p()
         check(lib().fzb_search_exact(self._h, pp, m, flags, ctypes.byref(r)))
         return Result(r)
+
+
+def comm_init_local(haystacks):
+    """Bind Haystack objects (one process, one or several GPUs) into a world of shards: haystacks[r] = rank r."""
+    arr = (ctypes.c_void_p * len(haystacks))(*[h._h for h in haystacks])
+    check(lib().fzb_comm_init_local(arr, len(haystacks)))
 
 
 class PinnedBuffer(object):

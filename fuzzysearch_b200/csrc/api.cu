@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstring>
 #include <dlfcn.h>
+#include <unistd.h>
 #include <mutex>
 #include <new>
 #include <string>
@@ -19,6 +20,7 @@
 #include "ham_kernels.cuh"
 #include "lp_kernels.cuh"
 #include "post_kernels.cuh"
+#include "p2p_kernels.cuh"
 #include "debug_kernels.cuh"
 
 using namespace fzb;
@@ -133,7 +135,20 @@ struct fzb_haystack {
     bool ev1_recorded = false;
     bool filter_attrs_set = false;
     double coll_prob = -1.0;  // sum_c p_c^2 of the byte distribution (sampled lazily; < 0 = unknown)
-    // multi-GPU reduction (FZB_F_GLOBAL)
+    // multi-GPU reduction (FZB_F_GLOBAL): peer-memory world (p2p_kernels.cuh) + NCCL for bootstrap / staged fallback
+    bool p2p = false;               // every rank of the world can store into every other rank's receive area
+    bool local_world = false;       // the world lives in this process (fzb_comm_init_local): no NCCL
+    uint8_t *d_p2p = nullptr;       // my receive area: [2 parities][world] slots + flags
+    uint8_t *peer_base[kMaxWorld] = {};
+    bool peer_opened[kMaxWorld] = {};
+    uint32_t p2p_cap = 4096;        // group rows per slot
+    uint64_t slot_bytes = 0, flags_off = 0;
+    uint32_t epoch = 0;             // number of FZB_F_GLOBAL searches issued on this handle
+    MergeScratch *d_ms = nullptr;
+    unsigned long long *d_mscore = nullptr;
+    uint32_t *d_mpos = nullptr;
+    int64_t *h_grows = nullptr;     // mapped: global final rows of the last global search (16 bytes each)
+    uint32_t *h_ghdr = nullptr;     // mapped: status, count, epoch
     void *comm = nullptr;  // ncclComm_t
     int rank = 0, world = 1;
     uint32_t gather_cap = 4096;     // rows per rank in one all-gather slot
@@ -153,7 +168,8 @@ struct fzb_haystack {
 struct fzb_result {
     std::vector<RawRec> raw;      // filled lazily from the owner's mapped staging buffer (fetch_raw)
     uint32_t raw_n = 0;           // number of raw records
-    fzb_haystack *owner = nullptr;  // non-null while the raw records still sit in owner->h_stage only
+    fzb_haystack *owner = nullptr;  // non-null while raw records / global rows still sit in the owner's mapped buffers
+    bool raw_in_stage = false;
     void fetch_raw();
     std::vector<RawRec> fin;
     std::vector<int64_t> hulls;  // (hull_start, hull_end) of the group behind each final match
@@ -162,11 +178,10 @@ struct fzb_result {
     bool device_post = false;  // the final list came from the device (k_post)
     bool raw_ordered = false;  // raw is already in its reference order
     bool has_global = false;   // FZB_F_GLOBAL: gfin is the global consolidated list of all shards
-    bool gather_valid = false;
-    bool fused_issued = false;
-    std::vector<int64_t> gathered;  // group rows of all shards (rank major)
-    std::vector<uint64_t> gathered_counts;  // rows per shard
-    size_t gather_slot_rows = 0;
+    bool global_on_device = false;  // ... produced by k_merge; its rows sit in owner->h_grows until fetched
+    bool fused_issued = false;      // a k_push / k_merge pair ran for this search
+    uint32_t fused_status = 0;      // MS_* of that merge
+    uint32_t gcount = 0;
     std::vector<RawRec> gfin;
     int raw_order = 0;         // 0 generation (ngram, idx) / 1 canonical / 2 generic n-grams (5 fields)
     void order_raw();
@@ -184,8 +199,23 @@ static std::mutex g_pending_mutex;
 void fzb_result::fetch_raw() {
     std::lock_guard<std::mutex> lock(g_pending_mutex);
     if (!owner) return;
-    raw.resize(raw_n);
-    if (raw_n) memcpy(raw.data(), owner->h_stage, (size_t)raw_n * sizeof(RawRec));
+    if (raw_in_stage) {
+        raw.resize(raw_n);
+        if (raw_n) memcpy(raw.data(), owner->h_stage, (size_t)raw_n * sizeof(RawRec));
+        raw_in_stage = false;
+    }
+    if (global_on_device) {  // rows: start, (end - start) << 32 | dist
+        gfin.resize(gcount);
+        for (uint32_t i = 0; i < gcount; i++) {
+            const int64_t s0 = owner->h_grows[2 * (size_t)i], v = owner->h_grows[2 * (size_t)i + 1];
+            gfin[i].start = s0;
+            gfin[i].end = s0 + (v >> 32);
+            gfin[i].dist = (int32_t)(v & 0xFFFFFFFF);
+            gfin[i].idx = -1;
+            gfin[i].ngram = -1;
+        }
+        global_on_device = false;
+    }
     owner->pending = nullptr;
     owner = nullptr;
 }
@@ -244,6 +274,8 @@ static int alloc_buffer(fzb_haystack *h) {
     return FZB_OK;
 }
 
+static void p2p_free(fzb_haystack *h);
+
 extern "C" void fzb_haystack_destroy(fzb_haystack *h) {
     if (!h) return;
     cudaSetDevice(h->device);
@@ -261,6 +293,7 @@ extern "C" void fzb_haystack_destroy(fzb_haystack *h) {
     if (h->h_send) cudaFreeHost(h->h_send);
     if (h->h_recv) cudaFreeHost(h->h_recv);
     if (h->comm) nccl_comm_destroy(h->comm);
+    p2p_free(h);
     if (h->h_counters) cudaFreeHost(h->h_counters);
     if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->h_fin) cudaFreeHost(h->h_fin);
@@ -497,6 +530,50 @@ static int ensure_gather_buffers(fzb_haystack *h, uint32_t cap) {
     return FZB_OK;
 }
 
+// Receive area + scratch of the peer-memory reduction (p2p_kernels.cuh).
+static int p2p_alloc(fzb_haystack *h) {
+    if (h->world > kMaxWorld) return fail(FZB_E_UNSUPPORTED, "world sizes above %d are not supported", kMaxWorld);
+    CK(cudaSetDevice(h->device));
+    h->slot_bytes = ((uint64_t)kHdrWords + (uint64_t)h->p2p_cap * kFinCols) * 8;
+    h->flags_off = round_up(2 * (uint64_t)h->world * h->slot_bytes, 256);
+    const size_t bytes = h->flags_off + 2 * kMaxWorld * sizeof(uint32_t) + 256;
+    if (!h->d_p2p) {
+        CK(cudaMalloc(&h->d_p2p, bytes));
+        CK(cudaMemset(h->d_p2p, 0, bytes));
+        CK(cudaMalloc(&h->d_ms, sizeof(MergeScratch)));
+        CK(cudaMemset(h->d_ms, 0, sizeof(MergeScratch)));
+        const size_t rows = (size_t)h->world * h->p2p_cap;
+        CK(cudaMalloc(&h->d_mscore, rows * sizeof(unsigned long long)));
+        CK(cudaMalloc(&h->d_mpos, rows * sizeof(uint32_t)));
+        const unsigned hflags = cudaHostAllocMapped | cudaHostAllocPortable;
+        CK(cudaHostAlloc(&h->h_grows, rows * 2 * sizeof(int64_t), hflags));
+        CK(cudaHostAlloc(&h->h_ghdr, 16 * sizeof(uint32_t), hflags));
+        memset(h->h_ghdr, 0, 16 * sizeof(uint32_t));
+    }
+    return FZB_OK;
+}
+
+static void p2p_free(fzb_haystack *h) {
+    for (int r = 0; r < kMaxWorld; r++) {
+        if (h->peer_opened[r] && h->peer_base[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
+        h->peer_opened[r] = false;
+        h->peer_base[r] = nullptr;
+    }
+    if (h->d_p2p) cudaFree(h->d_p2p);
+    if (h->d_ms) cudaFree(h->d_ms);
+    if (h->d_mscore) cudaFree(h->d_mscore);
+    if (h->d_mpos) cudaFree(h->d_mpos);
+    if (h->h_grows) cudaFreeHost(h->h_grows);
+    if (h->h_ghdr) cudaFreeHost(h->h_ghdr);
+    h->d_p2p = nullptr;
+    h->d_ms = nullptr;
+    h->d_mscore = nullptr;
+    h->d_mpos = nullptr;
+    h->h_grows = nullptr;
+    h->h_ghdr = nullptr;
+    h->p2p = false;
+}
+
 extern "C" int fzb_haystack_comm_init(fzb_haystack *h, const uint8_t id[FZB_NCCL_ID_BYTES], int rank,
                                       int world_size) {
     if (!h || !id || world_size < 1 || rank < 0 || rank >= world_size) return fail(FZB_E_INVALID, "bad arguments");
@@ -505,13 +582,117 @@ extern "C" int fzb_haystack_comm_init(fzb_haystack *h, const uint8_t id[FZB_NCCL
     CK(cudaSetDevice(h->device));
     if (h->comm) nccl_comm_destroy(h->comm);
     h->comm = nullptr;
+    p2p_free(h);
+    h->local_world = false;
     NcclId nid;
     memcpy(nid.b, id, FZB_NCCL_ID_BYTES);
     NCCLCK(g_nccl.CommInitRank(&h->comm, world_size, nid, rank));
     h->rank = rank;
     h->world = world_size;
-    return ensure_gather_buffers(h, h->gather_cap);
+    h->epoch = 0;
+    rc = ensure_gather_buffers(h, h->gather_cap);
+    if (rc) return rc;
+    // Peer-memory world: every rank exports its receive area through CUDA IPC; the handles travel over the
+    // fresh NCCL communicator (bootstrap only).  Any failure on any rank (no IPC in this container, no peer
+    // access between two GPUs) leaves p2p = false on ALL ranks and FZB_F_GLOBAL searches use the staged path.
+    struct Hello {
+        cudaIpcMemHandle_t handle;
+        int32_t ok, device;
+        long long pid;
+    };
+    static_assert(sizeof(Hello) <= 128, "hello record");
+    const size_t rec = 128;
+    Hello me{};
+    me.ok = world_size <= kMaxWorld && p2p_alloc(h) == FZB_OK &&
+            cudaIpcGetMemHandle(&me.handle, h->d_p2p) == cudaSuccess;
+    cudaGetLastError();
+    me.device = h->device;
+    me.pid = (long long)getpid();
+    std::vector<uint8_t> all(rec * world_size);
+    auto exchange = [&](const void *mine) -> int {  // all-gather one 128-byte record per rank
+        memset(h->h_send, 0, rec);
+        memcpy(h->h_send, mine, sizeof(Hello));
+        CK(cudaMemcpyAsync(h->d_send, h->h_send, rec, cudaMemcpyHostToDevice, h->stream));
+        NCCLCK(g_nccl.AllGather(h->d_send, h->d_recv, rec, /*ncclInt8*/ 0, h->comm, h->stream));
+        CK(cudaMemcpyAsync(h->h_recv, h->d_recv, rec * world_size, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        memcpy(all.data(), h->h_recv, rec * world_size);
+        return FZB_OK;
+    };
+    rc = exchange(&me);
+    if (rc) return rc;
+    bool ok = true;
+    for (int r = 0; r < world_size; r++) ok = ok && reinterpret_cast<Hello *>(all.data() + rec * r)->ok;
+    if (ok) {
+        for (int r = 0; r < world_size && ok; r++) {
+            const Hello *peer = reinterpret_cast<const Hello *>(all.data() + rec * r);
+            if (r == rank) {
+                h->peer_base[r] = h->d_p2p;
+            } else {
+                void *ptr = nullptr;
+                if (cudaIpcOpenMemHandle(&ptr, peer->handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                    cudaGetLastError();
+                    ok = false;
+                } else {
+                    h->peer_base[r] = (uint8_t *)ptr;
+                    h->peer_opened[r] = true;
+                }
+            }
+        }
+    }
+    Hello second{};
+    second.ok = ok;
+    rc = exchange(&second);  // everybody must have opened everybody
+    if (rc) return rc;
+    for (int r = 0; r < world_size; r++) ok = ok && reinterpret_cast<Hello *>(all.data() + rec * r)->ok;
+    h->p2p = ok;
+    if (!ok) {
+        for (int r = 0; r < kMaxWorld; r++) {
+            if (h->peer_opened[r] && h->peer_base[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
+            h->peer_opened[r] = false;
+            h->peer_base[r] = nullptr;
+        }
+    }
+    return FZB_OK;
 }
+
+extern "C" int fzb_comm_init_local(fzb_haystack **handles, int world_size) {
+    if (!handles || world_size < 1 || world_size > kMaxWorld) return fail(FZB_E_INVALID, "bad arguments");
+    for (int r = 0; r < world_size; r++)
+        if (!handles[r]) return fail(FZB_E_INVALID, "NULL handle");
+    for (int r = 0; r < world_size; r++) {
+        fzb_haystack *h = handles[r];
+        if (h->comm) nccl_comm_destroy(h->comm);
+        h->comm = nullptr;
+        p2p_free(h);
+        h->rank = r;
+        h->world = world_size;
+        h->epoch = 0;
+        h->local_world = true;
+        int rc = p2p_alloc(h);
+        if (rc) return rc;
+    }
+    for (int r = 0; r < world_size; r++) {
+        fzb_haystack *h = handles[r];
+        CK(cudaSetDevice(h->device));
+        for (int q = 0; q < world_size; q++) {
+            h->peer_base[q] = handles[q]->d_p2p;
+            if (handles[q]->device != h->device) {
+                int can = 0;
+                CK(cudaDeviceCanAccessPeer(&can, h->device, handles[q]->device));
+                if (!can) return fail(FZB_E_UNSUPPORTED, "no peer access between devices %d and %d", h->device, handles[q]->device);
+                cudaError_t e = cudaDeviceEnablePeerAccess(handles[q]->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                    return fail(FZB_E_CUDA, "cudaDeviceEnablePeerAccess failed: %s", cudaGetErrorString(e));
+                cudaGetLastError();
+            }
+        }
+        h->p2p = true;
+    }
+    return FZB_OK;
+}
+
+extern "C" int fzb_haystack_p2p_enabled(const fzb_haystack *h) { return h && h->p2p ? 1 : 0; }
 
 // ------------------------------------------------------------------------------------------------
 // consolidation (common.py:145-189).  Groups are the connected components of interval overlap
@@ -827,30 +1008,35 @@ static int run_emitting(fzb_haystack *h, fzb_result *res, F enqueue, PostPlan po
         k_post<<<h->sm_count, kPostThreads, kPostSmem, h->stream>>>(pa);
         CK(cudaGetLastError());
         res->stats.n_launches++;
-        // fused multi-GPU reduction: exactly one all-gather per search, in the FIRST attempt (so that
-        // a rank that has to retry locally never issues a collective the others do not)
-        const bool fused_gather = post.global && attempt == 0;
-        const size_t slot_rows = (size_t)h->gather_cap + 1, slot_bytes = slot_rows * kFinCols * sizeof(int64_t);
-        if (fused_gather) {
-            k_pack_groups<<<32, 256, 0, h->stream>>>(h->d_fin, h->d_counters, h->d_send, h->gather_cap);
+        // fused multi-GPU reduction over peer memory: exactly one push + merge per search, in the FIRST attempt
+        // (a rank that has to retry locally has pushed a header with valid = 0: every rank sees it and all of them
+        // take the staged path together)
+        const bool fused = post.global && attempt == 0 && h->p2p && !res->fused_issued;
+        if (fused) {
+            h->epoch++;
+            WorldArgs w{};
+            w.world = h->world;
+            w.rank = h->rank;
+            w.epoch = h->epoch;
+            w.cap = h->p2p_cap;
+            w.slot_bytes = h->slot_bytes;
+            w.flags_off = h->flags_off;
+            for (int r = 0; r < h->world; r++) w.peer[r] = h->peer_base[r];
+            k_push<<<kPushCtas, kPushThreads, 0, h->stream>>>(w, h->d_fin, h->d_counters, post.mode, h->d_ms);
+            MergeOut mo{h->d_mscore, h->d_mpos, h->h_grows, h->h_ghdr};
+            k_merge<<<h->world, kPostThreads, 0, h->stream>>>(w, h->d_ms, mo);
             CK(cudaGetLastError());
-            NCCLCK(g_nccl.AllGather(h->d_send, h->d_recv, slot_bytes, /*ncclInt8*/ 0, h->comm, h->stream));
-            CK(cudaMemcpyAsync(h->h_recv, h->d_recv, slot_bytes * h->world, cudaMemcpyDeviceToHost, h->stream));
             res->stats.n_launches += 2;
         }
         CK(cudaEventRecord(h->ev[2], h->stream));
         CK(cudaStreamSynchronize(h->stream));
         const uint32_t n = h->h_counters[CNT_OUT];
         res->stats.n_candidates = h->h_counters[CNT_CAND];
-        if (fused_gather) {  // every rank sees every header: all agree on whether the fused gather is usable
+        if (fused) {
             res->fused_issued = true;
-            res->gather_valid = true;
-            res->gathered.clear();
-            for (int r = 0; r < h->world; r++) {
-                const int64_t *base = h->h_recv + (size_t)r * slot_rows * kFinCols;
-                if (!base[1]) res->gather_valid = false;
-            }
-            res->gather_slot_rows = slot_rows;  // the rows stay in h->h_recv until finish_global merges them
+            res->fused_status = h->h_ghdr[0];
+            res->gcount = h->h_ghdr[1];
+            if (h->h_ghdr[2] != h->epoch && res->fused_status == MS_OK) res->fused_status = MS_TIMEOUT;
         }
         if (n > h->out_cap) {  // output buffer too small: grow and redo the whole attempt
             rc = ensure_out_cap(h, n);
@@ -861,11 +1047,14 @@ static int run_emitting(fzb_haystack *h, fzb_result *res, F enqueue, PostPlan po
         res->raw.clear();
         res->raw_n = n;
         res->raw_ordered = false;
-        if (posted) {  // the records are in h->h_stage: copied out lazily (fetch_raw)
+        if (posted || (res->fused_issued && res->fused_status == MS_OK)) {
+            // the raw records are in h->h_stage, the global rows in h->h_grows: copied out lazily (fetch_raw)
             std::lock_guard<std::mutex> lock(g_pending_mutex);
+            res->raw_in_stage = posted;
             res->owner = h;
             h->pending = res;
-        } else if (n) {  // list too long for k_post: fetch it, the host orders and consolidates
+        }
+        if (!posted && n) {  // list too long for k_post: fetch it, the host orders and consolidates
             res->raw.resize(n);
             CK(cudaMemcpyAsync(res->raw.data(), h->d_out, (size_t)n * sizeof(RawRec), cudaMemcpyDeviceToHost, h->stream));
             CK(cudaStreamSynchronize(h->stream));
@@ -1083,7 +1272,7 @@ static int search_lev_ngrams(fzb_haystack *h, const uint8_t *pattern, uint32_t m
         h->hits_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1u << 20, h->capacity / 256), 1u << 28);
         CK(cudaMalloc(&h->d_hits, (size_t)h->hits_cap * sizeof(uint64_t)));
     }
-    bool fuse_gather = post_mode == 1 && (flags & FZB_F_GLOBAL) != 0;
+    bool fuse_gather = post_mode != 0 && (flags & FZB_F_GLOBAL) != 0;
     if (flags & FZB_F_TINY_LIST) p.glist_cap = std::min(h->glist_cap, 8u);
 retry_without_hits:
     p.hits = use_hits ? h->d_hits : nullptr;
@@ -1161,8 +1350,8 @@ static int run_lp(fzb_haystack *h, fzb_result *res, F enqueue, PostPlan post = P
     return fail(FZB_E_UNSUPPORTED, "candidate explosion: more than 65536 live candidates for one start");
 }
 
-static int search_lev_lp(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint32_t k, fzb_result *res,
-                         int post_mode) {
+static int search_lev_lp(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint32_t k, uint32_t flags,
+                         fzb_result *res, int post_mode) {
     if (k > 0xFFFF) return fail(FZB_E_UNSUPPORTED, "max_l_dist too large");
     ScanParams p;
     fill_params(h, pattern, m, p);
@@ -1176,7 +1365,7 @@ static int search_lev_lp(fzb_haystack *h, const uint8_t *pattern, uint32_t m, ui
         k_lev_lp<<<grid, kLpThreads, 0, h->stream>>>(p, h->d_scratch, cap, h->d_out, h->out_cap, h->d_counters);
         res->stats.n_launches++;
         return FZB_OK;
-    }, PostPlan{post_mode, false});
+    }, PostPlan{post_mode, post_mode != 0 && (flags & FZB_F_GLOBAL) != 0});
     if (rc) return rc;
     res->raw_order = 1;
     return FZB_OK;
@@ -1209,7 +1398,7 @@ static int search_generic(fzb_haystack *h, const uint8_t *pattern, uint32_t m, u
                                                              h->d_counters);
             res->stats.n_launches++;
             return FZB_OK;
-        }, PostPlan{post_mode, false});
+        }, PostPlan{post_mode, post_mode != 0 && (flags & FZB_F_GLOBAL) != 0});
         if (rc) return rc;
         res->raw_order = 1;
         return FZB_OK;
@@ -1230,40 +1419,44 @@ static int search_generic(fzb_haystack *h, const uint8_t *pattern, uint32_t m, u
                                                              h->out_cap, h->d_counters);
         res->stats.n_launches++;
         return FZB_OK;
-    }, PostPlan{post_mode, false});
+    }, PostPlan{post_mode, post_mode != 0 && (flags & FZB_F_GLOBAL) != 0});
     if (rc) return rc;
     res->raw_order = 2;  // n-gram major, hit index, then the window's matches in canonical order
     return FZB_OK;
 }
 
 // FZB_F_GLOBAL epilogue of every search entry point: turn the per-shard groups into the global final list.
+// Fast path: k_push / k_merge already did it on the device (run_emitting).  Otherwise (no peer-memory world, a
+// shard whose list overflowed a buffer, pathological chaining across seams) every rank arrives here and the
+// rows go through the staged NCCL all-gather and the host merge.
 static int finish_global(fzb_haystack *h, fzb_result *res) {
-    if (!h->comm) return fail(FZB_E_INVALID, "FZB_F_GLOBAL needs fzb_haystack_comm_init");
+    if (h->world < 1 || (!h->comm && !h->local_world))
+        return fail(FZB_E_INVALID, "FZB_F_GLOBAL needs fzb_haystack_comm_init / fzb_comm_init_local");
+    if (res->fused_issued) {
+        if (res->fused_status == MS_OK) {
+            res->has_global = true;
+            res->global_on_device = true;
+            return FZB_OK;
+        }
+        if (res->fused_status == MS_TIMEOUT)
+            return fail(FZB_E_CUDA, "multi-GPU reduction timed out waiting for a peer (rank %d of %d)", h->rank, h->world);
+    }
+    if (h->local_world)
+        return fail(FZB_E_UNSUPPORTED, "in-process world: a shard produced more than %u groups (or more than %d raw "
+                    "matches); the staged fallback needs an NCCL communicator", h->p2p_cap, kPostMax);
     std::vector<int64_t> all;
     std::vector<uint64_t> counts;
-    if (res->fused_issued && res->gather_valid) {
-        // merge straight out of the pinned receive buffer (one run per rank)
-        std::vector<std::pair<const int64_t *, uint64_t>> runs;
-        for (int r = 0; r < h->world; r++) {
-            const int64_t *base = h->h_recv + (size_t)r * res->gather_slot_rows * kFinCols;
-            runs.push_back({base + kFinCols, (uint64_t)base[0]});
-        }
-        merge_group_runs(runs, res->gfin);
-        res->has_global = true;
-        return FZB_OK;
-    } else {  // staged: the local result is complete now, whatever it took
-        const std::vector<RawRec> &v = res->fin;
-        std::vector<int64_t> rows(v.size() * kFinCols);
-        for (size_t i = 0; i < v.size(); i++) {
-            rows[kFinCols * i + 0] = v[i].start;
-            rows[kFinCols * i + 1] = v[i].end;
-            rows[kFinCols * i + 2] = v[i].dist;
-            rows[kFinCols * i + 3] = res->hulls[2 * i];
-            rows[kFinCols * i + 4] = res->hulls[2 * i + 1];
-        }
-        int rc = allgather_groups_staged(h, rows, all, counts);
-        if (rc) return rc;
+    const std::vector<RawRec> &v = res->fin;
+    std::vector<int64_t> rows(v.size() * kFinCols);
+    for (size_t i = 0; i < v.size(); i++) {
+        rows[kFinCols * i + 0] = v[i].start;
+        rows[kFinCols * i + 1] = v[i].end;
+        rows[kFinCols * i + 2] = v[i].dist;
+        rows[kFinCols * i + 3] = res->hulls[2 * i];
+        rows[kFinCols * i + 4] = res->hulls[2 * i + 1];
     }
+    int rc = allgather_groups_staged(h, rows, all, counts);
+    if (rc) return rc;
     if (res->unconsolidated) {  // unconsolidated routes (exact, Hamming): the global list is the sorted union
         res->gfin.resize(all.size() / kFinCols);
         for (size_t i = 0; i < res->gfin.size(); i++) {
@@ -1283,6 +1476,7 @@ static int finish_global(fzb_haystack *h, fzb_result *res) {
         }
         merge_group_runs(runs, res->gfin);
     }
+    res->gcount = (uint32_t)res->gfin.size();
     res->has_global = true;
     return FZB_OK;
 }
@@ -1321,7 +1515,7 @@ extern "C" int fzb_search_levenshtein(fzb_haystack *h, const uint8_t *pattern, u
         if (ngrams)
             rc = search_lev_ngrams(h, pattern, m, k, flags, res, want_final ? 1 : 0);
         else
-            rc = search_lev_lp(h, pattern, m, k, res, want_final ? 1 : 0);
+            rc = search_lev_lp(h, pattern, m, k, flags, res, want_final ? 1 : 0);
         if (rc == FZB_OK && want_final && (flags & FZB_F_GLOBAL)) rc = finish_global(h, res);
     }
     if (rc) {
@@ -1458,7 +1652,7 @@ extern "C" int fzb_search_hamming(fzb_haystack *h, const uint8_t *pattern, uint3
                 }
                 res->stats.n_launches++;
                 return FZB_OK;
-            }, PostPlan{2, false});  // FINAL == RAW in (start, end, dist) order, ordered by k_post
+            }, PostPlan{2, (flags & FZB_F_GLOBAL) != 0});  // FINAL == RAW in (start, end, dist) order, ordered by k_post
             if (r2) return r2;
             res->raw_order = 1;
             return FZB_OK;
@@ -1614,7 +1808,7 @@ extern "C" int fzb_debug_expand(const uint8_t *subs, const uint32_t *sub_off, co
 // ------------------------------------------------------------------------------------------------
 extern "C" uint64_t fzb_result_count(const fzb_result *r, int which) {
     if (!r) return 0;
-    if (which != FZB_RAW && r->has_global) return r->gfin.size();
+    if (which != FZB_RAW && r->has_global) return r->gcount;
     if (which == FZB_RAW) return r->raw_n;
     return r->fin.size();
 }
@@ -1623,6 +1817,7 @@ extern "C" int fzb_result_copy(const fzb_result *r, int which, int64_t *start, i
                                int32_t *anchor_ngram, int64_t *anchor_idx) {
     if (!r) return fail(FZB_E_INVALID, "result is NULL");
     if (which == FZB_RAW) const_cast<fzb_result *>(r)->order_raw();
+    if (which != FZB_RAW && r->has_global) const_cast<fzb_result *>(r)->fetch_raw();  // global rows are fetched lazily
     const std::vector<RawRec> &v = (which != FZB_RAW && r->has_global) ? r->gfin : (which == FZB_RAW ? r->raw : r->fin);
     const bool anchors = (which == FZB_RAW) && (r->stats.route <= 2);
     for (size_t i = 0; i < v.size(); i++) {

@@ -98,27 +98,66 @@ __device__ bool sim_lev_lp(const ScanParams &p, const uint8_t *sP, const uint8_t
 constexpr int kLpThreads = 128;
 
 // One CTA works on tiles of kLpTile start positions: the tile (+ the m+k bytes a candidate can run
-// ahead) is staged in shared memory with coalesced loads; phase 1 tests every start against the
-// first-character table (levenshtein.py:44-49,75-80: only a character of P[:k+1] opens a candidate --
-// ~5 % of the starts on text) and queues the survivors; phase 2 hands the queued starts to the threads
-// one by one, so the expensive candidate simulation runs with every lane busy.
+// ahead) is staged in shared memory with coalesced loads; phase 1 discards the starts that cannot produce a
+// match and queues the survivors; phase 2 hands the queued starts to the threads one by one, so the
+// expensive candidate simulation runs with every lane busy.  Phase 1 applies two NECESSARY conditions:
+//   (a) the reference only opens a candidate on a character of P[:k+1] (levenshtein.py:44-49,75-80);
+//   (b) counting: a raw match (s, e, d <= k) aligns at least m - d pattern characters with EQUAL text
+//       characters (every pattern character is matched, substituted or deleted) and spans e - s <= m + k text
+//       characters, so the window H[s : s+m+k) must hold at least m - k characters that occur in P at all.
+//       A prefix count over the tile makes that one subtraction per start.  On text (95 symbols) (a) keeps
+//       ~5 % of the starts and (a)+(b) ~0.1 %: the simulation, which round 1 ran on every (a)-survivor
+//       (~70 ms per pattern on 4 GiB), becomes a small tail of an HBM-paced scan.
+// Both conditions only DROP starts whose simulation would emit nothing, so the raw multiset is unchanged.
 constexpr int kLpTile = 8192;
 constexpr int kLpHalo = 2 * kMaxPattern + 16;
+
+// Exclusive prefix counts of class[text[i]] over nchars characters into cnt[0..nchars]; all threads call.
+__device__ __forceinline__ void lp_prefix_counts(const uint8_t *text, int nchars, const uint8_t *cls, uint16_t *cnt,
+                                                 uint32_t *warp_tot) {
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int per = (nchars + kLpThreads - 1) / kLpThreads;
+    const int lo = min(tid * per, nchars), hi = min(lo + per, nchars);
+    uint32_t mine = 0;
+    for (int i = lo; i < hi; i++) mine += cls[text[i]];
+    uint32_t inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_tot[w] = inc;
+    __syncthreads();
+    uint32_t base = inc - mine;
+    for (int i = 0; i < w; i++) base += warp_tot[i];
+    for (int i = lo; i < hi; i++) {
+        cnt[i] = (uint16_t)base;
+        base += cls[text[i]];
+    }
+    if (hi == nchars && lo <= nchars) cnt[nchars] = (uint16_t)base;  // (several threads may write the same total)
+    __syncthreads();
+}
 
 __global__ void __launch_bounds__(kLpThreads)
 k_lev_lp(const ScanParams p, uint32_t *scratch, int cap, RawRec *out, uint32_t ocap, uint32_t *counters) {
     __shared__ uint8_t sP[256];
     __shared__ int16_t sFirst[256];
+    __shared__ uint8_t sClass[256];
     __shared__ __align__(16) uint8_t sH[kLpTile + kLpHalo];
+    __shared__ uint16_t sCnt[kLpTile + kLpHalo + 2];
     __shared__ uint16_t sQueue[kLpTile];
     __shared__ uint32_t sQn;
+    __shared__ uint32_t sWarpTot[kLpThreads / 32];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
         sP[i] = p.P[i];
         sFirst[i] = -1;
+        sClass[i] = 0;
     }
     __syncthreads();
-    if (threadIdx.x == 0)  // make_char2first_subseq_index: first index of each char within P[:k+1]
+    if (threadIdx.x == 0) {  // make_char2first_subseq_index: first index of each char within P[:k+1]
         for (int j = min(p.k, p.m - 1); j >= 0; j--) sFirst[p.P[j]] = (int16_t)j;
+        for (int j = 0; j < p.m; j++) sClass[p.P[j]] = 1;
+    }
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     uint32_t *A = scratch + tid * 2 * (int64_t)cap, *B = A + cap;
@@ -129,17 +168,21 @@ k_lev_lp(const ScanParams p, uint32_t *scratch, int cap, RawRec *out, uint32_t o
     }
     const int64_t hi = min(p.own_hi, p.N);
     const int ahead = p.m + p.k + 1;
+    const int win = p.m + p.k, need = p.m - p.k;
     for (int64_t tile_lo = p.own_lo + (int64_t)blockIdx.x * kLpTile; tile_lo < hi; tile_lo += (int64_t)gridDim.x * kLpTile) {
         const int tile_n = (int)min((int64_t)kLpTile, hi - tile_lo);
         const int64_t load_hi = min(min(tile_lo + tile_n + ahead, p.N), p.buf_lo + p.buf_len);
-        const int nwords = (int)((load_hi - tile_lo + 3) >> 2);  // tile_lo is a multiple of 16: aligned words
+        const int nload = (int)(load_hi - tile_lo);
+        const int nwords = (nload + 3) >> 2;  // tile_lo is a multiple of 16: aligned words
         const uint32_t *src = reinterpret_cast<const uint32_t *>(p.H + (tile_lo - p.buf_lo));
-        __syncthreads();  // previous tile fully consumed (also orders sFirst on the first pass)
+        __syncthreads();  // previous tile fully consumed (also orders sFirst / sClass on the first pass)
         for (int w = threadIdx.x; w < nwords; w += blockDim.x) reinterpret_cast<uint32_t *>(sH)[w] = __ldg(src + w);
         if (threadIdx.x == 0) sQn = 0;
         __syncthreads();
+        lp_prefix_counts(sH, nload, sClass, sCnt, sWarpTot);
         for (int i = threadIdx.x; i < tile_n; i += blockDim.x)
-            if (sFirst[sH[i]] >= 0) sQueue[atomicAdd(&sQn, 1u)] = (uint16_t)i;
+            if (sFirst[sH[i]] >= 0 && (int)sCnt[min(i + win, nload)] - (int)sCnt[i] >= need)
+                sQueue[atomicAdd(&sQn, 1u)] = (uint16_t)i;
         __syncthreads();
         const uint32_t qn = sQn;
         const uint8_t *W = sH - tile_lo;  // W[g]: byte at global position g
@@ -228,18 +271,54 @@ __device__ bool sim_generic(const ScanParams &p, const uint8_t *sP, const uint8_
     return true;
 }
 
+// Same tile scheme as k_lev_lp.  The generic NFA opens a candidate at EVERY index (generic_search.py:81), so
+// only the counting condition applies: a match costs l <= max_l, every pattern character it does not align with
+// an equal text character costs at least 1 (substitution, deletion, or the insertion+deletion pair of
+// :120-128), and it consumes at most m + max_l text characters -- so H[s : s+m+max_l) must hold at least
+// m - max_l characters that occur in the pattern.
 __global__ void __launch_bounds__(kLpThreads)
 k_generic_lp(const ScanParams p, uint32_t *scratch, int cap, RawRec *out, uint32_t ocap, uint32_t *counters) {
     __shared__ uint8_t sP[256];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) sP[i] = p.P[i];
+    __shared__ uint8_t sClass[256];
+    __shared__ __align__(16) uint8_t sH[kLpTile + kLpHalo];
+    __shared__ uint16_t sCnt[kLpTile + kLpHalo + 2];
+    __shared__ uint16_t sQueue[kLpTile];
+    __shared__ uint32_t sQn;
+    __shared__ uint32_t sWarpTot[kLpThreads / 32];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        sP[i] = p.P[i];
+        sClass[i] = 0;
+    }
     __syncthreads();
+    if (threadIdx.x == 0)
+        for (int j = 0; j < p.m; j++) sClass[p.P[j]] = 1;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     uint32_t *A = scratch + tid * 2 * (int64_t)cap, *B = A + cap;
     const int64_t hi = min(p.own_hi, p.N);
-    for (int64_t s = p.own_lo + tid; s < hi; s += stride)
-        if (!sim_generic(p, sP, p.H - p.buf_lo, s, p.N, A, B, cap, s, 1, out, ocap, counters))
-            atomicExch(&counters[CNT_OVERFLOW], 1u);
+    const int ahead = p.m + p.k + 1;
+    const int win = p.m + p.k, need = p.m - p.k;  // p.k = max_l
+    for (int64_t tile_lo = p.own_lo + (int64_t)blockIdx.x * kLpTile; tile_lo < hi; tile_lo += (int64_t)gridDim.x * kLpTile) {
+        const int tile_n = (int)min((int64_t)kLpTile, hi - tile_lo);
+        const int64_t load_hi = min(min(tile_lo + tile_n + ahead, p.N), p.buf_lo + p.buf_len);
+        const int nload = (int)(load_hi - tile_lo);
+        const int nwords = (nload + 3) >> 2;
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(p.H + (tile_lo - p.buf_lo));
+        __syncthreads();
+        for (int w = threadIdx.x; w < nwords; w += blockDim.x) reinterpret_cast<uint32_t *>(sH)[w] = __ldg(src + w);
+        if (threadIdx.x == 0) sQn = 0;
+        __syncthreads();
+        lp_prefix_counts(sH, nload, sClass, sCnt, sWarpTot);
+        for (int i = threadIdx.x; i < tile_n; i += blockDim.x)
+            if ((int)sCnt[min(i + win, nload)] - (int)sCnt[i] >= need) sQueue[atomicAdd(&sQn, 1u)] = (uint16_t)i;
+        __syncthreads();
+        const uint32_t qn = sQn;
+        const uint8_t *W = sH - tile_lo;  // W[g]: byte at global position g
+        for (uint32_t q = threadIdx.x; q < qn; q += blockDim.x) {
+            const int64_t st = tile_lo + sQueue[q];
+            if (!sim_generic(p, sP, W, st, p.N, A, B, cap, st, 1, out, ocap, counters))
+                atomicExch(&counters[CNT_OVERFLOW], 1u);
+        }
+    }
 }
 
 // Generic n-gram route: one warp per marked granule.  Phase 1: lane <-> anchor position, exact

@@ -59,10 +59,11 @@ extern "C" {
 #define FZB_F_TINY_LIST 16u   /* testing: cap the granule work list and the hit list at 8 entries (overflow paths) */
 #define FZB_F_FORCE_SAMPLED 64u /* testing: use the sampled filter whenever its lemma holds, even if the
                                  byte statistics say it is not selective */
-#define FZB_F_GLOBAL 32u      /* multi-GPU: FINAL becomes the GLOBAL consolidated list of all shards: the
-                                 per-shard groups are all-gathered with NCCL on the search's own stream,
-                                 right behind the kernels (needs fzb_haystack_comm_init on every rank;
-                                 collective: every rank must issue the same searches in the same order) */
+#define FZB_F_GLOBAL 32u      /* multi-GPU: FINAL becomes the GLOBAL consolidated list of all shards: every rank
+                                 stores its groups into every other rank's receive area over NVLink peer
+                                 memory and merges the seams on the device, on the search's own stream, right
+                                 behind the kernels (needs fzb_haystack_comm_init / fzb_comm_init_local on every
+                                 rank; collective: every rank must issue the same searches in the same order) */
 
 struct fzb_stats_s;
 typedef struct fzb_haystack fzb_haystack; /* a device-resident sequence (or one shard of it) */
@@ -125,6 +126,14 @@ int fzb_haystack_read(fzb_haystack *h, uint64_t global_offset, uint8_t *dst, uin
 void fzb_nccl_set_library(const char *path);
 int fzb_nccl_unique_id(uint8_t id[FZB_NCCL_ID_BYTES]);
 int fzb_haystack_comm_init(fzb_haystack *h, const uint8_t id[FZB_NCCL_ID_BYTES], int rank, int world_size);
+/* The same world inside ONE process: handles[r] becomes rank r of world_size shards (on one GPU or on several
+ * GPUs with peer access).  No NCCL: the shards reach each other's receive areas directly.  FZB_F_GLOBAL searches
+ * must then be issued on all handles CONCURRENTLY (one thread per handle): each one waits on the device for the
+ * others' groups (bounded by a timeout).  Used by the tests to run the multi-rank reduction on a single GPU. */
+int fzb_comm_init_local(fzb_haystack **handles, int world_size);
+/* 1 if FZB_F_GLOBAL searches on this handle reduce over peer memory (k_push / k_merge), 0 if they take the
+ * staged NCCL + host path (CUDA IPC or peer access unavailable). */
+int fzb_haystack_p2p_enabled(const fzb_haystack *h);
 
 /* Replace the contents of a whole-sequence handle with `n` new host bytes (n <= the capacity the
  * handle was created with); the device allocations are reused -- the analogue of the reference's

@@ -11,8 +11,12 @@ import pytest
 import oracle
 from corpus import ASCII, make_corpus
 from fuzzysearch_b200 import _native
-from fuzzysearch_b200.sharding import gather_and_merge_groups, gather_rows, merge_raw_streams, shard_bounds
+from fuzzysearch_b200.sharding import merge_raw_streams, rendezvous_bytes, shard_bounds
 from parity import tup
+
+import sys
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+from torch_reduce import gather_and_merge_groups, gather_rows  # noqa: E402  (torch twins, not in the product)
 
 
 def test_shard_bounds_partition_and_halo():
@@ -34,6 +38,36 @@ def _free_port():
     port = s.getsockname()[1]
     s.close()
     return port
+
+
+def _rdv_worker(rank, world, port, q):
+    payload = bytes(range(128)) if rank == 0 else b""
+    got = rendezvous_bytes(payload, rank, world, "127.0.0.1", port, timeout=60)
+    q.put((rank, got == bytes(range(128))))
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_torch_free_rendezvous(world):
+    """The product's own bootstrap (NCCL id from rank 0 to every rank over a TCP socket): no torch."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    # start the clients FIRST: they must retry until rank 0 listens
+    procs = [ctx.Process(target=_rdv_worker, args=(r, world, port, q)) for r in reversed(range(world))]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(results) == [(r, True) for r in range(world)]
+
+
+def test_product_sharding_module_is_torch_free():
+    import fuzzysearch_b200.sharding as sh
+    src = open(sh.__file__).read()
+    assert "import torch" not in src and "torch.distributed" not in src.replace("torch.distributed``", "")
 
 
 def _worker(rank, world, port, n, m, k, q):
