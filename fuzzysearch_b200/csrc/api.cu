@@ -1491,8 +1491,8 @@ static int make_result(fzb_result **out, fzb_result **res) {
 
 static int check_pattern(const fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint32_t flags = 0) {
     if (!h) return fail(FZB_E_INVALID, "haystack handle is NULL");
-    if ((flags & FZB_F_GLOBAL) && !h->comm)
-        return fail(FZB_E_INVALID, "FZB_F_GLOBAL needs fzb_haystack_comm_init on this handle");
+    if ((flags & FZB_F_GLOBAL) && !h->comm && !h->local_world)
+        return fail(FZB_E_INVALID, "FZB_F_GLOBAL needs fzb_haystack_comm_init / fzb_comm_init_local on this handle");
     if (!pattern || m == 0) return fail(FZB_E_INVALID, "Given subsequence is empty!");
     if (m > FZB_MAX_PATTERN) return fail(FZB_E_UNSUPPORTED, "pattern longer than %d bytes", FZB_MAX_PATTERN);
     return FZB_OK;
