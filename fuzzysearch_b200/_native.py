@@ -267,7 +267,7 @@ class Haystack(object):
         check(lib().fzb_haystack_upload(self._h, ptr(a), a.size))
 
     def debug_counters(self):
-        out = np.zeros(16, dtype=np.uint32)
+        out = np.zeros(32, dtype=np.uint32)
         check(lib().fzb_debug_counters(self._h, ptr(out)))
         return out.tolist()
 

@@ -5,6 +5,7 @@
 // O(N log N) consolidation of the (small) match list, which the reference also performs after its
 // search (common.py:185-189).
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cmath>
@@ -125,13 +126,12 @@ struct fzb_haystack {
     RawRec *d_out = nullptr;
     uint32_t out_cap = 0;
     uint32_t *d_counters = nullptr;
-    // k_post writes these three straight into MAPPED pinned host memory (no copy operations per search)
+    // k_post writes these straight into MAPPED pinned host memory (no copy operations per search)
     uint32_t *h_counters = nullptr;  // CNT_COUNT counters
-    RawRec *h_stage = nullptr;       // raw records, arrival order (kPostMax entries)
     int64_t *h_fin = nullptr;        // final rows (kPostMax x kFinCols)
     int64_t *d_fin = nullptr;        // device copy of the final rows (input of the multi-GPU reduction)
     uint64_t *d_sorted = nullptr;    // k_post scratch: the sorted canonical keys
-    fzb_result *pending = nullptr;   // the last result, while its raw records still sit in h_stage only
+    fzb_result *pending = nullptr;   // the last result, while its raw records still sit in d_out only
     bool ev1_recorded = false;
     bool filter_attrs_set = false;
     double coll_prob = -1.0;  // sum_c p_c^2 of the byte distribution (sampled lazily; < 0 = unknown)
@@ -144,6 +144,8 @@ struct fzb_haystack {
     uint32_t p2p_cap = 4096;        // group rows per slot
     uint64_t slot_bytes = 0, flags_off = 0;
     uint32_t epoch = 0;             // number of FZB_F_GLOBAL searches issued on this handle
+    uint32_t seq = 0;               // number of search attempts enqueued: the last kernel of each writes it to mapped
+                                    // memory as its final store and the host polls for it (wait_done)
     MergeScratch *d_ms = nullptr;
     unsigned long long *d_mscore = nullptr;
     uint32_t *d_mpos = nullptr;
@@ -190,18 +192,28 @@ struct fzb_result {
 
 static uint64_t round_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 
-// The raw records of the LAST search of a handle stay in its mapped staging buffer until somebody asks for
-// them (fzb_result_copy(FZB_RAW)), the next search on the handle is about to overwrite the buffer, or the
-// handle / the result dies: find_near_matches() only needs the consolidated list, and a 200 KB host
-// memcpy per search is 1 % of a 4 GiB scan.  One process-wide mutex guards the result <-> handle link.
+// The raw records of the LAST search of a handle stay in its DEVICE output buffer (and the global rows of a
+// multi-GPU search in its mapped host buffer) until somebody asks for them (fzb_result_copy), the next search
+// on the handle is about to overwrite the buffers, or the handle / the result dies: find_near_matches() only
+// needs the consolidated list, and shipping 200 KB of raw records over PCIe behind every search is 1-2 % of a
+// 4 GiB scan.  One process-wide mutex guards the result <-> handle link.
 static std::mutex g_pending_mutex;
 
 void fzb_result::fetch_raw() {
     std::lock_guard<std::mutex> lock(g_pending_mutex);
     if (!owner) return;
-    if (raw_in_stage) {
+    if (raw_in_stage) {  // the records are still in the owner's device buffer: one D2H copy, now
         raw.resize(raw_n);
-        if (raw_n) memcpy(raw.data(), owner->h_stage, (size_t)raw_n * sizeof(RawRec));
+        if (raw_n) {
+            cudaSetDevice(owner->device);
+            if (cudaMemcpyAsync(raw.data(), owner->d_out, (size_t)raw_n * sizeof(RawRec), cudaMemcpyDeviceToHost,
+                                owner->stream) != cudaSuccess ||
+                cudaStreamSynchronize(owner->stream) != cudaSuccess) {
+                cudaGetLastError();
+                raw.clear();  // (the handle's context is gone: nothing left to fetch)
+                raw_n = 0;
+            }
+        }
         raw_in_stage = false;
     }
     if (global_on_device) {  // rows: start, (end - start) << 32 | dist
@@ -220,7 +232,7 @@ void fzb_result::fetch_raw() {
     owner = nullptr;
 }
 
-static void detach_pending(fzb_haystack *h) {  // before h->h_stage is overwritten or freed
+static void detach_pending(fzb_haystack *h) {  // before h->d_out / h->h_grows are overwritten or freed
     fzb_result *r;
     {
         std::lock_guard<std::mutex> lock(g_pending_mutex);
@@ -243,7 +255,7 @@ static int haystack_common_init(fzb_haystack *h) {
     CK(cudaMalloc(&h->d_counters, CNT_COUNT * sizeof(uint32_t)));
     const unsigned hflags = cudaHostAllocMapped | cudaHostAllocPortable;
     CK(cudaHostAlloc(&h->h_counters, CNT_COUNT * sizeof(uint32_t), hflags));
-    CK(cudaHostAlloc(&h->h_stage, (size_t)kPostMax * sizeof(RawRec), hflags));
+    memset(h->h_counters, 0, CNT_COUNT * sizeof(uint32_t));  // the sequence word the host polls must not hold a stale value
     CK(cudaHostAlloc(&h->h_fin, (size_t)kPostMax * kFinCols * sizeof(int64_t), hflags));
     CK(cudaMalloc(&h->d_fin, (size_t)kPostMax * kFinCols * sizeof(int64_t)));
     CK(cudaMalloc(&h->d_sorted, (size_t)kPostMax * sizeof(uint64_t)));
@@ -295,7 +307,6 @@ extern "C" void fzb_haystack_destroy(fzb_haystack *h) {
     if (h->comm) nccl_comm_destroy(h->comm);
     p2p_free(h);
     if (h->h_counters) cudaFreeHost(h->h_counters);
-    if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->h_fin) cudaFreeHost(h->h_fin);
     if (h->d_fin) cudaFree(h->d_fin);
     if (h->d_sorted) cudaFree(h->d_sorted);
@@ -985,6 +996,32 @@ static int ensure_out_cap(fzb_haystack *h, uint64_t need) {
 // emitting kernels, writes the counters, the raw records and the final rows into mapped pinned host
 // memory, which the host reads as soon as the stream has drained.
 
+// Completion of a search attempt: its last kernel stores h->seq into mapped pinned memory after everything else
+// (fenced at system scope); polling that word returns a few microseconds earlier than cudaStreamSynchronize and
+// does not depend on the process's device scheduling flags (another library in the process -- e.g. a framework
+// that asked for blocking synchronisation -- would otherwise add its wake-up latency to every search).  Falls back to
+// the stream synchronisation if the word does not arrive (a failed launch), which also surfaces the error.
+static int wait_done(fzb_haystack *h, const volatile uint32_t *word) {
+    const uint32_t want = h->seq;
+    for (uint64_t spins = 0; *word != want; spins++) {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+        if ((spins & 0xFFF) == 0xFFF) {
+            const cudaError_t e = cudaStreamQuery(h->stream);
+            if (e == cudaSuccess) break;  // stream drained: the word is there (or the kernel never ran: error below)
+            if (e != cudaErrorNotReady) return fail(FZB_E_CUDA, "search failed: %s", cudaGetErrorString(e));
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    if (*word != want) {
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaGetLastError());
+        if (*word != want) return fail(FZB_E_CUDA, "search kernels did not complete");
+    }
+    return FZB_OK;
+}
+
 // What k_post should do behind the emitting kernels.
 struct PostPlan {
     int mode = 1;         // 0 raw stream only; 1 consolidate_overlapping_matches; 2 final = sorted raw list
@@ -1003,8 +1040,9 @@ static int run_emitting(fzb_haystack *h, fzb_result *res, F enqueue, PostPlan po
         int rc = enqueue();
         if (rc) return rc;
         CK(cudaGetLastError());
-        PostArgs pa{h->d_out, reinterpret_cast<const uint64_t *>(h->d_out + h->out_cap), h->out_cap, post.mode, 1,
-                    h->d_sorted, h->d_fin, h->h_fin, h->h_stage, h->h_counters, h->d_counters};
+        h->seq++;
+        PostArgs pa{reinterpret_cast<const uint64_t *>(h->d_out + h->out_cap), h->out_cap, post.mode,
+                    h->d_sorted, h->d_fin, h->h_fin, h->h_counters, h->d_counters, h->seq};
         k_post<<<h->sm_count, kPostThreads, kPostSmem, h->stream>>>(pa);
         CK(cudaGetLastError());
         res->stats.n_launches++;
@@ -1023,13 +1061,14 @@ static int run_emitting(fzb_haystack *h, fzb_result *res, F enqueue, PostPlan po
             w.flags_off = h->flags_off;
             for (int r = 0; r < h->world; r++) w.peer[r] = h->peer_base[r];
             k_push<<<kPushCtas, kPushThreads, 0, h->stream>>>(w, h->d_fin, h->d_counters, post.mode, h->d_ms);
-            MergeOut mo{h->d_mscore, h->d_mpos, h->h_grows, h->h_ghdr};
+            MergeOut mo{h->d_mscore, h->d_mpos, h->h_grows, h->h_ghdr, h->seq};
             k_merge<<<h->world, kPostThreads, 0, h->stream>>>(w, h->d_ms, mo);
             CK(cudaGetLastError());
             res->stats.n_launches += 2;
         }
         CK(cudaEventRecord(h->ev[2], h->stream));
-        CK(cudaStreamSynchronize(h->stream));
+        rc = wait_done(h, fused ? h->h_ghdr + 7 : h->h_counters + CNT_SEQ);
+        if (rc) return rc;
         const uint32_t n = h->h_counters[CNT_OUT];
         res->stats.n_candidates = h->h_counters[CNT_CAND];
         if (fused) {
@@ -1048,7 +1087,7 @@ static int run_emitting(fzb_haystack *h, fzb_result *res, F enqueue, PostPlan po
         res->raw_n = n;
         res->raw_ordered = false;
         if (posted || (res->fused_issued && res->fused_status == MS_OK)) {
-            // the raw records are in h->h_stage, the global rows in h->h_grows: copied out lazily (fetch_raw)
+            // the raw records are in h->d_out, the global rows in h->h_grows: copied out lazily (fetch_raw)
             std::lock_guard<std::mutex> lock(g_pending_mutex);
             res->raw_in_stage = posted;
             res->owner = h;
@@ -1084,6 +1123,8 @@ static int run_emitting(fzb_haystack *h, fzb_result *res, F enqueue, PostPlan po
             res->have_fin = true;
         }
         float ms = 0.f;
+        while (cudaEventQuery(h->ev[2]) == cudaErrorNotReady) {  // a microsecond behind the polled word
+        }
         cudaEventElapsedTime(&ms, h->ev[0], h->ev[2]);
         res->stats.gpu_ms = ms;
         res->stats.filter_ms = ms;
@@ -1747,9 +1788,11 @@ extern "C" int fzb_find_near_matches(const uint8_t *pattern, uint32_t m, const u
     return rc;
 }
 
-extern "C" int fzb_debug_counters(const fzb_haystack *h, uint32_t out[16]) {
+extern "C" int fzb_debug_counters(const fzb_haystack *h, uint32_t out[32]) {
     if (!h || !out) return fail(FZB_E_INVALID, "NULL argument");
+    memset(out, 0, 32 * sizeof(uint32_t));
     memcpy(out, h->h_counters, CNT_COUNT * sizeof(uint32_t));
+    if (h->h_ghdr) memcpy(out + 16, h->h_ghdr, 16 * sizeof(uint32_t));
     return FZB_OK;
 }
 

@@ -129,8 +129,18 @@ struct MergeOut {
     unsigned long long *score;  // device scratch [world * cap]
     uint32_t *pos;              // device scratch [world * cap]
     int64_t *h_rows;            // mapped host: global final rows, 2 x int64 each: start, (end-start) << 32 | dist
-    uint32_t *h_hdr;            // mapped host: [0] status, [1] number of global final rows, [2] epoch
+    uint32_t *h_hdr;            // mapped host: [0] status, [1] number of global final rows, [2] epoch, [7] seq (LAST)
+    uint32_t seq;
 };
+
+// CTA 0 / thread 0 only: publish the outcome; the sequence word goes last (the host polls it)
+__device__ __forceinline__ void merge_finish(const MergeOut &o, uint32_t status, uint32_t ng, uint32_t epoch) {
+    o.h_hdr[1] = ng;
+    o.h_hdr[2] = epoch;
+    o.h_hdr[0] = status;
+    __threadfence_system();
+    o.h_hdr[7] = o.seq;
+}
 
 __global__ void __launch_bounds__(kPostThreads, 1)
 k_merge(const WorldArgs w, MergeScratch *ms, const MergeOut o) {
@@ -141,6 +151,7 @@ k_merge(const WorldArgs w, MergeScratch *ms, const MergeOut o) {
     const uint32_t tid = threadIdx.x;
     const int q = blockIdx.x;  // my run
     const int W = w.world;
+    const uint32_t t_start = gtimer_lo();
     // ---- wait until every rank's slot of this epoch has landed in MY receive area ----------------------
     if (tid == 0) {
         const uint32_t *flags = reinterpret_cast<const uint32_t *>(w.peer[w.rank] + w.flags_off) + (w.epoch & 1u) * kMaxWorld;
@@ -166,13 +177,10 @@ k_merge(const WorldArgs w, MergeScratch *ms, const MergeOut o) {
     }
     __syncthreads();
     if (s_state != MS_OK) {
-        if (q == 0 && tid == 0) {
-            o.h_hdr[1] = 0;
-            o.h_hdr[2] = w.epoch;
-            o.h_hdr[0] = s_state;
-        }
+        if (q == 0 && tid == 0) merge_finish(o, s_state, 0, w.epoch);
         return;
     }
+    const uint32_t t_landed = gtimer_lo();
     const int mode = (int)__ldcg(reinterpret_cast<const int64_t *>(slot_ptr(w, w.rank, 0)) + 3);
     if (tid < (uint32_t)W) {
         const int64_t *rows = reinterpret_cast<const int64_t *>(slot_ptr(w, w.rank, tid)) + kHdrWords;
@@ -233,17 +241,13 @@ k_merge(const WorldArgs w, MergeScratch *ms, const MergeOut o) {
         }
     }
     if (!grid_barrier(ms, (uint32_t)W)) {
-        if (q == 0 && tid == 0) o.h_hdr[0] = MS_TIMEOUT;
+        if (q == 0 && tid == 0) merge_finish(o, MS_TIMEOUT, 0, w.epoch);
         return;
     }
     // ---- phase 2: group number = position - non-heads at or before it; winners by atomicMin ----------------
     const uint32_t nh = ld_volatile_u32(&ms->nh_count);
     if (nh > kMaxNonHeads) {  // pathological chaining across seams: the host does it
-        if (q == 0 && tid == 0) {
-            o.h_hdr[1] = 0;
-            o.h_hdr[2] = w.epoch;
-            o.h_hdr[0] = MS_OVERFLOW;
-        }
+        if (q == 0 && tid == 0) merge_finish(o, MS_OVERFLOW, 0, w.epoch);
         return;
     }
     for (uint32_t i = tid; i < nh; i += kPostThreads) s_nh[i] = __ldcg(ms->nh_pos + i);
@@ -259,7 +263,7 @@ k_merge(const WorldArgs w, MergeScratch *ms, const MergeOut o) {
         atomicMin(&o.score[pos - below], score);
     }
     if (!grid_barrier(ms, 2u * (uint32_t)W)) {
-        if (q == 0 && tid == 0) o.h_hdr[0] = MS_TIMEOUT;
+        if (q == 0 && tid == 0) merge_finish(o, MS_TIMEOUT, 0, w.epoch);
         return;
     }
     // ---- phase 3: decode the winners into the host rows (coalesced 16-byte stores) --------------------------
@@ -273,15 +277,16 @@ k_merge(const WorldArgs w, MergeScratch *ms, const MergeOut o) {
         row.y = (long long)((len << 32) | d);
         reinterpret_cast<longlong2 *>(o.h_rows)[g] = row;
     }
+    __threadfence_system();  // my rows are on their way to the host before the barrier says so
     if (!grid_barrier(ms, 3u * (uint32_t)W)) {
-        if (q == 0 && tid == 0) o.h_hdr[0] = MS_TIMEOUT;
+        if (q == 0 && tid == 0) merge_finish(o, MS_TIMEOUT, 0, w.epoch);
         return;
     }
     if (q == 0 && tid == 0) {
-        o.h_hdr[1] = ng;
-        o.h_hdr[2] = w.epoch;
-        __threadfence_system();
-        o.h_hdr[0] = MS_OK;
+        o.h_hdr[4] = t_landed - t_start;      // ns spent waiting for the peers' slots (fzb_debug_counters)
+        o.h_hdr[5] = gtimer_lo() - t_landed;  // ns of the merge itself
+        o.h_hdr[6] = nh;
+        merge_finish(o, MS_OK, ng, w.epoch);
     }
 }
 

@@ -4,8 +4,7 @@
 // lists of up to kPostMax records (the common case: matches are sparse); nothing waits for the host and
 // there is no device->host copy operation either: the kernel writes its outputs straight into MAPPED
 // pinned host memory, so a search ends with a single stream synchronisation.
-//   every CTA  (one per SM) copies its slice of the raw records (arrival order) to the host, loads the
-//              packed canonical keys (start, end-start, dist; written by emit() next to each record) of ALL
+//   every CTA  (one per SM) loads the packed canonical keys (start, end-start, dist; written by emit() next to each record) of ALL
 //              records into shared memory and ranks its slice of them against all of them (rank = number of
 //              smaller keys; a warp ranks two records per pass over the list), scatters its keys to their
 //              sorted positions in global memory and takes a ticket.  Measured alternatives for 7 K records:
@@ -17,7 +16,8 @@
 //              interval overlap), winner per group = min (dist, -(end-start)), ties -> first in
 //              (start, end) order.  Final rows (winner + hull) stay on the device (input of the multi-GPU
 //              reduction) and go to the host in coalesced 16-byte stores.
-// The host puts the raw stream into the reference's generation order lazily, only if a caller asks for it.
+// The raw records themselves stay in device memory; the host fetches them and puts them into the reference's
+// generation order lazily, only if a caller asks for the raw stream (api.cu: fetch_raw).
 // Larger lists fall back to the host implementation (consolidate_recs in api.cu), which computes
 // exactly the same thing.
 #pragma once
@@ -27,22 +27,20 @@ namespace fzb {
 
 constexpr int kPostMax = 16384;
 constexpr int kPostThreads = 1024;
-enum { CNT_POST_DONE = 5, CNT_NFINAL = 6, CNT_TICKET = 9 };
+enum { CNT_POST_DONE = 5, CNT_NFINAL = 6, CNT_TICKET = 9, CNT_SEQ = 15 };
 constexpr int kFinCols = 5;  // start, end, dist, hull_start, hull_end of the group
 constexpr size_t kPostSmem = (size_t)kPostMax * 8 + (size_t)kPostMax * 4;  // keys + per-group best
 
 struct PostArgs {
-    const RawRec *recs;    // raw records, arrival order
     const uint64_t *rkeys; // their canonical keys (same order)
     uint32_t cap;          // capacity of recs / rkeys
     int mode;              // 0 raw only; 1 consolidate; 2 final = the raw list in (start, end, dist) order
-    int copy_raw;          // copy the raw records to h_raw
     uint64_t *sorted;      // device scratch: kPostMax sorted keys
     int64_t *fin;          // device: final rows [kPostMax][kFinCols]
     int64_t *h_fin;        // mapped host: the same rows
-    RawRec *h_raw;         // mapped host: raw records
     uint32_t *h_counters;  // mapped host: CNT_COUNT counters
     uint32_t *counters;
+    uint32_t seq;          // written to h_counters[CNT_SEQ] LAST: the host polls it instead of synchronising the stream
 };
 
 __device__ __forceinline__ uint32_t gtimer_lo() {
@@ -128,16 +126,15 @@ k_post(const PostArgs a) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t G = gridDim.x, b = blockIdx.x;
     if (!fits) {  // the host fetches the list and does the rest
-        if (b == 0 && tid < CNT_COUNT) a.h_counters[tid] = a.counters[tid];  // POST_DONE stays 0
+        if (b == 0) {
+            if (tid < CNT_SEQ) a.h_counters[tid] = a.counters[tid];  // POST_DONE stays 0
+            __threadfence_system();
+            __syncthreads();
+            if (tid == 0) a.h_counters[CNT_SEQ] = a.seq;
+        }
         return;
     }
     const uint32_t t_start = gtimer_lo();
-    if (a.copy_raw) {  // my slice of the raw records -> host: 2 x 16 bytes per record, coalesced
-        const uint32_t rlo = (uint32_t)((uint64_t)nraw * b / G), rhi = (uint32_t)((uint64_t)nraw * (b + 1) / G);
-        const uint4 *src = reinterpret_cast<const uint4 *>(a.recs);
-        uint4 *dst = reinterpret_cast<uint4 *>(a.h_raw);
-        for (uint32_t i = 2 * rlo + tid; i < 2 * rhi; i += kPostThreads) dst[i] = src[i];
-    }
     const uint32_t lo = (uint32_t)((uint64_t)n * b / G), hi = (uint32_t)((uint64_t)n * (b + 1) / G);
     if (a.mode != 0 && n > 0) {
         for (uint32_t i = tid; i < n; i += kPostThreads) keys[i] = a.rkeys[i];
@@ -246,7 +243,10 @@ k_post(const PostArgs a) {
         a.counters[13] = gtimer_lo() - t_swept;
     }
     __syncthreads();
-    if (tid < CNT_COUNT) a.h_counters[tid] = a.counters[tid];
+    if (tid < CNT_SEQ) a.h_counters[tid] = a.counters[tid];
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) a.h_counters[CNT_SEQ] = a.seq;  // everything above is visible to the host before this word
 }
 
 // Pack this shard's groups for the all-gather: slot = header row {count, valid, 0, 0, 0} + up to `cap`

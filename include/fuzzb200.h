@@ -264,9 +264,11 @@ int fzb_debug_expand(const uint8_t *subs, const uint32_t *sub_off, const uint8_t
                      const uint32_t *seq_off, const int32_t *max_l, const int32_t *variant, uint32_t count,
                      int device, int32_t *out);
 
-/* TEST / PROFILING HOOK: the 16 device counters of the handle's last search (candidates, raw records, final
- * groups, and in slots 10-13 the phase times of k_post's last CTA in nanoseconds). */
-int fzb_debug_counters(const fzb_haystack *h, uint32_t out[16]);
+/* TEST / PROFILING HOOK: out[0..15] = the 16 device counters of the handle's last search (candidates, raw
+ * records, final groups, and in slots 10-13 the phase times of k_post's last CTA in nanoseconds); out[16..31] =
+ * the header of its last multi-GPU merge (status, global count, epoch, -, ns waiting for peers, ns merging,
+ * non-head rows). */
+int fzb_debug_counters(const fzb_haystack *h, uint32_t out[32]);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

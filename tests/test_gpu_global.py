@@ -155,8 +155,8 @@ def _worker(rank, world, port, devices, q):
         ham = hs.search_hamming(pat, 3, F.F_GLOBAL).triples(F.FINAL)
         ok = ok and ham == tup(oracle.substitutions(pat, hay, 3))
         # more groups than a slot holds -> every rank takes the staged NCCL path together
-        many = hs.search_exact(pat[:2], F.F_GLOBAL).triples(F.FINAL)
-        ok = ok and many == [(i, i + 2, 0) for i in oracle.search_exact(pat[:2], hay)] and len(many) > 4096
+        many = hs.search_exact(pat[:1], F.F_GLOBAL).triples(F.FINAL)
+        ok = ok and many == [(i, i + 1, 0) for i in oracle.search_exact(pat[:1], hay)] and len(many) > 4096
         q.put((rank, bool(ok), len(got), bool(p2p)))
         hs.close()
     except BaseException as e:  # noqa: BLE001
