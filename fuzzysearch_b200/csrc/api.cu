@@ -22,6 +22,8 @@
 #include "lp_kernels.cuh"
 #include "post_kernels.cuh"
 #include "p2p_kernels.cuh"
+#include "batch_kernels.cuh"
+#include <unordered_map>
 #include "debug_kernels.cuh"
 
 using namespace fzb;
@@ -165,6 +167,14 @@ struct fzb_haystack {
     uint32_t glist_cap = 0;
     uint32_t *d_scratch = nullptr;  // candidate lists of the LP / generic kernels
     uint64_t scratch_words = 0;
+    // single-pass multi-pattern batches (batch_kernels.cuh), allocated on first use
+    uint32_t *d_mbits = nullptr;
+    uint2 *d_gtab = nullptr;
+    uint32_t *d_postings = nullptr, *d_pinfo = nullptr;
+    BatchPat *d_bpats = nullptr;
+    unsigned long long *d_mset = nullptr;
+    WorkItem *d_mwork = nullptr;
+    uint32_t mset_slots = 0, mwork_cap = 0;
 };
 
 struct fzb_result {
@@ -298,6 +308,13 @@ extern "C" void fzb_haystack_destroy(fzb_haystack *h) {
     if (h->d_out) cudaFree(h->d_out);
     if (h->d_counters) cudaFree(h->d_counters);
     if (h->d_scratch) cudaFree(h->d_scratch);
+    if (h->d_mbits) cudaFree(h->d_mbits);
+    if (h->d_gtab) cudaFree(h->d_gtab);
+    if (h->d_postings) cudaFree(h->d_postings);
+    if (h->d_pinfo) cudaFree(h->d_pinfo);
+    if (h->d_bpats) cudaFree(h->d_bpats);
+    if (h->d_mset) cudaFree(h->d_mset);
+    if (h->d_mwork) cudaFree(h->d_mwork);
     if (h->d_glist) cudaFree(h->d_glist);
     if (h->d_hits) cudaFree(h->d_hits);
     if (h->d_send) cudaFree(h->d_send);
@@ -1567,21 +1584,232 @@ extern "C" int fzb_search_levenshtein(fzb_haystack *h, const uint8_t *pattern, u
     return FZB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Batches: one scan for all the patterns the q-sample lemma covers (batch_kernels.cuh)
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kGtabSlots = 1u << 17;     // gram table (open addressing, <= 50 % full)
+constexpr uint32_t kMaxBatchGrams = 60000;    // distinct grams of one pass
+constexpr uint32_t kMaxBatchPostings = 1u << 20;
+constexpr uint32_t kMaxBatchPats = 4096;      // patterns of one pass
+
+static int ensure_batch_buffers(fzb_haystack *h) {
+    if (h->d_mbits) return FZB_OK;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMalloc(&h->d_mbits, kMultiTblWords * sizeof(uint32_t)));
+    CK(cudaMalloc(&h->d_gtab, kGtabSlots * sizeof(uint2)));
+    CK(cudaMalloc(&h->d_postings, kMaxBatchPostings * sizeof(uint32_t)));
+    CK(cudaMalloc(&h->d_pinfo, kMaxBatchPats * sizeof(uint32_t)));
+    CK(cudaMalloc(&h->d_bpats, kMaxBatchPats * sizeof(BatchPat)));
+    h->mset_slots = 1u << 22;
+    h->mwork_cap = 1u << 21;
+    CK(cudaMalloc(&h->d_mset, (size_t)h->mset_slots * sizeof(unsigned long long)));
+    CK(cudaMemset(h->d_mset, 0, (size_t)h->mset_slots * sizeof(unsigned long long)));
+    CK(cudaMalloc(&h->d_mwork, (size_t)h->mwork_cap * sizeof(WorkItem)));
+    CK(cudaFuncSetAttribute(k_filter_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMultiSmem));
+    return FZB_OK;
+}
+
+// One pass over the haystack for the patterns ids[0..cnt): fills out[ids[i]].  Returns FZB_OK, an error, or +1 if
+// the pass overflowed a device structure (the caller then searches these patterns one by one).
+static int batch_pass(fzb_haystack *h, const uint8_t *patterns, const uint32_t *offsets, const uint32_t *ks,
+                      const std::vector<uint32_t> &ids, fzb_result **out, fzb_stats *sum) {
+    const uint32_t cnt = (uint32_t)ids.size();
+    std::vector<BatchPat> pats(cnt);
+    std::vector<uint32_t> pinfo(cnt);
+    std::unordered_map<uint32_t, std::vector<uint32_t>> grams;
+    grams.reserve(cnt * 48);
+    for (uint32_t i = 0; i < cnt; i++) {
+        const uint32_t id = ids[i], m = offsets[id + 1] - offsets[id], k = ks[id];
+        BatchPat &bp = pats[i];
+        memset(&bp, 0, sizeof bp);
+        memcpy(bp.P, patterns + offsets[id], m);
+        bp.m = (int)m;
+        bp.k = (int)k;
+        bp.L = (int)(m / (k + 1));
+        bp.n_ngrams = (int)m / bp.L;
+        pinfo[i] = m | (k << 8) | ((uint32_t)bp.L << 16);
+        for (uint32_t o = 0; o + 4 <= m; o++) {
+            uint32_t w;
+            memcpy(&w, bp.P + o, 4);
+            grams[w].push_back((i << 8) | o);
+        }
+    }
+    std::vector<uint32_t> bits(kMultiTblWords, 0), postings;
+    std::vector<uint2> gtab(kGtabSlots, make_uint2(0, 0));
+    for (auto &g : grams) {
+        const uint32_t w = g.first, hb = (w * kHashMul) >> (32 - kMultiTblBits);
+        bits[hb >> 5] |= 1u << (hb & 31u);
+        for (size_t first = 0; first < g.second.size(); first += 255) {
+            const uint32_t c = (uint32_t)std::min<size_t>(255, g.second.size() - first);
+            uint32_t slot = (w * kGramMul) & (kGtabSlots - 1);
+            while (gtab[slot].y != 0u) slot = (slot + 1) & (kGtabSlots - 1);
+            gtab[slot] = make_uint2(w, (uint32_t)postings.size() | (c << 24));
+            postings.insert(postings.end(), g.second.begin() + first, g.second.begin() + first + c);
+        }
+    }
+    int rc = ensure_batch_buffers(h);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    detach_pending(h);
+    CK(cudaMemcpyAsync(h->d_mbits, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_gtab, gtab.data(), gtab.size() * sizeof(uint2), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_postings, postings.data(), postings.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_pinfo, pinfo.data(), pinfo.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_bpats, pats.data(), pats.size() * sizeof(BatchPat), cudaMemcpyHostToDevice, h->stream));
+    MultiParams mp{};
+    mp.H = h->d;
+    mp.buf_lo = (int64_t)h->buf_lo;
+    mp.buf_len = (int64_t)h->buf_len;
+    mp.N = (int64_t)h->global_len;
+    mp.own_lo = (int64_t)h->own_lo;
+    mp.own_hi = (int64_t)h->own_hi;
+    mp.bits = h->d_mbits;
+    mp.gtab = h->d_gtab;
+    mp.gtab_mask = kGtabSlots - 1;
+    mp.postings = h->d_postings;
+    mp.pinfo = h->d_pinfo;
+    mp.set = h->d_mset;
+    mp.set_mask = h->mset_slots - 1;
+    mp.work = h->d_mwork;
+    mp.work_cap = h->mwork_cap;
+    mp.counters = h->d_counters;
+    const int64_t nvec = (int64_t)(round_up(h->buf_len, 16) / 16);
+    const int64_t ntiles = (nvec + kMultiTileVecs - 1) / kMultiTileVecs;
+    std::vector<RawRec> raw;
+    float gpu_ms = 0.f, filter_ms = 0.f;
+    uint32_t n_work = 0;
+    for (int attempt = 0;; attempt++) {
+        if (attempt == 8) return fail(FZB_E_CUDA, "output buffer kept overflowing");
+        CK(cudaMemsetAsync(h->d_counters, 0, CNT_COUNT * sizeof(uint32_t), h->stream));
+        CK(cudaEventRecord(h->ev[0], h->stream));
+        if (ntiles > 0) {
+            const int grid = (int)std::min<int64_t>(ntiles, h->sm_count);
+            k_filter_multi<<<grid, kMultiThreads, kMultiSmem, h->stream>>>(mp, nvec, ntiles);
+        }
+        CK(cudaEventRecord(h->ev[1], h->stream));
+        k_verify_multi<<<h->sm_count * 8, kVmThreads, 0, h->stream>>>(mp, h->d_bpats, h->d_out, h->out_cap, h->d_counters);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(h->ev[2], h->stream));
+        uint32_t cnts[CNT_COUNT];
+        CK(cudaMemcpyAsync(cnts, h->d_counters, sizeof cnts, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (cnts[CNT_OVERFLOW]) {  // work list / set too small for this batch: clean up, let the caller go one by one
+            CK(cudaMemsetAsync(h->d_mset, 0, (size_t)h->mset_slots * sizeof(unsigned long long), h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            return 1;
+        }
+        const uint32_t n = cnts[CNT_OUT];
+        if (n > h->out_cap) {
+            rc = ensure_out_cap(h, n);
+            if (rc) return rc;
+            continue;
+        }
+        raw.resize(n);
+        if (n) {
+            CK(cudaMemcpyAsync(raw.data(), h->d_out, (size_t)n * sizeof(RawRec), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+        }
+        n_work = cnts[CNT_CAND];
+        cudaEventElapsedTime(&gpu_ms, h->ev[0], h->ev[2]);
+        cudaEventElapsedTime(&filter_ms, h->ev[0], h->ev[1]);
+        break;
+    }
+    // split by pattern, consolidate each list on the host
+    std::vector<uint32_t> per(cnt, 0);
+    for (const RawRec &r : raw) per[(uint32_t)r.ngram >> 8]++;
+    for (uint32_t i = 0; i < cnt; i++) {
+        fzb_result *res = new (std::nothrow) fzb_result();
+        if (!res) return fail(FZB_E_CUDA, "out of host memory");
+        res->raw.reserve(per[i]);
+        res->stats.route = 1;
+        res->stats.bytes_scanned = i == 0 ? h->buf_len : 0;  // the haystack is read once for the whole pass
+        res->stats.gpu_ms = i == 0 ? gpu_ms : 0.0;
+        res->stats.filter_ms = i == 0 ? filter_ms : 0.0;
+        res->stats.n_candidates = i == 0 ? n_work : 0;
+        res->stats.n_launches = i == 0 ? 2 : 0;
+        out[ids[i]] = res;
+    }
+    for (const RawRec &r : raw) {
+        RawRec q = r;
+        q.ngram = r.ngram & 0xFF;
+        out[ids[(uint32_t)r.ngram >> 8]]->raw.push_back(q);
+    }
+    for (uint32_t i = 0; i < cnt; i++) {
+        fzb_result *res = out[ids[i]];
+        res->raw_n = (uint32_t)res->raw.size();
+        res->raw_order = 0;
+        consolidate_recs(res->raw, res->fin, &res->hulls);
+        res->have_fin = true;
+    }
+    sum->gpu_ms += gpu_ms;
+    sum->filter_ms += filter_ms;
+    sum->bytes_scanned += h->buf_len;
+    sum->n_candidates += n_work;
+    sum->n_launches += 2;
+    return FZB_OK;
+}
+
 extern "C" int fzb_search_levenshtein_batch(fzb_haystack *h, const uint8_t *patterns, const uint32_t *offsets,
                                             const uint32_t *max_l_dist, uint32_t count, uint32_t flags,
                                             fzb_result **out, fzb_stats *total) {
     if (!h || !out || (count && (!patterns || !offsets || !max_l_dist))) return fail(FZB_E_INVALID, "NULL argument");
     for (uint32_t i = 0; i < count; i++) out[i] = nullptr;
-    fzb_stats sum{};
-    for (uint32_t i = 0; i < count; i++) {
+    for (uint32_t i = 0; i < count; i++)
         if (offsets[i + 1] < offsets[i]) return fail(FZB_E_INVALID, "offsets must be non-decreasing");
+    fzb_stats sum{};
+    auto cleanup = [&]() {
+        for (uint32_t j = 0; j < count; j++) {
+            if (out[j]) fzb_result_destroy(out[j]);
+            out[j] = nullptr;
+        }
+    };
+    // patterns the shared scan can take: n-gram route, q-sample lemma holds, 4-grams selective on this haystack,
+    // short enough for the 64-bit match table; no special flags (forced routes, raw-only, multi-GPU reduction)
+    std::vector<uint32_t> shared;
+    if (flags == 0 && h->buf_len > 0) {
+        for (uint32_t i = 0; i < count; i++) {
+            const uint32_t m = offsets[i + 1] - offsets[i], k = max_l_dist[i];
+            if (m == 0 || m > (uint32_t)kBatchMaxM || k == 0 || k >= m) continue;
+            const uint32_t L = m / (k + 1);
+            if (L < 3 || !sampled_filter_applies(m, k, 0)) continue;
+            if (check_halo(h, (uint64_t)m + k) != FZB_OK) continue;
+            if (!sampled_is_selective(h, m, k, (int)L, (int)(m / L))) continue;
+            shared.push_back(i);
+        }
+    }
+    size_t done = 0;
+    while (done < shared.size()) {  // passes of bounded size (gram table / posting capacity)
+        std::vector<uint32_t> ids;
+        uint64_t ngr = 0;
+        while (done < shared.size() && ids.size() < kMaxBatchPats) {
+            const uint32_t m = offsets[shared[done] + 1] - offsets[shared[done]];
+            if (ngr + (m - 3) > kMaxBatchGrams) break;
+            ngr += m - 3;
+            ids.push_back(shared[done++]);
+        }
+        if (ids.size() < 2) {  // not worth a shared pass
+            done -= ids.size();
+            break;
+        }
+        int rc = batch_pass(h, patterns, offsets, max_l_dist, ids, out, &sum);
+        if (rc < 0) {
+            cleanup();
+            return rc;
+        }
+        if (rc > 0) {  // overflow: these patterns fall through to the one-by-one path
+            for (uint32_t id : ids)
+                if (out[id]) {
+                    fzb_result_destroy(out[id]);
+                    out[id] = nullptr;
+                }
+        }
+    }
+    for (uint32_t i = 0; i < count; i++) {
+        if (out[i]) continue;
         int rc = fzb_search_levenshtein(h, patterns + offsets[i], offsets[i + 1] - offsets[i], max_l_dist[i], flags,
                                         &out[i]);
         if (rc) {
-            for (uint32_t j = 0; j < i; j++) {
-                fzb_result_destroy(out[j]);
-                out[j] = nullptr;
-            }
+            cleanup();
             return rc;
         }
         sum.gpu_ms += out[i]->stats.gpu_ms;

@@ -682,7 +682,8 @@ constexpr int kWinBytes = 64 + 2 * (2 * kMaxPattern) + 32;  // 1116
 constexpr int kWinWords = (kWinBytes + 3) / 4;
 
 // Loads the window of granule `gbase` into sWin; returns the global position of sWin[0].
-__device__ __forceinline__ int64_t stage_window(const ScanParams &p, int64_t gbase, int halo, int lane,
+template <class PT>
+__device__ __forceinline__ int64_t stage_window(const PT &p, int64_t gbase, int halo, int lane,
                                                 uint32_t *sWin) {
     int64_t wlo = max(gbase - halo, p.buf_lo);
     int64_t whi = min(gbase + kGranule + halo, p.buf_lo + p.buf_len);
@@ -699,10 +700,18 @@ __device__ __forceinline__ int64_t stage_window(const ScanParams &p, int64_t gba
 // first finds the next n-gram that really occurs at its anchor (cheap), THEN the lanes that found one
 // run the two expansions side by side (converged), and the search for further n-grams resumes.
 // VM = verify_mode(m, L); S is only used (and only non-null) in mode 2.
-template <int VM>
-__device__ void verify_anchor_lev(const ScanParams &p, const uint8_t *sP, const unsigned long long *sPM,
+// PT: ScanParams, or the per-work-item VerifyCtx of the multi-pattern kernels (batch_kernels.cuh); `tag` is OR-ed
+// into the n-gram field of the emitted records (pattern number << 8 in a batch).
+struct VerifyCtx {
+    const uint8_t *H;
+    int64_t buf_lo, buf_len, N, own_lo, own_hi;
+    int32_t m, k, L, n_ngrams;
+};
+
+template <int VM, class PT>
+__device__ void verify_anchor_lev(const PT &p, const uint8_t *sP, const unsigned long long *sPM,
                                   const uint8_t *W, int64_t idx, bool valid, DpScratch *S, RawRec *out, uint32_t cap,
-                                  uint32_t *counters, int j_lo, int j_hi) {
+                                  uint32_t *counters, int j_lo, int j_hi, int tag = 0) {
     // W[g] is the haystack byte at global position g (shared-memory window); n-grams j_lo..j_hi-1
     const int m = p.m, k = p.k, L = p.L;
     const int64_t N = p.N;
@@ -760,7 +769,8 @@ __device__ void verify_anchor_lev(const ScanParams &p, const uint8_t *sP, const 
             const unsigned long long ident = ((unsigned long long)(idx - ls) << 18) |
                                              ((unsigned long long)(L + rs + ls) << 8) | (unsigned long long)(dl + dr);
             const unsigned peers = __match_any_sync(okm, ident);
-            emit(out, cap, counters, idx - ls, idx + L + rs, idx, dl + dr, j, (__ffs(peers) - 1) == (int)(threadIdx.x & 31));
+            emit(out, cap, counters, idx - ls, idx + L + rs, idx, dl + dr, j | tag,
+                 (__ffs(peers) - 1) == (int)(threadIdx.x & 31));
         }
         j++;
     }
@@ -771,11 +781,11 @@ __device__ void verify_anchor_lev(const ScanParams &p, const uint8_t *sP, const 
 // whole GPU instead of serialising on the warp that owns their bitmap words.  Each processed granule
 // clears its own bit; if the list overflows (dense candidates, e.g. small alphabets) the bits left
 // set are swept by the bitmap-scanning fallback loop of the same kernel launched in "scan" mode.
-template <int VM>
-__device__ __forceinline__ void verify_granule_lev(const ScanParams &p, const uint8_t *sP,
+template <int VM, class PT>
+__device__ __forceinline__ void verify_granule_lev(const PT &p, const uint8_t *sP,
                                                    const unsigned long long *sPM, uint32_t *sWin, int64_t granule,
                                                    int lane, DpScratch *S, RawRec *out, uint32_t cap,
-                                                   uint32_t *counters) {
+                                                   uint32_t *counters, int tag = 0) {
     const int64_t gbase = p.buf_lo + (granule << kGranuleShift);
     const int64_t alo = stage_window(p, gbase, p.m + p.k, lane, sWin);
     const uint8_t *W = reinterpret_cast<const uint8_t *>(sWin) - alo;
@@ -783,7 +793,7 @@ __device__ __forceinline__ void verify_granule_lev(const ScanParams &p, const ui
     for (int half = 0; half < kGranule / 32; half++) {
         const int64_t idx = gbase + half * 32 + lane;
         verify_anchor_lev<VM>(p, sP, sPM, W, idx, idx >= p.own_lo && idx < p.own_hi, S, out, cap, counters, 0,
-                              p.n_ngrams);
+                              p.n_ngrams, tag);
     }
 }
 

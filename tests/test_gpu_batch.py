@@ -29,7 +29,11 @@ def test_batch_matches_oracle(cuda_device):
             hay[pos:pos + len(v)] = np.frombuffer(v, dtype=np.uint8)
     hs = F.Haystack.from_host(hay)
     results, stats = hs.search_levenshtein_batch(pats, ks)
-    assert stats["route"] == "batch" and stats["n_launches"] >= len(pats)
+    assert stats["route"] == "batch"
+    # the shared scan read the haystack ONCE for all the patterns it took (the others cost one pass each)
+    shared = sum(1 for r in results if r.stats()["route"] == "ngrams/sampled-filter")
+    assert shared >= 24
+    assert stats["bytes_scanned"] == n * (1 + len(pats) - shared)
     routes = set()
     total = 0
     for pat, k, res in zip(pats, ks, results):
@@ -48,3 +52,48 @@ def test_batch_matches_oracle(cuda_device):
     got = find_near_matches_batch(pats[:5], hay.tobytes(), ks[:5])
     for pat, k, ms in zip(pats, ks, got):
         assert [(m.start, m.end, m.dist) for m in ms] == oracle.find_near_matches(pat, hay, max_l_dist=k)
+
+
+def test_batch_shared_scan_edge_cases(cuda_device):
+    """Patterns that share 4-grams (prefixes of one another, duplicates, repetitive patterns whose grams occur at
+    many offsets), a k = 0 entry (exact route, returns every overlapping occurrence), matches at both ends of
+    the sequence and clusters -- all through one call; every list must equal the single-pattern search."""
+    rng = np.random.default_rng(7)
+    n = 1 << 22
+    alpha = np.frombuffer(ASCII, dtype=np.uint8)
+    hay = alpha[rng.integers(0, len(alpha), size=n)].copy()
+    base = bytes(alpha[rng.integers(0, len(alpha), size=64)])
+    pats = [base, base[:40], base[:20], base[10:50], base, b"abcabcabcabcabcabcabcabcabcabcabcabc", b"a" * 30,
+            base[3:23], b"needle-in-a-haystack", b"xy" * 12]
+    ks = [4, 3, 2, 2, 1, 3, 2, 0, 1, 2]
+    for i in range(120):
+        m = int(rng.integers(12, 65))
+        pats.append(bytes(alpha[rng.integers(0, len(alpha), size=m)]))
+        ks.append(int(rng.integers(1, 5)))
+    for pat, k in zip(pats, ks):
+        for _ in range(4):
+            pos = int(rng.integers(100, n - 200))
+            v = mutate(rng, pat, ASCII, int(rng.integers(0, k + 2)))
+            hay[pos:pos + len(v)] = np.frombuffer(v, dtype=np.uint8)
+    hay[:64] = np.frombuffer(base, dtype=np.uint8)              # at the very start
+    hay[n - 60:] = np.frombuffer(base[:60], dtype=np.uint8)     # truncated at the very end
+    blob = (b"abc" * 40) + (b"a" * 70) + (b"xy" * 30)
+    hay[5000:5000 + len(blob)] = np.frombuffer(blob, dtype=np.uint8)  # long chains of overlapping matches
+    hs = F.Haystack.from_host(hay)
+    results, stats = hs.search_levenshtein_batch(pats, ks)
+    shared = 0
+    for pat, k, res in zip(pats, ks, results):
+        one = hs.search_levenshtein(pat, k)
+        shared += res.stats()["route"] == "ngrams/sampled-filter" and one.stats()["route"] == "ngrams/sampled-filter"
+        if one.stats()["route"] == "lp":
+            assert sorted(res.triples(F.RAW)) == sorted(one.triples(F.RAW))
+        else:
+            assert res.arrays(F.RAW, anchors=True)[3].tolist() == one.arrays(F.RAW, anchors=True)[3].tolist()
+            assert res.triples(F.RAW) == one.triples(F.RAW), (pat, k)
+        assert res.triples(F.FINAL) == one.triples(F.FINAL), (pat, k)
+        raw = oracle.levenshtein_raw(pat, hay, k)
+        assert res.triples(F.FINAL) == tup(oracle.consolidate(raw)) if k else res.triples(F.RAW) == tup(raw)
+        one.close()
+        res.close()
+    assert shared >= 100
+    hs.close()
