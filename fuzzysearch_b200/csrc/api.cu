@@ -11,8 +11,11 @@
 #include <cmath>
 #include <cstring>
 #include <dlfcn.h>
+#include <sched.h>
 #include <unistd.h>
+#include <condition_variable>
 #include <mutex>
+#include <thread>
 #include <new>
 #include <string>
 #include <vector>
@@ -297,6 +300,7 @@ static int alloc_buffer(fzb_haystack *h) {
 }
 
 static void p2p_free(fzb_haystack *h);
+static int upload_bytes(fzb_haystack *h, uint64_t dst_off, const uint8_t *host, uint64_t n);
 
 extern "C" void fzb_haystack_destroy(fzb_haystack *h) {
     if (!h) return;
@@ -354,11 +358,7 @@ extern "C" int fzb_haystack_create_shard(const uint8_t *host, uint64_t buf_len, 
     h->own_hi = own_hi;
     rc = alloc_buffer(h);
     if (rc == FZB_OK) rc = haystack_common_init(h);
-    if (rc == FZB_OK && buf_len) {
-        cudaError_t e = cudaMemcpyAsync(h->d, host, buf_len, cudaMemcpyHostToDevice, h->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-        if (e != cudaSuccess) rc = fail(FZB_E_CUDA, "H2D copy failed: %s", cudaGetErrorString(e));
-    }
+    if (rc == FZB_OK && buf_len) rc = upload_bytes(h, 0, host, buf_len);
     if (rc) {
         fzb_haystack_destroy(h);
         return rc;
@@ -479,6 +479,130 @@ extern "C" int fzb_haystack_read(fzb_haystack *h, uint64_t global_offset, uint8_
 
 extern "C" uint64_t fzb_haystack_len(const fzb_haystack *h) { return h ? h->global_len : 0; }
 
+// ------------------------------------------------------------------------------------------------
+// Upload of PAGEABLE host memory (what a Python bytes object is).  cudaMemcpy from pageable memory stages through
+// the driver's own bounce buffer at 7-10 GB/s on these hosts; page-locking the caller's buffer in place
+// (cudaHostRegister) costs more than the copy.  Instead: a ring of three 64 MiB pinned buffers; a small pool of
+// host threads copies slice i+1 of the caller's buffer into one of them while the DMA engine moves slice i
+// to the device -- the pipeline runs at min(host memcpy bandwidth of the pool, PCIe).
+// ------------------------------------------------------------------------------------------------
+class CopyPool {
+  public:
+    static CopyPool &get() {
+        static CopyPool *pool = new CopyPool();  // leaked on purpose: no joins at process exit
+        return *pool;
+    }
+    void copy(uint8_t *dst, const uint8_t *src, size_t n) {  // parallel memcpy; returns when all of it is done
+        if (n < (8u << 20) || threads_.empty()) {
+            memcpy(dst, src, n);
+            return;
+        }
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            dst_ = dst;
+            src_ = src;
+            n_ = n;
+            next_.store(0);
+            pending_ = (int)threads_.size();
+            gen_++;
+        }
+        cv_.notify_all();
+        work();  // the caller copies too
+        std::unique_lock<std::mutex> lock(m_);
+        done_.wait(lock, [&] { return pending_ == 0; });
+    }
+
+  private:
+    static constexpr size_t kSlice = 2u << 20;
+    CopyPool() {
+        unsigned want = 8;
+        if (const char *e = getenv("FZB_UPLOAD_THREADS")) want = (unsigned)std::max(0, atoi(e));
+        unsigned hw = std::thread::hardware_concurrency();
+        cpu_set_t set;
+        if (sched_getaffinity(0, sizeof set, &set) == 0) hw = (unsigned)CPU_COUNT(&set);
+        want = std::min(want, hw > 1 ? hw - 1 : 0u);
+        for (unsigned i = 0; i < want; i++) {
+            threads_.emplace_back([this] { loop(); });
+            threads_.back().detach();
+        }
+    }
+    void work() {
+        for (;;) {
+            const size_t off = next_.fetch_add(kSlice);
+            if (off >= n_) return;
+            memcpy(dst_ + off, src_ + off, std::min(kSlice, n_ - off));
+        }
+    }
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lock(m_);
+                cv_.wait(lock, [&] { return gen_ != seen; });
+                seen = gen_;
+            }
+            work();
+            std::lock_guard<std::mutex> lock(m_);
+            if (--pending_ == 0) done_.notify_all();
+        }
+    }
+    std::vector<std::thread> threads_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    uint8_t *dst_ = nullptr;
+    const uint8_t *src_ = nullptr;
+    size_t n_ = 0;
+    std::atomic<size_t> next_{0};
+    int pending_ = 0;
+    uint64_t gen_ = 0;
+};
+
+constexpr int kStageBufs = 3;
+constexpr size_t kStageBytes = 64u << 20;
+static std::mutex g_stage_mutex;  // one staged upload at a time per process (the ring is shared by all handles)
+static uint8_t *g_stage[kStageBufs];
+
+static bool is_pinned_host(const void *p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost;
+}
+
+// host -> h->d + dst_off, n bytes, on h->stream; returns when the caller may reuse `host`
+static int upload_bytes(fzb_haystack *h, uint64_t dst_off, const uint8_t *host, uint64_t n) {
+    if (n == 0) return FZB_OK;
+    if (n < (16u << 20) || is_pinned_host(host)) {
+        CK(cudaMemcpyAsync(h->d + dst_off, host, n, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return FZB_OK;
+    }
+    std::lock_guard<std::mutex> lock(g_stage_mutex);
+    for (auto &b : g_stage)
+        if (!b) CK(cudaHostAlloc(&b, kStageBytes, cudaHostAllocPortable));
+    cudaEvent_t ev[kStageBufs];
+    for (auto &e : ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    int rc = FZB_OK;
+    uint64_t off = 0;
+    for (int i = 0; off < n && rc == FZB_OK; i++, off += kStageBytes) {
+        const int b = i % kStageBufs;
+        const size_t len = (size_t)std::min<uint64_t>(kStageBytes, n - off);
+        cudaError_t e = i >= kStageBufs ? cudaEventSynchronize(ev[b]) : cudaSuccess;  // the DMA out of this buffer is done
+        if (e == cudaSuccess) {
+            CopyPool::get().copy(g_stage[b], host + off, len);
+            e = cudaMemcpyAsync(h->d + dst_off + off, g_stage[b], len, cudaMemcpyHostToDevice, h->stream);
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(ev[b], h->stream);
+        if (e != cudaSuccess) rc = fail(FZB_E_CUDA, "staged upload failed: %s", cudaGetErrorString(e));
+    }
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess && rc == FZB_OK) rc = fail(FZB_E_CUDA, "staged upload failed: %s", cudaGetErrorString(e));
+    for (auto &x : ev) cudaEventDestroy(x);
+    return rc;
+}
+
 extern "C" int fzb_haystack_upload(fzb_haystack *h, const uint8_t *host, uint64_t n) {
     if (!h || (!host && n)) return fail(FZB_E_INVALID, "bad arguments");
     if (!h->owned) return fail(FZB_E_INVALID, "upload needs an owned handle");
@@ -493,10 +617,8 @@ extern "C" int fzb_haystack_upload(fzb_haystack *h, const uint8_t *host, uint64_
     }
     h->padded_len = round_up(n, 128) + 128;
     h->coll_prob = -1.0;
-    if (n) CK(cudaMemcpyAsync(h->d, host, n, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemsetAsync(h->d + n, 0, h->padded_len - n, h->stream));
-    CK(cudaStreamSynchronize(h->stream));  // the caller may reuse `host` as soon as we return
-    return FZB_OK;
+    return upload_bytes(h, 0, host, n);  // the caller may reuse `host` as soon as we return
 }
 
 extern "C" void *fzb_host_alloc(uint64_t n) {

@@ -95,7 +95,7 @@ __device__ bool sim_lev_lp(const ScanParams &p, const uint8_t *sP, const uint8_t
     return true;
 }
 
-constexpr int kLpThreads = 128;
+constexpr int kLpThreads = 256;  // 4 CTAs per SM: 32 warps hide the shared-memory latency of the tile passes
 
 // One CTA works on tiles of kLpTile start positions: the tile (+ the m+k bytes a candidate can run
 // ahead) is staged in shared memory with coalesced loads; phase 1 discards the starts that cannot produce a
