@@ -36,10 +36,24 @@ def has_near_match(subsequence, sequence, max_substitutions=None, max_insertions
                    max_l_dist=None):
     """True iff find_near_matches(...) would return at least one match -- the public-API form of the
     reference's internal has_near_match_* helpers (substitutions_only.py:18-34,139-145,218-233;
-    generic_search.py:240-253).  Round 1: runs the full search (no grid-wide early exit yet)."""
+    generic_search.py:240-253), with early termination: the sequence is searched in chunks of growing size and
+    the call returns after the first chunk that holds a match (fzb_has_near_match)."""
+    from .search import _WORKSPACE_LOCK, DeviceSequence, _coerce, _prepare
     search_params = LevenshteinSearchParams(max_substitutions, max_insertions, max_deletions, max_l_dist)
-    search_class = choose_search_class(search_params)
-    return len(search_class.search(subsequence, sequence, search_params)) > 0
+    if len(subsequence) == 0:
+        raise ValueError("Given subsequence is empty!")
+    subs, ins, dels, l = search_params.unpacked
+    big = 1 << 29
+    subs, ins, dels = (big if subs is None else subs), (big if ins is None else ins), (big if dels is None else dels)
+    shared = not isinstance(sequence, DeviceSequence)
+    if shared:
+        _WORKSPACE_LOCK.acquire()
+    try:
+        pat, hay, _, _ = _prepare(subsequence, sequence)
+        return hay.has_near_match(pat, min(subs, big), min(ins, big), min(dels, big), l)
+    finally:
+        if shared:
+            _WORKSPACE_LOCK.release()
 
 
 def find_near_matches_batch(subsequences, sequence, max_l_dist):

@@ -77,6 +77,7 @@ SYMBOLS = {
     "fzb_search_exact": (_i32, [_vp, _u8p, _u32, _u32, _vpp]),
     "fzb_search_levenshtein_batch": (_i32, [_vp, _u8p, _vp, _vp, _u32, _u32, _vpp, ctypes.POINTER(Stats)]),
     "fzb_find_near_matches": (_i32, [_u8p, _u32, _u8p, _u64, _u32, _u32, _u32, _u32, _i32, _vpp]),
+    "fzb_has_near_match": (_i32, [_vp, _u8p, _u32, _u32, _u32, _u32, _u32, ctypes.POINTER(ctypes.c_int)]),
     "fzb_release_workspace": (None, []),
     "fzb_result_count": (_u64, [_vp, _i32]),
     "fzb_result_copy": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp]),
@@ -329,6 +330,13 @@ class Haystack(object):
         results = [Result(ctypes.c_void_p(out[i])) for i in range(len(pats))]
         return results, {"gpu_ms": st.gpu_ms, "filter_ms": st.filter_ms, "bytes_scanned": st.bytes_scanned,
                          "n_candidates": st.n_candidates, "n_launches": st.n_launches, "route": "batch"}
+
+    def has_near_match(self, pattern, max_subs, max_ins, max_dels, max_l):
+        """True iff the search would return at least one match; stops at the first chunk that holds one."""
+        p, pp, m = self._pat(pattern)
+        found = ctypes.c_int(0)
+        check(lib().fzb_has_near_match(self._h, pp, m, max_subs, max_ins, max_dels, max_l, ctypes.byref(found)))
+        return bool(found.value)
 
     def search_exact(self, pattern, flags=0):
         p, pp, m = self._pat(pattern)

@@ -2138,6 +2138,68 @@ extern "C" int fzb_find_near_matches(const uint8_t *pattern, uint32_t m, const u
     return rc;
 }
 
+// ------------------------------------------------------------------------------------------------
+// has_near_match: "is there any match?" with early termination.  The reference's has_near_match_* helpers
+// (substitutions_only.py:18-34,139-145,218-233; generic_search.py:240-253; _substitutions_only.c:4-17) stop at the
+// first hit of a left-to-right scan.  A GPU scans everywhere at once, so the stop is made coarse instead: the
+// sequence is searched in chunks of geometrically growing size (64 MiB, 256 MiB, 1 GiB, the rest), each chunk a
+// VIEW of the resident buffer searched exactly like a shard (own range = the chunk, halo from its neighbours,
+// window clipping at the global ends only -- so the union of the chunks' raw streams is the whole raw stream);
+// the call returns after the first chunk that yields a raw match.  A match near the start costs ~0.1 ms
+// whatever the length of the sequence; no match at all costs the full scan plus three chunk turn-arounds.
+// ------------------------------------------------------------------------------------------------
+extern "C" int fzb_has_near_match(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint32_t max_subs,
+                                  uint32_t max_ins, uint32_t max_dels, uint32_t max_l, int *found) {
+    if (!h || !found) return fail(FZB_E_INVALID, "NULL argument");
+    *found = 0;
+    int rc = check_pattern(h, pattern, m, 0);
+    if (rc) return rc;
+    struct Geometry {
+        uint8_t *d;
+        uint64_t buf_len, buf_lo, own_lo, own_hi, padded_len;
+    } const saved{h->d, h->buf_len, h->buf_lo, h->own_lo, h->own_hi, h->padded_len};
+    CK(cudaSetDevice(h->device));
+    if (h->buf_len) sample_collision_prob(h);  // byte statistics of the WHOLE buffer (the views reuse them)
+    const uint64_t halo = round_up((uint64_t)m + std::min<uint64_t>(max_l, m), 128) + 128;
+    uint64_t chunk = 64ull << 20, lo = saved.own_lo;
+    rc = FZB_OK;
+    do {  // (at least one pass: an empty sequence still has its k >= m matches)
+        uint64_t hi = std::min(saved.own_hi, round_up(lo + chunk, 128));
+        if (saved.own_hi - hi < chunk / 4) hi = saved.own_hi;  // no tiny last chunk
+        // view [vlo, vhi) of the buffer: the chunk plus its halo, 128-byte aligned relative to the buffer start
+        const uint64_t want_lo = lo > saved.buf_lo + halo ? lo - halo : saved.buf_lo;
+        const uint64_t vlo = saved.buf_lo + (want_lo - saved.buf_lo) / 128 * 128;
+        const uint64_t vhi = std::min(saved.buf_lo + saved.buf_len, hi + halo);
+        h->d = saved.d + (vlo - saved.buf_lo);
+        h->buf_lo = vlo;
+        h->buf_len = vhi - vlo;
+        h->padded_len = round_up(h->buf_len, 128) + 128;
+        h->own_lo = lo;
+        h->own_hi = hi;
+        fzb_result *res = nullptr;
+        // choose_search_class (__init__.py:60-83) on normalised limits; raw stream only
+        if (max_l == 0)
+            rc = fzb_search_exact(h, pattern, m, FZB_F_NO_FINAL, &res);
+        else if (max_ins == 0 && max_dels == 0)
+            rc = fzb_search_hamming(h, pattern, m, std::min(max_l, max_subs), FZB_F_NO_FINAL, &res);
+        else if (max_l <= std::min(max_subs, std::min(max_ins, max_dels)))
+            rc = fzb_search_levenshtein(h, pattern, m, max_l, FZB_F_NO_FINAL, &res);
+        else
+            rc = fzb_search_generic(h, pattern, m, max_subs, max_ins, max_dels, max_l, FZB_F_NO_FINAL, &res);
+        if (rc == FZB_OK && fzb_result_count(res, FZB_RAW) > 0) *found = 1;
+        if (res) fzb_result_destroy(res);
+        lo = hi;
+        chunk *= 4;
+    } while (rc == FZB_OK && !*found && lo < saved.own_hi);
+    h->d = saved.d;
+    h->buf_len = saved.buf_len;
+    h->buf_lo = saved.buf_lo;
+    h->own_lo = saved.own_lo;
+    h->own_hi = saved.own_hi;
+    h->padded_len = saved.padded_len;
+    return rc;
+}
+
 extern "C" int fzb_debug_counters(const fzb_haystack *h, uint32_t out[32]) {
     if (!h || !out) return fail(FZB_E_INVALID, "NULL argument");
     memset(out, 0, 32 * sizeof(uint32_t));

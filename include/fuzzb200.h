@@ -203,6 +203,17 @@ int fzb_find_near_matches(const uint8_t *pattern, uint32_t m, const uint8_t *hay
                           uint32_t max_subs, uint32_t max_ins, uint32_t max_dels,
                           uint32_t max_l_dist, int device, fzb_result **out);
 
+/*
+ * "Is there any near-match?" -- the boolean form of the four searches (has_near_match_substitutions_lp /
+ * _ngrams, substitutions_only.py:18-34,139-145,218-233; has_near_match_generic_ngrams, generic_search.py:240-253;
+ * substitutions_only_has_near_matches_*_byteslike, _substitutions_only.c:4-17), with early termination: the
+ * resident sequence is searched in chunks of growing size and the call returns after the first chunk that holds
+ * a match.  Limits are the already normalised ones of LevenshteinSearchParams (as for fzb_find_near_matches).
+ * *found = 1 iff find_near_matches would return a non-empty list.
+ */
+int fzb_has_near_match(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint32_t max_subs,
+                       uint32_t max_ins, uint32_t max_dels, uint32_t max_l_dist, int *found);
+
 /* fzb_find_near_matches keeps one device workspace per device (haystack buffer, bitmap, staging)
  * alive between calls so that a call costs one H2D copy + the kernels; this frees them. */
 void fzb_release_workspace(void);

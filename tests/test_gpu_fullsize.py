@@ -105,6 +105,16 @@ def test_levenshtein_4gib_ascii(cuda_device):
     exp_tail = [(s + n - 4096, e + n - 4096, d) for s, e, d in tup(oracle.levenshtein_ngrams_raw(pat, tail, k))
                 if s >= 2048]
     assert sorted(r[2:] for r in raw if r[2] >= n - 2048) == sorted(exp_tail)
+    # the WHOLE 4 GiB raw stream against the C oracle (SURVEY 8c "big-input oracle"): element for element, in
+    # generation order, with anchors; and the final list against consolidate_overlapping_matches of it
+    host = np.empty(n, dtype=np.uint8)
+    step = 256 << 20
+    for off in range(0, n, step):
+        host[off:off + step] = np.frombuffer(hs.read(off, min(step, n - off)), dtype=np.uint8)
+    raw_o, ng_o, ix_o = oracle.levenshtein_ngrams_raw(pat, host, k, with_anchor=True)
+    assert raw == [(int(g), int(i), int(s), int(e), int(d)) for (s, e, d), g, i in zip(raw_o.tolist(), ng_o.tolist(), ix_o.tolist())]
+    assert final == tup(oracle.consolidate(raw_o))
+    del host
     # sharding invariance on the same device memory
     halo = m + k
     got = []
