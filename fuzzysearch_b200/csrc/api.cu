@@ -170,6 +170,8 @@ struct fzb_haystack {
     uint32_t glist_cap = 0;
     uint32_t *d_scratch = nullptr;  // candidate lists of the LP / generic kernels
     uint64_t scratch_words = 0;
+    unsigned long long *d_lplist = nullptr;  // streaming LP route: starts that survived the scan
+    uint32_t lplist_cap = 0;
     // single-pass multi-pattern batches (batch_kernels.cuh), allocated on first use
     uint32_t *d_mbits = nullptr;
     uint2 *d_gtab = nullptr;
@@ -312,6 +314,7 @@ extern "C" void fzb_haystack_destroy(fzb_haystack *h) {
     if (h->d_out) cudaFree(h->d_out);
     if (h->d_counters) cudaFree(h->d_counters);
     if (h->d_scratch) cudaFree(h->d_scratch);
+    if (h->d_lplist) cudaFree(h->d_lplist);
     if (h->d_mbits) cudaFree(h->d_mbits);
     if (h->d_gtab) cudaFree(h->d_gtab);
     if (h->d_postings) cudaFree(h->d_postings);
@@ -1541,11 +1544,39 @@ static int search_lev_lp(fzb_haystack *h, const uint8_t *pattern, uint32_t m, ui
     CK(cudaSetDevice(h->device));
     res->stats.route = 3;
     res->stats.bytes_scanned = h->buf_len;
+    // streaming form (k_lp_scan + k_lp_verify) when the look-ahead masks cover the window; the list of surviving
+    // starts overflowing (low-entropy data: most starts survive) falls back to the tile kernel
+    bool streaming = k < m && m + k <= (uint32_t)kLpsMaxWin && !(flags & FZB_F_FORCE_DENSE) && h->buf_len > 0;
+    if (streaming && !h->d_lplist) {
+        h->lplist_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1u << 20, h->capacity / 64), 1u << 26);
+        CK(cudaMalloc(&h->d_lplist, (size_t)h->lplist_cap * sizeof(unsigned long long)));
+    }
+    const PostPlan plan{post_mode, post_mode != 0 && (flags & FZB_F_GLOBAL) != 0};
+    if (streaming) {
+        rc = run_lp(h, res, [&](int grid, int cap) -> int {
+            k_lp_scan<<<h->sm_count * 4, kLpsThreads, 0, h->stream>>>(p, h->d_lplist, h->lplist_cap);
+            CK(cudaEventRecord(h->ev[1], h->stream));
+            h->ev1_recorded = true;
+            k_lp_verify<<<grid, kLpThreads, 0, h->stream>>>(p, h->d_lplist, h->lplist_cap, h->d_scratch, cap, h->d_out,
+                                                            h->out_cap, h->d_counters);
+            res->stats.n_launches += 2;
+            return FZB_OK;
+        }, plan);
+        if (rc) return rc;
+        if (h->h_counters[CNT_LPWORK] == 0) {
+            res->raw_order = 1;
+            return FZB_OK;
+        }
+        res->fetch_raw();  // list overflow: nothing was verified (and the fused reduction saw an invalid shard)
+        res->raw.clear();
+        res->raw_n = 0;
+        res->fin.clear();
+    }
     rc = run_lp(h, res, [&](int grid, int cap) -> int {
         k_lev_lp<<<grid, kLpThreads, 0, h->stream>>>(p, h->d_scratch, cap, h->d_out, h->out_cap, h->d_counters);
         res->stats.n_launches++;
         return FZB_OK;
-    }, PostPlan{post_mode, post_mode != 0 && (flags & FZB_F_GLOBAL) != 0});
+    }, plan);
     if (rc) return rc;
     res->raw_order = 1;
     return FZB_OK;

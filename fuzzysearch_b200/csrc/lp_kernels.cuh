@@ -192,6 +192,203 @@ k_lev_lp(const ScanParams p, uint32_t *scratch, int cap, RawRec *out, uint32_t o
     }
 }
 
+// ---- streaming form of the Levenshtein LP search -------------------------------------------------------------
+// k_lp_scan streams the haystack like the n-gram filters do (coalesced 16-byte loads, every byte read once) and
+// applies conditions (a) and (b) of k_lev_lp with bit masks instead of per-tile prefix sums: each lane turns its 16
+// bytes into two 16-bit masks through a 256-byte table (bit 0: the byte occurs in P; bit 1: it occurs in P[:k+1]),
+// fetches the masks of the next three lanes by shuffle and tests popc(window of m+k bits) >= m-k at the few starts
+// whose first-character bit is set.  A warp covers 512 bytes and emits the starts of the first 464 (lanes 29-31
+// only supply the look-ahead), survivors are buffered per CTA in shared memory and flushed to a global list with
+// one atomic per ~1000 of them.  k_lp_verify then takes ONE SURVIVOR PER THREAD: the bit-parallel automaton
+// (state "next pattern index j at cost d" <-> bit j of R[d]; sets instead of the reference's
+// candidate lists, so it answers "does this start accept at all?" exactly) discards the starts that emit nothing,
+// and the literal simulation (sim_lev_lp: keeps the reference's duplicate candidates, hence its raw multiset) runs
+// on the rest.  4 GiB of text, m = 8..14, k = 2..4: ~1 ms per pattern instead of 15 (tile kernel) / 70 (round 1).
+constexpr int kLpsThreads = 256;
+constexpr int kLpsWarpBytes = 464;                                  // starts a warp emits per iteration (29 lanes)
+constexpr int kLpsCtaBytes = (kLpsThreads / 32) * kLpsWarpBytes;    // 3712
+constexpr int kLpsFlush = 1024;
+constexpr int kLpsBuf = kLpsFlush + kLpsCtaBytes;
+constexpr int kLpsMaxWin = 48;                                      // m + k: 15 + 48 <= 63 bits of look-ahead
+enum { CNT_LPLIST = 7, CNT_LPWORK = 8 };                            // (the hit-list slots of the dense route)
+
+__global__ void __launch_bounds__(kLpsThreads)
+k_lp_scan(const ScanParams p, unsigned long long *list, uint32_t list_cap) {
+    __shared__ uint8_t lut[256];
+    __shared__ unsigned long long sBuf[kLpsBuf];
+    __shared__ uint32_t sN, sBase;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = 0;
+    if (threadIdx.x == 0) sN = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int j = 0; j < p.m; j++) lut[p.P[j]] |= 1;
+        for (int j = 0; j <= min(p.k, p.m - 1); j++) lut[p.P[j]] |= 2;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int win = p.m + p.k, need = p.m - p.k;
+    const unsigned long long wmask = (1ull << win) - 1ull;
+    const int64_t hi = min(p.own_hi, p.N);                       // starts are < hi
+    const int64_t lim = min(p.N, p.buf_lo + p.buf_len);          // bytes at or beyond this count as "not in P"
+    const int64_t base = p.own_lo & ~(int64_t)15;
+    const int64_t niter = hi > base ? (hi - base + kLpsCtaBytes - 1) / kLpsCtaBytes : 0;
+    for (int64_t it = blockIdx.x; it < niter; it += gridDim.x) {
+        const int64_t g0 = base + it * kLpsCtaBytes + (int64_t)warp * kLpsWarpBytes + 16 * lane;  // my 16 bytes
+        uint4 d = make_uint4(0, 0, 0, 0);
+        if (g0 < lim) d = __ldg(reinterpret_cast<const uint4 *>(p.H + (g0 - p.buf_lo)));  // padded buffer; g0 % 16 == 0
+        const uint32_t ws[4] = {d.x, d.y, d.z, d.w};
+        uint32_t A = 0, Fm = 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const uint32_t v = lut[(ws[i >> 2] >> (8 * (i & 3))) & 0xFFu];
+            A |= (v & 1u) << i;
+            Fm |= (v >> 1) << i;
+        }
+        const int64_t nvalid = lim - g0;  // bytes of mine inside the sequence
+        if (nvalid < 16) {
+            const uint32_t keep = nvalid <= 0 ? 0u : ((1u << nvalid) - 1u);
+            A &= keep;
+            Fm &= keep;
+        }
+        const uint32_t n1 = __shfl_down_sync(0xFFFFFFFFu, A, 1), n2 = __shfl_down_sync(0xFFFFFFFFu, A, 2),
+                       n3 = __shfl_down_sync(0xFFFFFFFFu, A, 3);
+        const unsigned long long look = (unsigned long long)A | ((unsigned long long)n1 << 16) |
+                                        ((unsigned long long)n2 << 32) | ((unsigned long long)n3 << 48);
+        if (lane >= 29) Fm = 0;  // look-ahead lanes: the next warp / iteration owns these starts
+        while (Fm) {
+            const int i = __ffs(Fm) - 1;
+            Fm &= Fm - 1;
+            const int64_t s0 = g0 + i;
+            if (s0 < p.own_lo || s0 >= hi) continue;
+            if (__popcll((look >> i) & wmask) >= need) sBuf[atomicAdd(&sN, 1u)] = (unsigned long long)s0;
+        }
+        __syncthreads();
+        const uint32_t n = sN;
+        if (n >= (uint32_t)kLpsFlush) {
+            if (threadIdx.x == 0) sBase = atomicAdd(&p.counters[CNT_LPLIST], n);
+            __syncthreads();
+            const uint32_t b0 = sBase;
+            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+                if (b0 + i < list_cap) list[b0 + i] = sBuf[i];
+            __syncthreads();
+            if (threadIdx.x == 0) sN = 0;
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    const uint32_t n = sN;
+    if (n) {
+        if (threadIdx.x == 0) sBase = atomicAdd(&p.counters[CNT_LPLIST], n);
+        __syncthreads();
+        const uint32_t b0 = sBase;
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+            if (b0 + i < list_cap) list[b0 + i] = sBuf[i];
+    }
+}
+
+// Does the candidate born at `start` accept anywhere?  (see the header comment above; m <= 31, k <= K)
+template <int K>
+__device__ __forceinline__ bool lp_nfa_any(const uint32_t *sPM32, const uint8_t *H, int64_t start, int64_t N, int m,
+                                           int k, int j0) {
+    if (j0 + 1 == m) return true;  // levenshtein.py:78-79
+    uint32_t R[K + 1];
+#pragma unroll
+    for (int d = 0; d <= K; d++) R[d] = (d == j0) ? (1u << (j0 + 1)) : 0u;  // :80-81
+    const uint32_t last = 1u << (m - 1), full = (1u << m) - 1u;
+    for (int64_t i = start + 1; i < N; i++) {
+        const uint32_t M = sPM32[H[i]];
+        const bool can_sub = i + 1 < N;  // :106
+        uint32_t nR[K + 1];
+#pragma unroll
+        for (int d = 0; d <= K; d++) nR[d] = 0;
+#pragma unroll
+        for (int d = 0; d <= K; d++) {
+            const uint32_t r = R[d];
+            if (d > k || !r) continue;
+            const uint32_t adv = r & M;  // :85-93: a matching character only advances
+            if (adv & last) return true;
+            nR[d] |= adv << 1;
+            if (d < k) {  // :100-101
+                const uint32_t mis = r & ~M;
+                if (d + 1 <= K) {
+                    nR[d + 1] |= mis;                                // insertion (:104)
+                    if (can_sub) nR[d + 1] |= (mis & ~last) << 1;    // substitution (:106-112)
+                }
+                uint32_t u = mis;  // deletions, first rule that fires wins per state (:115-138)
+#pragma unroll
+                for (int t = 1; t <= K; t++) {
+                    if (t > k - d || !u || t > m) continue;
+                    if (u & (1u << (m - t))) return true;  // j + t == m
+                    const uint32_t hit = u & (M >> t);     // P[j+t] == c
+                    if (hit) {
+                        const uint32_t moved = hit << (t + 1);
+                        if (moved & (1u << m)) return true;  // j + t + 1 == m
+                        if (d + t <= K) nR[d + t] |= moved;
+                        u &= ~hit;
+                    }
+                }
+            }
+        }
+        uint32_t any = 0;
+#pragma unroll
+        for (int d = 0; d <= K; d++) {
+            R[d] = nR[d] & full;
+            any |= R[d];
+        }
+        if (!any) return false;
+    }
+#pragma unroll
+    for (int d = 0; d <= K; d++) {  // end of the sequence with live states (:145-148)
+        if (d > k) continue;
+        uint32_t r = R[d];
+        while (r) {
+            const int j = __ffs(r) - 1;
+            r &= r - 1;
+            if (d + m - j <= k) return true;
+        }
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(kLpThreads)
+k_lp_verify(const ScanParams p, const unsigned long long *list, uint32_t list_cap, uint32_t *scratch, int cap,
+            RawRec *out, uint32_t ocap, uint32_t *counters) {
+    __shared__ uint8_t sP[256];
+    __shared__ int16_t sFirst[256];
+    __shared__ uint32_t sPM32[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        sP[i] = p.P[i];
+        sFirst[i] = -1;
+        uint32_t v = 0;
+        for (int j = 0; j < p.m && j < 32; j++) v |= (uint32_t)(p.P[j] == i) << j;
+        sPM32[i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int j = min(p.k, p.m - 1); j >= 0; j--) sFirst[p.P[j]] = (int16_t)j;
+    __syncthreads();
+    const uint32_t n = counters[CNT_LPLIST];
+    if (n > list_cap) {  // the list overflowed: the host repeats the search with the tile kernel
+        if (blockIdx.x == 0 && threadIdx.x == 0) counters[CNT_LPWORK] = 1;
+        return;
+    }
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t *A = scratch + tid * 2 * (int64_t)cap, *B = A + cap;
+    const uint8_t *W = p.H - p.buf_lo;  // W[g]: byte at global position g
+    const bool use_nfa = p.m <= 31 && p.k <= 8;
+    for (int64_t i = tid; i < (int64_t)n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t st = (int64_t)list[i];
+        if (use_nfa) {
+            const int j0 = sFirst[W[st]];
+            const bool any = p.k <= 4 ? lp_nfa_any<4>(sPM32, W, st, p.N, p.m, p.k, j0)
+                                      : lp_nfa_any<8>(sPM32, W, st, p.N, p.m, p.k, j0);
+            if (!any) continue;
+        }
+        if (!sim_lev_lp(p, sP, W, st, A, B, cap, out, ocap, counters)) atomicExch(&counters[CNT_OVERFLOW], 1u);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counters[CNT_CAND], n);
+}
+
 // ---- generic NFA ---------------------------------------------------------------------------------
 // candidate = (subseq_index j, l_dist, n_subs, n_ins, n_dels) packed 8|6|6|6|6 bits
 __device__ __forceinline__ uint32_t gpack(int j, int l, int ns, int ni, int nd) {
