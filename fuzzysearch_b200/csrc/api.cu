@@ -518,7 +518,7 @@ class CopyPool {
   private:
     static constexpr size_t kSlice = 2u << 20;
     CopyPool() {
-        unsigned want = 8;
+        unsigned want = 12;  // enough to stay ahead of PCIe even when the source pages sit on a remote NUMA node
         if (const char *e = getenv("FZB_UPLOAD_THREADS")) want = (unsigned)std::max(0, atoi(e));
         unsigned hw = std::thread::hardware_concurrency();
         cpu_set_t set;

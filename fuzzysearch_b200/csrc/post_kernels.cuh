@@ -249,18 +249,4 @@ k_post(const PostArgs a) {
     if (tid == 0) a.h_counters[CNT_SEQ] = a.seq;  // everything above is visible to the host before this word
 }
 
-// Pack this shard's groups for the all-gather: slot = header row {count, valid, 0, 0, 0} + up to `cap`
-// group rows.  valid = the device-side consolidation ran and the groups fit the slot.
-__global__ void __launch_bounds__(256)
-k_pack_groups(const int64_t *fin, const uint32_t *counters, int64_t *slot, uint32_t cap) {
-    const uint32_t nf = counters[CNT_NFINAL];
-    const bool valid = counters[CNT_POST_DONE] != 0 && nf <= cap && counters[CNT_OVERFLOW] == 0;
-    if (blockIdx.x == 0 && threadIdx.x < kFinCols)
-        slot[threadIdx.x] = threadIdx.x == 0 ? (int64_t)nf : (threadIdx.x == 1 ? (int64_t)valid : 0);
-    if (!valid) return;
-    const uint32_t total = nf * kFinCols;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
-        slot[kFinCols + i] = fin[i];
-}
-
 }  // namespace fzb
