@@ -149,6 +149,7 @@ struct fzb_haystack {
     uint32_t p2p_cap = 4096;        // group rows per slot
     uint64_t slot_bytes = 0, flags_off = 0;
     uint32_t epoch = 0;             // number of FZB_F_GLOBAL searches issued on this handle
+    bool counters_clean = false;    // the device counters are all zero (the last search's final kernel left them so)
     uint32_t seq = 0;               // number of search attempts enqueued: the last kernel of each writes it to mapped
                                     // memory as its final store and the host polls for it (wait_done)
     MergeScratch *d_ms = nullptr;
@@ -1176,7 +1177,8 @@ template <class F>
 static int run_emitting(fzb_haystack *h, fzb_result *res, F enqueue, PostPlan post = PostPlan()) {
     detach_pending(h);  // k_post is about to overwrite the staging buffer an earlier result may still point at
     for (int attempt = 0; attempt < 8; attempt++) {
-        CK(cudaMemsetAsync(h->d_counters, 0, CNT_COUNT * sizeof(uint32_t), h->stream));
+        if (!h->counters_clean) CK(cudaMemsetAsync(h->d_counters, 0, CNT_COUNT * sizeof(uint32_t), h->stream));
+        h->counters_clean = false;
         CK(cudaEventRecord(h->ev[0], h->stream));
         h->ev1_recorded = false;
         int rc = enqueue();
@@ -1184,7 +1186,9 @@ static int run_emitting(fzb_haystack *h, fzb_result *res, F enqueue, PostPlan po
         CK(cudaGetLastError());
         h->seq++;
         PostArgs pa{reinterpret_cast<const uint64_t *>(h->d_out + h->out_cap), h->out_cap, post.mode,
-                    h->d_sorted, h->d_fin, h->h_fin, h->h_counters, h->d_counters, h->seq};
+                    h->d_sorted, h->d_fin, h->h_fin, h->h_counters, h->d_counters, h->seq, 0};
+        // fused multi-GPU reduction over peer memory (below): k_push reads the counters after k_post, and clears them
+        pa.clear = !(post.global && attempt == 0 && h->p2p && !res->fused_issued);
         k_post<<<h->sm_count, kPostThreads, kPostSmem, h->stream>>>(pa);
         CK(cudaGetLastError());
         res->stats.n_launches++;
@@ -1225,6 +1229,8 @@ static int run_emitting(fzb_haystack *h, fzb_result *res, F enqueue, PostPlan po
             continue;
         }
         const bool posted = h->h_counters[CNT_POST_DONE] != 0;
+        // k_post (or k_push behind it, if the shard was valid) zeroed the device counters on its way out
+        h->counters_clean = posted && (!fused || (res->fused_status == MS_OK));
         res->raw.clear();
         res->raw_n = n;
         res->raw_ordered = false;
@@ -1833,6 +1839,7 @@ static int batch_pass(fzb_haystack *h, const uint8_t *patterns, const uint32_t *
     uint32_t n_work = 0;
     for (int attempt = 0;; attempt++) {
         if (attempt == 8) return fail(FZB_E_CUDA, "output buffer kept overflowing");
+        h->counters_clean = false;  // (this pass leaves its counters behind)
         CK(cudaMemsetAsync(h->d_counters, 0, CNT_COUNT * sizeof(uint32_t), h->stream));
         CK(cudaEventRecord(h->ev[0], h->stream));
         if (ntiles > 0) {

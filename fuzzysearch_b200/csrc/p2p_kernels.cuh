@@ -94,6 +94,8 @@ k_push(const WorldArgs w, const int64_t *fin, const uint32_t *counters, int mode
         ms->nh_count = 0;
         ms->status = 0;
     }
+    // every CTA of this kernel has read the search's counters (before its ticket): leave them zeroed for the next search
+    if (valid && threadIdx.x < CNT_COUNT) const_cast<uint32_t *>(counters)[threadIdx.x] = 0;
 }
 
 // ---- merge -----------------------------------------------------------------------------------------

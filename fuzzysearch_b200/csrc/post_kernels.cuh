@@ -41,6 +41,8 @@ struct PostArgs {
     uint32_t *h_counters;  // mapped host: CNT_COUNT counters
     uint32_t *counters;
     uint32_t seq;          // written to h_counters[CNT_SEQ] LAST: the host polls it instead of synchronising the stream
+    int clear;             // zero the device counters on the way out (the next search then needs no memset); 0 when
+                           // k_push still has to read them
 };
 
 __device__ __forceinline__ uint32_t gtimer_lo() {
@@ -127,8 +129,8 @@ k_post(const PostArgs a) {
     const uint32_t G = gridDim.x, b = blockIdx.x;
     if (!fits) {  // the host fetches the list and does the rest
         if (b == 0) {
-            if (tid < CNT_SEQ) a.h_counters[tid] = a.counters[tid];  // POST_DONE stays 0
-            __threadfence_system();
+            if (tid < CNT_SEQ) a.h_counters[tid] = a.counters[tid];  // POST_DONE stays 0 (and the counters stay dirty:
+            __threadfence_system();                                   //  other CTAs may not have read them yet)
             __syncthreads();
             if (tid == 0) a.h_counters[CNT_SEQ] = a.seq;
         }
@@ -244,6 +246,7 @@ k_post(const PostArgs a) {
     }
     __syncthreads();
     if (tid < CNT_SEQ) a.h_counters[tid] = a.counters[tid];
+    if (a.clear && tid < CNT_COUNT) a.counters[tid] = 0;
     __threadfence_system();
     __syncthreads();
     if (tid == 0) a.h_counters[CNT_SEQ] = a.seq;  // everything above is visible to the host before this word
