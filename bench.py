@@ -469,9 +469,16 @@ def main():
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         from torch_reduce import gather_and_merge_groups
 
-    global_len = per_gpu * world
+    # the single-pattern workloads shard the haystack (weak scaling: N x 4 GiB, configs[3]); the batch (configs[4]:
+    # "1024 patterns over ONE 4 GiB haystack, 8 x B200") keeps the whole haystack on every GPU and splits the PATTERNS
+    # (strong scaling: nothing to merge, every pattern's list is complete on the rank that searched it)
+    global_len = per_gpu * world if kind != "batch" else per_gpu
     halo = m + k
-    blo, bhi, own_lo, own_hi = shard_bounds(global_len, world, rank, halo)
+    blo, bhi, own_lo, own_hi = (shard_bounds(global_len, world, rank, halo) if kind != "batch"
+                                else (0, per_gpu, 0, per_gpu))
+    if kind == "batch":
+        config["global_bytes"] = per_gpu
+        config["sharding"] = "haystack replicated, patterns split %d ways (pattern i on rank i %% N)" % world
     # device-resident shard generated ON the device (counter-based corpus keyed by global offset)
     hs = F.Haystack.alloc(bhi - blo, device=local_rank, buf_lo=blo, global_len=global_len, own_lo=own_lo,
                           own_hi=own_hi)
@@ -487,7 +494,7 @@ def main():
         if pos >= blo and pos + len(b) <= bhi:
             hs.write(pos, b)
 
-    in_library = world > 1 and args.reduce in ("p2p", "nccl")
+    in_library = world > 1 and args.reduce in ("p2p", "nccl") and kind != "batch"
     if in_library:
         init_shard_comm(hs)
         config["reduction"] = ("in-library, NVLink peer memory (k_push + k_merge on the search stream)"
@@ -508,6 +515,7 @@ def main():
             for _ in range(8):
                 pos = own_lo + 1000 + int(brng.integers(0, own_hi - own_lo - 2000))
                 hs.write(pos, mutate(brng, bp, alphabet, int(brng.integers(0, bk + 2)), False))
+        batch_pats, batch_ks = batch_pats[rank::world], batch_ks[rank::world]  # my share of the patterns
 
     def one_search(h):
         if kind == "lev":
@@ -572,6 +580,11 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_per_step = float(t.item())
     value = global_len / (ms_per_step * 1e-3) / 1e9
+    if dist is not None and kind == "batch":  # matches of all ranks' patterns
+        import torch
+        t = torch.tensor([nfinal], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        nfinal = int(t.item())
 
     # ---- parity: the oracle over every byte of every shard vs the lists the timed searches return ----
     parity = None
@@ -663,8 +676,8 @@ def main():
     traffic = ncu_traffic()
     line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
-            "matches_per_step": int(nfinal), "wall_ms_per_step": wall_ms / args.steps,
+            "scaling": "weak" if kind != "batch" else "strong", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic", "config": config, "matches_per_step": int(nfinal), "wall_ms_per_step": wall_ms / args.steps,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": ({"lev": "k_filter_sampled" if len(alphabet) > 16 else "k_filter_dense",
                                      "ham": "k_hamming_count"}.get(kind, "all scans of the batch")),

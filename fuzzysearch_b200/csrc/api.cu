@@ -181,6 +181,8 @@ struct fzb_haystack {
     unsigned long long *d_mset = nullptr;
     WorkItem *d_mwork = nullptr;
     uint32_t mset_slots = 0, mwork_cap = 0;
+    unsigned long long *d_mhits = nullptr;  // dense batch pass: (pattern, n-gram, position) hits
+    uint32_t mhits_cap = 0;
 };
 
 struct fzb_result {
@@ -323,6 +325,7 @@ extern "C" void fzb_haystack_destroy(fzb_haystack *h) {
     if (h->d_bpats) cudaFree(h->d_bpats);
     if (h->d_mset) cudaFree(h->d_mset);
     if (h->d_mwork) cudaFree(h->d_mwork);
+    if (h->d_mhits) cudaFree(h->d_mhits);
     if (h->d_glist) cudaFree(h->d_glist);
     if (h->d_hits) cudaFree(h->d_hits);
     if (h->d_send) cudaFree(h->d_send);
@@ -1770,8 +1773,10 @@ static int ensure_batch_buffers(fzb_haystack *h) {
 
 // One pass over the haystack for the patterns ids[0..cnt): fills out[ids[i]].  Returns FZB_OK, an error, or +1 if
 // the pass overflowed a device structure (the caller then searches these patterns one by one).
+// dense = false: the q-sample scan (k_filter_multi / k_verify_multi) over the 4-grams of the patterns;
+// dense = true: the n-gram-prefix scan at every position (k_filter_mdense / k_verify_mhits).
 static int batch_pass(fzb_haystack *h, const uint8_t *patterns, const uint32_t *offsets, const uint32_t *ks,
-                      const std::vector<uint32_t> &ids, fzb_result **out, fzb_stats *sum) {
+                      const std::vector<uint32_t> &ids, fzb_result **out, fzb_stats *sum, bool dense) {
     const uint32_t cnt = (uint32_t)ids.size();
     std::vector<BatchPat> pats(cnt);
     std::vector<uint32_t> pinfo(cnt);
@@ -1787,10 +1792,18 @@ static int batch_pass(fzb_haystack *h, const uint8_t *patterns, const uint32_t *
         bp.L = (int)(m / (k + 1));
         bp.n_ngrams = (int)m / bp.L;
         pinfo[i] = m | (k << 8) | ((uint32_t)bp.L << 16);
-        for (uint32_t o = 0; o + 4 <= m; o++) {
-            uint32_t w;
-            memcpy(&w, bp.P + o, 4);
-            grams[w].push_back((i << 8) | o);
+        if (dense) {  // key: the first 3 bytes of n-gram j; posting: pattern << 8 | j
+            for (int j = 0; j < bp.n_ngrams; j++) {
+                uint32_t w = 0;
+                memcpy(&w, bp.P + j * bp.L, 3);
+                grams[w].push_back((i << 8) | (uint32_t)j);
+            }
+        } else {
+            for (uint32_t o = 0; o + 4 <= m; o++) {
+                uint32_t w;
+                memcpy(&w, bp.P + o, 4);
+                grams[w].push_back((i << 8) | o);
+            }
         }
     }
     std::vector<uint32_t> bits(kMultiTblWords, 0), postings;
@@ -1809,6 +1822,11 @@ static int batch_pass(fzb_haystack *h, const uint8_t *patterns, const uint32_t *
     int rc = ensure_batch_buffers(h);
     if (rc) return rc;
     CK(cudaSetDevice(h->device));
+    if (dense && !h->d_mhits) {
+        h->mhits_cap = 1u << 23;
+        CK(cudaMalloc(&h->d_mhits, (size_t)h->mhits_cap * sizeof(unsigned long long)));
+        CK(cudaFuncSetAttribute(k_filter_mdense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMdenseSmem));
+    }
     detach_pending(h);
     CK(cudaMemcpyAsync(h->d_mbits, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_gtab, gtab.data(), gtab.size() * sizeof(uint2), cudaMemcpyHostToDevice, h->stream));
@@ -1842,19 +1860,26 @@ static int batch_pass(fzb_haystack *h, const uint8_t *patterns, const uint32_t *
         h->counters_clean = false;  // (this pass leaves its counters behind)
         CK(cudaMemsetAsync(h->d_counters, 0, CNT_COUNT * sizeof(uint32_t), h->stream));
         CK(cudaEventRecord(h->ev[0], h->stream));
+        MdenseParams dp{mp, h->d_bpats, h->d_mhits, h->mhits_cap};
         if (ntiles > 0) {
             const int grid = (int)std::min<int64_t>(ntiles, h->sm_count);
-            k_filter_multi<<<grid, kMultiThreads, kMultiSmem, h->stream>>>(mp, nvec, ntiles);
+            if (dense)
+                k_filter_mdense<<<grid, kMultiThreads, kMdenseSmem, h->stream>>>(dp, nvec, ntiles);
+            else
+                k_filter_multi<<<grid, kMultiThreads, kMultiSmem, h->stream>>>(mp, nvec, ntiles);
         }
         CK(cudaEventRecord(h->ev[1], h->stream));
-        k_verify_multi<<<h->sm_count * 8, kVmThreads, 0, h->stream>>>(mp, h->d_bpats, h->d_out, h->out_cap, h->d_counters);
+        if (dense)
+            k_verify_mhits<<<h->sm_count * 8, kMhThreads, 0, h->stream>>>(dp, h->d_out, h->out_cap, h->d_counters);
+        else
+            k_verify_multi<<<h->sm_count * 8, kVmThreads, 0, h->stream>>>(mp, h->d_bpats, h->d_out, h->out_cap, h->d_counters);
         CK(cudaGetLastError());
         CK(cudaEventRecord(h->ev[2], h->stream));
         uint32_t cnts[CNT_COUNT];
         CK(cudaMemcpyAsync(cnts, h->d_counters, sizeof cnts, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
-        if (cnts[CNT_OVERFLOW]) {  // work list / set too small for this batch: clean up, let the caller go one by one
-            CK(cudaMemsetAsync(h->d_mset, 0, (size_t)h->mset_slots * sizeof(unsigned long long), h->stream));
+        if (cnts[CNT_OVERFLOW]) {  // work list / set / hit list too small for this batch: clean up, let the caller go one by one
+            if (!dense) CK(cudaMemsetAsync(h->d_mset, 0, (size_t)h->mset_slots * sizeof(unsigned long long), h->stream));
             CK(cudaStreamSynchronize(h->stream));
             return 1;
         }
@@ -1881,7 +1906,7 @@ static int batch_pass(fzb_haystack *h, const uint8_t *patterns, const uint32_t *
         fzb_result *res = new (std::nothrow) fzb_result();
         if (!res) return fail(FZB_E_CUDA, "out of host memory");
         res->raw.reserve(per[i]);
-        res->stats.route = 1;
+        res->stats.route = dense ? 2 : 1;
         res->stats.bytes_scanned = i == 0 ? h->buf_len : 0;  // the haystack is read once for the whole pass
         res->stats.gpu_ms = i == 0 ? gpu_ms : 0.0;
         res->stats.filter_ms = i == 0 ? filter_ms : 0.0;
@@ -1951,7 +1976,7 @@ extern "C" int fzb_search_levenshtein_batch(fzb_haystack *h, const uint8_t *patt
             done -= ids.size();
             break;
         }
-        int rc = batch_pass(h, patterns, offsets, max_l_dist, ids, out, &sum);
+        int rc = batch_pass(h, patterns, offsets, max_l_dist, ids, out, &sum, false);
         if (rc < 0) {
             cleanup();
             return rc;
@@ -1963,6 +1988,36 @@ extern "C" int fzb_search_levenshtein_batch(fzb_haystack *h, const uint8_t *patt
                     out[id] = nullptr;
                 }
         }
+    }
+    // the n-gram-route patterns the lemma does not cover share a scan of their own (n-gram prefixes at every position)
+    std::vector<uint32_t> dense_ids;
+    if (flags == 0 && h->buf_len > 0 && sample_collision_prob(h) == FZB_OK) {
+        double expect = 0.0;  // expected prefix hits per haystack position
+        const double c3 = h->coll_prob * h->coll_prob * h->coll_prob;
+        for (uint32_t i = 0; i < count && dense_ids.size() < kMaxBatchPats; i++) {
+            if (out[i]) continue;
+            const uint32_t m = offsets[i + 1] - offsets[i], k = max_l_dist[i];
+            if (m == 0 || m > (uint32_t)kBatchMaxM || k == 0 || k >= m) continue;
+            const uint32_t L = m / (k + 1);
+            if (L < 3 || m - L > 32 || m + 2 * k + 12 > (uint32_t)kMhSlotBytes) continue;
+            if (check_halo(h, (uint64_t)m + k) != FZB_OK) continue;
+            if (expect + (m / L) * c3 > 0.02) continue;  // (low-entropy text: prefixes hit everywhere -> one by one)
+            expect += (m / L) * c3;
+            dense_ids.push_back(i);
+        }
+    }
+    if (dense_ids.size() >= 2) {
+        int rc = batch_pass(h, patterns, offsets, max_l_dist, dense_ids, out, &sum, true);
+        if (rc < 0) {
+            cleanup();
+            return rc;
+        }
+        if (rc > 0)
+            for (uint32_t id : dense_ids)
+                if (out[id]) {
+                    fzb_result_destroy(out[id]);
+                    out[id] = nullptr;
+                }
     }
     for (uint32_t i = 0; i < count; i++) {
         if (out[i]) continue;

@@ -150,6 +150,193 @@ k_filter_multi(const __grid_constant__ MultiParams p, int64_t nvec, int64_t ntil
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The patterns the q-sample lemma does NOT cover (short patterns / large k: "dense" class) share a scan too, built on
+// the reference's own filter -- at least one of the n-grams P[jL:(j+1)L] occurs exactly (levenshtein_ngram.py:159-198):
+//   k_filter_mdense  tests the 3-byte prefix of every n-gram of every such pattern (every n-gram is >= 3 bytes on the
+//        n-gram route) at EVERY haystack position against the same kind of 2^20-bit table (funnel shift, one hash,
+//        one bit test per position); a flagged lane probes the prefix -> postings (pattern, n-gram) table, compares
+//        the rest of the n-gram with the text and appends a HIT (pattern, n-gram, position) -- buffered per CTA in
+//        shared memory, one global atomic per flush.
+//   k_verify_mhits   one hit per LANE (like k_verify_hits): the lane stages its window and its own pattern in
+//        private shared-memory slots and runs verify_anchor_lev for that one n-gram, computing the Eq masks of the
+//        bit-parallel expansion on the fly (every lane has a different pattern).
+// ------------------------------------------------------------------------------------------------
+constexpr int kMdBuf = 3072;     // hits buffered per CTA
+constexpr int kMdFlush = 1024;
+constexpr size_t kMdenseSmem = kMultiSmem + (size_t)kMdBuf * 8 + 16;
+enum { CNT_MHITS = 7, CNT_MHITWORK = 8 };
+
+struct MdenseParams {
+    MultiParams mp;             // table pointers as for k_filter_multi (gtab keyed by the 3-byte prefix, postings pid << 8 | j)
+    const BatchPat *pats;
+    unsigned long long *hits;   // idx | j << 40 | pid << 48
+    uint32_t hits_cap;
+};
+
+__device__ __forceinline__ void mdense_append(const MdenseParams &p, unsigned long long *sBuf, uint32_t *sN,
+                                              unsigned long long hit) {
+    const uint32_t slot = atomicAdd(sN, 1u);
+    if (slot < (uint32_t)kMdBuf) {
+        sBuf[slot] = hit;
+    } else {  // CTA buffer full (a very dense tile): straight to the global list
+        const uint32_t g = atomicAdd(&p.mp.counters[CNT_MHITS], 1u);
+        if (g < p.hits_cap) p.hits[g] = hit;
+    }
+}
+
+// position `g` (global) starts with the 3-byte prefix `pre`: walk its postings, compare the rest of each n-gram
+__device__ __noinline__ void mdense_confirm(const MdenseParams &p, unsigned long long *sBuf, uint32_t *sN, uint32_t pre,
+                                            int64_t g) {
+    if (g < p.mp.own_lo || g >= p.mp.own_hi) return;
+    uint32_t slot = (pre * kGramMul) & p.mp.gtab_mask;
+    for (;;) {
+        const uint2 e = __ldg(p.mp.gtab + slot);
+        if (e.y == 0u) return;
+        if (e.x == pre) {
+            const uint32_t first = e.y & 0xFFFFFFu, cnt = e.y >> 24;
+            for (uint32_t i = 0; i < cnt; i++) {
+                const uint32_t post = __ldg(p.mp.postings + first + i);
+                const uint32_t pid = post >> 8, j = post & 0xFFu;
+                const BatchPat *bp = p.pats + pid;
+                const int L = bp->L, s = (int)j * L;
+                if (g + L > p.mp.N) continue;
+                const uint8_t *t = p.mp.H + (g - p.mp.buf_lo);
+                bool eq = true;
+                for (int b = 3; b < L; b++)
+                    if (__ldg(t + b) != bp->P[s + b]) {
+                        eq = false;
+                        break;
+                    }
+                if (eq) mdense_append(p, sBuf, sN, (unsigned long long)g | ((unsigned long long)j << 40) | ((unsigned long long)pid << 48));
+            }
+        }
+        slot = (slot + 1) & p.mp.gtab_mask;
+    }
+}
+
+__global__ void __launch_bounds__(kMultiThreads, 1)
+k_filter_mdense(const __grid_constant__ MdenseParams p, int64_t nvec, int64_t ntiles) {
+    extern __shared__ __align__(16) uint32_t mtbl[];
+    unsigned long long *sBuf = reinterpret_cast<unsigned long long *>(mtbl + kMultiTblWords);
+    uint32_t *sN = reinterpret_cast<uint32_t *>(sBuf + kMdBuf);
+    __shared__ uint32_t sBase;
+    for (int i = threadIdx.x; i < kMultiTblWords / 4; i += kMultiThreads)
+        reinterpret_cast<uint4 *>(mtbl)[i] = __ldg(reinterpret_cast<const uint4 *>(p.mp.bits) + i);
+    if (threadIdx.x == 0) *sN = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint4 *base = reinterpret_cast<const uint4 *>(p.mp.H);
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+#pragma unroll 1
+        for (int u = 0; u < kMultiUnroll; u++) {
+            const int64_t v = t * kMultiTileVecs + (int64_t)u * kMultiThreads + threadIdx.x;
+            const uint4 d = (v < nvec) ? ldg_stream(base + v) : make_uint4(0, 0, 0, 0);
+            uint32_t nx = __shfl_down_sync(0xFFFFFFFFu, d.x, 1);  // the 4 bytes after my 16
+            if (lane == 31) nx = (v + 1 < nvec + 8) ? __ldg(reinterpret_cast<const uint32_t *>(base + v + 1)) : 0u;  // padded buffer
+            const uint32_t ws[5] = {d.x, d.y, d.z, d.w, nx};
+            uint32_t acc = 0;  // bit (15 - b) <-> position b of my vector
+#pragma unroll
+            for (int b = 0; b < 16; b++) {
+                const uint32_t w = __funnelshift_r(ws[b >> 2], ws[(b >> 2) + 1], 8 * (b & 3)) & 0xFFFFFFu;
+                const uint32_t h = multi_hash(w);
+                acc = acc * 2u + ((mtbl[h >> 5] >> (h & 31u)) & 1u);
+            }
+            if (acc) {
+                const int64_t off = v * 16;
+                while (acc) {
+                    const int bit = 31 - __clz(acc);
+                    acc &= ~(1u << bit);
+                    const int b = 15 - bit;
+                    if (off + b + 3 > p.mp.buf_len) continue;
+                    const uint32_t w = __funnelshift_r(ws[b >> 2], ws[(b >> 2) + 1], 8 * (b & 3)) & 0xFFFFFFu;
+                    mdense_confirm(p, sBuf, sN, w, p.mp.buf_lo + off + b);
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t n = min(*sN, (uint32_t)kMdBuf);
+        if (n >= (uint32_t)kMdFlush) {
+            if (threadIdx.x == 0) sBase = atomicAdd(&p.mp.counters[CNT_MHITS], n);
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < n; i += kMultiThreads)
+                if (sBase + i < p.hits_cap) p.hits[sBase + i] = sBuf[i];
+            __syncthreads();
+            if (threadIdx.x == 0) *sN = 0;
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    const uint32_t n = min(*sN, (uint32_t)kMdBuf);
+    if (n) {
+        if (threadIdx.x == 0) sBase = atomicAdd(&p.mp.counters[CNT_MHITS], n);
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < n; i += kMultiThreads)
+            if (sBase + i < p.hits_cap) p.hits[sBase + i] = sBuf[i];
+    }
+}
+
+constexpr int kMhThreads = 128;
+constexpr int kMhSlotBytes = 160;  // per-lane window slot: m + 2k + alignment slack (m <= 64, m + 2k + 8 <= 160)
+
+__global__ void __launch_bounds__(kMhThreads)
+k_verify_mhits(const __grid_constant__ MdenseParams p, RawRec *out, uint32_t cap, uint32_t *counters) {
+    __shared__ __align__(16) uint8_t slots[kMhThreads][kMhSlotBytes];
+    __shared__ __align__(16) uint8_t pats[kMhThreads][kBatchMaxM];
+    const uint32_t nhits = counters[CNT_MHITS];
+    if (nhits > p.hits_cap) {  // list overflowed: the host searches these patterns one by one
+        if (blockIdx.x == 0 && threadIdx.x == 0) counters[CNT_OVERFLOW] = 1;
+        return;
+    }
+    const int lane = threadIdx.x & 31;
+    uint8_t *slot = slots[threadIdx.x];
+    uint8_t *myP = pats[threadIdx.x];
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&counters[CNT_MHITWORK], 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= nhits) break;
+        const uint32_t item = base + lane;
+        const bool valid = item < nhits;
+        VerifyCtx c;
+        c.H = p.mp.H;
+        c.buf_lo = p.mp.buf_lo;
+        c.buf_len = p.mp.buf_len;
+        c.N = p.mp.N;
+        c.own_lo = p.mp.own_lo;
+        c.own_hi = p.mp.own_hi;
+        c.m = c.k = 1;
+        c.L = 1;
+        c.n_ngrams = 1;
+        int64_t idx = 0, alo = 0;
+        int j = 0, tag = 0;
+        if (valid) {
+            const unsigned long long hv = p.hits[item];
+            idx = (int64_t)(hv & ((1ull << 40) - 1));
+            j = (int)((hv >> 40) & 0xFFu);
+            const uint32_t pid = (uint32_t)(hv >> 48);
+            tag = (int)(pid << 8);
+            const BatchPat *bp = p.pats + pid;
+            c.m = bp->m;
+            c.k = bp->k;
+            c.L = bp->L;
+            c.n_ngrams = bp->n_ngrams;
+            for (int w = 0; w < kBatchMaxM / 4; w++)
+                reinterpret_cast<uint32_t *>(myP)[w] = __ldg(reinterpret_cast<const uint32_t *>(bp->P) + w);
+            const int64_t p0 = idx - (int64_t)j * c.L;
+            const int64_t wlo = max(max(p0 - c.k, (int64_t)0), c.buf_lo);
+            const int64_t whi = min(min(p0 + c.m + c.k, c.N), c.buf_lo + c.buf_len);
+            alo = wlo & ~(int64_t)3;
+            const int nwords = (int)((whi - alo + 3) >> 2);
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(c.H + (alo - c.buf_lo));
+            uint32_t *dst = reinterpret_cast<uint32_t *>(slot);
+            for (int w = 0; w < nwords; w++) dst[w] = __ldg(src + w);
+        }
+        verify_anchor_lev<3>(c, myP, nullptr, slot - alo, idx, valid, nullptr, out, cap, counters, j, j + 1, tag);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counters[CNT_CAND], nhits);
+}
+
 constexpr int kVmThreads = 128;
 
 __global__ void __launch_bounds__(kVmThreads)

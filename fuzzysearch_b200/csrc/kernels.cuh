@@ -636,6 +636,55 @@ struct DpHolder<2> {
     __device__ __forceinline__ DpScratch *get() { return &s; }
 };
 
+// Same recurrence with the Eq mask computed on the fly from the sub-pattern's characters (no per-pattern table):
+// used where every LANE verifies a different pattern (k_verify_mhits, batch_kernels.cuh) and a 2 KiB table per lane
+// is out of the question.  sub[DIR * i] is character i of the sub-pattern; sublen <= 32.
+template <int DIR>
+__device__ __forceinline__ bool expand_bp_otf(const uint8_t *sub, int sublen, const uint8_t *seq, int seqlen,
+                                              int max_l, int &dist, int &len) {
+    if (sublen == 0) {
+        dist = 0;
+        len = 0;
+        return true;
+    }
+    const bool is_long = sublen > max(2 * max_l, 10);  // levenshtein_ngram.py:16
+    uint32_t VP = ~0u, VN = 0;
+    const uint32_t top = 1u << (sublen - 1);
+    int score = sublen, min_score = sublen, min_idx = -1;
+    for (int si = 0; si < seqlen; si++) {
+        const uint8_t ch = seq[DIR * si];
+        uint32_t Eq = 0;
+        for (int i = 0; i < sublen; i++) Eq |= (uint32_t)(sub[DIR * i] == ch) << i;
+        const uint32_t Xv = Eq | VN;
+        const uint32_t Xh = (((Eq & VP) + VP) ^ VP) | Eq;
+        uint32_t HP = VN | ~(Xh | VP);
+        uint32_t HN = VP & Xh;
+        score += (HP & top) ? 1 : 0;
+        score -= (HN & top) ? 1 : 0;
+        HP = (HP << 1) | 1u;
+        HN <<= 1;
+        VP = HN | ~(Xv | HP);
+        VN = HP & Xv;
+        if (score <= min_score) {
+            min_score = score;
+            min_idx = si;
+        } else if (!is_long) {
+            int v = si + 1, row_min = 1 << 30;
+            for (int j = 0; j < sublen; j++) {
+                v += (int)((VP >> j) & 1) - (int)((VN >> j) & 1);
+                row_min = min(row_min, v);
+            }
+            if (row_min >= min_score) break;
+        }
+    }
+    if (min_score <= max_l) {
+        dist = min_score;
+        len = min_idx + 1;
+        return true;
+    }
+    return false;
+}
+
 // Verification mode of a pattern: 0 = bit-parallel, 32-bit words (m <= 64, m-L <= 32); 1 = bit-parallel, 64-bit
 // words (m <= 64); 2 = cell-by-cell DP with the row in registers / local memory (longer patterns).
 __host__ __device__ __forceinline__ int verify_mode(int m, int L) { return m > 64 ? 2 : (m - L <= 32 ? 0 : 1); }
@@ -699,7 +748,8 @@ __device__ __forceinline__ int64_t stage_window(const PT &p, int64_t gbase, int 
 // All lanes of the warp call this together (lanes without an anchor pass valid = false).  Each lane
 // first finds the next n-gram that really occurs at its anchor (cheap), THEN the lanes that found one
 // run the two expansions side by side (converged), and the search for further n-grams resumes.
-// VM = verify_mode(m, L); S is only used (and only non-null) in mode 2.
+// VM = verify_mode(m, L); S is only used (and only non-null) in mode 2.  Mode 3 (batch hit lists): m, k, L, the pattern
+// bytes sP and the tag differ from lane to lane.
 // PT: ScanParams, or the per-work-item VerifyCtx of the multi-pattern kernels (batch_kernels.cuh); `tag` is OR-ed
 // into the n-gram field of the emitted records (pattern number << 8 in a batch).
 struct VerifyCtx {
@@ -745,7 +795,9 @@ __device__ void verify_anchor_lev(const PT &p, const uint8_t *sP, const unsigned
         if (ok) {
             const int64_t rhi = min(N, p0 + m + k);
             const int rlen = (int)max((int64_t)0, rhi - (idx + L));
-            if (VM == 0)
+            if (VM == 3)  // per-lane patterns: Eq on the fly (m - L <= 32)
+                ok = expand_bp_otf<1>(sP + s + L, m - s - L, h + L, rlen, k, dr, rs);
+            else if (VM == 0)
                 ok = expand_bp<uint32_t, 1>(sPM, s + L, m - s - L, h + L, rlen, k, dr, rs);
             else if (VM == 1)
                 ok = expand_bp<unsigned long long, 1>(sPM, s + L, m - s - L, h + L, rlen, k, dr, rs);
@@ -756,7 +808,9 @@ __device__ void verify_anchor_lev(const PT &p, const uint8_t *sP, const unsigned
         if (ok) {
             const int64_t llo = max((int64_t)0, p0 - (k - dr));
             const int llen = (int)max((int64_t)0, idx - llo);
-            if (VM == 0)
+            if (VM == 3)
+                ok = expand_bp_otf<-1>(sP + s - 1, s, h - 1, llen, k - dr, dl, ls);
+            else if (VM == 0)
                 ok = expand_bp<uint32_t, -1>(sPM, s, s, h - 1, llen, k - dr, dl, ls);
             else if (VM == 1)
                 ok = expand_bp<unsigned long long, -1>(sPM, s, s, h - 1, llen, k - dr, dl, ls);
