@@ -1348,6 +1348,7 @@ static int set_filter_attrs(size_t smem) {
     CK(cudaFuncSetAttribute(k_filter_dense<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDenseSmem));
     CK(cudaFuncSetAttribute(k_filter_dense<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDenseSmem));
     CK(cudaFuncSetAttribute(k_filter_dense<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDenseSmem));
+    CK(cudaFuncSetAttribute(k_filter_dense2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDense2Smem));
     return FZB_OK;
 }
 
@@ -1404,9 +1405,15 @@ static bool sampled_is_selective(fzb_haystack *h, uint32_t m, uint32_t k, int L,
 static int enqueue_filter(fzb_haystack *h, const ScanParams &p, bool sampled, fzb_result *res) {
     const int64_t nvec = (int64_t)(round_up(h->buf_len, 16) / 16);
     const int64_t ntiles = (nvec + kTileVecs - 1) / kTileVecs;
+    // dense route on a low-entropy haystack (about six effective symbols or fewer): index the table with 2-bit codes
+    bool two_bit = false;
+    if (!sampled && h->buf_len > 0 && sample_collision_prob(h) == FZB_OK) two_bit = h->coll_prob >= 0.15;
     if (ntiles > 0) {
         int per_sm = 4;
-        if (!sampled) {  // persistent grid = exactly the resident CTAs of the chosen instantiation
+        if (two_bit) {
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_filter_dense2, kFilterThreads, kDense2Smem));
+            per_sm = std::max(per_sm, 1);
+        } else if (!sampled) {  // persistent grid = exactly the resident CTAs of the chosen instantiation
             const void *fn = p.q < 4    ? (const void *)k_filter_dense<0>
                              : p.q == 4 ? (const void *)k_filter_dense<1>
                              : p.q < 8  ? (const void *)k_filter_dense<2>
@@ -1417,6 +1424,8 @@ static int enqueue_filter(fzb_haystack *h, const ScanParams &p, bool sampled, fz
         int grid = (int)std::min<int64_t>(ntiles, (int64_t)h->sm_count * per_sm);
         if (sampled)
             k_filter_sampled<<<grid, kFilterThreads, kFilterSmem, h->stream>>>(p, nvec, ntiles);
+        else if (two_bit)
+            k_filter_dense2<<<grid, kFilterThreads, kDense2Smem, h->stream>>>(p, nvec, ntiles);
         else if (p.q < 4)
             k_filter_dense<0><<<grid, kFilterThreads, kDenseSmem, h->stream>>>(p, nvec, ntiles);
         else if (p.q == 4)

@@ -357,6 +357,156 @@ k_filter_dense(const ScanParams p, int64_t nvec, int64_t ntiles) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Dense filter for LOW-ENTROPY haystacks (DNA and the like), where the dense route actually runs.  The text is
+// reduced to 2-bit codes, code(c) = (c >> 1) & 3 -- distinct for A, C, G, T; any other byte merely aliases with one
+// of them, which can only add candidates (the confirmation compares the real bytes).  A lane packs its 16 bytes into
+// one 32-bit word (one multiply per 4 bytes) and fetches 8 more codes from its neighbour; then ONE table lookup
+// answers THREE positions: the table is indexed by 8 consecutive codes (16 bits, 64 KiB of bytes in shared memory)
+// and entry bit i says whether the min(L,6)-code window starting at code i is the prefix of some n-gram.  Six
+// lookups per 16 positions: ~4 thread-instructions per position where the hashing k_filter_dense spends ~19.
+// Table hits are confirmed by the flagged lane itself against the n-grams' real bytes (a few dozen instructions
+// per hit, several flagged lanes run side by side) and go to the warp's hit buffer / the granule bitmap as in
+// k_filter_dense.
+// ------------------------------------------------------------------------------------------------
+constexpr int kD2Bases = 6;                   // codes of an n-gram the table looks at
+constexpr int kD2Span = 8;                    // codes per table index: three windows of six
+constexpr size_t kDense2Smem = (size_t)(1 << (2 * kD2Span)) + 256 * 8 + 8 * kDenseWarpScratch * 4;
+
+__host__ __device__ __forceinline__ uint32_t pack2(uint32_t w) {  // 4 bytes -> 4 two-bit codes in bits 0..7
+    return (((w >> 1) & 0x03030303u) * 0x01041040u) >> 24;
+}
+
+__global__ void __launch_bounds__(kFilterThreads, 3)
+k_filter_dense2(const ScanParams p, int64_t nvec, int64_t ntiles) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t *tbl = smem;                                                          // [65536] bits 0..2
+    uint2 *grams = reinterpret_cast<uint2 *>(smem + (1 << (2 * kD2Span)));       // (lo, hi) per n-gram (<= 255)
+    uint32_t *scratch = reinterpret_cast<uint32_t *>(smem + (1 << (2 * kD2Span)) + 256 * 8) +
+                        (threadIdx.x >> 5) * kDenseWarpScratch;                   // this warp's hit buffer
+    if ((threadIdx.x & 31) == 0) scratch[8] = 0;
+    for (int i = threadIdx.x; i < (1 << (2 * kD2Span)) / 16; i += blockDim.x)
+        reinterpret_cast<uint4 *>(tbl)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    const int q = p.q;  // 1..8 raw bytes compared by the confirmation
+    const int qc = min(q, kD2Bases);
+    const uint32_t cmask = (1u << (2 * qc)) - 1u;
+    const uint32_t mlo = q >= 4 ? 0xFFFFFFFFu : ((1u << (8 * q)) - 1u);
+    const uint32_t mhi = q <= 4 ? 0u : (q >= 8 ? 0xFFFFFFFFu : ((1u << (8 * (q - 4))) - 1u));
+    __shared__ uint32_t sSet[128];  // 4096-bit set of the n-grams' code prefixes (build phase only)
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) sSet[i] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int j = 0; j < p.n_ngrams; j++) {
+            uint32_t lo = 0, hi = 0, code = 0;
+            for (int b = 0; b < q; b++) {
+                const uint32_t c = p.P[j * p.L + b];
+                if (b < 4) lo |= c << (8 * b); else hi |= c << (8 * (b - 4));
+                if (b < qc) code |= ((c >> 1) & 3u) << (2 * b);
+            }
+            grams[j] = make_uint2(lo, hi);
+            sSet[code >> 5] |= 1u << (code & 31);
+        }
+    }
+    __syncthreads();
+    for (uint32_t e = threadIdx.x; e < (1u << (2 * kD2Span)); e += blockDim.x) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const uint32_t c = (e >> (2 * i)) & cmask;
+            v |= ((sSet[c >> 5] >> (c & 31)) & 1u) << i;
+        }
+        tbl[e] = (uint8_t)v;
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const MarkCtx mc = mark_ctx(p);
+    unsigned long long *hbuf = reinterpret_cast<unsigned long long *>(scratch + 10);
+    const uint4 *base = reinterpret_cast<const uint4 *>(p.H);
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t v0 = t * kTileVecs + threadIdx.x;
+#pragma unroll 1
+        for (int uh = 0; uh < kFilterUnroll; uh += 2) {
+        uint4 dd[2];
+        uint2 nn[2];
+#pragma unroll
+        for (int u2 = 0; u2 < 2; u2++) {
+            const int64_t v = v0 + (int64_t)(uh + u2) * kFilterThreads;
+            dd[u2] = (v < nvec) ? ldg_stream(base + v) : make_uint4(0, 0, 0, 0);
+            nn[u2] = make_uint2(0, 0);
+            if (lane == 31 && v < nvec) nn[u2] = __ldg(reinterpret_cast<const uint2 *>(base + v + 1));  // padded buffer
+        }
+#pragma unroll
+        for (int u2 = 0; u2 < 2; u2++) {
+            const int u = uh + u2;
+            const uint4 d = dd[u2];
+            uint32_t n0 = __shfl_down_sync(0xFFFFFFFFu, d.x, 1), n1 = __shfl_down_sync(0xFFFFFFFFu, d.y, 1);
+            if (lane == 31) {
+                n0 = nn[u2].x;
+                n1 = nn[u2].y;
+            }
+            const uint32_t pk = pack2(d.x) | (pack2(d.y) << 8) | (pack2(d.z) << 16) | (pack2(d.w) << 24);
+            const uint32_t nx = pack2(n0) | (pack2(n1) << 8);
+            uint32_t acc = 0;  // bit i <-> position i of my vector
+#pragma unroll
+            for (int g3 = 0; g3 < 6; g3++)  // positions 3*g3 .. 3*g3+2 (the last lookup's bits 16, 17 are dropped)
+                acc |= (uint32_t)tbl[__funnelshift_r(pk, nx, 6 * g3) & 0xFFFFu] << (3 * g3);
+            acc &= 0xFFFFu;
+            if (acc) {  // rare; flagged lanes confirm their own positions side by side
+                const int64_t off = (t * kTileVecs + threadIdx.x + (int64_t)u * kFilterThreads) * 16;
+                while (acc) {
+                    const int i = __ffs(acc) - 1;
+                    acc &= acc - 1;
+                    const int sel = i >> 2, sh = 8 * (i & 3);
+                    const uint32_t w0 = sel == 0 ? d.x : sel == 1 ? d.y : sel == 2 ? d.z : d.w;
+                    const uint32_t w1 = sel == 0 ? d.y : sel == 1 ? d.z : sel == 2 ? d.w : n0;
+                    const uint32_t w2 = sel == 0 ? d.z : sel == 1 ? d.w : sel == 2 ? n0 : n1;
+                    const uint32_t lo = __funnelshift_r(w0, w1, sh) & mlo, hi = __funnelshift_r(w1, w2, sh) & mhi;
+                    const int64_t g = mc.buf_lo + off + i;
+                    if (g < mc.own_lo || g >= mc.own_hi) continue;
+                    for (int j = 0; j < p.n_ngrams; j++) {
+                        if (grams[j].x != lo || grams[j].y != hi) continue;
+                        if (mc.hits_cap) {
+                            const unsigned long long ent = ((unsigned long long)g << 8) | (unsigned long long)j;
+                            const uint32_t slot = atomicAdd(&scratch[8], 1u);
+                            if (slot < 32u) {
+                                hbuf[slot] = ent;
+                            } else {  // warp buffer full: straight to the list
+                                const uint32_t gs = atomicAdd(&mc.counters[CNT_HITS], 1u);
+                                if (gs < mc.hits_cap) mc.hits[gs] = ent;
+                            }
+                        } else {
+                            mark_granule(mc.bitmap, mc.glist, mc.glist_cap, mc.counters, (g - mc.buf_lo) >> kGranuleShift);
+                            break;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (mc.hits_cap && scratch[8] >= 16u) {  // warp-uniform (shared memory)
+                const uint32_t n = min(scratch[8], 32u);
+                uint32_t b0 = 0;
+                if (lane == 0) b0 = atomicAdd(&mc.counters[CNT_HITS], n);
+                b0 = __shfl_sync(0xFFFFFFFFu, b0, 0);
+                if ((uint32_t)lane < n && b0 + lane < mc.hits_cap) mc.hits[b0 + lane] = hbuf[lane];
+                __syncwarp();
+                if (lane == 0) scratch[8] = 0;
+                __syncwarp();
+            }
+        }
+        }
+    }
+    __syncwarp();
+    if (mc.hits_cap && scratch[8]) {
+        const uint32_t n = min(scratch[8], 32u);
+        uint32_t b0 = 0;
+        if (lane == 0) b0 = atomicAdd(&mc.counters[CNT_HITS], n);
+        b0 = __shfl_sync(0xFFFFFFFFu, b0, 0);
+        if ((uint32_t)lane < n && b0 + lane < mc.hits_cap) mc.hits[b0 + lane] = hbuf[lane];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Expansion DP -- literal device restatement of levenshtein_ngram.py:8-143 (the CPU test oracle restates
 // the same statements independently).  `sub` lives in shared memory, `seq` in global memory; both
 // are walked with a stride of +1 (right expansion) or -1 (left expansion, reversed slices of
