@@ -183,6 +183,9 @@ struct fzb_haystack {
     uint32_t mset_slots = 0, mwork_cap = 0;
     unsigned long long *d_mhits = nullptr;  // dense batch pass: (pattern, n-gram, position) hits
     uint32_t mhits_cap = 0;
+    ulonglong2 *d_lmlut = nullptr;          // LP batch pass: per-byte pattern-set vectors
+    unsigned long long *d_lmlist = nullptr; // ... and its survivor list
+    uint32_t lmlist_cap = 0;
 };
 
 struct fzb_result {
@@ -326,6 +329,8 @@ extern "C" void fzb_haystack_destroy(fzb_haystack *h) {
     if (h->d_mset) cudaFree(h->d_mset);
     if (h->d_mwork) cudaFree(h->d_mwork);
     if (h->d_mhits) cudaFree(h->d_mhits);
+    if (h->d_lmlut) cudaFree(h->d_lmlut);
+    if (h->d_lmlist) cudaFree(h->d_lmlist);
     if (h->d_glist) cudaFree(h->d_glist);
     if (h->d_hits) cudaFree(h->d_hits);
     if (h->d_send) cudaFree(h->d_send);
@@ -1943,6 +1948,147 @@ static int batch_pass(fzb_haystack *h, const uint8_t *patterns, const uint32_t *
     return FZB_OK;
 }
 
+// One shared scan for up to 64 LP-route patterns (k_lp_scan_multi / k_lp_verify_multi).  Same return convention
+// as batch_pass.
+static int batch_pass_lp(fzb_haystack *h, const uint8_t *patterns, const uint32_t *offsets, const uint32_t *ks,
+                         const std::vector<uint32_t> &ids, fzb_result **out, fzb_stats *sum) {
+    const uint32_t cnt = (uint32_t)ids.size();
+    std::vector<BatchPat> pats(cnt);
+    std::vector<ulonglong2> lut(256, make_ulonglong2(0ull, 0ull));
+    std::vector<uint32_t> pm32((size_t)cnt * 256, 0u);
+    LpMultiParams lp{};
+    int wmax = 0;
+    for (uint32_t i = 0; i < cnt; i++) {
+        const uint32_t id = ids[i], m = offsets[id + 1] - offsets[id], k = ks[id];
+        BatchPat &bp = pats[i];
+        memset(&bp, 0, sizeof bp);
+        memcpy(bp.P, patterns + offsets[id], m);
+        bp.m = (int)m;
+        bp.k = (int)k;
+        bp.L = 0;
+        bp.n_ngrams = 0;
+        for (uint32_t j = 0; j < m; j++) {
+            lut[bp.P[j]].x |= 1ull << i;
+            pm32[(size_t)i * 256 + bp.P[j]] |= 1u << j;
+        }
+        for (uint32_t j = 0; j <= std::min(k, m - 1); j++) lut[bp.P[j]].y |= 1ull << i;
+        const uint32_t bias = 32 - (m - k);  // need = m - k in [1, 31]
+        for (int b = 0; b < 6; b++)
+            if ((bias >> b) & 1u) lp.bias[b] |= 1ull << i;
+        wmax = std::max(wmax, (int)(m + k));
+    }
+    int rc = ensure_batch_buffers(h);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    if (!h->d_lmlut) {
+        CK(cudaMalloc(&h->d_lmlut, 256 * sizeof(ulonglong2) + 64 * 256 * sizeof(uint32_t)));  // vectors + match masks
+        h->lmlist_cap = (uint32_t)std::min<uint64_t>(1u << 26, std::max<uint64_t>(1u << 22, h->capacity / 16));
+        CK(cudaMalloc(&h->d_lmlist, (size_t)h->lmlist_cap * sizeof(unsigned long long)));
+        CK(cudaFuncSetAttribute(k_lp_scan_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLmSmem));
+    }
+    detach_pending(h);
+    CK(cudaMemcpyAsync(h->d_lmlut, lut.data(), 256 * sizeof(ulonglong2), cudaMemcpyHostToDevice, h->stream));
+    uint32_t *d_pm32 = reinterpret_cast<uint32_t *>(h->d_lmlut + 256);
+    CK(cudaMemcpyAsync(d_pm32, pm32.data(), pm32.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_bpats, pats.data(), pats.size() * sizeof(BatchPat), cudaMemcpyHostToDevice, h->stream));
+    lp.H = h->d;
+    lp.buf_lo = (int64_t)h->buf_lo;
+    lp.buf_len = (int64_t)h->buf_len;
+    lp.N = (int64_t)h->global_len;
+    lp.lut = h->d_lmlut;
+    lp.wmax = wmax;
+    lp.pats = h->d_bpats;
+    lp.pm32 = d_pm32;
+    lp.list = h->d_lmlist;
+    lp.list_cap = h->lmlist_cap;
+    lp.counters = h->d_counters;
+    int per_sm = 2;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lp_scan_multi, kLmThreads, kLmSmem));
+    per_sm = std::max(per_sm, 1);
+    const int vgrid = h->sm_count * 4, sim_cap = 256;
+    rc = ensure_scratch(h, (uint64_t)vgrid * kLpThreads * 2 * sim_cap);
+    if (rc) return rc;
+    const uint64_t chunk = 256ull << 20;  // starts per scan: bounds the survivor list
+    std::vector<RawRec> raw;
+    float gpu_ms = 0.f, filter_ms = 0.f;
+    uint64_t n_work = 0;
+    for (int attempt = 0;; attempt++) {
+        if (attempt == 8) return fail(FZB_E_CUDA, "output buffer kept overflowing");
+        h->counters_clean = false;
+        CK(cudaMemsetAsync(h->d_counters, 0, CNT_COUNT * sizeof(uint32_t), h->stream));
+        CK(cudaEventRecord(h->ev[0], h->stream));
+        bool overflow = false;
+        float scan_ms = 0.f;
+        for (uint64_t lo = h->own_lo; lo < h->own_hi && !overflow; lo += chunk) {
+            lp.own_lo = (int64_t)lo;
+            lp.own_hi = (int64_t)std::min<uint64_t>(h->own_hi, lo + chunk);
+            CK(cudaMemsetAsync(h->d_counters + CNT_LMLIST, 0, 2 * sizeof(uint32_t), h->stream));  // list length + flag
+            CK(cudaEventRecord(h->ev[1], h->stream));
+            k_lp_scan_multi<<<h->sm_count * per_sm, kLmThreads, kLmSmem, h->stream>>>(lp);
+            CK(cudaEventRecord(h->ev[2], h->stream));
+            k_lp_verify_multi<<<vgrid, kLpThreads, 0, h->stream>>>(lp, h->d_scratch, sim_cap, h->d_out, h->out_cap,
+                                                                   h->d_counters);
+            CK(cudaGetLastError());
+            uint32_t cnts[CNT_COUNT];
+            CK(cudaMemcpyAsync(cnts, h->d_counters, sizeof cnts, cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]);
+            scan_ms += ms;
+            n_work += cnts[CNT_LMLIST];
+            sum->n_launches += 2;
+            if (cnts[CNT_LMWORK] || cnts[CNT_OVERFLOW]) overflow = true;  // survivor list / candidate lists too small
+        }
+        if (overflow) return 1;
+        CK(cudaEventRecord(h->ev[2], h->stream));
+        uint32_t cnts[CNT_COUNT];
+        CK(cudaMemcpyAsync(cnts, h->d_counters, sizeof cnts, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        const uint32_t n = cnts[CNT_OUT];
+        if (n > h->out_cap) {
+            rc = ensure_out_cap(h, n);
+            if (rc) return rc;
+            n_work = 0;
+            continue;
+        }
+        raw.resize(n);
+        if (n) {
+            CK(cudaMemcpyAsync(raw.data(), h->d_out, (size_t)n * sizeof(RawRec), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+        }
+        cudaEventElapsedTime(&gpu_ms, h->ev[0], h->ev[2]);
+        filter_ms = scan_ms;
+        break;
+    }
+    for (uint32_t i = 0; i < cnt; i++) {
+        fzb_result *res = new (std::nothrow) fzb_result();
+        if (!res) return fail(FZB_E_CUDA, "out of host memory");
+        res->stats.route = 3;
+        res->stats.bytes_scanned = i == 0 ? h->buf_len : 0;  // the haystack is read once for the whole pass
+        res->stats.gpu_ms = i == 0 ? gpu_ms : 0.0;
+        res->stats.filter_ms = i == 0 ? filter_ms : 0.0;
+        res->stats.n_candidates = i == 0 ? n_work : 0;
+        out[ids[i]] = res;
+    }
+    for (const RawRec &r : raw) {
+        RawRec q = r;
+        q.ngram = r.ngram & 0xFF;
+        out[ids[(uint32_t)r.ngram >> 8]]->raw.push_back(q);
+    }
+    for (uint32_t i = 0; i < cnt; i++) {
+        fzb_result *res = out[ids[i]];
+        res->raw_n = (uint32_t)res->raw.size();
+        res->raw_order = 1;
+        consolidate_recs(res->raw, res->fin, &res->hulls);
+        res->have_fin = true;
+    }
+    sum->gpu_ms += gpu_ms;
+    sum->filter_ms += filter_ms;
+    sum->bytes_scanned += h->buf_len;
+    sum->n_candidates += n_work;
+    return FZB_OK;
+}
+
 extern "C" int fzb_search_levenshtein_batch(fzb_haystack *h, const uint8_t *patterns, const uint32_t *offsets,
                                             const uint32_t *max_l_dist, uint32_t count, uint32_t flags,
                                             fzb_result **out, fzb_stats *total) {
@@ -2023,6 +2169,33 @@ extern "C" int fzb_search_levenshtein_batch(fzb_haystack *h, const uint8_t *patt
         }
         if (rc > 0)
             for (uint32_t id : dense_ids)
+                if (out[id]) {
+                    fzb_result_destroy(out[id]);
+                    out[id] = nullptr;
+                }
+    }
+    // LP-route patterns (m // (k+1) < 3) share scans of 64 patterns each (bit-sliced window counters)
+    std::vector<uint32_t> lp_ids;
+    if (flags == 0 && h->buf_len > 0) {
+        for (uint32_t i = 0; i < count; i++) {
+            if (out[i]) continue;
+            const uint32_t m = offsets[i + 1] - offsets[i], k = max_l_dist[i];
+            if (m == 0 || k == 0 || k >= m || m / (k + 1) >= 3) continue;
+            if (m > 31 || k > 8 || m + k > 31) continue;  // automaton masks / 6-bit window counters
+            if (check_halo(h, (uint64_t)m + k) != FZB_OK) continue;
+            lp_ids.push_back(i);
+        }
+    }
+    for (size_t first = 0; first + 2 <= lp_ids.size(); first += 64) {
+        std::vector<uint32_t> ids(lp_ids.begin() + first, lp_ids.begin() + std::min(lp_ids.size(), first + 64));
+        if (ids.size() < 2) break;
+        int rc = batch_pass_lp(h, patterns, offsets, max_l_dist, ids, out, &sum);
+        if (rc < 0) {
+            cleanup();
+            return rc;
+        }
+        if (rc > 0)
+            for (uint32_t id : ids)
                 if (out[id]) {
                     fzb_result_destroy(out[id]);
                     out[id] = nullptr;

@@ -16,7 +16,7 @@
 //        with the pattern number.  The set slot is cleared on the way out (the set is empty between batches).
 // The host splits the records by pattern and consolidates each list (api.cu).
 #pragma once
-#include "kernels.cuh"
+#include "lp_kernels.cuh"
 
 namespace fzb {
 
@@ -335,6 +335,198 @@ k_verify_mhits(const __grid_constant__ MdenseParams p, RawRec *out, uint32_t cap
         verify_anchor_lev<3>(c, myP, nullptr, slot - alo, idx, valid, nullptr, out, cap, counters, j, j + 1, tag);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counters[CNT_CAND], nhits);
+}
+
+// ------------------------------------------------------------------------------------------------
+// The LP-route patterns (m // (k+1) < 3) of a batch share a scan as well, 64 at a time.  The two necessary conditions
+// of k_lp_scan -- first character in P[:k+1], and at least m-k characters of the window H[s : s+m+k) that occur in P
+// -- are evaluated for ALL patterns at once with BIT-SLICED counters: a 256-entry table gives, per byte, the 64-bit
+// vectors A (bit p: the byte occurs in pattern p) and F (bit p: it occurs in P_p[:k_p+1]); six 64-bit words hold, bit
+// position p, the 6-bit number  (32 - need_p) + #{bytes of the sliding window in pattern p's set},  so bit-slice 5
+// IS the vector "count_p >= need_p".  Sliding the window by one position adds the entering byte's A and removes the
+// leaving byte's with one ripple over the six slices.  The window is the LONGEST m+k of the pass (a superset for the
+// shorter patterns: still necessary); k_lp_verify_multi re-tests each survivor with its own pattern's exact window
+// before running the bit-parallel automaton and, on acceptance, the literal simulation -- all per lane.
+//   k_lp_scan_multi    CTA tile = 256 threads x 128 positions staged in shared memory (padded: conflict-free walks);
+//                      survivors (pattern, start) buffered per CTA, one global atomic per flush.
+//   k_lp_verify_multi  one survivor per thread.
+// ------------------------------------------------------------------------------------------------
+constexpr int kLmThreads = 256;
+constexpr int kLmRun = 128;                         // positions a thread walks
+constexpr int kLmTile = kLmThreads * kLmRun;        // 32768
+constexpr int kLmHalo = 64;                         // >= longest window
+constexpr int kLmBuf = 6144;
+constexpr int kLmFlush = 2048;
+constexpr size_t kLmTileBytes = ((size_t)(kLmTile + kLmHalo) / 128 * 132 + 132 + 15) / 16 * 16;  // padded tile, 16-aligned
+constexpr size_t kLmSmem = kLmTileBytes + 256 * 16 + (size_t)kLmBuf * 8 + 16;
+enum { CNT_LMLIST = 7, CNT_LMWORK = 8 };
+
+struct LpMultiParams {
+    const uint8_t *H;
+    int64_t buf_lo, buf_len, N, own_lo, own_hi;   // own range = this chunk of starts
+    const ulonglong2 *lut;                         // per byte: x = A vector, y = F vector
+    unsigned long long bias[6];                    // bit slices of (32 - need_p)
+    int wmax;                                      // longest m + k of the pass
+    const BatchPat *pats;
+    const uint32_t *pm32;                          // per pattern: 256 match masks {j : P[j] == c} (k_lp_verify_multi)
+    unsigned long long *list;                      // start | pattern << 40
+    uint32_t list_cap;
+    uint32_t *counters;
+};
+
+__device__ __forceinline__ uint32_t lm_addr(uint32_t i) { return i + 4u * (i >> 7); }  // 128-byte runs 132 bytes apart
+
+__global__ void __launch_bounds__(kLmThreads)
+k_lp_scan_multi(const __grid_constant__ LpMultiParams p) {
+    extern __shared__ __align__(16) uint8_t lm_smem[];
+    uint8_t *sH = lm_smem;
+    ulonglong2 *sLut = reinterpret_cast<ulonglong2 *>(lm_smem + kLmTileBytes);
+    unsigned long long *sBuf = reinterpret_cast<unsigned long long *>(sLut + 256);
+    uint32_t *sN = reinterpret_cast<uint32_t *>(sBuf + kLmBuf);
+    __shared__ uint32_t sBase;
+    for (int i = threadIdx.x; i < 256; i += kLmThreads) sLut[i] = p.lut[i];
+    if (threadIdx.x == 0) *sN = 0;
+    __syncthreads();
+    const int64_t hi = min(p.own_hi, p.N);                  // starts are < hi
+    const int64_t lim = min(p.N, p.buf_lo + p.buf_len);     // bytes at or beyond this belong to no pattern's set
+    const int64_t base = p.own_lo & ~(int64_t)127;          // tiles start on 128-byte boundaries (aligned word loads)
+    const int64_t ntiles = hi > base ? (hi - base + kLmTile - 1) / kLmTile : 0;
+    const int wmax = p.wmax;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t tile_lo = base + t * kLmTile;
+        __syncthreads();  // the previous tile is consumed
+        {   // stage [tile_lo, tile_lo + kLmTile + kLmHalo) : coalesced 4-byte loads into the padded layout
+            const int nwords = (kLmTile + kLmHalo) / 4;
+            const uint8_t *src = p.H + (tile_lo - p.buf_lo);  // (may point before the buffer: guarded below)
+            const int64_t first = p.buf_lo - tile_lo;                  // bytes of the tile before the buffer
+            const int64_t avail = p.buf_lo + p.buf_len + 128 - tile_lo;  // readable bytes (padded buffer)
+            for (int w = threadIdx.x; w < nwords; w += kLmThreads) {
+                const int64_t b = (int64_t)w * 4;
+                const uint32_t v = (b >= first && b + 4 <= avail) ? __ldg(reinterpret_cast<const uint32_t *>(src + b)) : 0u;
+                *reinterpret_cast<uint32_t *>(sH + lm_addr((uint32_t)w * 4u)) = v;
+            }
+        }
+        __syncthreads();
+        const uint32_t r0 = threadIdx.x * kLmRun;            // my run inside the tile
+        const int64_t s0 = tile_lo + r0;
+        unsigned long long C[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++) C[i] = p.bias[i];
+        for (int j = 0; j < wmax; j++) {                      // count over [s0, s0 + wmax)
+            unsigned long long carry = (s0 + j < lim) ? sLut[sH[lm_addr(r0 + j)]].x : 0ull;
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                const unsigned long long c = C[i];
+                C[i] = c ^ carry;
+                carry &= c;
+            }
+        }
+        for (int r = 0; r < kLmRun; r++) {
+            const int64_t s = s0 + r;
+            ulonglong2 lf = make_ulonglong2(0ull, 0ull);
+            if (s < lim) lf = sLut[sH[lm_addr(r0 + r)]];
+            unsigned long long surv = C[5] & lf.y;            // count_p >= need_p  and  first character of p
+            if (surv && s >= p.own_lo && s < hi) {
+                const uint32_t n = (uint32_t)__popcll(surv);
+                uint32_t slot = atomicAdd(sN, n);
+                while (surv) {
+                    const int pid = __ffsll((long long)surv) - 1;
+                    surv &= surv - 1;
+                    const unsigned long long ent = (unsigned long long)s | ((unsigned long long)pid << 40);
+                    if (slot < (uint32_t)kLmBuf) {
+                        sBuf[slot] = ent;
+                    } else {  // CTA buffer full: straight to the list
+                        const uint32_t g = atomicAdd(&p.counters[CNT_LMLIST], 1u);
+                        if (g < p.list_cap) p.list[g] = ent;
+                    }
+                    slot++;
+                }
+            }
+            // slide: the byte at s leaves, the byte at s + wmax enters
+            const unsigned long long ae = (s + wmax < lim) ? sLut[sH[lm_addr(r0 + r + wmax)]].x : 0ull;
+            unsigned long long up = ae & ~lf.x, dn = lf.x & ~ae;
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                const unsigned long long c = C[i];
+                C[i] = c ^ up ^ dn;
+                up &= c;
+                dn &= ~c;
+            }
+        }
+        __syncthreads();
+        const uint32_t n = min(*sN, (uint32_t)kLmBuf);
+        if (n >= (uint32_t)kLmFlush) {
+            if (threadIdx.x == 0) sBase = atomicAdd(&p.counters[CNT_LMLIST], n);
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < n; i += kLmThreads)
+                if (sBase + i < p.list_cap) p.list[sBase + i] = sBuf[i];
+            __syncthreads();
+            if (threadIdx.x == 0) *sN = 0;
+        }
+    }
+    __syncthreads();
+    const uint32_t n = min(*sN, (uint32_t)kLmBuf);
+    if (n) {
+        if (threadIdx.x == 0) sBase = atomicAdd(&p.counters[CNT_LMLIST], n);
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < n; i += kLmThreads)
+            if (sBase + i < p.list_cap) p.list[sBase + i] = sBuf[i];
+    }
+}
+
+struct LpLaneCtx {  // what sim_lev_lp needs
+    int32_t m, k;
+    int64_t N;
+};
+
+__global__ void __launch_bounds__(kLpThreads)
+k_lp_verify_multi(const __grid_constant__ LpMultiParams p, uint32_t *scratch, int cap, RawRec *out, uint32_t ocap,
+                  uint32_t *counters) {
+    __shared__ __align__(4) uint8_t sPat[kLpThreads][kBatchMaxM / 2];  // LP patterns are at most 31 bytes
+    const uint32_t n = counters[CNT_LMLIST];
+    if (n > p.list_cap) {  // the list overflowed: the host searches these patterns one by one
+        if (blockIdx.x == 0 && threadIdx.x == 0) counters[CNT_LMWORK] = 1;
+        return;
+    }
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t *A = scratch + tid * 2 * (int64_t)cap, *B = A + cap;
+    const uint8_t *W = p.H - p.buf_lo;  // W[g]: byte at global position g
+    const int64_t lim = min(p.N, p.buf_lo + p.buf_len);
+    uint8_t *myP = sPat[threadIdx.x];
+    for (int64_t i = tid; i < (int64_t)n; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long ent = p.list[i];
+        const int64_t st = (int64_t)(ent & ((1ull << 40) - 1));
+        const uint32_t pid = (uint32_t)(ent >> 40);
+        const BatchPat *bp = p.pats + pid;
+        LpLaneCtx c;
+        c.m = bp->m;
+        c.k = bp->k;
+        c.N = p.N;
+        for (int w = 0; w < kBatchMaxM / 8; w++)
+            reinterpret_cast<uint32_t *>(myP)[w] = __ldg(reinterpret_cast<const uint32_t *>(bp->P) + w);
+        // exact counting condition for THIS pattern's window (the scan used the longest window of the pass)
+        const uint32_t *pm = p.pm32 + (size_t)pid * 256;  // L1/L2-resident: 1 KiB per pattern
+        const int win = c.m + c.k, need = c.m - c.k;
+        int cnt = 0;
+        for (int j = 0; j < win && st + j < lim; j++) cnt += __ldg(pm + W[st + j]) != 0u;
+        if (cnt < need) continue;
+        int j0 = -1;  // make_char2first_subseq_index (levenshtein.py:44-49)
+        {
+            const uint8_t ch = W[st];
+            for (int j = 0; j <= min(c.k, c.m - 1); j++)
+                if (myP[j] == ch) {
+                    j0 = j;
+                    break;
+                }
+        }
+        if (j0 < 0) continue;
+        const bool any = c.k <= 4 ? lp_nfa_any<4>(pm, W, st, p.N, c.m, c.k, j0)
+                                  : lp_nfa_any<8>(pm, W, st, p.N, c.m, c.k, j0);
+        if (!any) continue;
+        if (!sim_lev_lp(c, myP, W, st, A, B, cap, out, ocap, counters, 1 | (int)(pid << 8)))
+            atomicExch(&counters[CNT_OVERFLOW], 1u);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counters[CNT_CAND], n);
 }
 
 constexpr int kVmThreads = 128;

@@ -27,8 +27,11 @@ __device__ __forceinline__ bool lp_push(uint32_t *list, int &n, int cap, int j, 
 
 // Simulates the candidates whose start is `start` (global).  Returns false on list overflow.
 // H[g] must be the haystack byte at global position g (global memory or a staged tile).
-__device__ bool sim_lev_lp(const ScanParams &p, const uint8_t *sP, const uint8_t *H, int64_t start, uint32_t *A,
-                           uint32_t *B, int cap, RawRec *out, uint32_t ocap, uint32_t *counters) {
+// PT: anything with m, k, N (ScanParams, or the per-survivor context of the batch kernels); `tag` goes into the
+// records' n-gram field (1 = multiplicity; batches add the pattern number << 8).
+template <class PT>
+__device__ bool sim_lev_lp(const PT &p, const uint8_t *sP, const uint8_t *H, int64_t start, uint32_t *A,
+                           uint32_t *B, int cap, RawRec *out, uint32_t ocap, uint32_t *counters, int tag = 1) {
     const int m = p.m, k = p.k;
     const int64_t N = p.N;
     int nA = 0;
@@ -44,7 +47,7 @@ __device__ bool sim_lev_lp(const ScanParams &p, const uint8_t *sP, const uint8_t
             }
         if (j0 < 0) return true;  // :76-77
         if (j0 + 1 == m) {        // :78-79
-            emit(out, ocap, counters, start, start + 1, start, j0, 1);
+            emit(out, ocap, counters, start, start + 1, start, j0, tag);
             return true;
         }
         A[0] = (uint32_t)(j0 + 1) | ((uint32_t)j0 << 16);  // :80-81
@@ -58,7 +61,7 @@ __device__ bool sim_lev_lp(const ScanParams &p, const uint8_t *sP, const uint8_t
             const int j = (int)(A[c] & 0xFFFFu), d = (int)(A[c] >> 16);
             if (sP[j] == ch) {  // :85
                 if (j + 1 == m)
-                    emit(out, ocap, counters, start, i + 1, start, d, 1);  // :87-88
+                    emit(out, ocap, counters, start, i + 1, start, d, tag);  // :87-88
                 else if (!lp_push(B, nB, cap, j + 1, d))                  // :90-93
                     return false;
             } else {
@@ -68,11 +71,11 @@ __device__ bool sim_lev_lp(const ScanParams &p, const uint8_t *sP, const uint8_t
                     if (!lp_push(B, nB, cap, j + 1, d + 1)) return false;  // :109-112
                 for (int t = 1; t <= k - d; t++) {                    // :115
                     if (j + t == m) {                                 // :118
-                        emit(out, ocap, counters, start, i + 1, start, d + t, 1);
+                        emit(out, ocap, counters, start, i + 1, start, d + t, tag);
                         break;
                     } else if (sP[j + t] == ch) {  // :126
                         if (j + t + 1 == m)        // :129
-                            emit(out, ocap, counters, start, i + 1, start, d + t, 1);
+                            emit(out, ocap, counters, start, i + 1, start, d + t, tag);
                         else if (!lp_push(B, nB, cap, j + 1 + t, d + t))  // :135-138
                             return false;
                         break;
@@ -89,7 +92,7 @@ __device__ bool sim_lev_lp(const ScanParams &p, const uint8_t *sP, const uint8_t
         for (int c = 0; c < nA; c++) {
             const int j = (int)(A[c] & 0xFFFFu), d = (int)(A[c] >> 16);
             const int dist = d + m - j;
-            if (dist <= k) emit(out, ocap, counters, start, N, start, dist, 1);
+            if (dist <= k) emit(out, ocap, counters, start, N, start, dist, tag);
         }
     }
     return true;
@@ -287,16 +290,27 @@ k_lp_scan(const ScanParams p, unsigned long long *list, uint32_t list_cap) {
 }
 
 // Does the candidate born at `start` accept anywhere?  (see the header comment above; m <= 31, k <= K)
-template <int K>
-__device__ __forceinline__ bool lp_nfa_any(const uint32_t *sPM32, const uint8_t *H, int64_t start, int64_t N, int m,
+// OTF: no per-pattern table -- sPM32 then points at the pattern's bytes and M is assembled per step (batches: every
+// lane simulates a different pattern).
+template <int K, bool OTF = false>
+__device__ __forceinline__ bool lp_nfa_any(const void *table_or_pattern, const uint8_t *H, int64_t start, int64_t N, int m,
                                            int k, int j0) {
+    const uint32_t *sPM32 = static_cast<const uint32_t *>(table_or_pattern);
+    const uint8_t *pat = static_cast<const uint8_t *>(table_or_pattern);
     if (j0 + 1 == m) return true;  // levenshtein.py:78-79
     uint32_t R[K + 1];
 #pragma unroll
     for (int d = 0; d <= K; d++) R[d] = (d == j0) ? (1u << (j0 + 1)) : 0u;  // :80-81
     const uint32_t last = 1u << (m - 1), full = (1u << m) - 1u;
     for (int64_t i = start + 1; i < N; i++) {
-        const uint32_t M = sPM32[H[i]];
+        uint32_t M;
+        if (OTF) {
+            const uint8_t c = H[i];
+            M = 0;
+            for (int j = 0; j < m; j++) M |= (uint32_t)(pat[j] == c) << j;
+        } else {
+            M = sPM32[H[i]];
+        }
         const bool can_sub = i + 1 < N;  // :106
         uint32_t nR[K + 1];
 #pragma unroll

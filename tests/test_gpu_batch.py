@@ -31,13 +31,14 @@ def test_batch_matches_oracle(cuda_device):
     results, stats = hs.search_levenshtein_batch(pats, ks)
     assert stats["route"] == "batch"
     # ONE scan for all the patterns the q-sample lemma covers, ONE for the other n-gram-route patterns (n-gram
-    # prefixes at every position); only the LP-route patterns still cost a pass each
+    # prefixes at every position)
     per_route = {}
     for r in results:
         per_route[r.stats()["route"]] = per_route.get(r.stats()["route"], 0) + 1
     assert per_route.get("ngrams/sampled-filter", 0) >= 24 and per_route.get("ngrams/dense-filter", 0) >= 4
     assert stats["bytes_scanned"] == sum(r.stats()["bytes_scanned"] for r in results)
-    assert stats["bytes_scanned"] == n * (2 + per_route.get("lp", 0))
+    # ... and the LP-route patterns share scans of 64 patterns: three or four passes over the haystack in all
+    assert stats["bytes_scanned"] <= n * 4
     routes = set()
     total = 0
     for pat, k, res in zip(pats, ks, results):
