@@ -184,7 +184,9 @@ struct fzb_haystack {
     unsigned long long *d_mhits = nullptr;  // dense batch pass: (pattern, n-gram, position) hits
     uint32_t mhits_cap = 0;
     ulonglong2 *d_lmlut = nullptr;          // LP batch pass: per-byte pattern-set vectors
-    unsigned long long *d_lmlist = nullptr; // ... and its survivor list
+    unsigned long long *d_lmlist = nullptr; // ... its survivor list (after the sort: grouped by pattern)
+    unsigned long long *d_lmkept = nullptr; // ... the survivors of the exact per-pattern window test
+    uint32_t *d_lmhist = nullptr;
     uint32_t lmlist_cap = 0;
 };
 
@@ -331,6 +333,8 @@ extern "C" void fzb_haystack_destroy(fzb_haystack *h) {
     if (h->d_mhits) cudaFree(h->d_mhits);
     if (h->d_lmlut) cudaFree(h->d_lmlut);
     if (h->d_lmlist) cudaFree(h->d_lmlist);
+    if (h->d_lmkept) cudaFree(h->d_lmkept);
+    if (h->d_lmhist) cudaFree(h->d_lmhist);
     if (h->d_glist) cudaFree(h->d_glist);
     if (h->d_hits) cudaFree(h->d_hits);
     if (h->d_send) cudaFree(h->d_send);
@@ -1984,6 +1988,8 @@ static int batch_pass_lp(fzb_haystack *h, const uint8_t *patterns, const uint32_
         CK(cudaMalloc(&h->d_lmlut, 256 * sizeof(ulonglong2) + 64 * 256 * sizeof(uint32_t)));  // vectors + match masks
         h->lmlist_cap = (uint32_t)std::min<uint64_t>(1u << 26, std::max<uint64_t>(1u << 22, h->capacity / 16));
         CK(cudaMalloc(&h->d_lmlist, (size_t)h->lmlist_cap * sizeof(unsigned long long)));
+        CK(cudaMalloc(&h->d_lmkept, (size_t)h->lmlist_cap * sizeof(unsigned long long)));
+        CK(cudaMalloc(&h->d_lmhist, 256 * sizeof(uint32_t)));  // per-pattern counts [64] + kept total [1] | cursors [64]
         CK(cudaFuncSetAttribute(k_lp_scan_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLmSmem));
     }
     detach_pending(h);
@@ -2026,8 +2032,13 @@ static int batch_pass_lp(fzb_haystack *h, const uint8_t *patterns, const uint32_
             CK(cudaEventRecord(h->ev[1], h->stream));
             k_lp_scan_multi<<<h->sm_count * per_sm, kLmThreads, kLmSmem, h->stream>>>(lp);
             CK(cudaEventRecord(h->ev[2], h->stream));
-            k_lp_verify_multi<<<vgrid, kLpThreads, 0, h->stream>>>(lp, h->d_scratch, sim_cap, h->d_out, h->out_cap,
-                                                                   h->d_counters);
+            // exact per-pattern windows, then a counting sort by pattern: the scan's list becomes the sorted output
+            CK(cudaMemsetAsync(h->d_lmhist, 0, 256 * sizeof(uint32_t), h->stream));
+            k_lm_refine<<<h->sm_count * 8, kLmSortThreads, 0, h->stream>>>(lp, h->d_lmkept, h->d_lmhist);
+            k_lm_scatter<<<h->sm_count * 8, kLmSortThreads, 0, h->stream>>>(h->d_lmkept, h->d_lmhist, h->d_lmhist + 128,
+                                                                              h->d_lmlist);
+            k_lp_verify_multi<<<vgrid, kLpThreads, 0, h->stream>>>(lp, h->d_lmlist, h->d_lmhist, h->d_scratch, sim_cap,
+                                                                   h->d_out, h->out_cap, h->d_counters);
             CK(cudaGetLastError());
             uint32_t cnts[CNT_COUNT];
             CK(cudaMemcpyAsync(cnts, h->d_counters, sizeof cnts, cudaMemcpyDeviceToHost, h->stream));
@@ -2036,7 +2047,7 @@ static int batch_pass_lp(fzb_haystack *h, const uint8_t *patterns, const uint32_
             cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]);
             scan_ms += ms;
             n_work += cnts[CNT_LMLIST];
-            sum->n_launches += 2;
+            sum->n_launches += 4;
             if (cnts[CNT_LMWORK] || cnts[CNT_OVERFLOW]) overflow = true;  // survivor list / candidate lists too small
         }
         if (overflow) return 1;

@@ -474,27 +474,104 @@ k_lp_scan_multi(const __grid_constant__ LpMultiParams p) {
     }
 }
 
+// Between scan and verification: k_lm_refine applies each survivor's OWN window (the scan used the longest one of the
+// pass) and keeps the exact survivors, counting them per pattern; k_lm_scatter then groups them by pattern (counting
+// sort), so that the lanes of a warp of k_lp_verify_multi run the automaton of the SAME pattern (same m, k, loop
+// bounds) almost always.
+constexpr int kLmSortThreads = 256;
+
+__global__ void __launch_bounds__(kLmSortThreads)
+k_lm_refine(const __grid_constant__ LpMultiParams p, unsigned long long *kept, uint32_t *hist /* [64] + kept count at [64] */) {
+    __shared__ uint32_t sHist[64];
+    __shared__ unsigned long long sKeep[kLmSortThreads];
+    __shared__ uint32_t sN, sBase;
+    const uint32_t n = p.counters[CNT_LMLIST];
+    if (n > p.list_cap) return;  // overflow: k_lp_verify_multi reports it
+    const uint8_t *W = p.H - p.buf_lo;
+    const int64_t lim = min(p.N, p.buf_lo + p.buf_len);
+    if (threadIdx.x < 64) sHist[threadIdx.x] = 0;
+    for (uint32_t base = blockIdx.x * kLmSortThreads; base < n; base += gridDim.x * kLmSortThreads) {
+        if (threadIdx.x == 0) sN = 0;
+        __syncthreads();
+        const uint32_t i = base + threadIdx.x;
+        if (i < n) {
+            const unsigned long long ent = p.list[i];
+            const int64_t st = (int64_t)(ent & ((1ull << 40) - 1));
+            const uint32_t pid = (uint32_t)(ent >> 40);
+            const BatchPat *bp = p.pats + pid;
+            const int m = bp->m, k = bp->k, win = m + k, need = m - k;
+            const uint32_t *pm = p.pm32 + (size_t)pid * 256;
+            int cnt = 0;
+            for (int j = 0; j < win && st + j < lim; j++) cnt += __ldg(pm + W[st + j]) != 0u;
+            if (cnt >= need) {
+                sKeep[atomicAdd(&sN, 1u)] = ent;
+                atomicAdd(&sHist[pid], 1u);
+            }
+        }
+        __syncthreads();
+        const uint32_t kn = sN;
+        if (kn) {
+            if (threadIdx.x == 0) sBase = atomicAdd(&hist[64], kn);
+            __syncthreads();
+            if (threadIdx.x < kn) kept[sBase + threadIdx.x] = sKeep[threadIdx.x];
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (threadIdx.x < 64 && sHist[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sHist[threadIdx.x]);
+}
+
+// kept[0 .. hist[64]) -> sorted[...] grouped by pattern; cursors[64] start at zero
+__global__ void __launch_bounds__(kLmSortThreads)
+k_lm_scatter(const unsigned long long *kept, const uint32_t *hist, uint32_t *cursors, unsigned long long *sorted) {
+    __shared__ uint32_t sOff[64], sCnt[64], sBase[64];
+    const uint32_t n = hist[64];
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int q = 0; q < 64; q++) {
+            sOff[q] = acc;
+            acc += hist[q];
+        }
+    }
+    for (uint32_t base = blockIdx.x * kLmSortThreads; base < n; base += gridDim.x * kLmSortThreads) {
+        if (threadIdx.x < 64) sCnt[threadIdx.x] = 0;
+        __syncthreads();
+        const uint32_t i = base + threadIdx.x;
+        unsigned long long ent = 0;
+        uint32_t pid = 0, rank = 0;
+        if (i < n) {
+            ent = kept[i];
+            pid = (uint32_t)(ent >> 40);
+            rank = atomicAdd(&sCnt[pid], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < 64 && sCnt[threadIdx.x]) sBase[threadIdx.x] = atomicAdd(&cursors[threadIdx.x], sCnt[threadIdx.x]);
+        __syncthreads();
+        if (i < n) sorted[sOff[pid] + sBase[pid] + rank] = ent;
+        __syncthreads();
+    }
+}
+
 struct LpLaneCtx {  // what sim_lev_lp needs
     int32_t m, k;
     int64_t N;
 };
 
 __global__ void __launch_bounds__(kLpThreads)
-k_lp_verify_multi(const __grid_constant__ LpMultiParams p, uint32_t *scratch, int cap, RawRec *out, uint32_t ocap,
-                  uint32_t *counters) {
+k_lp_verify_multi(const __grid_constant__ LpMultiParams p, const unsigned long long *sorted, const uint32_t *hist,
+                  uint32_t *scratch, int cap, RawRec *out, uint32_t ocap, uint32_t *counters) {
     __shared__ __align__(4) uint8_t sPat[kLpThreads][kBatchMaxM / 2];  // LP patterns are at most 31 bytes
-    const uint32_t n = counters[CNT_LMLIST];
-    if (n > p.list_cap) {  // the list overflowed: the host searches these patterns one by one
+    if (counters[CNT_LMLIST] > p.list_cap) {  // the scan's list overflowed: the host searches these patterns one by one
         if (blockIdx.x == 0 && threadIdx.x == 0) counters[CNT_LMWORK] = 1;
         return;
     }
+    const uint32_t n = hist[64];  // exact survivors, grouped by pattern
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t *A = scratch + tid * 2 * (int64_t)cap, *B = A + cap;
     const uint8_t *W = p.H - p.buf_lo;  // W[g]: byte at global position g
-    const int64_t lim = min(p.N, p.buf_lo + p.buf_len);
     uint8_t *myP = sPat[threadIdx.x];
     for (int64_t i = tid; i < (int64_t)n; i += (int64_t)gridDim.x * blockDim.x) {
-        const unsigned long long ent = p.list[i];
+        const unsigned long long ent = sorted[i];
         const int64_t st = (int64_t)(ent & ((1ull << 40) - 1));
         const uint32_t pid = (uint32_t)(ent >> 40);
         const BatchPat *bp = p.pats + pid;
@@ -504,12 +581,7 @@ k_lp_verify_multi(const __grid_constant__ LpMultiParams p, uint32_t *scratch, in
         c.N = p.N;
         for (int w = 0; w < kBatchMaxM / 8; w++)
             reinterpret_cast<uint32_t *>(myP)[w] = __ldg(reinterpret_cast<const uint32_t *>(bp->P) + w);
-        // exact counting condition for THIS pattern's window (the scan used the longest window of the pass)
         const uint32_t *pm = p.pm32 + (size_t)pid * 256;  // L1/L2-resident: 1 KiB per pattern
-        const int win = c.m + c.k, need = c.m - c.k;
-        int cnt = 0;
-        for (int j = 0; j < win && st + j < lim; j++) cnt += __ldg(pm + W[st + j]) != 0u;
-        if (cnt < need) continue;
         int j0 = -1;  // make_char2first_subseq_index (levenshtein.py:44-49)
         {
             const uint8_t ch = W[st];
@@ -526,7 +598,7 @@ k_lp_verify_multi(const __grid_constant__ LpMultiParams p, uint32_t *scratch, in
         if (!sim_lev_lp(c, myP, W, st, A, B, cap, out, ocap, counters, 1 | (int)(pid << 8)))
             atomicExch(&counters[CNT_OVERFLOW], 1u);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counters[CNT_CAND], n);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counters[CNT_CAND], counters[CNT_LMLIST]);
 }
 
 constexpr int kVmThreads = 128;
