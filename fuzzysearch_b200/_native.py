@@ -64,6 +64,9 @@ SYMBOLS = {
     "fzb_haystack_comm_init": (_i32, [_vp, _vp, _i32, _i32]),
     "fzb_comm_init_local": (_i32, [_vp, _i32]),
     "fzb_haystack_p2p_enabled": (_i32, [_vp]),
+    "fzb_p2p_export": (_i32, [_vp, _i32, _i32, _vp]),
+    "fzb_p2p_connect": (_i32, [_vp, _vp]),
+    "fzb_p2p_disable": (None, [_vp]),
     "fzb_haystack_upload": (_i32, [_vp, _u8p, _u64]),
     "fzb_host_alloc": (_vp, [_u64]),
     "fzb_host_free": (None, [_vp]),
@@ -259,6 +262,20 @@ class Haystack(object):
         _prefer_bundled_nccl()
         buf = (ctypes.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
         check(lib().fzb_haystack_comm_init(self._h, buf, rank, world_size))
+
+    def p2p_export(self, rank, world_size):
+        """-> this rank's 64-byte CUDA IPC handle (NCCL-free world, step 1)."""
+        buf = (ctypes.c_uint8 * 64)()
+        check(lib().fzb_p2p_export(self._h, rank, world_size, buf))
+        return bytes(buf)
+
+    def p2p_connect(self, handles):
+        """handles: the rank-major concatenation of every rank's handle (step 2)."""
+        buf = (ctypes.c_uint8 * len(handles)).from_buffer_copy(bytes(handles))
+        check(lib().fzb_p2p_connect(self._h, buf))
+
+    def p2p_disable(self):
+        lib().fzb_p2p_disable(self._h)
 
     def p2p_enabled(self):
         return bool(lib().fzb_haystack_p2p_enabled(self._h))

@@ -858,6 +858,63 @@ extern "C" int fzb_comm_init_local(fzb_haystack **handles, int world_size) {
     return FZB_OK;
 }
 
+// The same peer-memory world WITHOUT NCCL: the caller all-gathers the 64-byte CUDA IPC handles itself (any transport;
+// fuzzysearch_b200.sharding does it over its TCP rendezvous).  Also works for several processes sharing ONE GPU,
+// which NCCL refuses.  Such a world has no staged fallback: a shard that overflows a slot makes the search fail on
+// every rank (FZB_E_UNSUPPORTED) instead of silently returning a partial list.
+extern "C" int fzb_p2p_export(fzb_haystack *h, int rank, int world_size, uint8_t handle[FZB_IPC_HANDLE_BYTES]) {
+    if (!h || !handle || world_size < 1 || world_size > kMaxWorld || rank < 0 || rank >= world_size)
+        return fail(FZB_E_INVALID, "bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == FZB_IPC_HANDLE_BYTES, "IPC handle size");
+    CK(cudaSetDevice(h->device));
+    if (h->comm) nccl_comm_destroy(h->comm);
+    h->comm = nullptr;
+    p2p_free(h);
+    h->rank = rank;
+    h->world = world_size;
+    h->epoch = 0;
+    h->local_world = false;
+    int rc = p2p_alloc(h);
+    if (rc) return rc;
+    cudaIpcMemHandle_t mine;
+    CK(cudaIpcGetMemHandle(&mine, h->d_p2p));
+    memcpy(handle, &mine, sizeof mine);
+    return FZB_OK;
+}
+
+extern "C" int fzb_p2p_connect(fzb_haystack *h, const uint8_t *handles) {
+    if (!h || !handles || !h->d_p2p) return fail(FZB_E_INVALID, "fzb_p2p_export first");
+    CK(cudaSetDevice(h->device));
+    for (int r = 0; r < h->world; r++) {
+        if (r == h->rank) {
+            h->peer_base[r] = h->d_p2p;
+            continue;
+        }
+        cudaIpcMemHandle_t peer;
+        memcpy(&peer, handles + (size_t)r * FZB_IPC_HANDLE_BYTES, sizeof peer);
+        void *ptr = nullptr;
+        const cudaError_t e = cudaIpcOpenMemHandle(&ptr, peer, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            for (int q = 0; q < kMaxWorld; q++) {
+                if (h->peer_opened[q] && h->peer_base[q]) cudaIpcCloseMemHandle(h->peer_base[q]);
+                h->peer_opened[q] = false;
+                h->peer_base[q] = nullptr;
+            }
+            return fail(FZB_E_CUDA, "cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
+        }
+        h->peer_base[r] = (uint8_t *)ptr;
+        h->peer_opened[r] = true;
+    }
+    h->p2p = true;
+    h->local_world = true;  // (no NCCL communicator behind this world: no staged fallback)
+    return FZB_OK;
+}
+
+extern "C" void fzb_p2p_disable(fzb_haystack *h) {
+    if (h) p2p_free(h);
+}
+
 extern "C" int fzb_haystack_p2p_enabled(const fzb_haystack *h) { return h && h->p2p ? 1 : 0; }
 
 // ------------------------------------------------------------------------------------------------
@@ -1680,8 +1737,8 @@ static int finish_global(fzb_haystack *h, fzb_result *res) {
             return fail(FZB_E_CUDA, "multi-GPU reduction timed out waiting for a peer (rank %d of %d)", h->rank, h->world);
     }
     if (h->local_world)
-        return fail(FZB_E_UNSUPPORTED, "in-process world: a shard produced more than %u groups (or more than %d raw "
-                    "matches); the staged fallback needs an NCCL communicator", h->p2p_cap, kPostMax);
+        return fail(FZB_E_UNSUPPORTED, "NCCL-free world: a shard produced more than %u groups (or more than %d raw "
+                    "matches); the staged fallback needs an NCCL communicator (fzb_haystack_comm_init)", h->p2p_cap, kPostMax);
     std::vector<int64_t> all;
     std::vector<uint64_t> counts;
     const std::vector<RawRec> &v = res->fin;

@@ -26,7 +26,8 @@ import time
 
 import numpy as np
 
-__all__ = ["shard_bounds", "merge_raw_streams", "rendezvous_bytes", "init_shard_comm", "init_local_world", "search_all"]
+__all__ = ["shard_bounds", "merge_raw_streams", "rendezvous_bytes", "allgather_bytes", "init_shard_comm",
+           "init_shard_world_ipc", "init_local_world", "search_all"]
 
 ALIGN = 16  # shard buffers start on 16-byte boundaries of the global sequence (uint4 loads)
 
@@ -50,52 +51,110 @@ def shard_bounds(global_len, world_size, rank, halo):
     return buf_lo, buf_hi, own_lo, own_hi
 
 
-def rendezvous_bytes(payload, rank, world_size, addr=None, port=None, timeout=120.0):
-    """rank 0's `payload` (bytes) -> every rank, over a plain TCP socket: rank 0 listens on (addr, port), the
-    others connect (retrying until it is up) and read.  Defaults: MASTER_ADDR and FZB_RDV_PORT, else
-    MASTER_PORT + 17 (torchrun's own store owns MASTER_PORT itself).  No torch involved."""
+_ROUND = [0]  # collectives issued by this process: every rank issues the same sequence, so the number identifies one
+
+
+def _exchange(payload, rank, world_size, addr, port, timeout, gather):
+    """One collective over TCP.  gather = False: rank 0's payload -> every rank.  gather = True: every rank's payload
+    (equal lengths) -> the rank-major concatenation on every rank.  Rank 0 listens, the others connect (retrying until
+    it is up); every connection starts with (magic, round, rank) so that a fast rank that is already in the NEXT
+    collective cannot be mistaken for a participant of this one (it is turned away and retries)."""
+    _ROUND[0] += 1
+    rnd = _ROUND[0]
     if world_size == 1:
-        return payload
+        return bytes(payload)
     addr = addr or os.environ.get("MASTER_ADDR", "127.0.0.1")
     if port is None:
         port = int(os.environ.get("FZB_RDV_PORT", 0)) or int(os.environ.get("MASTER_PORT", "29500")) + 17
     deadline = time.time() + timeout
+    n = len(payload)
+
+    def recv_exact(conn, count):
+        data = b""
+        while len(data) < count:
+            chunk = conn.recv(count - len(data))
+            if not chunk:
+                raise ConnectionError("rendezvous closed early")
+            data += chunk
+        return data
+
     if rank == 0:
         srv = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
         srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
-        srv.bind((addr, port))
-        srv.listen(world_size)
+        while True:
+            try:
+                srv.bind((addr, port))
+                break
+            except OSError:  # the previous collective's listener is still closing
+                if time.time() > deadline:
+                    raise
+                time.sleep(0.02)
+        srv.listen(4 * world_size)
         srv.settimeout(timeout)
+        parts, conns = {0: bytes(payload)}, []
         try:
-            for _ in range(world_size - 1):
+            while len(conns) < world_size - 1:
                 conn, _ = srv.accept()
-                with conn:
-                    conn.sendall(struct.pack("<I", len(payload)) + payload)
+                conn.settimeout(timeout)
+                try:
+                    magic, r_rnd, r = struct.unpack("<4sII", recv_exact(conn, 12))
+                    if magic != b"FZBR" or r_rnd != rnd or not (0 < r < world_size) or r in parts:
+                        conn.close()  # somebody else's round (or noise): the sender retries
+                        continue
+                    parts[r] = recv_exact(conn, n) if gather else b""
+                except (ConnectionError, socket.timeout, OSError, struct.error):
+                    conn.close()
+                    continue
+                conns.append(conn)
+            blob = b"".join(parts[r] for r in range(world_size)) if gather else bytes(payload)
+            for conn in conns:
+                conn.sendall(struct.pack("<I", len(blob)) + blob)
         finally:
+            for conn in conns:
+                conn.close()
             srv.close()
-        return payload
+        return blob
     while True:
         try:
             with socket.create_connection((addr, port), timeout=5.0) as conn:
                 conn.settimeout(max(1.0, deadline - time.time()))
-                head = b""
-                while len(head) < 4:
-                    chunk = conn.recv(4 - len(head))
-                    if not chunk:
-                        raise ConnectionError("rendezvous closed early")
-                    head += chunk
-                (n,) = struct.unpack("<I", head)
-                data = b""
-                while len(data) < n:
-                    chunk = conn.recv(n - len(data))
-                    if not chunk:
-                        raise ConnectionError("rendezvous closed early")
-                    data += chunk
-                return data
+                conn.sendall(struct.pack("<4sII", b"FZBR", rnd, rank) + (bytes(payload) if gather else b""))
+                (m,) = struct.unpack("<I", recv_exact(conn, 4))
+                return recv_exact(conn, m)
         except (ConnectionRefusedError, ConnectionError, socket.timeout, OSError):
             if time.time() > deadline:
                 raise
             time.sleep(0.05)
+
+
+def rendezvous_bytes(payload, rank, world_size, addr=None, port=None, timeout=120.0):
+    """rank 0's `payload` (bytes) -> every rank, over a plain TCP socket on (addr, port).  Defaults: MASTER_ADDR and
+    FZB_RDV_PORT, else MASTER_PORT + 17 (torchrun's own store owns MASTER_PORT itself).  No torch involved."""
+    return _exchange(payload, rank, world_size, addr, port, timeout, gather=False)
+
+
+def allgather_bytes(payload, rank, world_size, addr=None, port=None, timeout=120.0):
+    """Every rank's `payload` (equal lengths) -> the rank-major concatenation on every rank (same transport)."""
+    return _exchange(payload, rank, world_size, addr, port, timeout, gather=True)
+
+
+def init_shard_world_ipc(haystack, rank=None, world_size=None, addr=None, port=None):
+    """Collective: the peer-memory world WITHOUT NCCL -- the CUDA IPC handles of the receive areas are all-gathered
+    over the TCP rendezvous.  Also works for several processes sharing one GPU.  Returns True if every rank could map
+    every other rank's receive area (else the world is disabled on all ranks)."""
+    rank = int(os.environ.get("RANK", "0")) if rank is None else rank
+    world_size = int(os.environ.get("WORLD_SIZE", "1")) if world_size is None else world_size
+    handles = allgather_bytes(haystack.p2p_export(rank, world_size), rank, world_size, addr, port)
+    ok = True
+    try:
+        haystack.p2p_connect(handles)
+    except Exception:  # noqa: BLE001 -- reported to the other ranks below
+        ok = False
+    flags = allgather_bytes(b"\x01" if ok else b"\x00", rank, world_size, addr, port)
+    if flags != b"\x01" * world_size:
+        haystack.p2p_disable()
+        return False
+    return True
 
 
 def init_shard_comm(haystack, rank=None, world_size=None, addr=None, port=None):

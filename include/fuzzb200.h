@@ -131,6 +131,15 @@ int fzb_haystack_comm_init(fzb_haystack *h, const uint8_t id[FZB_NCCL_ID_BYTES],
  * must then be issued on all handles CONCURRENTLY (one thread per handle): each one waits on the device for the
  * others' groups (bounded by a timeout).  Used by the tests to run the multi-rank reduction on a single GPU. */
 int fzb_comm_init_local(fzb_haystack **handles, int world_size);
+/* The multi-process world without NCCL: every rank calls fzb_p2p_export (allocates its receive area, returns its CUDA
+ * IPC handle), the caller all-gathers the handles by any means (rank-major, FZB_IPC_HANDLE_BYTES each), every rank
+ * calls fzb_p2p_connect; if any rank failed, all call fzb_p2p_disable.  Works for processes on different GPUs of a node
+ * AND for processes sharing one GPU.  No staged fallback in such a world (a shard with more groups than a slot holds
+ * makes the search fail with FZB_E_UNSUPPORTED on every rank). */
+#define FZB_IPC_HANDLE_BYTES 64
+int fzb_p2p_export(fzb_haystack *h, int rank, int world_size, uint8_t handle[FZB_IPC_HANDLE_BYTES]);
+int fzb_p2p_connect(fzb_haystack *h, const uint8_t *handles);
+void fzb_p2p_disable(fzb_haystack *h);
 /* 1 if FZB_F_GLOBAL searches on this handle reduce over peer memory (k_push / k_merge), 0 if they take the
  * staged NCCL + host path (CUDA IPC or peer access unavailable). */
 int fzb_haystack_p2p_enabled(const fzb_haystack *h);

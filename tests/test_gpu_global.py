@@ -143,36 +143,51 @@ def _free_port():
 
 def _worker(rank, world, port, devices, q):
     try:
+        from fuzzysearch_b200.sharding import init_shard_world_ipc
         n, m, k = (1 << 22) + 40, 20, 2
         pat, hay = _seamy_corpus(31, n, ASCII, m, k, world, 256)
         blo, bhi, lo, hi = shard_bounds(n, world, rank, m + k)
-        hs = F.Haystack.from_host(hay[blo:bhi], device=devices[rank], buf_lo=blo, global_len=n, own_lo=lo, own_hi=hi)
-        init_shard_comm(hs, rank, world, "127.0.0.1", port)   # torch-free bootstrap
-        p2p = hs.p2p_enabled()
-        got = hs.search_levenshtein(pat, k, F.F_GLOBAL).triples(F.FINAL)
         exp = oracle.find_near_matches(pat, hay, max_l_dist=k)
-        ok = got == exp
-        ham = hs.search_hamming(pat, 3, F.F_GLOBAL).triples(F.FINAL)
-        ok = ok and ham == tup(oracle.substitutions(pat, hay, 3))
-        # more groups than a slot holds -> every rank takes the staged NCCL path together
-        many = hs.search_exact(pat[:1], F.F_GLOBAL).triples(F.FINAL)
-        ok = ok and many == [(i, i + 1, 0) for i in oracle.search_exact(pat[:1], hay)] and len(many) > 4096
-        q.put((rank, bool(ok), len(got), bool(p2p)))
+        exp_ham = tup(oracle.substitutions(pat, hay, 3))
+        # (1) the NCCL-free world: CUDA IPC handles over the TCP rendezvous -- also between processes on ONE GPU
+        hs = F.Haystack.from_host(hay[blo:bhi], device=devices[rank], buf_lo=blo, global_len=n, own_lo=lo, own_hi=hi)
+        ok = init_shard_world_ipc(hs, rank, world, "127.0.0.1", port) and hs.p2p_enabled()
+        for _ in range(3):
+            ok = ok and hs.search_levenshtein(pat, k, F.F_GLOBAL).triples(F.FINAL) == exp
+        ok = ok and hs.search_hamming(pat, 3, F.F_GLOBAL).triples(F.FINAL) == exp_ham
+        try:  # more groups than a slot holds and no NCCL behind this world: must refuse, on every rank
+            hs.search_exact(pat[:1], F.F_GLOBAL).count(F.FINAL)
+            ok = False
+        except F.UnsupportedError:
+            pass
         hs.close()
+        nccl = len(set(devices)) == world  # (2) the NCCL-bootstrapped world needs one GPU per rank
+        if nccl:
+            hs = F.Haystack.from_host(hay[blo:bhi], device=devices[rank], buf_lo=blo, global_len=n, own_lo=lo, own_hi=hi)
+            init_shard_comm(hs, rank, world, "127.0.0.1", port)   # torch-free bootstrap of the NCCL id
+            ok = ok and hs.p2p_enabled()
+            ok = ok and hs.search_levenshtein(pat, k, F.F_GLOBAL).triples(F.FINAL) == exp
+            ok = ok and hs.search_hamming(pat, 3, F.F_GLOBAL).triples(F.FINAL) == exp_ham
+            # more groups than a slot holds -> every rank takes the staged NCCL path together
+            many = hs.search_exact(pat[:1], F.F_GLOBAL).triples(F.FINAL)
+            ok = ok and many == [(i, i + 1, 0) for i in oracle.search_exact(pat[:1], hay)] and len(many) > 4096
+            hs.close()
+        q.put((rank, bool(ok), len(exp), nccl))
     except BaseException as e:  # noqa: BLE001
         q.put((rank, False, repr(e), False))
         raise
 
 
-def test_global_two_processes_two_gpus(cuda_device):
-    """One process per GPU (the production layout): NCCL bootstrap over the TCP rendezvous, CUDA IPC peer memory."""
-    if F.device_count() < 2:
-        pytest.skip("needs 2 GPUs (the same kernels are covered on one GPU by test_multi_rank_world_on_one_gpu)")
+def test_global_multi_process_world(cuda_device):
+    """One process per rank (the production layout).  With two GPUs: rank r on GPU r, both the NCCL-free and the
+    NCCL-bootstrapped world.  With ONE GPU: both processes on device 0 through the NCCL-free world (CUDA IPC between
+    processes sharing a GPU) -- so this test never skips."""
     import multiprocessing as mp
+    devices = [0, 1] if F.device_count() >= 2 else [0, 0]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, [0, 1], q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, devices, q)) for r in range(2)]
     for p in procs:
         p.start()
     results = [q.get(timeout=300) for _ in range(2)]

@@ -11,7 +11,7 @@ import pytest
 import oracle
 from corpus import ASCII, make_corpus
 from fuzzysearch_b200 import _native
-from fuzzysearch_b200.sharding import merge_raw_streams, rendezvous_bytes, shard_bounds
+from fuzzysearch_b200.sharding import allgather_bytes, merge_raw_streams, rendezvous_bytes, shard_bounds
 from parity import tup
 
 import sys
@@ -43,7 +43,13 @@ def _free_port():
 def _rdv_worker(rank, world, port, q):
     payload = bytes(range(128)) if rank == 0 else b""
     got = rendezvous_bytes(payload, rank, world, "127.0.0.1", port, timeout=60)
-    q.put((rank, got == bytes(range(128))))
+    ok = got == bytes(range(128))
+    # all-gather of equal-sized records (what carries the CUDA IPC handles of the NCCL-free world), twice in a row
+    for rep in range(2):
+        mine = bytes([rank * 16 + rep]) * 64
+        allg = allgather_bytes(mine, rank, world, "127.0.0.1", port, timeout=60)
+        ok = ok and allg == b"".join(bytes([r * 16 + rep]) * 64 for r in range(world))
+    q.put((rank, ok))
 
 
 @pytest.mark.parametrize("world", [2, 3])

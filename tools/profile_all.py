@@ -29,14 +29,13 @@ pats, ks = [], []
 for i in range(1024):
     bm, bk = int(brng.integers(8, 65)), int(brng.integers(1, 5))
     bp = bytes(alpha[brng.integers(0, len(alpha), size=bm)])
-    if bm // (bk + 1) >= 3 and (bm - bk - 3) // 4 >= bk + 1:   # the shared-scan class only
-        pats.append(bp)
-        ks.append(bk)
-        for _ in range(8):
-            hs.write(1000 + int(brng.integers(0, n - 2000)), bench.mutate(brng, bp, bench.ASCII, int(brng.integers(0, bk + 2)), False))
+    pats.append(bp)
+    ks.append(bk)
+    for _ in range(8):
+        hs.write(1000 + int(brng.integers(0, n - 2000)), bench.mutate(brng, bp, bench.ASCII, int(brng.integers(0, bk + 2)), False))
 for _ in range(reps):
-    res, _ = hs.search_levenshtein_batch(pats, ks)             # k_filter_multi, k_verify_multi
-    for r in res:
+    res, _ = hs.search_levenshtein_batch(pats, ks)             # k_filter_multi/k_verify_multi, k_filter_mdense/
+    for r in res:                                              # k_verify_mhits, k_lp_scan_multi/k_lm_*/k_lp_verify_multi
         r.close()
 hs.close()
 # --- DNA: Hamming (TMA counting filter) and Levenshtein (dense filter + hit list) -----------------------------
@@ -49,6 +48,6 @@ for pos, b in bench.make_plants(seed + 8, 0, n, 32, 3, p32, bench.DNA, 4096, Tru
     dna.write(pos, b)
 for _ in range(reps):
     dna.search_hamming(p32, 3).close()                         # k_hamming_count, k_verify_ham
-    dna.search_levenshtein(p20, 2).close()                     # k_filter_dense, k_verify_hits
+    dna.search_levenshtein(p20, 2).close()                     # k_filter_dense2, k_verify_hits
 dna.close()
 print("done")
