@@ -484,7 +484,9 @@ def main():
                           own_hi=own_hi)
     hs.fill_synthetic(alphabet, seed)
     plants = []
-    for r in range(world):  # every rank knows every plant (needed for seam plants + checking)
+    if kind == "batch":  # replicated haystack: the same corpus whatever N is
+        plants = make_plants(seed + 1, 0, per_gpu, m, k, pat, alphabet, 4096, False)
+    for r in range(world if kind != "batch" else 0):  # every rank knows every plant (needed for seam plants + checking)
         lo_r, hi_r = shard_bounds(global_len, world, r, halo)[2:]
         plants += make_plants(seed + 1 + r, lo_r, hi_r, m, k, pat, alphabet, 4096, kind == "ham")
         if r > 0:  # straddle the seam (tests/test_find_near_matches_in_file.py:84-86 deltas)
