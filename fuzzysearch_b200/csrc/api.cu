@@ -2019,6 +2019,7 @@ static int batch_pass_lp(fzb_haystack *h, const uint8_t *patterns, const uint32_
     std::vector<uint32_t> pm32((size_t)cnt * 256, 0u);
     LpMultiParams lp{};
     int wmax = 0;
+    uint32_t kmax = 0;
     for (uint32_t i = 0; i < cnt; i++) {
         const uint32_t id = ids[i], m = offsets[id + 1] - offsets[id], k = ks[id];
         BatchPat &bp = pats[i];
@@ -2037,6 +2038,7 @@ static int batch_pass_lp(fzb_haystack *h, const uint8_t *patterns, const uint32_
         for (int b = 0; b < 6; b++)
             if ((bias >> b) & 1u) lp.bias[b] |= 1ull << i;
         wmax = std::max(wmax, (int)(m + k));
+        kmax = std::max(kmax, k);
     }
     int rc = ensure_batch_buffers(h);
     if (rc) return rc;
@@ -2086,6 +2088,7 @@ static int batch_pass_lp(fzb_haystack *h, const uint8_t *patterns, const uint32_
             lp.own_lo = (int64_t)lo;
             lp.own_hi = (int64_t)std::min<uint64_t>(h->own_hi, lo + chunk);
             CK(cudaMemsetAsync(h->d_counters + CNT_LMLIST, 0, 2 * sizeof(uint32_t), h->stream));  // list length + flag
+            CK(cudaMemsetAsync(h->d_counters + CNT_LMNEXT, 0, sizeof(uint32_t), h->stream));       // verify work counter
             CK(cudaEventRecord(h->ev[1], h->stream));
             k_lp_scan_multi<<<h->sm_count * per_sm, kLmThreads, kLmSmem, h->stream>>>(lp);
             CK(cudaEventRecord(h->ev[2], h->stream));
@@ -2094,8 +2097,12 @@ static int batch_pass_lp(fzb_haystack *h, const uint8_t *patterns, const uint32_
             k_lm_refine<<<h->sm_count * 8, kLmSortThreads, 0, h->stream>>>(lp, h->d_lmkept, h->d_lmhist);
             k_lm_scatter<<<h->sm_count * 8, kLmSortThreads, 0, h->stream>>>(h->d_lmkept, h->d_lmhist, h->d_lmhist + 128,
                                                                               h->d_lmlist);
-            k_lp_verify_multi<<<vgrid, kLpThreads, 0, h->stream>>>(lp, h->d_lmlist, h->d_lmhist, h->d_scratch, sim_cap,
-                                                                   h->d_out, h->out_cap, h->d_counters);
+            if (kmax <= 4)
+                k_lp_verify_multi<4><<<vgrid, kLpThreads, 0, h->stream>>>(lp, h->d_lmlist, h->d_lmhist, h->d_scratch, sim_cap,
+                                                                          h->d_out, h->out_cap, h->d_counters);
+            else
+                k_lp_verify_multi<8><<<vgrid, kLpThreads, 0, h->stream>>>(lp, h->d_lmlist, h->d_lmhist, h->d_scratch, sim_cap,
+                                                                          h->d_out, h->out_cap, h->d_counters);
             CK(cudaGetLastError());
             uint32_t cnts[CNT_COUNT];
             CK(cudaMemcpyAsync(cnts, h->d_counters, sizeof cnts, cudaMemcpyDeviceToHost, h->stream));

@@ -557,6 +557,13 @@ struct LpLaneCtx {  // what sim_lev_lp needs
     int64_t N;
 };
 
+// One survivor per LANE, with refill: the automata of different survivors die after very different numbers of
+// characters, so a lane whose survivor is finished fetches the next one (warp-aggregated atomic on a work counter)
+// instead of idling until the slowest of its 31 neighbours is done -- every iteration of the loop is one automaton
+// step for (almost) all lanes.  An accepting lane runs the literal simulation (rare) and goes back to the pool.
+enum { CNT_LMNEXT = 10 };
+
+template <int K>
 __global__ void __launch_bounds__(kLpThreads)
 k_lp_verify_multi(const __grid_constant__ LpMultiParams p, const unsigned long long *sorted, const uint32_t *hist,
                   uint32_t *scratch, int cap, RawRec *out, uint32_t ocap, uint32_t *counters) {
@@ -567,36 +574,83 @@ k_lp_verify_multi(const __grid_constant__ LpMultiParams p, const unsigned long l
     }
     const uint32_t n = hist[64];  // exact survivors, grouped by pattern
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
     uint32_t *A = scratch + tid * 2 * (int64_t)cap, *B = A + cap;
     const uint8_t *W = p.H - p.buf_lo;  // W[g]: byte at global position g
     uint8_t *myP = sPat[threadIdx.x];
-    for (int64_t i = tid; i < (int64_t)n; i += (int64_t)gridDim.x * blockDim.x) {
-        const unsigned long long ent = sorted[i];
-        const int64_t st = (int64_t)(ent & ((1ull << 40) - 1));
-        const uint32_t pid = (uint32_t)(ent >> 40);
-        const BatchPat *bp = p.pats + pid;
-        LpLaneCtx c;
-        c.m = bp->m;
-        c.k = bp->k;
-        c.N = p.N;
-        for (int w = 0; w < kBatchMaxM / 8; w++)
-            reinterpret_cast<uint32_t *>(myP)[w] = __ldg(reinterpret_cast<const uint32_t *>(bp->P) + w);
-        const uint32_t *pm = p.pm32 + (size_t)pid * 256;  // L1/L2-resident: 1 KiB per pattern
-        int j0 = -1;  // make_char2first_subseq_index (levenshtein.py:44-49)
-        {
-            const uint8_t ch = W[st];
-            for (int j = 0; j <= min(c.k, c.m - 1); j++)
-                if (myP[j] == ch) {
-                    j0 = j;
-                    break;
+    bool have = false, drained = false;
+    int64_t st = 0, i = 0;
+    uint32_t pid = 0;
+    LpLaneCtx c;
+    c.m = 2;
+    c.k = 1;
+    c.N = p.N;
+    const uint32_t *pm = p.pm32;
+    uint32_t R[K + 1];
+#pragma unroll
+    for (int d = 0; d <= K; d++) R[d] = 0;
+    for (;;) {
+        const unsigned want = __ballot_sync(0xFFFFFFFFu, !have && !drained);
+        bool accept = false;
+        if (want) {
+            const int leader = __ffs(want) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(&counters[CNT_LMNEXT], (uint32_t)__popc(want));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (!have && !drained) {
+                const uint32_t idx = base + (uint32_t)__popc(want & ((1u << lane) - 1u));
+                if (idx >= n) {
+                    drained = true;
+                } else {
+                    const unsigned long long ent = sorted[idx];
+                    st = (int64_t)(ent & ((1ull << 40) - 1));
+                    pid = (uint32_t)(ent >> 40);
+                    const BatchPat *bp = p.pats + pid;
+                    c.m = bp->m;
+                    c.k = bp->k;
+                    pm = p.pm32 + (size_t)pid * 256;
+                    for (int w = 0; w < kBatchMaxM / 8; w++)
+                        reinterpret_cast<uint32_t *>(myP)[w] = __ldg(reinterpret_cast<const uint32_t *>(bp->P) + w);
+                    int j0 = -1;  // make_char2first_subseq_index (levenshtein.py:44-49)
+                    const uint8_t ch = W[st];
+                    for (int j = 0; j <= min(c.k, c.m - 1); j++)
+                        if (myP[j] == ch) {
+                            j0 = j;
+                            break;
+                        }
+                    if (j0 >= 0) {
+                        if (j0 + 1 == c.m) {
+                            accept = true;  // :78-79
+                        } else {
+#pragma unroll
+                            for (int d = 0; d <= K; d++) R[d] = (d == j0) ? (1u << (j0 + 1)) : 0u;  // :80-81
+                            i = st + 1;
+                            have = true;
+                        }
+                    }
                 }
+            }
         }
-        if (j0 < 0) continue;
-        const bool any = c.k <= 4 ? lp_nfa_any<4>(pm, W, st, p.N, c.m, c.k, j0)
-                                  : lp_nfa_any<8>(pm, W, st, p.N, c.m, c.k, j0);
-        if (!any) continue;
-        if (!sim_lev_lp(c, myP, W, st, A, B, cap, out, ocap, counters, 1 | (int)(pid << 8)))
-            atomicExch(&counters[CNT_OVERFLOW], 1u);
+        if (__all_sync(0xFFFFFFFFu, drained && !have && !accept)) break;
+        if (have) {  // one character
+            if (i >= p.N) {
+                accept = lp_nfa_end<K>(R, c.m, c.k);
+                have = false;
+            } else {
+                bool alive = true;
+                if (lp_nfa_step<K>(R, __ldg(pm + W[i]), i + 1 < p.N, c.m, c.k, alive)) {
+                    accept = true;
+                    have = false;
+                } else if (!alive) {
+                    have = false;
+                }
+                i++;
+            }
+        }
+        if (accept) {  // this start emits something: the literal simulation produces the records (with multiplicities)
+            if (!sim_lev_lp(c, myP, W, st, A, B, cap, out, ocap, counters, 1 | (int)(pid << 8)))
+                atomicExch(&counters[CNT_OVERFLOW], 1u);
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counters[CNT_CAND], counters[CNT_LMLIST]);
 }

@@ -290,69 +290,57 @@ k_lp_scan(const ScanParams p, unsigned long long *list, uint32_t list_cap) {
 }
 
 // Does the candidate born at `start` accept anywhere?  (see the header comment above; m <= 31, k <= K)
-// OTF: no per-pattern table -- sPM32 then points at the pattern's bytes and M is assembled per step (batches: every
-// lane simulates a different pattern).
-template <int K, bool OTF = false>
-__device__ __forceinline__ bool lp_nfa_any(const void *table_or_pattern, const uint8_t *H, int64_t start, int64_t N, int m,
-                                           int k, int j0) {
-    const uint32_t *sPM32 = static_cast<const uint32_t *>(table_or_pattern);
-    const uint8_t *pat = static_cast<const uint8_t *>(table_or_pattern);
-    if (j0 + 1 == m) return true;  // levenshtein.py:78-79
-    uint32_t R[K + 1];
-#pragma unroll
-    for (int d = 0; d <= K; d++) R[d] = (d == j0) ? (1u << (j0 + 1)) : 0u;  // :80-81
+// One step of the automaton on the match mask M of the next text character: returns 1 if some state accepts, else 0
+// and sets `alive`.  (line numbers are levenshtein.py's.)
+template <int K>
+__device__ __forceinline__ int lp_nfa_step(uint32_t (&R)[K + 1], uint32_t M, bool can_sub, int m, int k, bool &alive) {
     const uint32_t last = 1u << (m - 1), full = (1u << m) - 1u;
-    for (int64_t i = start + 1; i < N; i++) {
-        uint32_t M;
-        if (OTF) {
-            const uint8_t c = H[i];
-            M = 0;
-            for (int j = 0; j < m; j++) M |= (uint32_t)(pat[j] == c) << j;
-        } else {
-            M = sPM32[H[i]];
-        }
-        const bool can_sub = i + 1 < N;  // :106
-        uint32_t nR[K + 1];
+    uint32_t nR[K + 1];
 #pragma unroll
-        for (int d = 0; d <= K; d++) nR[d] = 0;
+    for (int d = 0; d <= K; d++) nR[d] = 0;
 #pragma unroll
-        for (int d = 0; d <= K; d++) {
-            const uint32_t r = R[d];
-            if (d > k || !r) continue;
-            const uint32_t adv = r & M;  // :85-93: a matching character only advances
-            if (adv & last) return true;
-            nR[d] |= adv << 1;
-            if (d < k) {  // :100-101
-                const uint32_t mis = r & ~M;
-                if (d + 1 <= K) {
-                    nR[d + 1] |= mis;                                // insertion (:104)
-                    if (can_sub) nR[d + 1] |= (mis & ~last) << 1;    // substitution (:106-112)
-                }
-                uint32_t u = mis;  // deletions, first rule that fires wins per state (:115-138)
+    for (int d = 0; d <= K; d++) {
+        const uint32_t r = R[d];
+        if (d > k || !r) continue;
+        const uint32_t adv = r & M;  // :85-93: a matching character only advances
+        if (adv & last) return 1;
+        nR[d] |= adv << 1;
+        if (d < k) {  // :100-101
+            const uint32_t mis = r & ~M;
+            if (d + 1 <= K) {
+                nR[d + 1] |= mis;                                // insertion (:104)
+                if (can_sub) nR[d + 1] |= (mis & ~last) << 1;    // substitution (:106-112)
+            }
+            uint32_t u = mis;  // deletions, first rule that fires wins per state (:115-138)
 #pragma unroll
-                for (int t = 1; t <= K; t++) {
-                    if (t > k - d || !u || t > m) continue;
-                    if (u & (1u << (m - t))) return true;  // j + t == m
-                    const uint32_t hit = u & (M >> t);     // P[j+t] == c
-                    if (hit) {
-                        const uint32_t moved = hit << (t + 1);
-                        if (moved & (1u << m)) return true;  // j + t + 1 == m
-                        if (d + t <= K) nR[d + t] |= moved;
-                        u &= ~hit;
-                    }
+            for (int t = 1; t <= K; t++) {
+                if (t > k - d || !u || t > m) continue;
+                if (u & (1u << (m - t))) return 1;     // j + t == m
+                const uint32_t hit = u & (M >> t);     // P[j+t] == c
+                if (hit) {
+                    const uint32_t moved = hit << (t + 1);
+                    if (moved & (1u << m)) return 1;     // j + t + 1 == m
+                    if (d + t <= K) nR[d + t] |= moved;
+                    u &= ~hit;
                 }
             }
         }
-        uint32_t any = 0;
-#pragma unroll
-        for (int d = 0; d <= K; d++) {
-            R[d] = nR[d] & full;
-            any |= R[d];
-        }
-        if (!any) return false;
     }
+    uint32_t any = 0;
 #pragma unroll
-    for (int d = 0; d <= K; d++) {  // end of the sequence with live states (:145-148)
+    for (int d = 0; d <= K; d++) {
+        R[d] = nR[d] & full;
+        any |= R[d];
+    }
+    alive = any != 0;
+    return 0;
+}
+
+// live states at the end of the sequence accept iff d + m - j <= k (:145-148)
+template <int K>
+__device__ __forceinline__ bool lp_nfa_end(const uint32_t (&R)[K + 1], int m, int k) {
+#pragma unroll
+    for (int d = 0; d <= K; d++) {
         if (d > k) continue;
         uint32_t r = R[d];
         while (r) {
@@ -362,6 +350,22 @@ __device__ __forceinline__ bool lp_nfa_any(const void *table_or_pattern, const u
         }
     }
     return false;
+}
+
+// Does the candidate born at `start` accept anywhere?  sPM32: the pattern's 256 match masks (shared or global).
+template <int K>
+__device__ __forceinline__ bool lp_nfa_any(const uint32_t *sPM32, const uint8_t *H, int64_t start, int64_t N, int m,
+                                           int k, int j0) {
+    if (j0 + 1 == m) return true;  // levenshtein.py:78-79
+    uint32_t R[K + 1];
+#pragma unroll
+    for (int d = 0; d <= K; d++) R[d] = (d == j0) ? (1u << (j0 + 1)) : 0u;  // :80-81
+    for (int64_t i = start + 1; i < N; i++) {
+        bool alive = true;
+        if (lp_nfa_step<K>(R, sPM32[H[i]], i + 1 < N, m, k, alive)) return true;
+        if (!alive) return false;
+    }
+    return lp_nfa_end<K>(R, m, k);
 }
 
 __global__ void __launch_bounds__(kLpThreads)
