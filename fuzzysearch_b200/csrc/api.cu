@@ -531,7 +531,7 @@ class CopyPool {
   private:
     static constexpr size_t kSlice = 2u << 20;
     CopyPool() {
-        unsigned want = 12;  // enough to stay ahead of PCIe even when the source pages sit on a remote NUMA node
+        unsigned want = 16;  // enough to stay ahead of PCIe even when the source pages sit on a remote NUMA node
         if (const char *e = getenv("FZB_UPLOAD_THREADS")) want = (unsigned)std::max(0, atoi(e));
         unsigned hw = std::thread::hardware_concurrency();
         cpu_set_t set;
@@ -2150,12 +2150,22 @@ static int batch_pass_lp(fzb_haystack *h, const uint8_t *patterns, const uint32_
         q.ngram = r.ngram & 0xFF;
         out[ids[(uint32_t)r.ngram >> 8]]->raw.push_back(q);
     }
-    for (uint32_t i = 0; i < cnt; i++) {
-        fzb_result *res = out[ids[i]];
-        res->raw_n = (uint32_t)res->raw.size();
-        res->raw_order = 1;
-        consolidate_recs(res->raw, res->fin, &res->hulls);
-        res->have_fin = true;
+    {  // consolidate the lists in parallel (LP patterns on text have tens of thousands of raw matches each)
+        const unsigned nthreads = std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency()));
+        std::atomic<uint32_t> next{0};
+        auto work = [&]() {
+            for (uint32_t i = next.fetch_add(1); i < cnt; i = next.fetch_add(1)) {
+                fzb_result *res = out[ids[i]];
+                res->raw_n = (uint32_t)res->raw.size();
+                res->raw_order = 1;
+                consolidate_recs(res->raw, res->fin, &res->hulls);
+                res->have_fin = true;
+            }
+        };
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < nthreads; t++) pool.emplace_back(work);
+        work();
+        for (auto &t : pool) t.join();
     }
     sum->gpu_ms += gpu_ms;
     sum->filter_ms += filter_ms;

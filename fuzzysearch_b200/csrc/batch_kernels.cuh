@@ -484,9 +484,11 @@ __global__ void __launch_bounds__(kLmSortThreads)
 k_lm_refine(const __grid_constant__ LpMultiParams p, unsigned long long *kept, uint32_t *hist /* [64] + kept count at [64] */) {
     __shared__ uint32_t sHist[64];
     __shared__ unsigned long long sKeep[kLmSortThreads];
+    __shared__ unsigned long long sA[256];  // per byte: bit p = the byte occurs in pattern p
     __shared__ uint32_t sN, sBase;
     const uint32_t n = p.counters[CNT_LMLIST];
     if (n > p.list_cap) return;  // overflow: k_lp_verify_multi reports it
+    for (int i = threadIdx.x; i < 256; i += kLmSortThreads) sA[i] = p.lut[i].x;
     const uint8_t *W = p.H - p.buf_lo;
     const int64_t lim = min(p.N, p.buf_lo + p.buf_len);
     if (threadIdx.x < 64) sHist[threadIdx.x] = 0;
@@ -500,9 +502,8 @@ k_lm_refine(const __grid_constant__ LpMultiParams p, unsigned long long *kept, u
             const uint32_t pid = (uint32_t)(ent >> 40);
             const BatchPat *bp = p.pats + pid;
             const int m = bp->m, k = bp->k, win = m + k, need = m - k;
-            const uint32_t *pm = p.pm32 + (size_t)pid * 256;
             int cnt = 0;
-            for (int j = 0; j < win && st + j < lim; j++) cnt += __ldg(pm + W[st + j]) != 0u;
+            for (int j = 0; j < win && st + j < lim; j++) cnt += (int)((sA[W[st + j]] >> pid) & 1ull);
             if (cnt >= need) {
                 sKeep[atomicAdd(&sN, 1u)] = ent;
                 atomicAdd(&sHist[pid], 1u);
