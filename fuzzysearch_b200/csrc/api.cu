@@ -1540,6 +1540,7 @@ static int search_lev_ngrams(fzb_haystack *h, const uint8_t *pattern, uint32_t m
         CK(cudaMalloc(&h->d_hits, (size_t)h->hits_cap * sizeof(uint64_t)));
     }
     bool fuse_gather = post_mode != 0 && (flags & FZB_F_GLOBAL) != 0;
+    bool bitmap_mode = false;
     if (flags & FZB_F_TINY_LIST) p.glist_cap = std::min(h->glist_cap, 8u);
 retry_without_hits:
     p.hits = use_hits ? h->d_hits : nullptr;
@@ -1557,7 +1558,8 @@ retry_without_hits:
             res->stats.n_launches++;
             return FZB_OK;
         }
-        for (int scan_mode = 0; scan_mode < 2; scan_mode++) {
+        {   // one verify launch: the granule work list -- or, second attempt after the list overflowed, the whole bitmap
+            const int scan_mode = bitmap_mode ? 1 : 0;
             const int grid = h->sm_count * kVerifyCtasPerSm;
             if (vm == 0)
                 k_verify_lev<0><<<grid, kVerifyThreads, 0, h->stream>>>(p, h->bitmap_words, h->d_glist, p.glist_cap,
@@ -1569,10 +1571,22 @@ retry_without_hits:
                 k_verify_lev<2><<<grid, kVerifyThreads, 0, h->stream>>>(p, h->bitmap_words, h->d_glist, p.glist_cap,
                                                                         scan_mode, h->d_out, h->out_cap, h->d_counters);
         }
-        res->stats.n_launches += 2;
+        res->stats.n_launches += 1;
         return FZB_OK;
     }, PostPlan{post_mode, fuse_gather});  // the raw stream's order (n-gram, hit index) is restored lazily
     if (rc) return rc;
+    if (!use_hits && !bitmap_mode && h->h_counters[CNT_GRAN] > p.glist_cap) {
+        // more marked granules than the work list holds: the verify kernel raised CNT_OVERFLOW and did nothing (so a fused
+        // reduction, if any, went out invalid); redo the search with the list switched off, sweeping the bitmap
+        bitmap_mode = true;
+        fuse_gather = false;
+        p.glist_cap = 0;
+        res->fetch_raw();
+        res->raw.clear();
+        res->raw_n = 0;
+        res->fin.clear();
+        goto retry_without_hits;
+    }
     if (use_hits && h->h_counters[CNT_HITS] > p.hits_cap) {
         // the fused all-gather (if any) went out with valid = 0 (k_verify_hits raised CNT_OVERFLOW), so every
         // rank will take finish_global's staged round; the retry itself must not issue another collective
@@ -2385,6 +2399,9 @@ extern "C" int fzb_search_hamming(fzb_haystack *h, const uint8_t *pattern, uint3
                 if (r3) return r3;
                 CK(cudaFuncSetAttribute(k_hamming_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHcSmem));
             }
+            bool bitmap_mode = false;
+            PostPlan plan{2, (flags & FZB_F_GLOBAL) != 0};  // FINAL == RAW in (start, end, dist) order, ordered by k_post
+        retry_bitmap:
             int r2 = run_emitting(h, res, [&]() -> int {
                 if (counting) {
                     const int64_t ntiles = (hp.nrows + kHcThreads - 1) / kHcThreads;
@@ -2392,19 +2409,29 @@ extern "C" int fzb_search_hamming(fzb_haystack *h, const uint8_t *pattern, uint3
                     k_hamming_count<<<grid, kHcThreads, kHcSmem, h->stream>>>(p, hp, map256, map8);
                     CK(cudaEventRecord(h->ev[1], h->stream));
                     h->ev1_recorded = true;
-                    for (int scan_mode = 0; scan_mode < 2; scan_mode++)
-                        k_verify_ham<<<h->sm_count * 4, kVerifyThreads, 0, h->stream>>>(
-                            p, h->bitmap_words, h->d_glist, h->glist_cap, scan_mode, h->d_out, h->out_cap,
-                            h->d_counters);
-                    res->stats.n_launches += 2;
+                    // one verify launch: the granule work list -- or, after it overflowed, the whole bitmap
+                    k_verify_ham<<<h->sm_count * 4, kVerifyThreads, 0, h->stream>>>(
+                        p, h->bitmap_words, h->d_glist, p.glist_cap, bitmap_mode ? 1 : 0, h->d_out, h->out_cap,
+                        h->d_counters);
+                    res->stats.n_launches += 1;
                 } else {
                     k_hamming_scan<<<h->sm_count * 8, kHamThreads, 0, h->stream>>>(p, h->d_out, h->out_cap,
                                                                                    h->d_counters);
                 }
                 res->stats.n_launches++;
                 return FZB_OK;
-            }, PostPlan{2, (flags & FZB_F_GLOBAL) != 0});  // FINAL == RAW in (start, end, dist) order, ordered by k_post
+            }, plan);
             if (r2) return r2;
+            if (counting && !bitmap_mode && h->h_counters[CNT_GRAN] > p.glist_cap) {  // work list overflowed (see search_lev_ngrams)
+                bitmap_mode = true;
+                plan.global = false;
+                p.glist_cap = 0;
+                res->fetch_raw();
+                res->raw.clear();
+                res->raw_n = 0;
+                res->fin.clear();
+                goto retry_bitmap;
+            }
             res->raw_order = 1;
             return FZB_OK;
         }();

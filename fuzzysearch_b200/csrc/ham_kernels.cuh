@@ -222,13 +222,16 @@ k_verify_ham(const ScanParams p, uint64_t bitmap_words, const uint32_t *glist, u
     __shared__ uint8_t sP[256];
     __shared__ uint32_t sWinAll[kVerifyThreads / 32][kWinWords];
     const uint32_t ngran = counters[CNT_GRAN];
-    if (scan_mode && ngran <= glist_cap) return;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) sP[i] = p.P[i];
     __syncthreads();
     const int lane = threadIdx.x & 31;
     uint32_t *sWin = sWinAll[threadIdx.x >> 5];
     if (!scan_mode) {
-        const uint32_t nitems = min(ngran, glist_cap);
+        if (ngran > glist_cap) {  // work list overflowed: the host repeats the search in bitmap mode
+            if (blockIdx.x == 0 && threadIdx.x == 0) counters[CNT_OVERFLOW] = 1;
+            return;
+        }
+        const uint32_t nitems = ngran;
         for (;;) {
             uint32_t item = 0;
             if (lane == 0) item = atomicAdd(&counters[CNT_WORK], 1u);

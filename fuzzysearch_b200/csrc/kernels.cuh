@@ -1001,8 +1001,8 @@ __device__ __forceinline__ void verify_granule_lev(const PT &p, const uint8_t *s
     }
 }
 
-// scan_mode == 0: process glist[0 .. min(CNT_GRAN, glist_cap)) one granule per warp.
-// scan_mode == 1: only if the list overflowed, sweep the bitmap for the bits still set.
+// scan_mode == 0: process glist[0 .. CNT_GRAN) one granule per warp (the normal case: ONE verify launch per search).
+// scan_mode == 1: no list -- sweep the whole bitmap (the host's second attempt after the list overflowed).
 template <int VM>
 __global__ void __launch_bounds__(kVerifyThreads)
 k_verify_lev(const ScanParams p, uint64_t bitmap_words, const uint32_t *glist, uint32_t glist_cap, int scan_mode,
@@ -1011,7 +1011,6 @@ k_verify_lev(const ScanParams p, uint64_t bitmap_words, const uint32_t *glist, u
     __shared__ unsigned long long sPM[VM < 2 ? 256 : 1];
     __shared__ uint32_t sWinAll[kVerifyThreads / 32][kWinWords];
     const uint32_t ngran = counters[CNT_GRAN];
-    if (scan_mode && ngran <= glist_cap) return;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) sP[i] = p.P[i];
     if (VM < 2) build_pm(sPM, p.P, p.m, threadIdx.x, blockDim.x);
     __syncthreads();
@@ -1020,7 +1019,11 @@ k_verify_lev(const ScanParams p, uint64_t bitmap_words, const uint32_t *glist, u
     const int lane = threadIdx.x & 31;
     uint32_t *sWin = sWinAll[threadIdx.x >> 5];
     if (!scan_mode) {
-        const uint32_t nitems = min(ngran, glist_cap);
+        if (ngran > glist_cap) {  // the work list overflowed (pathologically dense marks): the host repeats the search in
+            if (blockIdx.x == 0 && threadIdx.x == 0) counters[CNT_OVERFLOW] = 1;  // bitmap mode (scan_mode = 1, no list)
+            return;
+        }
+        const uint32_t nitems = ngran;
         for (;;) {
             uint32_t item = 0;
             if (lane == 0) item = atomicAdd(&counters[CNT_WORK], 1u);
