@@ -2247,6 +2247,7 @@ extern "C" int fzb_search_levenshtein_batch(fzb_haystack *h, const uint8_t *patt
     std::vector<uint32_t> dense_ids;
     if (flags == 0 && h->buf_len > 0 && sample_collision_prob(h) == FZB_OK) {
         double expect = 0.0;  // expected prefix hits per haystack position
+        uint32_t dense_grams = 0;
         const double c3 = h->coll_prob * h->coll_prob * h->coll_prob;
         for (uint32_t i = 0; i < count && dense_ids.size() < kMaxBatchPats; i++) {
             if (out[i]) continue;
@@ -2256,7 +2257,9 @@ extern "C" int fzb_search_levenshtein_batch(fzb_haystack *h, const uint8_t *patt
             if (L < 3 || m - L > 32 || m + 2 * k + 12 > (uint32_t)kMhSlotBytes) continue;
             if (check_halo(h, (uint64_t)m + k) != FZB_OK) continue;
             if (expect + (m / L) * c3 > 0.02) continue;  // (low-entropy text: prefixes hit everywhere -> one by one)
+            if (dense_grams + m / L > kMaxBatchGrams) continue;  // prefix table capacity
             expect += (m / L) * c3;
+            dense_grams += m / L;
             dense_ids.push_back(i);
         }
     }
