@@ -686,7 +686,9 @@ def main():
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "kernel_ms": filt,
                          "algorithmic_bytes_per_launch": bhi - blo,
-                         "traffic": (traffic or {}).get("dram_bytes_per_launch") if (kind == "lev" and len(alphabet) > 16) else None},
+                         "traffic": (traffic or {}).get("dram_bytes_per_launch") if (kind == "lev" and len(alphabet) > 16) else None,
+                         "traffic_source": "profiles/filter_traffic.json (ncu --set full capture of this kernel; a constant, not "
+                                           "measured in this run)"},
             "clocks": clocks}
     if secondary is not None:
         line["secondary"] = secondary
