@@ -1846,7 +1846,7 @@ constexpr uint32_t kMaxBatchPats = 4096;      // patterns of one pass
 static int ensure_batch_buffers(fzb_haystack *h) {
     if (h->d_mbits) return FZB_OK;
     CK(cudaSetDevice(h->device));
-    CK(cudaMalloc(&h->d_mbits, kMultiTblWords * sizeof(uint32_t)));
+    CK(cudaMalloc(&h->d_mbits, (kMultiTblWords + kMulti2Words) * sizeof(uint32_t)));  // first + second level tables
     CK(cudaMalloc(&h->d_gtab, kGtabSlots * sizeof(uint2)));
     CK(cudaMalloc(&h->d_postings, kMaxBatchPostings * sizeof(uint32_t)));
     CK(cudaMalloc(&h->d_pinfo, kMaxBatchPats * sizeof(uint32_t)));
@@ -1895,11 +1895,15 @@ static int batch_pass(fzb_haystack *h, const uint8_t *patterns, const uint32_t *
             }
         }
     }
-    std::vector<uint32_t> bits(kMultiTblWords, 0), postings;
+    std::vector<uint32_t> bits(kMultiTblWords + (dense ? 0 : kMulti2Words), 0), postings;
     std::vector<uint2> gtab(kGtabSlots, make_uint2(0, 0));
     for (auto &g : grams) {
         const uint32_t w = g.first, hb = (w * kHashMul) >> (32 - kMultiTblBits);
         bits[hb >> 5] |= 1u << (hb & 31u);
+        if (!dense) {
+            const uint32_t h2 = multi_hash2(w);
+            bits[kMultiTblWords + (h2 >> 5)] |= 1u << (h2 & 31u);
+        }
         for (size_t first = 0; first < g.second.size(); first += 255) {
             const uint32_t c = (uint32_t)std::min<size_t>(255, g.second.size() - first);
             uint32_t slot = (w * kGramMul) & (kGtabSlots - 1);
@@ -1930,6 +1934,7 @@ static int batch_pass(fzb_haystack *h, const uint8_t *patterns, const uint32_t *
     mp.own_lo = (int64_t)h->own_lo;
     mp.own_hi = (int64_t)h->own_hi;
     mp.bits = h->d_mbits;
+    mp.bits2 = dense ? nullptr : h->d_mbits + kMultiTblWords;
     mp.gtab = h->d_gtab;
     mp.gtab_mask = kGtabSlots - 1;
     mp.postings = h->d_postings;

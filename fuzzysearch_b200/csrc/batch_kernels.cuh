@@ -27,6 +27,10 @@ constexpr size_t kMultiSmem = (size_t)kMultiTblWords * 4;
 constexpr int kMultiUnroll = 4;                            // uint4 loads in flight per thread
 constexpr int kMultiTileVecs = kMultiThreads * kMultiUnroll;
 constexpr uint32_t kGramMul = 0x85EBCA77u;
+constexpr int kMulti2Bits = 23;                            // 1 MiB second-level bit table
+constexpr int kMulti2Words = 1 << (kMulti2Bits - 5);
+constexpr uint32_t kGramMul2 = 0xC2B2AE35u;
+__host__ __device__ __forceinline__ uint32_t multi_hash2(uint32_t w) { return ((w ^ (w >> 15)) * kGramMul2) >> (32 - kMulti2Bits); }
 constexpr int kBatchMaxM = 64;
 
 struct BatchPat {  // device copy of one pattern
@@ -42,6 +46,9 @@ struct MultiParams {
     const uint8_t *H;
     int64_t buf_lo, buf_len, N, own_lo, own_hi;
     const uint32_t *bits;      // global copy of the bit table (kMultiTblWords words)
+    const uint32_t *bits2;     // second-level table (kMulti2Words words, L2-resident, independent hash): a word that
+                               // passes the shared-memory test (3 % false positives) must pass this one too before a
+                               // lane walks the postings (k_filter_multi only; nullptr = skip)
     const uint2 *gtab;         // open addressing: .x gram, .y = first posting | count << 24 (0 = empty slot)
     uint32_t gtab_mask;
     const uint32_t *postings;  // pid << 8 | offset
@@ -141,10 +148,14 @@ k_filter_multi(const __grid_constant__ MultiParams p, int64_t nvec, int64_t ntil
                 if (!nib) continue;
                 const int64_t off = (v0 + (int64_t)u * kMultiThreads) * 16;
                 if (off >= p.buf_len) continue;  // zero padding behind the buffer
-                if (nib & 8u) multi_confirm(p, d[u].x, off);
-                if (nib & 4u) multi_confirm(p, d[u].y, off + 4);
-                if (nib & 2u) multi_confirm(p, d[u].z, off + 8);
-                if (nib & 1u) multi_confirm(p, d[u].w, off + 12);
+                const uint32_t ws[4] = {d[u].x, d[u].y, d[u].z, d[u].w};
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (!(nib & (8u >> i))) continue;
+                    const uint32_t h2 = multi_hash2(ws[i]);
+                    if (p.bits2 && !((__ldg(p.bits2 + (h2 >> 5)) >> (h2 & 31u)) & 1u)) continue;  // second level: L2
+                    multi_confirm(p, ws[i], off + 4 * i);
+                }
             }
         }
     }
