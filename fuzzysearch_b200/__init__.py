@@ -12,11 +12,11 @@ __version__ = "0.1.0"
 
 __all__ = ["find_near_matches", "find_near_matches_batch", "find_near_matches_in_file", "has_near_match", "Match", "LevenshteinSearchParams",
            "DeviceSequence", "ExactSearch", "SubstitutionsOnlySearch", "LevenshteinSearch",
-           "GenericSearch", "choose_search_class"]
+           "GenericSearch", "choose_search_class", "search_exact"]
 
 from .common import LevenshteinSearchParams, Match
 from .search import (DeviceSequence, ExactSearch, GenericSearch, LevenshteinSearch,
-                     SubstitutionsOnlySearch)
+                     SubstitutionsOnlySearch, search_exact)
 
 
 def find_near_matches(subsequence, sequence, max_substitutions=None, max_insertions=None,
@@ -38,7 +38,7 @@ def has_near_match(subsequence, sequence, max_substitutions=None, max_insertions
     reference's internal has_near_match_* helpers (substitutions_only.py:18-34,139-145,218-233;
     generic_search.py:240-253), with early termination: the sequence is searched in chunks of growing size and
     the call returns after the first chunk that holds a match (fzb_has_near_match)."""
-    from .search import _WORKSPACE_LOCK, DeviceSequence, _coerce, _prepare
+    from .search import _WORKSPACE_LOCK, DeviceSequence, _prepare
     search_params = LevenshteinSearchParams(max_substitutions, max_insertions, max_deletions, max_l_dist)
     if len(subsequence) == 0:
         raise ValueError("Given subsequence is empty!")
@@ -62,7 +62,6 @@ def find_near_matches_batch(subsequences, sequence, max_l_dist):
     `max_l_dist` is one int or one per pattern.  Equivalent to
     ``[find_near_matches(p, sequence, max_l_dist=k) for p, k in zip(subsequences, ks)]``."""
     from . import _native
-    from .search import _coerce, _prepare
     subsequences = list(subsequences)
     ks = [max_l_dist] * len(subsequences) if isinstance(max_l_dist, int) else list(max_l_dist)
     if len(ks) != len(subsequences):
@@ -73,14 +72,15 @@ def find_near_matches_batch(subsequences, sequence, max_l_dist):
             raise ValueError("Given subsequence is empty!")
     if not subsequences:
         return []
-    from .search import _WORKSPACE_LOCK, DeviceSequence
-    pats = [_coerce(p) for p in subsequences]
-    seq_is_str = sequence._is_str if isinstance(sequence, DeviceSequence) else isinstance(sequence, str)
-    if any(is_str != seq_is_str for _, is_str in pats):
-        raise TypeError("subsequence and sequence must both be str or both be byte-like")
+    from .search import _WORKSPACE_LOCK, AlphabetTooLarge, _prepare_many
     with _WORKSPACE_LOCK:
-        _, hay, slicer, _ = _prepare(subsequences[0], sequence)
-        results, _ = hay.search_levenshtein_batch([p for p, _ in pats], ks)
+        try:
+            pats, hay, slicer = _prepare_many(subsequences, sequence)
+        except AlphabetTooLarge:
+            # wide symbols and more than 255 distinct ones over all the patterns: no common byte alphabet,
+            # so the patterns go one by one (each reduces the sequence to its own alphabet)
+            return [find_near_matches(p, sequence, max_l_dist=k) for p, k in zip(subsequences, ks)]
+        results, _ = hay.search_levenshtein_batch(pats, ks)
         out = []
         for res, k in zip(results, ks):
             # max_l_dist == 0 selects ExactSearch in find_near_matches (__init__.py:65-66), whose result is

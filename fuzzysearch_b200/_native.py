@@ -68,6 +68,7 @@ SYMBOLS = {
     "fzb_p2p_connect": (_i32, [_vp, _vp]),
     "fzb_p2p_disable": (None, [_vp]),
     "fzb_haystack_upload": (_i32, [_vp, _u8p, _u64]),
+    "fzb_haystack_upload_symbols": (_i32, [_vp, _vp, _u64, _u32, _vp, _u32]),
     "fzb_host_alloc": (_vp, [_u64]),
     "fzb_host_free": (None, [_vp]),
     "fzb_timer_start": (_i32, [_vp]),
@@ -78,6 +79,7 @@ SYMBOLS = {
     "fzb_search_hamming": (_i32, [_vp, _u8p, _u32, _u32, _u32, _vpp]),
     "fzb_search_generic": (_i32, [_vp, _u8p, _u32, _u32, _u32, _u32, _u32, _u32, _vpp]),
     "fzb_search_exact": (_i32, [_vp, _u8p, _u32, _u32, _vpp]),
+    "fzb_search_exact_window": (_i32, [_vp, _u8p, _u32, _u64, _u64, _u32, _vpp]),
     "fzb_search_levenshtein_batch": (_i32, [_vp, _u8p, _vp, _vp, _u32, _u32, _vpp, ctypes.POINTER(Stats)]),
     "fzb_find_near_matches": (_i32, [_u8p, _u32, _u8p, _u64, _u32, _u32, _u32, _u32, _i32, _vpp]),
     "fzb_has_near_match": (_i32, [_vp, _u8p, _u32, _u32, _u32, _u32, _u32, ctypes.POINTER(ctypes.c_int)]),
@@ -284,6 +286,16 @@ class Haystack(object):
         a = as_u8(data)
         check(lib().fzb_haystack_upload(self._h, ptr(a), a.size))
 
+    def upload_symbols(self, units, alphabet):
+        """units: numpy uint16 / uint32 code units; alphabet: the pattern's distinct symbols, ascending.
+        The device reduces every unit to one byte: 1 + its rank in `alphabet`, 0 if absent."""
+        units = np.ascontiguousarray(units)
+        if units.dtype not in (np.uint16, np.uint32):
+            raise TypeError("code units must be uint16 or uint32")
+        alpha = np.ascontiguousarray(alphabet, dtype=np.uint32)
+        check(lib().fzb_haystack_upload_symbols(self._h, ptr(units), units.size, units.dtype.itemsize, ptr(alpha),
+                                                alpha.size))
+
     def debug_counters(self):
         out = np.zeros(32, dtype=np.uint32)
         check(lib().fzb_debug_counters(self._h, ptr(out)))
@@ -355,10 +367,17 @@ class Haystack(object):
         check(lib().fzb_has_near_match(self._h, pp, m, max_subs, max_ins, max_dels, max_l, ctypes.byref(found)))
         return bool(found.value)
 
-    def search_exact(self, pattern, flags=0):
+    def search_exact(self, pattern, flags=0, start=None, end=None):
+        """All occurrences; with start / end: those wholly inside [start, end) (only that window is scanned)."""
         p, pp, m = self._pat(pattern)
         r = ctypes.c_void_p()
-        check(lib().fzb_search_exact(self._h, pp, m, flags, ctypes.byref(r)))
+        if start is None and end is None:
+            check(lib().fzb_search_exact(self._h, pp, m, flags, ctypes.byref(r)))
+        else:
+            n = len(self)
+            start = 0 if start is None else max(0, min(int(start), n))
+            end = n if end is None else max(0, min(int(end), n))
+            check(lib().fzb_search_exact_window(self._h, pp, m, start, end, flags, ctypes.byref(r)))
         return Result(r)
 
 

@@ -8,20 +8,24 @@
 __all__ = ["Match", "LevenshteinSearchParams", "FuzzySearchBase", "consolidate_overlapping_matches"]
 
 
-class Match(object):
-    """fuzzysearch.common.Match (common.py:15-32)."""
+def _check_match_fields(start, end, dist, matched):  # common.py:21-32
+    if not (isinstance(start, int) and start >= 0):
+        raise ValueError("start must be a non-negative integer")
+    if not (isinstance(end, int) and end >= start):
+        raise ValueError("end must be an integer no smaller than start")
+    if not (isinstance(dist, int) and dist >= 0):
+        raise ValueError("dist must be a non-negative integer")
+    if matched is None:
+        raise ValueError("matched must be supplied")
+
+
+class _PlainMatch(object):
+    """fuzzysearch.common.Match (common.py:15-32) without the attrs dependency."""
     __slots__ = ("start", "end", "dist", "matched")
 
     def __init__(self, start, end, dist, matched=None):
-        if __debug__:  # common.py:21-32
-            if not (isinstance(start, int) and start >= 0):
-                raise ValueError("start must be a non-negative integer")
-            if not (isinstance(end, int) and end >= start):
-                raise ValueError("end must be an integer no smaller than start")
-            if not (isinstance(dist, int) and dist >= 0):
-                raise ValueError("dist must be a non-negative integer")
-            if matched is None:
-                raise ValueError("matched must be supplied")
+        if __debug__:
+            _check_match_fields(start, end, dist, matched)
         object.__setattr__(self, "start", start)
         object.__setattr__(self, "end", end)
         object.__setattr__(self, "dist", dist)
@@ -77,6 +81,36 @@ class Match(object):
     def __setstate__(self, state):
         for name, value in zip(self.__slots__, state):
             object.__setattr__(self, name, value)
+
+
+def _make_attrs_match(attr):
+    """The same record as an attrs class, as in the reference (common.py:15-32: frozen, slots; eq / hash / order
+    over (start, end, dist) only), so that code written against the reference keeps working on our results:
+    ``attr.evolve(match, start=...)`` (the reference's own file search does this, __init__.py:160-162),
+    ``attr.asdict``, ``attr.fields(Match)``."""
+    def post_init(self):
+        _check_match_fields(self.start, self.end, self.dist, self.matched)
+
+    body = {
+        "start": attr.ib(type=int, eq=True, hash=True),
+        "end": attr.ib(type=int, eq=True, hash=True),
+        "dist": attr.ib(type=int, eq=True, hash=True),
+        "matched": attr.ib(eq=False, hash=False),
+    }
+    cls = type("Match", (object,), dict(body, **({"__attrs_post_init__": post_init} if __debug__ else {})))
+    cls.__doc__ = "fuzzysearch.common.Match (common.py:15-32)."
+    cls.__module__ = __name__
+    cls.__qualname__ = "Match"
+    return attr.s(frozen=True, slots=True)(cls)
+
+
+try:  # attrs is the reference's one runtime dependency (setup.py:131): present wherever the reference runs
+    import attr as _attr
+except ImportError:  # pragma: no cover
+    Match = _PlainMatch
+    Match.__name__ = Match.__qualname__ = "Match"
+else:
+    Match = _make_attrs_match(_attr)
 
 
 class LevenshteinSearchParams(object):

@@ -26,6 +26,7 @@
 #include "post_kernels.cuh"
 #include "p2p_kernels.cuh"
 #include "batch_kernels.cuh"
+#include "sym_kernels.cuh"
 #include <unordered_map>
 #include "debug_kernels.cuh"
 
@@ -635,6 +636,69 @@ extern "C" int fzb_haystack_upload(fzb_haystack *h, const uint8_t *host, uint64_
     h->coll_prob = -1.0;
     CK(cudaMemsetAsync(h->d + n, 0, h->padded_len - n, h->stream));
     return upload_bytes(h, 0, host, n);  // the caller may reuse `host` as soon as we return
+}
+
+// Wide-symbol sequences (sym_kernels.cuh): the code units travel to a device scratch chunk by chunk and
+// k_reduce_symbols writes one byte per symbol into the handle's buffer.
+extern "C" int fzb_haystack_upload_symbols(fzb_haystack *h, const void *host, uint64_t n, uint32_t width,
+                                           const uint32_t *alphabet, uint32_t n_alpha) {
+    if (!h || (!host && n) || (!alphabet && n_alpha)) return fail(FZB_E_INVALID, "bad arguments");
+    if (width != 2 && width != 4) return fail(FZB_E_INVALID, "symbol width must be 2 or 4 bytes");
+    if (n_alpha > (uint32_t)kMaxPattern) return fail(FZB_E_UNSUPPORTED, "more than %d distinct pattern symbols", kMaxPattern);
+    for (uint32_t i = 1; i < n_alpha; i++)
+        if (alphabet[i - 1] >= alphabet[i]) return fail(FZB_E_INVALID, "the alphabet must be strictly ascending");
+    if (!h->owned) return fail(FZB_E_INVALID, "upload needs an owned handle");
+    if (round_up(n, 128) + 128 > h->capacity) return fail(FZB_E_INVALID, "upload larger than the handle's capacity");
+    if (h->buf_lo != 0 || h->global_len != h->buf_len || h->own_lo != 0 || h->own_hi != h->buf_len)
+        return fail(FZB_E_INVALID, "symbol uploads replace a whole (unsharded) sequence");
+    CK(cudaSetDevice(h->device));
+    h->buf_len = h->global_len = h->own_hi = n;
+    h->padded_len = round_up(n, 128) + 128;
+    h->coll_prob = -1.0;
+    CK(cudaMemsetAsync(h->d + n, 0, h->padded_len - n, h->stream));
+    if (n == 0) {
+        CK(cudaStreamSynchronize(h->stream));
+        return FZB_OK;
+    }
+    constexpr uint64_t kChunk = 16u << 20;  // symbols per chunk (a multiple of 4: the kernel stores 32-bit words)
+    const uint64_t chunk = std::min<uint64_t>(kChunk, round_up(n, 4));
+    uint8_t *d_tmp = nullptr;   // every operation below is on h->stream: a chunk's copy is ordered behind the
+    uint32_t *d_alpha = nullptr;  // reduction of the previous chunk, so one scratch buffer is enough
+    int rc = FZB_OK;
+    auto cleanup = [&]() {
+        if (d_tmp) cudaFree(d_tmp);
+        if (d_alpha) cudaFree(d_alpha);
+    };
+#define SYMCK(call)                                                                                \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            rc = fail(FZB_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));                 \
+            cudaStreamSynchronize(h->stream);                                                      \
+            cleanup();                                                                             \
+            return rc;                                                                             \
+        }                                                                                          \
+    } while (0)
+    SYMCK(cudaMalloc(&d_alpha, 256 * sizeof(uint32_t)));
+    if (n_alpha) SYMCK(cudaMemcpyAsync(d_alpha, alphabet, n_alpha * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    SYMCK(cudaMalloc(&d_tmp, chunk * width));
+    const uint8_t *src = static_cast<const uint8_t *>(host);
+    for (uint64_t off = 0; off < n; off += chunk) {
+        const uint64_t cnt = std::min<uint64_t>(chunk, n - off);
+        SYMCK(cudaMemcpyAsync(d_tmp, src + off * width, cnt * width, cudaMemcpyHostToDevice, h->stream));
+        const int grid = (int)std::min<uint64_t>((uint64_t)h->sm_count * 8, (cnt / 4 + kSymThreads - 1) / kSymThreads + 1);
+        if (width == 4)
+            k_reduce_symbols<uint32_t><<<grid, kSymThreads, 0, h->stream>>>(reinterpret_cast<const uint32_t *>(d_tmp), cnt,
+                                                                            d_alpha, n_alpha, h->d + off);
+        else
+            k_reduce_symbols<uint16_t><<<grid, kSymThreads, 0, h->stream>>>(reinterpret_cast<const uint16_t *>(d_tmp), cnt,
+                                                                            d_alpha, n_alpha, h->d + off);
+        SYMCK(cudaGetLastError());
+    }
+    SYMCK(cudaStreamSynchronize(h->stream));
+#undef SYMCK
+    cleanup();
+    return FZB_OK;
 }
 
 extern "C" void *fzb_host_alloc(uint64_t n) {
@@ -2349,6 +2413,59 @@ extern "C" int fzb_search_exact(fzb_haystack *h, const uint8_t *pattern, uint32_
     }
     *out = res;
     return FZB_OK;
+}
+
+// search_exact(subsequence, sequence, start_index, end_index) (search_exact.py:22-56): the occurrences lying wholly
+// inside [start, end).  The window is a VIEW of the resident buffer treated like a shard of a sequence that ends
+// at `end` (anchors owned from `start`, occurrences clipped at the view's global end), so the bytes outside the
+// window are not scanned.
+extern "C" int fzb_search_exact_window(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint64_t start,
+                                       uint64_t end, uint32_t flags, fzb_result **out) {
+    if (!h || !out) return fail(FZB_E_INVALID, "NULL argument");
+    *out = nullptr;
+    if (flags & FZB_F_GLOBAL) return fail(FZB_E_INVALID, "windowed exact search is per handle");
+    if (h->buf_lo != 0 || h->global_len != h->buf_len || h->own_lo != 0 || h->own_hi != h->buf_len)
+        return fail(FZB_E_INVALID, "windowed exact search needs a whole (unsharded) sequence");
+    // clamp (search_exact.py:29-30): start into [0, n], end into [start, n]
+    start = std::min<uint64_t>(start, h->global_len);
+    end = std::max<uint64_t>(start, std::min<uint64_t>(end, h->global_len));
+    if (end - start < m) {  // no room for an occurrence (also: the empty window): nothing to launch
+        int rc0 = check_pattern(h, pattern, m, flags);
+        if (rc0 == FZB_E_INVALID) rc0 = fail(FZB_E_INVALID, "subsequence must not be empty");
+        if (rc0) return rc0;
+        fzb_result *res;
+        rc0 = make_result(out, &res);
+        if (rc0) return rc0;
+        res->unconsolidated = true;
+        res->have_fin = true;
+        *out = res;
+        return FZB_OK;
+    }
+    struct Geometry {
+        uint8_t *d;
+        uint64_t buf_len, buf_lo, own_lo, own_hi, padded_len, global_len;
+        double coll_prob;
+    } const saved{h->d, h->buf_len, h->buf_lo, h->own_lo, h->own_hi, h->padded_len, h->global_len, h->coll_prob};
+    const uint64_t vlo = start / 128 * 128;  // the view starts on a 128-byte boundary of the buffer
+    h->d = saved.d + vlo;
+    h->buf_lo = vlo;
+    h->buf_len = end - vlo;
+    h->padded_len = round_up(h->buf_len, 128) + 128;
+    h->global_len = end;
+    h->own_lo = start;
+    h->own_hi = end;
+    h->coll_prob = -1.0;
+    const int rc = fzb_search_exact(h, pattern, m, flags, out);
+    if (rc == FZB_OK && *out) (*out)->fetch_raw();  // the records leave the view's buffers before the geometry changes back
+    h->d = saved.d;
+    h->buf_len = saved.buf_len;
+    h->buf_lo = saved.buf_lo;
+    h->own_lo = saved.own_lo;
+    h->own_hi = saved.own_hi;
+    h->padded_len = saved.padded_len;
+    h->global_len = saved.global_len;
+    h->coll_prob = saved.coll_prob;
+    return rc;
 }
 
 // TMA descriptors of the buffer viewed as rows of 128 bytes (k_hamming_count): box 256 rows / 8 rows,

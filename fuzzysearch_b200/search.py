@@ -15,27 +15,64 @@ from . import _native
 from .common import FuzzySearchBase, Match, consolidate_overlapping_matches
 
 __all__ = ["DeviceSequence", "ExactSearch", "SubstitutionsOnlySearch", "LevenshteinSearch",
-           "GenericSearch", "RawMatches"]
+           "GenericSearch", "RawMatches", "search_exact"]
 
 
 class DeviceSequence(object):
     """A haystack kept resident in HBM so that several searches reuse one upload.
 
     ``find_near_matches(pattern, DeviceSequence(data), ...)`` behaves like
-    ``find_near_matches(pattern, data, ...)``."""
+    ``find_near_matches(pattern, data, ...)``.  Byte-like data and latin-1 encodable ``str`` are uploaded
+    once; a general-Unicode ``str`` (or a list / tuple of hashable items) is reduced to bytes relative to the
+    PATTERN's alphabet (see ``_reduce``), so it is uploaded again whenever a search brings a pattern with a
+    different set of symbols."""
 
     def __init__(self, data=None, device=0, _haystack=None, _host=None):
+        self._wide = None        # the original str / list / tuple when the byte form depends on the pattern
+        self._alphabet = None    # ... and the pattern alphabet the resident bytes were reduced with
+        self._is_str = False
+        self._kind = "bytes"
         if _haystack is not None:
             self.haystack, self._host = _haystack, _host
+            return
+        self._kind = _kind(data)
+        self._is_str = self._kind == "str"
+        host = _narrow(data, self._kind)
+        if host is not None:
+            self._host = host
+            self.haystack = _native.Haystack.from_host(host, device=device)
         else:
-            self._host, self._is_str = _coerce(data)
-            self.haystack = _native.Haystack.from_host(self._host, device=device)
-        self._is_str = getattr(self, "_is_str", False)
+            self._host = None
+            self._wide = data
+            self.haystack = _native.Haystack.alloc(max(len(data), 1), device=device)
 
     def __len__(self):
-        return len(self.haystack)
+        return len(self._wide) if self._wide is not None else len(self.haystack)
+
+    def _bind(self, subsequence):
+        """-> the pattern as bytes in this sequence's byte alphabet (re-reducing the sequence if needed)."""
+        return self._bind_many([subsequence])[0]
+
+    def _bind_many(self, subsequences):
+        kinds = set(_kind(p) for p in subsequences)
+        if kinds != {self._kind}:
+            raise TypeError("subsequence and sequence must both be str or both be byte-like")
+        if self._wide is None:
+            pats = [_narrow(p, self._kind) for p in subsequences]
+            if all(p is not None for p in pats):
+                return pats
+            # a pattern with symbols outside latin-1 over a latin-1 sequence: those symbols match nothing,
+            # but the search still has to run with them in place -- reduce both sides
+            self._wide = self.slice(0, len(self))
+        alphabet = _make_alphabet(subsequences, self._kind)
+        if alphabet != self._alphabet:
+            _upload_reduced(self.haystack, self._wide, self._kind, alphabet)
+            self._alphabet = alphabet
+        return [_rename(p, self._kind, alphabet) for p in subsequences]
 
     def slice(self, start, end):
+        if self._wide is not None:
+            return self._wide[start:end]
         if self._host is not None:
             b = bytes(memoryview(self._host)[start:end])
         else:
@@ -46,17 +83,88 @@ class DeviceSequence(object):
         self.haystack.close()
 
 
-def _coerce(seq):
-    """-> (uint8 view, is_str).  bytes-like stay zero-copy; latin-1 encodable str are encoded."""
+def _kind(seq):
+    """'str' | 'items' (list / tuple of hashable items) | 'bytes' (anything byte-like)"""
     if isinstance(seq, str):
-        try:
-            return np.frombuffer(seq.encode("latin-1"), dtype=np.uint8), True
-        except UnicodeEncodeError:
-            raise TypeError("str sequences must be latin-1 encodable (single-byte symbols); "
-                            "fuzzysearch_b200 has no CPU fallback for general Unicode")
+        return "str"
     if isinstance(seq, (list, tuple)):
-        raise TypeError("unsupported sequence type: %s (byte-like sequences only)" % type(seq))
-    return _native.as_u8(seq), False
+        return "items"
+    return "bytes"
+
+
+def _narrow(seq, kind):
+    """-> uint8 view when `seq` has single-byte symbols of its own (byte-like: zero-copy; latin-1 encodable
+    str: encoded), else None."""
+    if kind == "str":
+        try:
+            return np.frombuffer(seq.encode("latin-1"), dtype=np.uint8)
+        except UnicodeEncodeError:
+            return None
+    if kind == "items":
+        return None
+    return _native.as_u8(seq)
+
+
+def _coerce(seq):
+    """-> (uint8 view, is_str) for sequences with single-byte symbols."""
+    kind = _kind(seq)
+    a = _narrow(seq, kind)
+    if a is None:
+        raise TypeError("a sequence of single-byte symbols is required here (got %s)" % type(seq).__name__)
+    return a, kind == "str"
+
+
+class AlphabetTooLarge(_native.UnsupportedError):
+    pass
+
+
+def _make_alphabet(subsequences, kind):
+    """The reduction every algorithm on the path is invariant under (they only ever compare a pattern symbol
+    with a sequence symbol -- levenshtein_ngram.py:49,113, levenshtein.py:83, generic_search.py:86,
+    substitutions_only.py:93-99, search_exact.py:45-56): pattern symbol -> 1 + its rank among the distinct
+    symbols of the pattern(s), any other sequence symbol -> 0.
+
+    str: the sorted code points (the device reduces the sequence side, k_reduce_symbols);
+    items: {item: byte} (Python objects can only be numbered by the interpreter)."""
+    if kind == "str":
+        alphabet = sorted(set(ord(c) for p in subsequences for c in p))
+        if len(alphabet) > _native.FZB_MAX_PATTERN:
+            raise AlphabetTooLarge("more than %d distinct pattern symbols" % _native.FZB_MAX_PATTERN)
+        return alphabet
+    ids = {}
+    for p in subsequences:
+        for item in p:
+            if item not in ids:
+                if len(ids) == _native.FZB_MAX_PATTERN:
+                    raise AlphabetTooLarge("more than %d distinct pattern symbols" % _native.FZB_MAX_PATTERN)
+                ids[item] = len(ids) + 1
+    return ids
+
+
+def _rename(subsequence, kind, alphabet):
+    if kind == "str":
+        rank = {c: i + 1 for i, c in enumerate(alphabet)}
+        return np.fromiter((rank[ord(c)] for c in subsequence), dtype=np.uint8, count=len(subsequence))
+    return np.fromiter((alphabet[x] for x in subsequence), dtype=np.uint8, count=len(subsequence))
+
+
+def _code_units(text):
+    """str -> its code units as a numpy array: UCS-2 (uint16) when every character is in the BMP, else
+    UTF-32 (uint32).  Lone surrogates are symbols like any other ('surrogatepass')."""
+    if not text or max(text) < "\U00010000":
+        return np.frombuffer(text.encode("utf-16-le", "surrogatepass"), dtype=np.uint16)
+    return np.frombuffer(text.encode("utf-32-le", "surrogatepass"), dtype=np.uint32)
+
+
+def _upload_reduced(hay, sequence, kind, alphabet):
+    if kind == "str":
+        hay.upload_symbols(_code_units(sequence), alphabet)
+    else:
+        get = alphabet.get
+        try:
+            hay.upload(np.fromiter((get(x, 0) for x in sequence), dtype=np.uint8, count=len(sequence)))
+        except TypeError:
+            raise TypeError("sequence items must be hashable")
 
 
 class RawMatches(Sequence):
@@ -110,20 +218,28 @@ class RawMatches(Sequence):
 
 def _prepare(subsequence, sequence):
     """-> (pattern u8, haystack handle, slicer, owns_handle)"""
-    pat, pat_is_str = _coerce(subsequence)
-    if isinstance(sequence, DeviceSequence):
-        return pat, sequence.haystack, sequence.slice, False
-    host, is_str = _coerce(sequence)
-    if is_str != pat_is_str:
-        raise TypeError("subsequence and sequence must both be str or both be byte-like")
-    hay = _workspace(host.size)
-    hay.upload(host)
-    if is_str:
-        text = sequence
+    pats, hay, slicer = _prepare_many([subsequence], sequence)
+    return pats[0], hay, slicer, False
 
-        def slicer(s, e):
-            return text[s:e]
-    elif isinstance(sequence, (bytes, bytearray)):
+
+def _prepare_many(subsequences, sequence):
+    """-> (patterns as u8 arrays, haystack handle holding the sequence, slicer)"""
+    if isinstance(sequence, DeviceSequence):
+        return sequence._bind_many(subsequences), sequence.haystack, sequence.slice
+    kind = _kind(sequence)
+    if any(_kind(p) != kind for p in subsequences):
+        raise TypeError("subsequence and sequence must both be str or both be byte-like")
+    pats = [_narrow(p, kind) for p in subsequences]
+    host = _narrow(sequence, kind) if all(p is not None for p in pats) else None
+    if host is not None:
+        hay = _workspace(host.size)
+        hay.upload(host)
+    else:  # wide symbols on either side: reduce both to the patterns' alphabet
+        alphabet = _make_alphabet(subsequences, kind)
+        pats = [_rename(p, kind, alphabet) for p in subsequences]
+        hay = _workspace(len(sequence))
+        _upload_reduced(hay, sequence, kind, alphabet)
+    if kind != "bytes" or isinstance(sequence, (bytes, bytearray)):
         def slicer(s, e):
             return sequence[s:e]
     else:
@@ -131,7 +247,7 @@ def _prepare(subsequence, sequence):
 
         def slicer(s, e):
             return bytes(mv[s:e])
-    return pat, hay, slicer, False
+    return pats, hay, slicer
 
 
 _WORKSPACE = {}
@@ -182,6 +298,40 @@ def _run(subsequence, sequence, call, consolidated):
     finally:
         if shared:
             _WORKSPACE_LOCK.release()
+
+
+def search_exact(subsequence, sequence, start_index=0, end_index=None):
+    """fuzzysearch.search_exact.search_exact (search_exact.py:22-56): the start indexes of the (overlapping)
+    occurrences of `subsequence` lying wholly inside ``sequence[start_index:end_index]``, ascending.
+
+    Only the window travels to / is scanned on the device: a host sequence is sliced before the upload, a
+    ``DeviceSequence`` is searched through a view of its resident buffer (fzb_search_exact_window)."""
+    if len(subsequence) == 0:
+        raise ValueError("subsequence must not be empty")
+    n = len(sequence)
+    if end_index is None:
+        end_index = n
+    start_index = max(0, min(start_index, n))               # clamp(...) search_exact.py:29-30
+    end_index = max(start_index, min(end_index, n))
+    if isinstance(sequence, DeviceSequence):
+        pat = sequence._bind(subsequence)
+        res = sequence.haystack.search_exact(pat, start=start_index, end=end_index)
+        starts = res.arrays(_native.RAW)[0]  # positions are already those of the whole sequence
+        res.close()
+        return starts.tolist()
+    else:
+        if _kind(sequence) == "bytes" and not isinstance(sequence, (bytes, bytearray)):
+            window = memoryview(_native.as_u8(sequence))[start_index:end_index]
+        elif start_index == 0 and end_index == n:
+            window = sequence
+        else:
+            window = sequence[start_index:end_index]
+        with _WORKSPACE_LOCK:
+            pat, hay, _, _ = _prepare(subsequence, window)
+            res = hay.search_exact(pat)
+            starts = res.arrays(_native.RAW)[0]
+            res.close()
+        return (starts + start_index).tolist() if start_index else starts.tolist()
 
 
 class ExactSearch(FuzzySearchBase):

@@ -149,6 +149,17 @@ int fzb_haystack_p2p_enabled(const fzb_haystack *h);
  * reusable chunk buffer in _search_binary_file (__init__.py:141-171). */
 int fzb_haystack_upload(fzb_haystack *h, const uint8_t *host, uint64_t n);
 
+/* The same for a sequence of WIDE symbols -- a general-Unicode str as UTF-32 (width 4) or UCS-2 (width 2)
+ * code units, or any sequence whose items the caller has numbered -- which the reference searches through
+ * str.find / list.index (search_exact.py:11-19,32-51) and per-item `!=` (levenshtein_ngram.py:49,113).
+ * Every algorithm on the path only ever compares a pattern symbol with a sequence symbol, so the sequence is
+ * reduced ON THE DEVICE to one byte per symbol: `alphabet` = the pattern's distinct symbols, strictly
+ * ascending, n_alpha <= FZB_MAX_PATTERN; symbol alphabet[i] becomes byte i+1 and every other symbol byte 0.
+ * Search it with the pattern renamed the same way (pattern byte = 1 + rank of the symbol in `alphabet`);
+ * positions in the results are symbol indexes.  The handle must be a whole (unsharded) sequence. */
+int fzb_haystack_upload_symbols(fzb_haystack *h, const void *host, uint64_t n, uint32_t width,
+                                const uint32_t *alphabet, uint32_t n_alpha);
+
 /* Page-locked host memory for fast host<->device copies (cudaHostAlloc); NULL on failure. */
 void *fzb_host_alloc(uint64_t n);
 void fzb_host_free(void *p);
@@ -192,9 +203,10 @@ int fzb_search_generic(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint
  * Batch of Levenshtein searches over ONE resident haystack (BASELINE.json configs[4]): `count` patterns
  * concatenated in `patterns` (pattern i = patterns[offsets[i] : offsets[i+1]]), each with its own
  * max_l_dist[i].  out[i] receives an ordinary fzb_result for pattern i (the caller destroys each).
- * Round 1: the patterns are searched one after another on the handle's stream (the haystack is read
- * once per pattern); the single-pass multi-pattern filter is described in DESIGN.md section 8.
- * `total` (optional) sums the statistics.  On error nothing is returned.
+ * The patterns share passes over the haystack: ONE scan for every pattern the
+ * q-sample lemma covers, ONE for the other n-gram-route patterns, ONE per 64 LP-route patterns; patterns
+ * longer than 64 bytes are searched one by one.  Each out[i] is exactly what fzb_search_levenshtein would
+ * return for pattern i.  `total` (optional) sums the statistics.  On error nothing is returned.
  */
 int fzb_search_levenshtein_batch(fzb_haystack *h, const uint8_t *patterns, const uint32_t *offsets,
                                  const uint32_t *max_l_dist, uint32_t count, uint32_t flags,
@@ -203,6 +215,11 @@ int fzb_search_levenshtein_batch(fzb_haystack *h, const uint8_t *patterns, const
 /* ExactSearch.search (search_exact.py:80-85): all (overlapping) occurrences. FINAL == RAW. */
 int fzb_search_exact(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint32_t flags,
                      fzb_result **out);
+/* search_exact(subsequence, sequence, start_index, end_index) (search_exact.py:22-56; _common.c:5-112): the
+ * occurrences lying wholly inside [start, end), both clamped as the reference clamps them (:29-30).  Only
+ * the window is scanned.  Whole-sequence handles only. */
+int fzb_search_exact_window(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint64_t start, uint64_t end,
+                            uint32_t flags, fzb_result **out);
 
 /*
  * One-shot convenience with HOST buffers (what find_near_matches() does): upload, dispatch like

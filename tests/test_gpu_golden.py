@@ -4,7 +4,7 @@ replayed on the device; results must be bit-exact (raw streams) / tie-aware equa
 import pytest
 
 import oracle
-from fuzzysearch_b200 import _native, find_near_matches
+from fuzzysearch_b200 import _native, find_near_matches, search_exact
 from parity import assert_final_parity, load_golden, tup
 
 pytestmark = pytest.mark.gpu
@@ -18,6 +18,7 @@ def _b(h):
 
 def _replay(records, cuda_device):
     counts = {}
+    windowed = 0
     for rec in records:
         fn, a = rec["fn"], rec["args"]
         ctx = "%s%r" % (fn, a)
@@ -76,9 +77,12 @@ def _replay(records, cuda_device):
                 assert r.triples(F.RAW) == tup(exp), ctx
                 r.close()
             elif fn == "search_exact":
-                if a[2] != 0 or a[3] is not None:
-                    continue
-                r = hs.search_exact(pat)
+                if a[2] == 0 and a[3] is None:
+                    r = hs.search_exact(pat)
+                else:  # the window form (search_exact.py:22-56): a view of the resident buffer
+                    r = hs.search_exact(pat, start=a[2], end=a[3])
+                    assert search_exact(pat, hay, a[2], a[3]) == list(exp), ctx  # host sequence: sliced first
+                    windowed += 1
                 assert [s for s, _, _ in r.triples(F.RAW)] == list(exp), ctx
                 r.close()
             else:
@@ -86,6 +90,7 @@ def _replay(records, cuda_device):
             counts[fn] = counts.get(fn, 0) + 1
         finally:
             hs.close()
+    counts["search_exact_windowed"] = windowed
     return counts
 
 
@@ -94,6 +99,7 @@ def test_gpu_replays_reference_suite_calls(cuda_device):
     for fn in ("lev_ngrams_raw", "lev_lp_raw", "generic_lp_raw", "generic_ngrams_raw", "subs_lp",
                "subs_ngrams", "search_exact", "find_near_matches"):
         assert counts.get(fn, 0) > 0, fn
+    assert counts["search_exact_windowed"] > 300
 
 
 def test_gpu_replays_reference_fuzz(cuda_device):

@@ -1,0 +1,173 @@
+"""GPU: wide-symbol sequences (general-Unicode str, list / tuple of hashable items) through the public API,
+against outputs of the REAL reference (tests/golden/ref_symbols.json) -- SURVEY 8(f) rank 2.
+
+The device reduces the code units of the sequence to one byte per symbol (k_reduce_symbols) and the byte
+kernels do the rest; the final lists must be the reference's (tie-aware), ``matched`` must be the slice of the
+ORIGINAL sequence."""
+import io
+
+import numpy as np
+import pytest
+
+import oracle
+from fuzzysearch_b200 import (DeviceSequence, _native, find_near_matches, find_near_matches_batch,
+                              find_near_matches_in_file, has_near_match, search_exact)
+from parity import assert_final_parity, load_golden, tup
+from symbols import decode_items, reduce_to_bytes
+
+pytestmark = pytest.mark.gpu
+F = _native
+
+
+def _t(ms):
+    return [(m.start, m.end, m.dist) for m in ms]
+
+
+def _check_fnm(rec, ours, ctx):
+    pat_b, hay_b = reduce_to_bytes(rec["pattern"], rec["sequence"])
+    a = rec["args"][:4]
+    subs, ins, dels, l = oracle.normalize_params(*a)
+    if l == 0 or (ins == 0 and dels == 0):
+        assert ours == tup(rec["result"]), ctx
+    else:
+        _, raw = oracle.find_near_matches(pat_b, hay_b, *a, return_raw=True)
+        assert_final_parity(ours, rec["result"], raw, ctx)
+
+
+def _check_file(rec, ours, ctx):
+    """The text-file loop (__init__.py:174-200) re-run with the byte oracle as the per-chunk search: its raw
+    stream (chunk-local window clipping included) explains the reference's final list and ours."""
+    from fuzzysearch_b200 import LevenshteinSearchParams, choose_search_class
+    pat_b, hay_b = reduce_to_bytes(rec["pattern"], rec["sequence"])
+    a, chunk_size = rec["args"][:4], rec["args"][4]
+    params = LevenshteinSearchParams(*a)
+    cls = choose_search_class(params)
+    keep = len(pat_b) - 1 + cls.extra_items_for_chunked_search(pat_b, params)
+    raw, f = [], io.BytesIO(hay_b)
+    chunk, offset = f.read(chunk_size), 0
+    while chunk:
+        _, r = oracle.find_near_matches(pat_b, chunk, *a, return_raw=True)
+        raw += [(s + offset, e + offset, d) for s, e, d in tup(r)]
+        n_keep = min(keep, len(chunk))
+        offset += len(chunk) - n_keep
+        if n_keep:
+            chunk = chunk[-n_keep:] + f.read(chunk_size)
+            if len(chunk) == n_keep:
+                break
+        else:
+            chunk = f.read(chunk_size)
+    subs, ins, dels, l = params.unpacked
+    if l == 0 or (ins == 0 and dels == 0):
+        assert ours == tup(rec["result"]) == raw, ctx  # unconsolidated classes: the concatenated chunk lists
+    else:
+        assert_final_parity(ours, rec["result"], raw, ctx)
+
+
+def test_reference_results_on_wide_symbols(cuda_device):
+    counts = {}
+    for rec in load_golden("ref_symbols.json"):
+        kind = rec["kind"]
+        pat, seq = decode_items(rec["pattern"], kind), decode_items(rec["sequence"], kind)
+        ctx = "%s %s %r %r" % (rec["fn"], kind, rec["pattern"], rec["args"])
+        if rec["fn"] == "search_exact":
+            assert search_exact(pat, seq, *rec["args"]) == list(rec["result"]), ctx
+        elif rec["fn"] == "find_near_matches_in_file":
+            ms = find_near_matches_in_file(pat, io.StringIO(seq), *rec["args"][:4], _chunk_size=rec["args"][4])
+            _check_file(rec, _t(ms), ctx)
+        else:
+            ms = find_near_matches(pat, seq, *rec["args"])
+            _check_fnm(rec, _t(ms), ctx)
+            for m in ms:  # matched: the slice of the ORIGINAL sequence, same type
+                assert m.matched == seq[m.start:m.end] and type(m.matched) is type(seq[0:0]), ctx
+        counts[(rec["fn"], kind)] = counts.get((rec["fn"], kind), 0) + 1
+    assert counts[("find_near_matches", "str")] > 800 and counts[("find_near_matches", "list")] > 100
+    assert counts[("search_exact", "str")] > 100 and counts[("find_near_matches_in_file", "str")] > 50
+
+
+@pytest.mark.parametrize("dtype,n", [(np.uint16, 1000), (np.uint32, 1003), (np.uint32, (16 << 20) + 5),
+                                     (np.uint16, (16 << 20) * 2 + 2), (np.uint32, 0), (np.uint16, 3)])
+def test_device_reduction_of_code_units(cuda_device, dtype, n):
+    """k_reduce_symbols against numpy, across chunk boundaries, for both unit widths."""
+    rng = np.random.default_rng(n + 1)
+    hi = 0xFFFF if dtype == np.uint16 else 0x10FFFF
+    alphabet = np.unique(rng.integers(0, hi + 1, size=200, dtype=np.uint32))
+    alphabet = np.unique(np.concatenate([alphabet, np.array([0, hi], dtype=np.uint32)]))[:255]
+    units = rng.integers(0, hi + 1, size=n, dtype=np.uint32)
+    pick = rng.random(n) < 0.6   # most units come from the alphabet, incl. its first and last entries
+    units[pick] = alphabet[rng.integers(0, alphabet.size, size=int(pick.sum()))]
+    units = units.astype(dtype)
+    hs = F.Haystack.alloc(max(n, 1))
+    try:
+        hs.upload_symbols(units, alphabet)
+        assert len(hs) == n
+        got = np.frombuffer(hs.read(0, n), dtype=np.uint8) if n else np.zeros(0, np.uint8)
+        pos = np.searchsorted(alphabet, units.astype(np.uint32))
+        pos_c = np.minimum(pos, alphabet.size - 1)
+        exp = np.where(alphabet[pos_c] == units, pos_c + 1, 0).astype(np.uint8)
+        assert np.array_equal(got, exp)
+        if n:  # an empty alphabet: everything is "other"
+            hs.upload_symbols(units[:1000], np.zeros(0, np.uint32))
+            assert not np.frombuffer(hs.read(0, min(n, 1000)), dtype=np.uint8).any()
+    finally:
+        hs.close()
+
+
+def test_resident_wide_sequence_and_batches(cuda_device):
+    rng = np.random.default_rng(5)
+    letters = [chr(c) for c in range(0x430, 0x450)] + ["\U0001F600", "e", "中"]
+    text = "".join(letters[i] for i in rng.integers(0, len(letters), size=200000))
+    pats = ["".join(letters[i] for i in rng.integers(0, len(letters), size=m)) for m in (9, 12, 20, 33)]
+    for i, p in enumerate(pats):  # plant each pattern twice, once with an edit
+        at = 1000 + 40000 * i
+        text = text[:at] + p + text[at + len(p):at + 5000] + p[:3] + p[4:] + text[at + 5000 + len(p) - 1:]
+    ds = DeviceSequence(text)
+    try:
+        assert len(ds) == len(text)
+        for p in pats + [pats[0]]:  # a new alphabet per pattern: the sequence is reduced again each time
+            for k in (0, 1, 2):
+                got = find_near_matches(p, ds, max_l_dist=k)
+                assert _t(got) == _t(find_near_matches(p, text, max_l_dist=k))
+                pb, hb = reduce_to_bytes(p, text)
+                assert _t(got) == oracle.find_near_matches(pb, hb, max_l_dist=k)
+                assert all(m.matched == text[m.start:m.end] for m in got) and len(got) >= (1 if k == 0 else 2)
+            assert has_near_match(p, ds, max_l_dist=1) and has_near_match(p, text, max_l_dist=1)
+            assert search_exact(p[:5], ds, 10, len(text) - 10) == search_exact(p[:5], text, 10, len(text) - 10)
+        assert not has_near_match("中" * 12, ds, max_l_dist=2)
+        batch = find_near_matches_batch(pats, ds, [1, 2, 2, 3])
+        assert [_t(b) for b in batch] == [_t(find_near_matches(p, text, max_l_dist=k))
+                                          for p, k in zip(pats, [1, 2, 2, 3])]
+        assert [_t(b) for b in find_near_matches_batch(pats, text, 1)] == \
+            [_t(find_near_matches(p, text, max_l_dist=1)) for p in pats]
+        # a latin-1 resident sequence searched with a pattern holding a symbol outside latin-1
+        ds2 = DeviceSequence("abcabcabXcabc")
+        assert _t(find_near_matches("abЖc", ds2, max_l_dist=1)) == \
+            oracle.find_near_matches(*reduce_to_bytes("abЖc", "abcabcabXcabc"), max_l_dist=1)
+        assert _t(find_near_matches("abc", ds2, max_l_dist=0)) == [(0, 3, 0), (3, 6, 0), (10, 13, 0)]
+        ds2.close()
+    finally:
+        ds.close()
+    # more than 255 distinct symbols over the patterns of a batch: one by one, same results
+    many = ["".join(chr(0x1000 + 40 * j + i) for i in range(40)) for j in range(8)]
+    seq = "".join(many) * 3
+    got = find_near_matches_batch(many, seq, 2)
+    assert [_t(g) for g in got] == [_t(find_near_matches(p, seq, max_l_dist=2)) for p in many]
+    assert all(len(g) == 3 for g in got)
+    with pytest.raises(F.UnsupportedError):
+        find_near_matches("".join(chr(0x1000 + i) for i in range(256)), seq, max_l_dist=2)
+
+
+def test_items_resident_and_mixed_types(cuda_device):
+    seq = [("t", i % 7) for i in range(5000)] + ["x", 3.5, None, "x", 3.5, None] + list(range(100))
+    pat = ["x", 3.5, None, "x", 3.5]
+    got = find_near_matches(pat, seq, max_l_dist=1)
+    pb, hb = reduce_to_bytes(pat, seq)
+    assert _t(got) == oracle.find_near_matches(pb, hb, max_l_dist=1) and got and got[0].matched == seq[got[0].start:got[0].end]
+    ds = DeviceSequence(tuple(seq))
+    assert _t(find_near_matches(tuple(pat), ds, max_substitutions=1, max_insertions=0, max_deletions=0)) == \
+        oracle.find_near_matches(pb, hb, 1, 0, 0)
+    assert isinstance(find_near_matches(tuple(pat), ds, max_l_dist=0)[0].matched, tuple)
+    ds.close()
+    with pytest.raises(TypeError):
+        find_near_matches("abc", b"abcabc", max_l_dist=1)
+    with pytest.raises(TypeError):
+        find_near_matches(["a"], "abc", max_l_dist=1)

@@ -50,8 +50,25 @@ def test_match_semantics():
     for bad in [(-1, 2, 0), (3, 2, 0), (1, 2, -1)]:
         with pytest.raises(ValueError):
             Match(*bad, matched=b"")
-    with pytest.raises(ValueError):
+    with pytest.raises(TypeError):  # `matched` has no default in the reference (common.py:20)
         Match(1, 2, 0)
+    with pytest.raises(ValueError):
+        Match(1, 2, 0, matched=None)
+    # the reference's Match is an attrs class and its own file search relies on it (__init__.py:160-162)
+    import attr
+    import pickle
+    from fuzzysearch_b200.common import _PlainMatch
+    assert attr.evolve(a, start=0, end=2) == Match(0, 2, 0, b"xy") and attr.evolve(a, start=0).matched == b"xy"
+    assert attr.asdict(a) == {"start": 1, "end": 3, "dist": 0, "matched": b"xy"}
+    assert [f.name for f in attr.fields(Match)] == ["start", "end", "dist", "matched"]
+    assert pickle.loads(pickle.dumps(a)) == a and pickle.loads(pickle.dumps(a)).matched == b"xy"
+    # the attrs-free twin (used only where attrs is not installed) behaves the same
+    pa, pb = _PlainMatch(1, 3, 0, matched=b"xy"), _PlainMatch(1, 3, 0, matched=b"zz")
+    assert pa == pb and hash(pa) == hash(pb) and repr(pa) == repr(a) and pa < _PlainMatch(1, 3, 1, b"")
+    with pytest.raises(AttributeError):
+        pa.start = 4
+    with pytest.raises(ValueError):
+        _PlainMatch(1, 2, 0)
 
 
 def test_params_normalisation_matches_oracle_restatement():
@@ -101,10 +118,15 @@ def test_no_gpu_fails_loudly():
 def test_argument_errors_before_any_device_work():
     with pytest.raises(ValueError):
         find_near_matches(b"", b"TEXT", max_l_dist=1)
-    with pytest.raises(TypeError):
-        find_near_matches(["a"], ["a", "b"], max_l_dist=1)
-    with pytest.raises(TypeError):
+    with pytest.raises(TypeError):  # str / byte-like / item sequences do not mix (str.find(bytes) in the reference)
         find_near_matches(b"a", "aሴ", max_l_dist=1)
+    with pytest.raises(TypeError):
+        find_near_matches(["a"], "ab", max_l_dist=1)
+    with pytest.raises(TypeError):  # items are numbered through a dict: they must be hashable
+        find_near_matches([[1]], [[1], [2]], max_l_dist=1)
+    from fuzzysearch_b200 import search_exact
+    with pytest.raises(ValueError):
+        search_exact(b"", b"abc")
 
 
 def _random_raw(rng, n, span, with_empty):
