@@ -2497,6 +2497,14 @@ static int make_row_maps(fzb_haystack *h, CUtensorMap *map256, CUtensorMap *map8
     return FZB_OK;
 }
 
+// Counter layout of k_hamming_count (ham_recur.h).  FZB_HAM_COUNTERS=nibble|sliced overrides the default.
+static bool ham_sliced_counters() {  // (read per search: a probe can flip it between two searches)
+    const char *e = getenv("FZB_HAM_COUNTERS");
+    if (e && !strcmp(e, "nibble")) return false;
+    if (e && !strcmp(e, "sliced")) return true;
+    return false;
+}
+
 extern "C" int fzb_search_hamming(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint32_t k,
                                   uint32_t flags, fzb_result **out) {
     fzb_result *res;
@@ -2522,8 +2530,10 @@ extern "C" int fzb_search_hamming(fzb_haystack *h, const uint8_t *pattern, uint3
                 hp.nrows = (int64_t)(round_up(h->buf_len, kHcRowBytes) / kHcRowBytes);
                 int r3 = make_row_maps(h, &map256, &map8);
                 if (r3) return r3;
-                CK(cudaFuncSetAttribute(k_hamming_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHcSmem));
+                CK(cudaFuncSetAttribute(k_hamming_count<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHcSmem));
+                CK(cudaFuncSetAttribute(k_hamming_count<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHcSmem));
             }
+            const bool sliced = ham_sliced_counters();
             bool bitmap_mode = false;
             PostPlan plan{2, (flags & FZB_F_GLOBAL) != 0};  // FINAL == RAW in (start, end, dist) order, ordered by k_post
         retry_bitmap:
@@ -2531,7 +2541,10 @@ extern "C" int fzb_search_hamming(fzb_haystack *h, const uint8_t *pattern, uint3
                 if (counting) {
                     const int64_t ntiles = (hp.nrows + kHcThreads - 1) / kHcThreads;
                     const int grid = (int)std::min<int64_t>(ntiles, (int64_t)h->sm_count * 2);
-                    k_hamming_count<<<grid, kHcThreads, kHcSmem, h->stream>>>(p, hp, map256, map8);
+                    if (sliced)
+                        k_hamming_count<1><<<grid, kHcThreads, kHcSmem, h->stream>>>(p, hp, map256, map8);
+                    else
+                        k_hamming_count<0><<<grid, kHcThreads, kHcSmem, h->stream>>>(p, hp, map256, map8);
                     CK(cudaEventRecord(h->ev[1], h->stream));
                     h->ev1_recorded = true;
                     // one verify launch: the granule work list -- or, after it overflowed, the whole bitmap

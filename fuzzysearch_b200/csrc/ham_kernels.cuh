@@ -22,6 +22,7 @@
 #pragma once
 #include <cuda.h>
 
+#include "ham_recur.h"
 #include "kernels.cuh"
 
 namespace fzb {
@@ -84,13 +85,9 @@ constexpr int kHcHaloRows = 8;                // one swizzle atom; only its last
 constexpr int kHcTileRows = kHcHaloRows + kHcThreads;            // 264
 constexpr int kHcStageBytes = kHcTileRows * kHcRowBytes;         // 33792 (multiple of 1024)
 constexpr int kHcStages = 2;
-constexpr int kHcBuckets = 256;
-constexpr int kHcTableBytes = kHcBuckets * 8 * 16;               // 32 KiB
+constexpr int kHcTableBytes = kHcBuckets * 8 * 16;               // 32 KiB (nibble fields: 8 replicas x 16 B;
+                                                                 //         bit-sliced: 32 replicas x 4 B)
 constexpr size_t kHcSmem = (size_t)kHcStages * kHcStageBytes + kHcTableBytes + 64;
-constexpr uint32_t kHcHashMul = 0x9E3779B1u;
-
-__device__ __forceinline__ uint32_t hc_bucket(uint32_t w) { return (w * kHcHashMul) >> 24; }
-
 struct HamCountParams {
     int Wc;        // counted words per occurrence (<= 8)
     int bias;      // 8 - (Wc - k)
@@ -109,38 +106,55 @@ __device__ __forceinline__ uint32_t hc_chunk(uint32_t stage, int r, int j) {
     return stage + r * kHcRowBytes + ((j ^ (r & 7)) << 4);
 }
 
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
+    uint32_t r;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(saddr));
+    return r;
+}
+
+// SLICED = 0: nibble fields, 16-byte table entries (4 wavefronts per lookup);  SLICED = 1: bit-sliced counters,
+// 4-byte table entries (1 wavefront per lookup, more ALU work per word) -- see ham_recur.h.
+template <int SLICED>
 __global__ void __launch_bounds__(kHcThreads, 2)
 k_hamming_count(const ScanParams p, const HamCountParams hp, const __grid_constant__ CUtensorMap map256,
                 const __grid_constant__ CUtensorMap map8) {
     extern __shared__ __align__(1024) uint8_t hc_smem[];  // SWIZZLE_128B tiles need 1024-byte alignment
     uint8_t *base = hc_smem;
     uint4 *table = reinterpret_cast<uint4 *>(base + kHcStages * kHcStageBytes);
+    uint32_t *table32 = reinterpret_cast<uint32_t *>(table);
     uint64_t *full = reinterpret_cast<uint64_t *>(base + kHcStages * kHcStageBytes + kHcTableBytes);
     const int tid = threadIdx.x, lane = tid & 31;
     const int Wc = hp.Wc;
 
-    // table: every bucket starts with the bias in field 0 of all four classes
-    for (int i = tid; i < kHcBuckets * 8; i += kHcThreads)
-        table[i] = make_uint4((uint32_t)hp.bias, (uint32_t)hp.bias, (uint32_t)hp.bias, (uint32_t)hp.bias);
+    if (SLICED) {  // bucket b, replica r (= lane): word b * 32 + r; bit 8 * o0 + i <-> w == P[o0+4i : o0+4i+4)
+        for (int i = tid; i < kHcBuckets * 32; i += kHcThreads) table32[i] = 0u;
+    } else {       // every bucket starts with the bias in field 0 of all four classes
+        for (int i = tid; i < kHcBuckets * 8; i += kHcThreads)
+            table[i] = make_uint4((uint32_t)hp.bias, (uint32_t)hp.bias, (uint32_t)hp.bias, (uint32_t)hp.bias);
+    }
     if (tid == 0) {
         for (int s = 0; s < kHcStages; s++) mbar_init(&full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (tid < 8) {  // replica `tid` of the table: add the pattern's 4-grams (serial per replica: no races)
+    if (tid < (SLICED ? 32 : 8)) {  // replica `tid` of the table: add the pattern's 4-grams (serial per replica: no races)
         for (int o0 = 0; o0 < 4; o0++)
-            for (int i = 0; i < Wc; i++) {  // each (class, field) pair exactly once -> plain add
-                const int o = o0 + 4 * i;
-                const uint32_t w = (uint32_t)p.P[o] | ((uint32_t)p.P[o + 1] << 8) | ((uint32_t)p.P[o + 2] << 16) |
-                                   ((uint32_t)p.P[o + 3] << 24);
-                uint32_t *e = reinterpret_cast<uint32_t *>(&table[hc_bucket(w) * 8 + tid]);
-                e[o0] += 1u << (4 * i);
+            for (int i = 0; i < Wc; i++) {  // each (class, field) pair exactly once
+                const uint32_t w = hc_gram(p.P, o0 + 4 * i);
+                if (SLICED) {
+                    table32[hc_bucket(w) * 32 + tid] |= 1u << (8 * o0 + i);
+                } else {
+                    uint32_t *e = reinterpret_cast<uint32_t *>(&table[hc_bucket(w) * 8 + tid]);
+                    e[o0] += 1u << (4 * i);
+                }
             }
     }
     __syncthreads();
 
     const int64_t ntiles = (hp.nrows + kHcThreads - 1) / kHcThreads;
     const uint32_t flag_bit = 8u << (4 * (Wc - 1));
+    const uint32_t B0 = (hp.bias & 1) ? 0x01010101u : 0u, B1 = (hp.bias & 2) ? 0x01010101u : 0u,
+                   B2 = (hp.bias & 4) ? 0x01010101u : 0u;
     auto issue = [&](int64_t tile, int s) {  // one elected thread: 264 rows = 8 (halo atom) + 256
         const int r0 = (int)(tile * kHcThreads) - kHcHaloRows;
         uint8_t *dst = base + s * kHcStageBytes;
@@ -153,7 +167,8 @@ k_hamming_count(const ScanParams p, const HamCountParams hp, const __grid_consta
         if (tile < ntiles) issue(tile, 0);
         if (tile + gridDim.x < ntiles) issue(tile + gridDim.x, 1);
     }
-    const uint32_t my_table = smem_u32(table) + ((lane & 7) << 4);  // my replica: bank group = lane % 8
+    // my replica of the table: bank group = lane % 8 (16-byte entries) / bank = lane (4-byte entries)
+    const uint32_t my_table = smem_u32(table) + (SLICED ? (lane << 2) : ((lane & 7) << 4));
     const uint32_t stage0 = smem_u32(base);
     uint32_t phases = 0;  // bit s = parity to wait for on stage s
     for (int it = 0; tile < ntiles; tile += gridDim.x, it++) {
@@ -162,7 +177,30 @@ k_hamming_count(const ScanParams p, const HamCountParams hp, const __grid_consta
         phases ^= 1u << s;
         const uint32_t st = stage0 + s * kHcStageBytes;
         const int r = kHcHaloRows + tid;
-        uint32_t S0 = 0, S1 = 0, S2 = 0, S3 = 0, acc = 0;
+        bool flagged;
+        if (SLICED) {
+            HamSliced cnt{0u, 0u, 0u};
+            uint32_t acc = 0;
+#define HS_STEP(WORD, track)                                                                 \
+    {                                                                                        \
+        const uint32_t M = lds32(my_table + (hc_bucket(WORD) << 7));                         \
+        const uint32_t c = ham_sliced_step(cnt, M, B0, B1, B2);                              \
+        if (track) acc |= c;                                                                 \
+    }
+            {  // warm-up: the last 7 words of the previous row (their candidates belong to that row's thread)
+                const uint4 a = lds128(hc_chunk(st, r - 1, 6)), b = lds128(hc_chunk(st, r - 1, 7));
+                HS_STEP(a.y, false) HS_STEP(a.z, false) HS_STEP(a.w, false)
+                HS_STEP(b.x, false) HS_STEP(b.y, false) HS_STEP(b.z, false) HS_STEP(b.w, false)
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const uint4 d = lds128(hc_chunk(st, r, j));
+                HS_STEP(d.x, true) HS_STEP(d.y, true) HS_STEP(d.z, true) HS_STEP(d.w, true)
+            }
+#undef HS_STEP
+            flagged = acc != 0;
+        } else {
+            uint32_t S0 = 0, S1 = 0, S2 = 0, S3 = 0, acc = 0;
 #define HC_STEP(WORD, track)                                               \
     {                                                                      \
         const uint4 T = lds128(my_table + (hc_bucket(WORD) << 7));         \
@@ -172,22 +210,27 @@ k_hamming_count(const ScanParams p, const HamCountParams hp, const __grid_consta
         S3 = S3 * 16u + T.w;                                               \
         if (track) acc |= S0 | S1 | S2 | S3;                               \
     }
-        {  // warm-up: the last 7 words of the previous row (no flags: they belong to that row's thread)
-            const uint4 a = lds128(hc_chunk(st, r - 1, 6)), b = lds128(hc_chunk(st, r - 1, 7));
-            HC_STEP(a.y, false) HC_STEP(a.z, false) HC_STEP(a.w, false)
-            HC_STEP(b.x, false) HC_STEP(b.y, false) HC_STEP(b.z, false) HC_STEP(b.w, false)
-        }
+            {  // warm-up: the last 7 words of the previous row (no flags: they belong to that row's thread)
+                const uint4 a = lds128(hc_chunk(st, r - 1, 6)), b = lds128(hc_chunk(st, r - 1, 7));
+                HC_STEP(a.y, false) HC_STEP(a.z, false) HC_STEP(a.w, false)
+                HC_STEP(b.x, false) HC_STEP(b.y, false) HC_STEP(b.z, false) HC_STEP(b.w, false)
+            }
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const uint4 d = lds128(hc_chunk(st, r, j));
-            HC_STEP(d.x, true) HC_STEP(d.y, true) HC_STEP(d.z, true) HC_STEP(d.w, true)
-        }
+            for (int j = 0; j < 8; j++) {
+                const uint4 d = lds128(hc_chunk(st, r, j));
+                HC_STEP(d.x, true) HC_STEP(d.y, true) HC_STEP(d.z, true) HC_STEP(d.w, true)
+            }
 #undef HC_STEP
-        if (acc & flag_bit) {
-            // some start whose last counted word lies in my row passed the filter (rare: true
-            // near-matches): mark its granules; k_verify_ham re-checks them exactly
+            flagged = (acc & flag_bit) != 0;
+        }
+        if (flagged) {
+            // some start passed the filter at a word of my row (rare: true near-matches): mark its granules;
+            // k_verify_ham re-checks them exactly.  Nibble fields fire at the occurrence's LAST counted word
+            // (first counted word = that word - Wc + 1); the sliced counters fire at the word of the
+            // (Wc-k)-th match, anywhere from the first to the last counted word.
             const int64_t grow = tile * kHcThreads + tid;  // buffer row index
-            const int64_t pr_lo = 4 * (grow * 32 - Wc + 1) - 3, pr_hi = 4 * (grow * 32 + 31 - Wc + 1);
+            const int64_t pr_lo = 4 * (grow * 32 - Wc + 1) - 3;
+            const int64_t pr_hi = 4 * (grow * 32 + 31 - (SLICED ? 0 : Wc - 1));
             mark_range_inline(p, p.buf_lo + max(pr_lo, (int64_t)0), p.buf_lo + pr_hi);
         }
         __syncthreads();  // everyone is done with stage s
