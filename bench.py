@@ -293,6 +293,55 @@ def parity_check(F, hs, pat, kind, k, blo, bhi, own_lo, own_hi, global_final, di
             "d2h_s": round(t1 - t0, 2), "oracle_s": round(t2 - t1, 2)}
 
 
+def batch_parity(F, hs, pats, ks, n):
+    """Parity of the 1024-pattern batch at full size (untimed): (1) EVERY pattern's final list from the batch call
+    equals the single-pattern search of the same 4 GiB (the path whose whole-shard oracle comparison is the
+    headline's "parity" block); (2) the CPU oracle directly, for a sample of patterns of every route: over a window
+    around each match the batch reported (same matches, nothing else nearby) and over a 16 MiB prefix of the
+    sequence (nothing missed, nothing invented in the bulk)."""
+    import oracle
+    results, _ = hs.search_levenshtein_batch(pats, ks)
+    finals, route_of = [], []
+    for r in results:
+        finals.append(r.triples(F.FINAL))
+        route_of.append(r.stats()["route"])
+        r.close()
+    differ = []
+    for i, (bp, bk) in enumerate(zip(pats, ks)):
+        r = hs.search_levenshtein(bp, bk)
+        if r.triples(F.FINAL) != finals[i]:
+            differ.append(i)
+        r.close()
+    sample, seen = [], {}
+    for i, rt in enumerate(route_of):  # the first 8 patterns of every route
+        if seen.setdefault(rt, 0) < 8:
+            seen[rt] += 1
+            sample.append(i)
+    margin, pad = 512, 4096
+    win_ok, n_windows = True, 0
+    for i in sample:
+        bp, bk = pats[i], ks[i]
+        for s0, e0, _ in finals[i]:
+            lo, hi = max(0, s0 - pad), min(n, e0 + pad)
+            host = hs.read(lo, hi - lo)
+            inner = lambda t: (t[0] >= lo + margin or lo == 0) and (t[1] <= hi - margin or hi == n)  # noqa: E731
+            want = [(a + lo, b + lo, d) for a, b, d in oracle.find_near_matches(bp, host, max_l_dist=bk)]
+            got = [t for t in finals[i] if t[0] >= lo and t[1] <= hi]
+            win_ok &= [t for t in want if inner(t)] == [t for t in got if inner(t)]
+            n_windows += 1
+    plen = 16 << 20
+    prefix = hs.read(0, plen)
+    pre_ok = True
+    pre_ids = sample[::4][:6]
+    for i in pre_ids:
+        want = [t for t in oracle.find_near_matches(pats[i], prefix, max_l_dist=ks[i]) if t[1] <= plen - margin]
+        pre_ok &= want == [t for t in finals[i] if t[1] <= plen - margin]
+    return {"patterns_vs_single_search": len(pats), "differing": differ[:8], "single_ok": not differ,
+            "oracle_windows": n_windows, "oracle_windows_ok": bool(win_ok),
+            "oracle_prefix_bytes": plen, "oracle_prefix_patterns": len(pre_ids), "oracle_prefix_ok": bool(pre_ok),
+            "ok": bool(not differ and win_ok and pre_ok)}
+
+
 # -------------------------------------------------------------------------------------------------
 # secondary workloads: short, driver-visible runs of the other BASELINE configs on one GPU
 # -------------------------------------------------------------------------------------------------
@@ -366,11 +415,16 @@ def run_secondary(F, main_hs, main_alphabet, seed, peak):
             return st, c
         ms, _, cnt = timed(main_hs, batch, 2, 1)
         shared_ms = routes.get("ngrams/sampled-filter", [0, 0.0])[1]
+        try:
+            bparity = batch_parity(F, main_hs, pats, ks, n)
+        except Exception as e:  # noqa: BLE001
+            bparity = {"ok": False, "error": repr(e)[:200]}
         out["ascii4g_batch1024"] = {
             "value": n / (ms * 1e-3) / 1e9, "unit": "GB/s of haystack per 1024-pattern batch", "ms_per_step": ms,
             "steps": 2, "warmup": 1, "patterns": 1024, "pattern_GB_per_s": 1024 * n / (ms * 1e-3) / 1e9,
             "matches_per_step": int(cnt),
             "routes": {r: {"patterns": v[0], "device_ms": v[1]} for r, v in sorted(routes.items())},
+            "parity": bparity,
             "roofline": {"kernel": "k_filter_multi + k_verify_multi (one scan for all lemma-eligible patterns)",
                          "kernel_ms": shared_ms, "achieved": n / (shared_ms * 1e-3) / 1e9 if shared_ms else 0.0,
                          "peak": peak, "frac": (n / (shared_ms * 1e-3) / 1e9 / peak) if shared_ms else 0.0,

@@ -2446,7 +2446,10 @@ extern "C" int fzb_search_exact_window(fzb_haystack *h, const uint8_t *pattern, 
         uint64_t buf_len, buf_lo, own_lo, own_hi, padded_len, global_len;
         double coll_prob;
     } const saved{h->d, h->buf_len, h->buf_lo, h->own_lo, h->own_hi, h->padded_len, h->global_len, h->coll_prob};
-    const uint64_t vlo = start / 128 * 128;  // the view starts on a 128-byte boundary of the buffer
+    // the view starts a halo before the window (the shard geometry check of the search wants one on both sides;
+    // the right one ends at the view's global end), on a 128-byte boundary of the buffer
+    const uint64_t halo = round_up((uint64_t)m, 128) + 128;
+    const uint64_t vlo = (start > halo ? start - halo : 0) / 128 * 128;
     h->d = saved.d + vlo;
     h->buf_lo = vlo;
     h->buf_len = end - vlo;

@@ -171,3 +171,43 @@ def test_items_resident_and_mixed_types(cuda_device):
         find_near_matches("abc", b"abcabc", max_l_dist=1)
     with pytest.raises(TypeError):
         find_near_matches(["a"], "abc", max_l_dist=1)
+
+
+def test_wide_cases_of_the_reference_suite(cuda_device, tmp_path):
+    """The handful of non-byte cases the reference's own tests hold (inputs and expected outcomes as asserted
+    there): test_search_exact.py:122-123, test_substitutions_only.py:236-243, test_generic_search.py:306-361,
+    test_find_near_matches_in_file.py:57-72."""
+    from fuzzysearch_b200 import GenericSearch, LevenshteinSearchParams, Match
+    sigma_gamma, text = "ΣΓ", "ΠΣΓΔ"
+    assert search_exact(sigma_gamma, text) == [1]
+    got = find_near_matches(sigma_gamma, text, max_substitutions=0, max_insertions=0, max_deletions=0)
+    assert got == [Match(1, 3, 0, matched=text[1:3])] and got[0].matched == text[1:3]
+
+    def generic(p, s, *limits):
+        return GenericSearch.consolidate_matches(GenericSearch.search(p, s, LevenshteinSearchParams(*limits)))
+
+    for klass in (list, tuple):
+        assert generic(klass([1, 2, 3]), klass([1, 2, 3]), 0, 0, 0, 0) == [Match(0, 3, 0, klass([1, 2, 3]))]
+        assert generic(klass([1, 2, 3]), klass([1, 2, 3]), 1, 1, 1, 1) == [Match(0, 3, 0, klass([1, 2, 3]))]
+        assert generic(klass([1, 2, 3]), klass([1, 2, 4]), 0, 0, 0, 0) == []
+        r = generic(klass([1, 2, 3]), klass([1, 2, 4]), 1, 1, 1, 1)
+        assert r == [Match(0, 3, 1, klass([1, 2, 4]))] and r[0].matched == klass([1, 2, 4])
+        r = generic(klass([1, 2, 3]), klass([1, 2, 4]), 0, 0, 1, 1)
+        assert r == [Match(0, 2, 1, klass([1, 2]))] and r[0].matched == klass([1, 2])
+    sequence = "the big brown fox jumped over the lazy dog".split()
+    hit = [Match(4, 9, 1, matched="jumped over the lazy dog".split())]
+    for sub, table in (("jumped over the a lazy dog".split(),
+                        [((0, 0, 0, 0), []), ((1, 0, 0, 1), []), ((0, 1, 0, 1), []), ((0, 0, 1, 1), hit),
+                         ((1, 1, 1, 1), hit), ((2, 2, 2, 2), hit)]),
+                       ("jumped over lazy dog".split(),
+                        [((0, 0, 0, 0), []), ((1, 0, 0, 1), []), ((0, 1, 0, 1), hit), ((0, 0, 1, 1), []),
+                         ((1, 1, 1, 1), hit), ((2, 2, 2, 2), hit)])):
+        for limits, expected in table:
+            r = generic(sub, sequence, *limits)
+            assert r == expected and [m.matched for m in r] == [m.matched for m in expected], (sub, limits)
+    for encoding in ("ascii", "latin-1", "utf-8", "utf-16"):
+        path = tmp_path / ("hay_" + encoding)
+        path.write_bytes("---PATERN---".encode(encoding))
+        with io.open(path, "r", encoding=encoding) as f:
+            r = find_near_matches_in_file("PATTERN", f, max_l_dist=1)
+            assert r == [Match(3, 9, 1, "PATERN")] and r[0].matched == "PATERN"
