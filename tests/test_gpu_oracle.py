@@ -176,8 +176,9 @@ def test_edge_cases(cuda_device):
         find_near_matches(b"a", b"a")
     with pytest.raises(TypeError):
         find_near_matches(b"a", b"a", max_l_dist=-1)
+    assert t(find_near_matches(["a"], ["a"], max_l_dist=1)) == [(0, 1, 0)]  # item sequences: tests/test_gpu_symbols.py
     with pytest.raises(TypeError):
-        find_near_matches(["a"], ["a"], max_l_dist=1)
+        find_near_matches(["a"], b"a", max_l_dist=1)
 
 
 def test_python_surface_variants(cuda_device):
