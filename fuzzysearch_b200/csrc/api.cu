@@ -2501,11 +2501,13 @@ static int make_row_maps(fzb_haystack *h, CUtensorMap *map256, CUtensorMap *map8
 }
 
 // Counter layout of k_hamming_count (ham_recur.h).  FZB_HAM_COUNTERS=nibble|sliced overrides the default.
-static bool ham_sliced_counters() {  // (read per search: a probe can flip it between two searches)
+// -> 0 nibble fields / 1 three slices / 2 two slices (thresholds <= 4 only)
+static int ham_counter_layout(int threshold) {  // (read per search: a probe can flip it between two searches)
     const char *e = getenv("FZB_HAM_COUNTERS");
-    if (e && !strcmp(e, "nibble")) return false;
-    if (e && !strcmp(e, "sliced")) return true;
-    return true;  // measured on 4 GiB of DNA, m = 32, k = 3: 0.881 ms (sliced) vs 0.948 ms (nibble fields)
+    if (e && !strcmp(e, "nibble")) return 0;
+    if (e && !strcmp(e, "sliced3")) return 1;
+    // measured on 4 GiB of DNA, m = 32, k = 3: 0.881 ms (three slices) vs 0.948 ms (nibble fields)
+    return threshold <= 4 ? 2 : 1;
 }
 
 extern "C" int fzb_search_hamming(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint32_t k,
@@ -2535,8 +2537,10 @@ extern "C" int fzb_search_hamming(fzb_haystack *h, const uint8_t *pattern, uint3
                 if (r3) return r3;
                 CK(cudaFuncSetAttribute(k_hamming_count<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHcSmem));
                 CK(cudaFuncSetAttribute(k_hamming_count<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHcSmem));
+                CK(cudaFuncSetAttribute(k_hamming_count<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHcSmem));
             }
-            const bool sliced = ham_sliced_counters();
+            const int layout = counting ? ham_counter_layout(hp.Wc - p.k) : 0;
+            if (layout == 2) hp.bias = 4 - (hp.Wc - p.k);
             bool bitmap_mode = false;
             PostPlan plan{2, (flags & FZB_F_GLOBAL) != 0};  // FINAL == RAW in (start, end, dist) order, ordered by k_post
         retry_bitmap:
@@ -2544,7 +2548,9 @@ extern "C" int fzb_search_hamming(fzb_haystack *h, const uint8_t *pattern, uint3
                 if (counting) {
                     const int64_t ntiles = (hp.nrows + kHcThreads - 1) / kHcThreads;
                     const int grid = (int)std::min<int64_t>(ntiles, (int64_t)h->sm_count * 2);
-                    if (sliced)
+                    if (layout == 2)
+                        k_hamming_count<2><<<grid, kHcThreads, kHcSmem, h->stream>>>(p, hp, map256, map8);
+                    else if (layout == 1)
                         k_hamming_count<1><<<grid, kHcThreads, kHcSmem, h->stream>>>(p, hp, map256, map8);
                     else
                         k_hamming_count<0><<<grid, kHcThreads, kHcSmem, h->stream>>>(p, hp, map256, map8);

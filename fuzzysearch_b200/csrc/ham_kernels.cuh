@@ -113,7 +113,8 @@ __device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
 }
 
 // SLICED = 0: nibble fields, 16-byte table entries (4 wavefronts per lookup);  SLICED = 1: bit-sliced counters,
-// 4-byte table entries (1 wavefront per lookup, more ALU work per word) -- see ham_recur.h.
+// 4-byte table entries (1 wavefront per lookup, more ALU work per word);  SLICED = 2: the same with two slices
+// (thresholds Wc - k <= 4; hp.bias is then 4 - (Wc - k)) -- see ham_recur.h.
 template <int SLICED>
 __global__ void __launch_bounds__(kHcThreads, 2)
 k_hamming_count(const ScanParams p, const HamCountParams hp, const __grid_constant__ CUtensorMap map256,
@@ -180,11 +181,13 @@ k_hamming_count(const ScanParams p, const HamCountParams hp, const __grid_consta
         bool flagged;
         if (SLICED) {
             HamSliced cnt{0u, 0u, 0u};
+            HamSliced2 cnt2{0u, 0u};
             uint32_t acc = 0;
 #define HS_STEP(WORD, track)                                                                 \
     {                                                                                        \
         const uint32_t M = lds32(my_table + (hc_bucket(WORD) << 7));                         \
-        const uint32_t c = ham_sliced_step(cnt, M, B0, B1, B2);                              \
+        const uint32_t c = SLICED == 2 ? ham_sliced2_step(cnt2, M, B0, B1)                   \
+                                       : ham_sliced_step(cnt, M, B0, B1, B2);                \
         if (track) acc |= c;                                                                 \
     }
             {  // warm-up: the last 7 words of the previous row (their candidates belong to that row's thread)

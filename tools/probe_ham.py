@@ -1,4 +1,4 @@
-"""A/B of the two counter layouts of k_hamming_count (FZB_HAM_COUNTERS=nibble|sliced) on a DNA corpus:
+"""A/B of the counter layouts of k_hamming_count (FZB_HAM_COUNTERS=nibble|sliced3|auto) on a DNA corpus:
 same plants, same pattern; results must be identical; prints per-variant filter / whole-search times.
 usage: python tools/probe_ham.py [n_bytes] [out.json]"""
 import json
@@ -25,7 +25,7 @@ for m, k in ((32, 3), (20, 1), (64, 7), (48, 5)):
         hs.write(int(rng.integers(0, n - m)), bytes(v))
     case = {"m": m, "k": k}
     ref = None
-    for variant in ("nibble", "sliced", "nibble", "sliced"):
+    for variant in ("nibble", "sliced3", "auto", "nibble", "sliced3", "auto"):  # auto: two slices when Wc - k <= 4
         os.environ["FZB_HAM_COUNTERS"] = variant
         for _ in range(3):
             hs.search_hamming(pat, k).close()
