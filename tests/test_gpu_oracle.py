@@ -176,7 +176,10 @@ def test_edge_cases(cuda_device):
         find_near_matches(b"a", b"a")
     with pytest.raises(TypeError):
         find_near_matches(b"a", b"a", max_l_dist=-1)
-    assert t(find_near_matches(["a"], ["a"], max_l_dist=1)) == [(0, 1, 0)]  # item sequences: tests/test_gpu_symbols.py
+    # item sequences (tests/test_gpu_symbols.py); max_l_dist >= len(subsequence): the LP route's empty match at
+    # every index (levenshtein.py:62-65) -- what the reference returns for these very inputs
+    assert t(find_near_matches(["a"], ["a"], max_l_dist=1)) == [(0, 0, 1), (1, 1, 1)]
+    assert t(find_near_matches(["a", "b"], ["a", "b", "c"], max_l_dist=1)) == [(0, 2, 0)]
     with pytest.raises(TypeError):
         find_near_matches(["a"], b"a", max_l_dist=1)
 
