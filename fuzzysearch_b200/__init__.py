@@ -38,22 +38,16 @@ def has_near_match(subsequence, sequence, max_substitutions=None, max_insertions
     reference's internal has_near_match_* helpers (substitutions_only.py:18-34,139-145,218-233;
     generic_search.py:240-253), with early termination: the sequence is searched in chunks of growing size and
     the call returns after the first chunk that holds a match (fzb_has_near_match)."""
-    from .search import _WORKSPACE_LOCK, DeviceSequence, _prepare
+    from .search import _lock_for, _prepare
     search_params = LevenshteinSearchParams(max_substitutions, max_insertions, max_deletions, max_l_dist)
     if len(subsequence) == 0:
         raise ValueError("Given subsequence is empty!")
     subs, ins, dels, l = search_params.unpacked
     big = 1 << 29
     subs, ins, dels = (big if subs is None else subs), (big if ins is None else ins), (big if dels is None else dels)
-    shared = not isinstance(sequence, DeviceSequence)
-    if shared:
-        _WORKSPACE_LOCK.acquire()
-    try:
+    with _lock_for(sequence):
         pat, hay, _, _ = _prepare(subsequence, sequence)
         return hay.has_near_match(pat, min(subs, big), min(ins, big), min(dels, big), l)
-    finally:
-        if shared:
-            _WORKSPACE_LOCK.release()
 
 
 def find_near_matches_batch(subsequences, sequence, max_l_dist):
@@ -72,8 +66,8 @@ def find_near_matches_batch(subsequences, sequence, max_l_dist):
             raise ValueError("Given subsequence is empty!")
     if not subsequences:
         return []
-    from .search import _WORKSPACE_LOCK, AlphabetTooLarge, _prepare_many
-    with _WORKSPACE_LOCK:
+    from .search import AlphabetTooLarge, _lock_for, _prepare_many
+    with _lock_for(sequence):
         try:
             pats, hay, slicer = _prepare_many(subsequences, sequence)
         except AlphabetTooLarge:

@@ -119,6 +119,8 @@ static void nccl_comm_destroy(void *comm) {
 // handles
 // ------------------------------------------------------------------------------------------------
 struct fzb_haystack {
+    std::recursive_mutex mu;  // one search / upload at a time per handle (HandleLock); recursive: has_near_match and
+                              // the windowed exact search call the search entry points on their own handle
     int device = 0;
     uint8_t *d = nullptr;  // H[0] == global position buf_lo
     bool owned = true;
@@ -215,6 +217,21 @@ struct fzb_result {
 };
 
 static uint64_t round_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+
+// Every entry point that touches a handle's device state (buffer, counters, output area, stream order) holds the
+// handle's mutex for the whole call: two threads sharing one resident sequence take turns, like callers of the
+// reference under the GIL.  (Results are separate objects; their lazy raw fetch is guarded by g_pending_mutex.)
+struct HandleLock {
+    std::recursive_mutex *m;
+    explicit HandleLock(fzb_haystack *h) : m(h ? &h->mu : nullptr) {
+        if (m) m->lock();
+    }
+    ~HandleLock() {
+        if (m) m->unlock();
+    }
+    HandleLock(const HandleLock &) = delete;
+    HandleLock &operator=(const HandleLock &) = delete;
+};
 
 // The raw records of the LAST search of a handle stay in its DEVICE output buffer (and the global rows of a
 // multi-GPU search in its mapped host buffer) until somebody asks for them (fzb_result_copy), the next search
@@ -455,6 +472,7 @@ extern "C" void fzb_synth_host(uint8_t *dst, uint64_t global_offset, uint64_t n,
 
 extern "C" int fzb_haystack_fill_synthetic(fzb_haystack *h, const uint8_t *alphabet, uint32_t alphabet_len,
                                            uint64_t seed) {
+    HandleLock handle_lock(h);
     if (!h || !alphabet || alphabet_len == 0 || alphabet_len > 256) return fail(FZB_E_INVALID, "bad arguments");
     if (!h->owned) return fail(FZB_E_INVALID, "cannot fill an adopted buffer");
     CK(cudaSetDevice(h->device));
@@ -475,6 +493,7 @@ extern "C" int fzb_haystack_fill_synthetic(fzb_haystack *h, const uint8_t *alpha
 }
 
 extern "C" int fzb_haystack_write(fzb_haystack *h, uint64_t global_offset, const uint8_t *src, uint64_t n) {
+    HandleLock handle_lock(h);
     if (!h || (!src && n)) return fail(FZB_E_INVALID, "bad arguments");
     if (global_offset < h->buf_lo || global_offset + n > h->buf_lo + h->buf_len)
         return fail(FZB_E_INVALID, "write outside the buffer");
@@ -485,6 +504,7 @@ extern "C" int fzb_haystack_write(fzb_haystack *h, uint64_t global_offset, const
 }
 
 extern "C" int fzb_haystack_read(fzb_haystack *h, uint64_t global_offset, uint8_t *dst, uint64_t n) {
+    HandleLock handle_lock(h);
     if (!h || (!dst && n)) return fail(FZB_E_INVALID, "bad arguments");
     if (global_offset < h->buf_lo || global_offset + n > h->buf_lo + h->buf_len)
         return fail(FZB_E_INVALID, "read outside the buffer");
@@ -621,6 +641,7 @@ static int upload_bytes(fzb_haystack *h, uint64_t dst_off, const uint8_t *host, 
 }
 
 extern "C" int fzb_haystack_upload(fzb_haystack *h, const uint8_t *host, uint64_t n) {
+    HandleLock handle_lock(h);
     if (!h || (!host && n)) return fail(FZB_E_INVALID, "bad arguments");
     if (!h->owned) return fail(FZB_E_INVALID, "upload needs an owned handle");
     if (round_up(n, 128) + 128 > h->capacity) return fail(FZB_E_INVALID, "upload larger than the handle's capacity");
@@ -642,6 +663,7 @@ extern "C" int fzb_haystack_upload(fzb_haystack *h, const uint8_t *host, uint64_
 // k_reduce_symbols writes one byte per symbol into the handle's buffer.
 extern "C" int fzb_haystack_upload_symbols(fzb_haystack *h, const void *host, uint64_t n, uint32_t width,
                                            const uint32_t *alphabet, uint32_t n_alpha) {
+    HandleLock handle_lock(h);
     if (!h || (!host && n) || (!alphabet && n_alpha)) return fail(FZB_E_INVALID, "bad arguments");
     if (width != 2 && width != 4) return fail(FZB_E_INVALID, "symbol width must be 2 or 4 bytes");
     if (n_alpha > (uint32_t)kMaxPattern) return fail(FZB_E_UNSUPPORTED, "more than %d distinct pattern symbols", kMaxPattern);
@@ -1873,6 +1895,7 @@ static int check_pattern(const fzb_haystack *h, const uint8_t *pattern, uint32_t
 
 extern "C" int fzb_search_levenshtein(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint32_t k,
                                       uint32_t flags, fzb_result **out) {
+    HandleLock handle_lock(h);
     fzb_result *res;
     int rc = make_result(out, &res);
     if (rc) return rc;
@@ -2260,6 +2283,7 @@ static int batch_pass_lp(fzb_haystack *h, const uint8_t *patterns, const uint32_
 extern "C" int fzb_search_levenshtein_batch(fzb_haystack *h, const uint8_t *patterns, const uint32_t *offsets,
                                             const uint32_t *max_l_dist, uint32_t count, uint32_t flags,
                                             fzb_result **out, fzb_stats *total) {
+    HandleLock handle_lock(h);
     if (!h || !out || (count && (!patterns || !offsets || !max_l_dist))) return fail(FZB_E_INVALID, "NULL argument");
     for (uint32_t i = 0; i < count; i++) out[i] = nullptr;
     for (uint32_t i = 0; i < count; i++)
@@ -2393,6 +2417,7 @@ extern "C" int fzb_search_levenshtein_batch(fzb_haystack *h, const uint8_t *patt
 
 extern "C" int fzb_search_exact(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint32_t flags,
                                 fzb_result **out) {
+    HandleLock handle_lock(h);
     fzb_result *res;
     int rc = make_result(out, &res);
     if (rc) return rc;
@@ -2421,6 +2446,7 @@ extern "C" int fzb_search_exact(fzb_haystack *h, const uint8_t *pattern, uint32_
 // window are not scanned.
 extern "C" int fzb_search_exact_window(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint64_t start,
                                        uint64_t end, uint32_t flags, fzb_result **out) {
+    HandleLock handle_lock(h);
     if (!h || !out) return fail(FZB_E_INVALID, "NULL argument");
     *out = nullptr;
     if (flags & FZB_F_GLOBAL) return fail(FZB_E_INVALID, "windowed exact search is per handle");
@@ -2512,6 +2538,7 @@ static int ham_counter_layout(int threshold) {  // (read per search: a probe can
 
 extern "C" int fzb_search_hamming(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint32_t k,
                                   uint32_t flags, fzb_result **out) {
+    HandleLock handle_lock(h);
     fzb_result *res;
     int rc = make_result(out, &res);
     if (rc) return rc;
@@ -2602,6 +2629,7 @@ extern "C" int fzb_search_hamming(fzb_haystack *h, const uint8_t *pattern, uint3
 extern "C" int fzb_search_generic(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint32_t max_subs,
                                   uint32_t max_ins, uint32_t max_dels, uint32_t max_l, uint32_t flags,
                                   fzb_result **out) {
+    HandleLock handle_lock(h);
     fzb_result *res;
     int rc = make_result(out, &res);
     if (rc) return rc;
@@ -2684,6 +2712,7 @@ extern "C" int fzb_find_near_matches(const uint8_t *pattern, uint32_t m, const u
 // ------------------------------------------------------------------------------------------------
 extern "C" int fzb_has_near_match(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint32_t max_subs,
                                   uint32_t max_ins, uint32_t max_dels, uint32_t max_l, int *found) {
+    HandleLock handle_lock(h);
     if (!h || !found) return fail(FZB_E_INVALID, "NULL argument");
     *found = 0;
     int rc = check_pattern(h, pattern, m, 0);

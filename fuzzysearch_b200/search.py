@@ -28,6 +28,9 @@ class DeviceSequence(object):
     different set of symbols."""
 
     def __init__(self, data=None, device=0, _haystack=None, _host=None):
+        # held across bind (re-reduction to a new pattern alphabet) + search + copy-out of the consolidated list:
+        # threads sharing one resident sequence take turns, like callers of the reference under the GIL
+        self._lock = threading.RLock()
         self._wide = None        # the original str / list / tuple when the byte form depends on the pattern
         self._alphabet = None    # ... and the pattern alphabet the resident bytes were reduced with
         self._is_str = False
@@ -253,9 +256,13 @@ def _prepare_many(subsequences, sequence):
 _WORKSPACE = {}
 # One lock per process around upload + search + copy-out of the SHARED workspace: ctypes drops the GIL
 # during the native calls, so without it two threads calling find_near_matches() would overwrite each
-# other's haystack mid-search.  (The reference is serialised by the GIL; DeviceSequence handles are
-# serialised per handle inside the library.)
+# other's haystack mid-search.  (The reference is serialised by the GIL.)  A DeviceSequence has its own lock
+# (and the library serialises the calls on one handle), so searches of different resident sequences overlap.
 _WORKSPACE_LOCK = threading.RLock()
+
+
+def _lock_for(sequence):
+    return sequence._lock if isinstance(sequence, DeviceSequence) else _WORKSPACE_LOCK
 
 
 def _workspace(nbytes, device=0):
@@ -284,10 +291,7 @@ def _to_matches(result, which, slicer):
 
 
 def _run(subsequence, sequence, call, consolidated):
-    shared = not isinstance(sequence, DeviceSequence)
-    if shared:
-        _WORKSPACE_LOCK.acquire()
-    try:
+    with _lock_for(sequence):
         pat, hay, slicer, _ = _prepare(subsequence, sequence)
         res = call(hay, pat)
         try:
@@ -295,9 +299,6 @@ def _run(subsequence, sequence, call, consolidated):
         except BaseException:
             res.close()
             raise
-    finally:
-        if shared:
-            _WORKSPACE_LOCK.release()
 
 
 def search_exact(subsequence, sequence, start_index=0, end_index=None):
@@ -314,10 +315,11 @@ def search_exact(subsequence, sequence, start_index=0, end_index=None):
     start_index = max(0, min(start_index, n))               # clamp(...) search_exact.py:29-30
     end_index = max(start_index, min(end_index, n))
     if isinstance(sequence, DeviceSequence):
-        pat = sequence._bind(subsequence)
-        res = sequence.haystack.search_exact(pat, start=start_index, end=end_index)
-        starts = res.arrays(_native.RAW)[0]  # positions are already those of the whole sequence
-        res.close()
+        with sequence._lock:
+            pat = sequence._bind(subsequence)
+            res = sequence.haystack.search_exact(pat, start=start_index, end=end_index)
+            starts = res.arrays(_native.RAW)[0]  # positions are already those of the whole sequence
+            res.close()
         return starts.tolist()
     else:
         if _kind(sequence) == "bytes" and not isinstance(sequence, (bytes, bytearray)):

@@ -17,7 +17,8 @@
  * Conventions: every function returns 0 on success or a negative FZB_E_* code; the message is
  * available from fzb_last_error() (thread-local).  No C++ exceptions, Python objects or torch types
  * cross the ABI.  The caller owns every input buffer (copied during the call, never retained) and
- * every handle (explicit destroy).  Distinct handles may be used from distinct threads.
+ * every handle (explicit destroy).  Distinct handles may be used from distinct threads concurrently;
+ * calls on one handle are serialised inside the library (per-handle mutex).
  *
  * Semantics are bit-exact with the reference's PURE-PYTHON path: raw match
  * streams are element-for-element those of the cited generators; the consolidated list follows

@@ -38,6 +38,71 @@ def test_find_near_matches_is_thread_safe(cuda_device):
     assert not errors, errors
 
 
+def test_threads_share_one_resident_sequence(cuda_device):
+    """Four threads search ONE DeviceSequence with different patterns and limits at the same time (the natural way
+    to use a resident corpus): every call must return its own pattern's matches.  Byte sequence: the library
+    serialises the calls on the handle; wide str: the Python lock also covers the re-reduction of the sequence to
+    each pattern's alphabet."""
+    from fuzzysearch_b200 import DeviceSequence, find_near_matches_batch, search_exact
+    from symbols import reduce_to_bytes
+    rng = np.random.default_rng(77)
+    n = 1 << 21
+    alpha = np.frombuffer(ASCII, dtype=np.uint8)
+    hay = alpha[rng.integers(0, len(alpha), size=n)].copy()
+    pats = [bytes(alpha[rng.integers(0, len(alpha), size=m)]) for m in (20, 9, 32, 14)]
+    ks = [2, 3, 3, 1]
+    for i, p in enumerate(pats):
+        for j in range(6):
+            pos = 5000 + 30000 * (4 * j + i)
+            v = bytearray(p)
+            if j % 2:
+                v[len(v) // 2] ^= 1
+            hay[pos:pos + len(v)] = np.frombuffer(bytes(v), dtype=np.uint8)
+    hay_b = hay.tobytes()
+    letters = [chr(c) for c in range(0x3B1, 0x3C9)] + ["\U0001F642", "x"]
+    text = "".join(letters[i] for i in rng.integers(0, len(letters), size=200000))
+    wpats = []
+    for i in range(4):  # four patterns over four DIFFERENT alphabets (each thread forces a re-reduction)
+        sub = letters[6 * i:6 * i + 6] + ["x"]
+        w = "".join(sub[j] for j in rng.integers(0, len(sub), size=16))
+        wpats.append(w)
+        text = text[:7000 * (i + 1)] + w + text[7000 * (i + 1) + 16:]
+    exp_b = [oracle.find_near_matches(p, hay_b, max_l_dist=k) for p, k in zip(pats, ks)]
+    exp_h = [oracle.find_near_matches(p, hay_b, 2, 0, 0) for p in pats]
+    exp_w = [oracle.find_near_matches(*reduce_to_bytes(w, text), max_l_dist=1) for w in wpats]
+    assert all(len(e) >= 6 for e in exp_b) and all(len(e) >= 1 for e in exp_w)
+    ds, dw = DeviceSequence(hay_b), DeviceSequence(text)
+    errors = []
+
+    def run(t):
+        try:
+            for _ in range(5):
+                got = find_near_matches(pats[t], ds, max_l_dist=ks[t])
+                assert [(m.start, m.end, m.dist) for m in got] == exp_b[t]
+                assert all(m.matched == hay_b[m.start:m.end] for m in got)
+                got = find_near_matches(pats[t], ds, max_substitutions=2, max_insertions=0, max_deletions=0)
+                assert [(m.start, m.end, m.dist) for m in got] == exp_h[t]
+                assert has_near_match(pats[t], ds, max_l_dist=ks[t])
+                assert search_exact(pats[t][:6], ds, 100, n - 100) == oracle.search_exact(pats[t][:6], hay_b, 100, n - 100)
+                got = find_near_matches(wpats[t], dw, max_l_dist=1)
+                assert [(m.start, m.end, m.dist) for m in got] == exp_w[t]
+                assert all(m.matched == text[m.start:m.end] for m in got)
+                if t == 0:
+                    b = find_near_matches_batch(pats, ds, ks)
+                    assert [[(m.start, m.end, m.dist) for m in x] for x in b] == exp_b
+        except BaseException as e:  # noqa: BLE001
+            errors.append((t, repr(e)))
+
+    threads = [threading.Thread(target=run, args=(t,)) for t in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    ds.close()
+    dw.close()
+    assert not errors, errors
+
+
 def test_large_pageable_input_goes_through_the_upload_ring(cuda_device):
     """200 MiB of pageable memory (more than the three 64 MiB ring buffers): the staged, multi-threaded upload must
     deliver every byte in order -- matches planted in every ring slice and across slice boundaries are found."""
