@@ -117,7 +117,7 @@ int fzb_haystack_write(fzb_haystack *h, uint64_t global_offset, const uint8_t *s
 int fzb_haystack_read(fzb_haystack *h, uint64_t global_offset, uint8_t *dst, uint64_t n);
 
 /* NCCL plumbing for FZB_F_GLOBAL (one process per GPU).  Rank 0 obtains a unique id and ships it to
- * the other ranks by any means (bench.py: torch.distributed broadcast); then every rank calls
+ * the other ranks by any means (fuzzysearch_b200/sharding.py: a plain TCP rendezvous); then every rank calls
  * fzb_haystack_comm_init with its shard handle (collective, blocking).  libnccl.so.2 is resolved at
  * run time (dlopen), so the library has no link-time NCCL dependency. */
 #define FZB_NCCL_ID_BYTES 128

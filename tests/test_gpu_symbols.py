@@ -12,55 +12,11 @@ import pytest
 import oracle
 from fuzzysearch_b200 import (DeviceSequence, _native, find_near_matches, find_near_matches_batch,
                               find_near_matches_in_file, has_near_match, search_exact)
-from parity import assert_final_parity, load_golden, tup
-from symbols import decode_items, reduce_to_bytes
+from parity import load_golden, tup
+from symbols import check_file as _check_file, check_fnm as _check_fnm, decode_items, reduce_to_bytes, triples as _t
 
 pytestmark = pytest.mark.gpu
 F = _native
-
-
-def _t(ms):
-    return [(m.start, m.end, m.dist) for m in ms]
-
-
-def _check_fnm(rec, ours, ctx):
-    pat_b, hay_b = reduce_to_bytes(rec["pattern"], rec["sequence"])
-    a = rec["args"][:4]
-    subs, ins, dels, l = oracle.normalize_params(*a)
-    if l == 0 or (ins == 0 and dels == 0):
-        assert ours == tup(rec["result"]), ctx
-    else:
-        _, raw = oracle.find_near_matches(pat_b, hay_b, *a, return_raw=True)
-        assert_final_parity(ours, rec["result"], raw, ctx)
-
-
-def _check_file(rec, ours, ctx):
-    """The text-file loop (__init__.py:174-200) re-run with the byte oracle as the per-chunk search: its raw
-    stream (chunk-local window clipping included) explains the reference's final list and ours."""
-    from fuzzysearch_b200 import LevenshteinSearchParams, choose_search_class
-    pat_b, hay_b = reduce_to_bytes(rec["pattern"], rec["sequence"])
-    a, chunk_size = rec["args"][:4], rec["args"][4]
-    params = LevenshteinSearchParams(*a)
-    cls = choose_search_class(params)
-    keep = len(pat_b) - 1 + cls.extra_items_for_chunked_search(pat_b, params)
-    raw, f = [], io.BytesIO(hay_b)
-    chunk, offset = f.read(chunk_size), 0
-    while chunk:
-        _, r = oracle.find_near_matches(pat_b, chunk, *a, return_raw=True)
-        raw += [(s + offset, e + offset, d) for s, e, d in tup(r)]
-        n_keep = min(keep, len(chunk))
-        offset += len(chunk) - n_keep
-        if n_keep:
-            chunk = chunk[-n_keep:] + f.read(chunk_size)
-            if len(chunk) == n_keep:
-                break
-        else:
-            chunk = f.read(chunk_size)
-    subs, ins, dels, l = params.unpacked
-    if l == 0 or (ins == 0 and dels == 0):
-        assert ours == tup(rec["result"]) == raw, ctx  # unconsolidated classes: the concatenated chunk lists
-    else:
-        assert_final_parity(ours, rec["result"], raw, ctx)
 
 
 def test_reference_results_on_wide_symbols(cuda_device):
