@@ -51,6 +51,14 @@ k_hamming_scan(const ScanParams p, RawRec *out, uint32_t cap, uint32_t *counters
 // ---- TMA / mbarrier primitives (sm_90+ PTX) ------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+#ifdef FZB_EMU  // tests/emu: mbarrier / TMA semantics restated in C++ (tests/emu/include/cuda.h)
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) { emu::mbar_init(bar, count); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { emu::mbar_expect_tx(bar, bytes); }
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) { emu::mbar_wait(bar, parity); }
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    emu::tma_load_2d(dst, map, c0, c1, bar);
+}
+#else
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -77,6 +85,7 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
         "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
         : "memory");
 }
+#endif
 
 // ---- counting filter --------------------------------------------------------------------------------
 constexpr int kHcThreads = 256;               // one 128-byte row per thread; 2 CTAs per SM
@@ -96,9 +105,13 @@ struct HamCountParams {
 
 // explicit shared-space 128-bit load (32-bit shared address: no generic-address arithmetic)
 __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+#ifdef FZB_EMU
+    return *reinterpret_cast<const uint4 *>(emu::smem_base() + saddr);
+#else
     uint4 r;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr));
     return r;
+#endif
 }
 
 // swizzled shared address of 16-byte chunk j of local row r (SWIZZLE_128B: chunk index ^= row % 8)
@@ -107,9 +120,13 @@ __device__ __forceinline__ uint32_t hc_chunk(uint32_t stage, int r, int j) {
 }
 
 __device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
+#ifdef FZB_EMU
+    return *reinterpret_cast<const uint32_t *>(emu::smem_base() + saddr);
+#else
     uint32_t r;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(saddr));
     return r;
+#endif
 }
 
 // SLICED = 0: nibble fields, 16-byte table entries (4 wavefronts per lookup);  SLICED = 1: bit-sliced counters,
@@ -135,7 +152,9 @@ k_hamming_count(const ScanParams p, const HamCountParams hp, const __grid_consta
     }
     if (tid == 0) {
         for (int s = 0; s < kHcStages; s++) mbar_init(&full[s], 1);
+#ifndef FZB_EMU
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
     }
     __syncthreads();
     if (tid < (SLICED ? 32 : 8)) {  // replica `tid` of the table: add the pattern's 4-grams (serial per replica: no races)

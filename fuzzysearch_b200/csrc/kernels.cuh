@@ -23,11 +23,15 @@ constexpr int kTileVecs = kFilterThreads * kFilterUnroll;  // uint4s per CTA til
 __device__ __forceinline__ uint32_t hash_word(uint32_t w) { return (w * kHashMul) >> (32 - kTblBits); }
 
 __device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
+#ifdef FZB_EMU  // tests/emu: the CPU replay of these sources has no PTX
+    return *p;
+#else
     uint4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                  : "l"(p));
     return r;
+#endif
 }
 
 // Mark granule g.  The bitmap de-duplicates; the thread that flips the bit 0 -> 1 also appends the
@@ -339,7 +343,11 @@ k_filter_dense(const ScanParams p, int64_t nvec, int64_t ntiles) {
                     key = dense_key(lo, hi);
                 }
                 uint32_t row;
+#ifdef FZB_EMU
+                row = *reinterpret_cast<const uint32_t *>(emu::smem_base() + my_bank + ((key >> 5) << 7));
+#else
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(row) : "r"(my_bank + ((key >> 5) << 7)));
+#endif
                 acc = acc * 2u + (__funnelshift_r(row, 0u, key) & 1u);  // bit (key & 31) of the row
             }
             unsigned flagged = __ballot_sync(0xFFFFFFFFu, acc != 0);

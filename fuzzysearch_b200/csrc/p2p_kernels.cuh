@@ -100,9 +100,13 @@ k_push(const WorldArgs w, const int64_t *fin, const uint32_t *counters, int mode
 
 // ---- merge -----------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) {
+#ifdef FZB_EMU
+    return *reinterpret_cast<const volatile uint32_t *>(p);
+#else
     uint32_t v;
     asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
+#endif
 }
 
 // all CTAs of the grid arrive; returns false on timeout

@@ -46,9 +46,13 @@ struct PostArgs {
 };
 
 __device__ __forceinline__ uint32_t gtimer_lo() {
+#ifdef FZB_EMU
+    return (uint32_t)clock64();
+#else
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return (uint32_t)t;
+#endif
 }
 
 // Block-wide exclusive scans of one value per thread (1024 threads = 32 warps); *total = sum / max of all.

@@ -1,0 +1,708 @@
+// tests/emu/include/cuda_runtime.h -- TEST INFRASTRUCTURE, never shipped, never loaded by the product.
+//
+// A small CUDA execution-model emulator for the CPU suite: tests/emu/build_emu.py compiles the PRODUCT sources
+// (fuzzysearch_b200/csrc/api.cu + *.cuh, textually unchanged except for the launch syntax, see the script) with g++
+// against this header instead of the CUDA toolkit's, into tests/emu/_build/libfuzzb200_emu.so.  The library exports
+// the same C-ABI, so the `-m gpu` parity tests can be replayed here, without a GPU, against the kernels' real source:
+// host logic (api.cu), kernel logic, work lists, overflow paths, the post-processing kernel -- everything except
+// timing, memory-system behaviour and the multi-GPU worlds.
+//
+// Model: one launch at a time (global mutex); CTAs of a grid run one after another; the threads of a CTA are
+// fibers (own stacks, hand-written x86-64 context switch) scheduled round-robin; a fiber runs until it blocks in
+// __syncthreads(), a warp collective (*_sync: rendezvous of the lanes named in the mask) or an explicit spin-wait.
+// __shared__ variables are function-local statics (CTAs are sequential), dynamic shared memory is one static
+// buffer.  Device memory is host memory filled with 0xCD on allocation (an uninitialised read shows).
+#pragma once
+#if !defined(__x86_64__)
+#error "the CUDA emulator's context switch is written for x86-64"
+#endif
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+
+#include <algorithm>
+#include <chrono>
+#include <functional>
+#include <mutex>
+#include <tuple>
+#include <type_traits>
+#include <utility>
+#include <vector>
+
+// ---- qualifiers -------------------------------------------------------------------------------------------------
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __noinline__ __attribute__((noinline))
+#define __launch_bounds__(...)
+#define __grid_constant__
+#define __align__(n) __attribute__((aligned(n)))
+#define __shared__ static
+
+// ---- vector types -----------------------------------------------------------------------------------------------
+struct uint3 {
+    unsigned int x, y, z;
+};
+struct dim3 {
+    unsigned int x, y, z;
+    dim3(unsigned int x_ = 1, unsigned int y_ = 1, unsigned int z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+struct __attribute__((aligned(8))) uint2 {
+    unsigned int x, y;
+};
+struct __attribute__((aligned(16))) uint4 {
+    unsigned int x, y, z, w;
+};
+struct __attribute__((aligned(16))) ulonglong2 {
+    unsigned long long x, y;
+};
+struct __attribute__((aligned(16))) longlong2 {
+    long long x, y;
+};
+static inline uint2 make_uint2(unsigned int x, unsigned int y) { return uint2{x, y}; }
+static inline uint4 make_uint4(unsigned int x, unsigned int y, unsigned int z, unsigned int w) { return uint4{x, y, z, w}; }
+static inline ulonglong2 make_ulonglong2(unsigned long long x, unsigned long long y) { return ulonglong2{x, y}; }
+static inline longlong2 make_longlong2(long long x, long long y) { return longlong2{x, y}; }
+
+// CUDA's min/max overload set follows the usual arithmetic conversions for mixed arguments
+template <class A, class B, class = typename std::enable_if<std::is_arithmetic<A>::value && std::is_arithmetic<B>::value>::type>
+static inline typename std::common_type<A, B>::type min(A a, B b) {
+    typedef typename std::common_type<A, B>::type T;
+    return (T)a < (T)b ? (T)a : (T)b;
+}
+template <class A, class B, class = typename std::enable_if<std::is_arithmetic<A>::value && std::is_arithmetic<B>::value>::type>
+static inline typename std::common_type<A, B>::type max(A a, B b) {
+    typedef typename std::common_type<A, B>::type T;
+    return (T)a > (T)b ? (T)a : (T)b;
+}
+
+// ---- the fiber scheduler ----------------------------------------------------------------------------------------
+extern "C" void fzb_emu_switch(void **save_sp, void *load_sp);
+asm(R"(
+        .text
+        .type fzb_emu_switch,@function
+fzb_emu_switch:
+        pushq %rbp
+        pushq %rbx
+        pushq %r12
+        pushq %r13
+        pushq %r14
+        pushq %r15
+        movq %rsp, (%rdi)
+        movq %rsi, %rsp
+        popq %r15
+        popq %r14
+        popq %r13
+        popq %r12
+        popq %rbx
+        popq %rbp
+        ret
+        .size fzb_emu_switch, .-fzb_emu_switch
+)");
+
+namespace emu {
+
+constexpr unsigned kMaxThreads = 1024;
+constexpr size_t kStackBytes = 256 * 1024;
+constexpr size_t kDynSmemBytes = 232448;  // 227 KiB
+constexpr int kRendezvous = 4;            // concurrent collectives per warp (disjoint masks)
+
+enum Op { OP_SYNCWARP, OP_SHFL, OP_SHFL_UP, OP_SHFL_DOWN, OP_SHFL_XOR, OP_BALLOT, OP_ANY, OP_ALL, OP_MATCH, OP_REDUCE };
+
+struct Rendezvous {
+    uint32_t mask = 0;       // 0 = free
+    uint32_t arrived = 0;
+    uint32_t departed = 0;
+    uint32_t complete = 0;   // set once every live lane of the mask has arrived
+    uint32_t gen = 0;        // bumps on completion (what the waiters watch)
+    int op = 0;
+    uint64_t val[32];
+};
+
+struct Warp {
+    uint32_t alive = 0;
+    Rendezvous rv[kRendezvous];
+};
+
+struct Fiber {
+    void *sp = nullptr;
+    bool done = true;
+    const volatile uint32_t *wait_word = nullptr;  // runnable iff !wait_word || *wait_word != wait_val
+    uint32_t wait_val = 0;
+    uint3 tid{0, 0, 0};
+    unsigned lin = 0;
+};
+
+struct State {
+    Fiber fib[kMaxThreads];
+    Warp warp[kMaxThreads / 32];
+    unsigned nthreads = 0, alive = 0;
+    unsigned bar_arrived = 0;
+    uint32_t bar_gen = 0;
+    void *sched_sp = nullptr;
+    Fiber *cur = nullptr;
+    uint3 bid{0, 0, 0};
+    dim3 bdim, gdim;
+    const std::function<void()> *body = nullptr;
+    char *stacks = nullptr;
+    unsigned long long clock = 0;
+};
+
+inline State &st() {
+    static State s;
+    return s;
+}
+inline std::recursive_mutex &launch_mutex() {
+    static std::recursive_mutex m;
+    return m;
+}
+alignas(1024) static uint8_t g_dyn_smem[kDynSmemBytes];
+inline uint8_t *smem_base() { return g_dyn_smem; }
+template <class T>
+inline T *dyn_smem() {
+    return reinterpret_cast<T *>(g_dyn_smem);
+}
+
+[[noreturn]] inline void die(const char *what) {
+    State &s = st();
+    fprintf(stderr, "cuda-emu: %s (block %u,%u,%u thread %u)\n", what, s.bid.x, s.bid.y, s.bid.z, s.cur ? s.cur->lin : 0u);
+    abort();
+}
+
+inline void yield() {  // still runnable: spin-wait on memory some other fiber (or OS thread) writes
+    State &s = st();
+    Fiber *f = s.cur;
+    f->wait_word = nullptr;
+    fzb_emu_switch(&f->sp, s.sched_sp);
+}
+inline void block_on(const volatile uint32_t *word, uint32_t val) {
+    State &s = st();
+    Fiber *f = s.cur;
+    while (*word == val) {
+        f->wait_word = word;
+        f->wait_val = val;
+        fzb_emu_switch(&f->sp, s.sched_sp);
+    }
+    f->wait_word = nullptr;
+}
+
+inline void rv_check_complete(Warp &w, Rendezvous &r) {
+    const uint32_t need = r.mask & w.alive;
+    if (!r.complete && r.mask && (r.arrived & need) == need) {
+        r.complete = 1;
+        r.gen++;
+    }
+}
+
+inline void fiber_exit() {
+    State &s = st();
+    Fiber *f = s.cur;
+    f->done = true;
+    s.alive--;
+    Warp &w = s.warp[f->lin >> 5];
+    w.alive &= ~(1u << (f->lin & 31));
+    for (int i = 0; i < kRendezvous; i++) rv_check_complete(w, w.rv[i]);  // a lane others were waiting for has left
+    if (s.bar_arrived && s.bar_arrived == s.alive) {                       // ... or the CTA barrier was waiting for it
+        s.bar_arrived = 0;
+        s.bar_gen++;
+    }
+    void *dummy;
+    fzb_emu_switch(&dummy, s.sched_sp);
+    die("resumed a finished fiber");
+}
+
+extern "C" inline void fzb_emu_trampoline() {
+    (*st().body)();
+    fiber_exit();
+}
+
+inline void run_block() {
+    State &s = st();
+    const unsigned n = s.bdim.x * s.bdim.y * s.bdim.z;
+    if (n == 0 || n > kMaxThreads) die("bad block size");
+    if (!s.stacks) {
+        s.stacks = (char *)mmap(nullptr, kStackBytes * kMaxThreads, PROT_READ | PROT_WRITE,
+                                MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+        if (s.stacks == (char *)MAP_FAILED) die("cannot map fiber stacks");
+    }
+    s.nthreads = s.alive = n;
+    s.bar_arrived = 0;
+    for (unsigned w = 0; w < (n + 31) / 32; w++) {
+        s.warp[w] = Warp();
+        const unsigned cnt = std::min(32u, n - 32 * w);
+        s.warp[w].alive = cnt == 32 ? 0xFFFFFFFFu : ((1u << cnt) - 1u);
+    }
+    for (unsigned i = 0; i < n; i++) {
+        Fiber &f = s.fib[i];
+        f.done = false;
+        f.wait_word = nullptr;
+        f.lin = i;
+        f.tid.x = i % s.bdim.x;
+        f.tid.y = (i / s.bdim.x) % s.bdim.y;
+        f.tid.z = i / (s.bdim.x * s.bdim.y);
+        uint64_t *top = reinterpret_cast<uint64_t *>(s.stacks + (size_t)(i + 1) * kStackBytes);  // 16-byte aligned
+        top[-1] = 0;                                                                            // fake return address
+        top[-2] = reinterpret_cast<uint64_t>(&fzb_emu_trampoline);
+        for (int r = 3; r <= 8; r++) top[-r] = 0;  // rbp rbx r12 r13 r14 r15
+        f.sp = top - 8;
+    }
+    while (s.alive) {
+        bool ran = false;
+        for (unsigned i = 0; i < n; i++) {
+            Fiber &f = s.fib[i];
+            if (f.done) continue;
+            if (f.wait_word && *f.wait_word == f.wait_val) continue;
+            s.cur = &f;
+            ran = true;
+            fzb_emu_switch(&s.sched_sp, f.sp);
+        }
+        if (!ran) die("deadlock: every live thread of the CTA is blocked (divergent barrier or collective?)");
+    }
+    s.cur = nullptr;
+}
+
+// one kernel launch: CTAs in order, arguments evaluated once (by the caller's lambda capture)
+template <class Body>
+inline void launch(dim3 grid, dim3 block, size_t smem, Body &&body) {
+    std::lock_guard<std::recursive_mutex> lock(launch_mutex());
+    if (smem > kDynSmemBytes) die("dynamic shared memory request too large");
+    State &s = st();
+    if (s.cur) die("nested launch");
+    const std::function<void()> fn = std::forward<Body>(body);
+    s.body = &fn;
+    s.gdim = grid;
+    s.bdim = block;
+    for (unsigned z = 0; z < grid.z; z++)
+        for (unsigned y = 0; y < grid.y; y++)
+            for (unsigned x = 0; x < grid.x; x++) {
+                s.bid = uint3{x, y, z};
+                memset(g_dyn_smem, 0xA5, smem);  // shared memory starts as garbage, like on the device
+                run_block();
+            }
+    s.body = nullptr;
+}
+
+// ---- warp collectives ---------------------------------------------------------------------------------------
+inline Rendezvous &rv_arrive(uint32_t mask, int op, uint64_t v, int *lane_out) {
+    State &s = st();
+    Fiber *f = s.cur;
+    const int lane = f->lin & 31;
+    *lane_out = lane;
+    Warp &w = s.warp[f->lin >> 5];
+    if (!(mask & (1u << lane))) die("collective: the calling lane is not in its own mask");
+    Rendezvous *r = nullptr;
+    for (int i = 0; i < kRendezvous && !r; i++)
+        if (w.rv[i].mask == mask && !w.rv[i].complete && !(w.rv[i].arrived & (1u << lane))) r = &w.rv[i];
+    if (!r) {
+        for (int i = 0; i < kRendezvous && !r; i++)
+            if (w.rv[i].mask == 0) r = &w.rv[i];
+        if (!r) die("collective: too many concurrent rendezvous in one warp");
+        r->mask = mask;
+        r->arrived = r->departed = r->complete = 0;
+        r->op = op;
+    }
+    if (r->op != op) die("collective: lanes of one mask met in different operations (divergence bug)");
+    r->val[lane] = v;
+    r->arrived |= 1u << lane;
+    const uint32_t g = r->gen;
+    rv_check_complete(w, *r);
+    if (!r->complete) block_on(&r->gen, g);
+    return *r;
+}
+inline void rv_depart(Rendezvous &r, int lane) {
+    r.departed |= 1u << lane;
+    if (r.departed == r.arrived) r.mask = 0;  // free
+}
+
+template <class T>
+inline uint64_t to_bits(T v) {
+    static_assert(sizeof(T) <= 8, "collective operand wider than 64 bits");
+    uint64_t b = 0;
+    memcpy(&b, &v, sizeof(T));
+    return b;
+}
+template <class T>
+inline T from_bits(uint64_t b) {
+    T v;
+    memcpy(&v, &b, sizeof(T));
+    return v;
+}
+template <class T>
+inline T shfl_generic(uint32_t mask, T v, int op, int arg, int width) {
+    int lane;
+    Rendezvous &r = rv_arrive(mask, op, to_bits(v), &lane);
+    const int seg = lane & ~(width - 1);
+    int src;
+    bool ok;
+    if (op == OP_SHFL) {
+        src = seg + (arg & (width - 1));
+        ok = true;
+    } else if (op == OP_SHFL_UP) {
+        src = lane - arg;
+        ok = src >= seg;
+    } else if (op == OP_SHFL_DOWN) {
+        src = lane + arg;
+        ok = src < seg + width;
+    } else {
+        src = lane ^ arg;
+        ok = src < seg + width;
+    }
+    T out = v;
+    if (ok && (r.arrived & (1u << src))) out = from_bits<T>(r.val[src]);
+    rv_depart(r, lane);
+    return out;
+}
+
+}  // namespace emu
+
+#define threadIdx (emu::st().cur->tid)
+#define blockIdx (emu::st().bid)
+#define blockDim (emu::st().bdim)
+#define gridDim (emu::st().gdim)
+#define warpSize 32
+
+static inline void __syncthreads() {
+    emu::State &s = emu::st();
+    const uint32_t g = s.bar_gen;
+    if (++s.bar_arrived == s.alive) {
+        s.bar_arrived = 0;
+        s.bar_gen++;
+        return;
+    }
+    emu::block_on(&s.bar_gen, g);
+}
+static inline void __syncwarp(unsigned mask = 0xFFFFFFFFu) {
+    int lane;
+    emu::Rendezvous &r = emu::rv_arrive(mask, emu::OP_SYNCWARP, 0, &lane);
+    emu::rv_depart(r, lane);
+}
+template <class T>
+static inline T __shfl_sync(unsigned mask, T v, int src, int width = 32) {
+    return emu::shfl_generic(mask, v, emu::OP_SHFL, src, width);
+}
+template <class T>
+static inline T __shfl_up_sync(unsigned mask, T v, unsigned delta, int width = 32) {
+    return emu::shfl_generic(mask, v, emu::OP_SHFL_UP, (int)delta, width);
+}
+template <class T>
+static inline T __shfl_down_sync(unsigned mask, T v, unsigned delta, int width = 32) {
+    return emu::shfl_generic(mask, v, emu::OP_SHFL_DOWN, (int)delta, width);
+}
+template <class T>
+static inline T __shfl_xor_sync(unsigned mask, T v, int lanemask, int width = 32) {
+    return emu::shfl_generic(mask, v, emu::OP_SHFL_XOR, lanemask, width);
+}
+static inline unsigned __ballot_sync(unsigned mask, int pred) {
+    int lane;
+    emu::Rendezvous &r = emu::rv_arrive(mask, emu::OP_BALLOT, pred ? 1 : 0, &lane);
+    unsigned out = 0;
+    for (int i = 0; i < 32; i++)
+        if ((r.arrived >> i) & 1u) out |= (unsigned)(r.val[i] & 1u) << i;
+    emu::rv_depart(r, lane);
+    return out;
+}
+static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
+static inline int __all_sync(unsigned mask, int pred) {
+    int lane;
+    emu::Rendezvous &r = emu::rv_arrive(mask, emu::OP_ALL, pred ? 1 : 0, &lane);
+    int out = 1;
+    for (int i = 0; i < 32; i++)
+        if (((r.arrived >> i) & 1u) && !(r.val[i] & 1u)) out = 0;
+    emu::rv_depart(r, lane);
+    return out;
+}
+template <class T>
+static inline unsigned __match_any_sync(unsigned mask, T v) {
+    int lane;
+    const uint64_t mine = emu::to_bits(v);
+    emu::Rendezvous &r = emu::rv_arrive(mask, emu::OP_MATCH, mine, &lane);
+    unsigned out = 0;
+    for (int i = 0; i < 32; i++)
+        if (((r.arrived >> i) & 1u) && r.val[i] == mine) out |= 1u << i;
+    emu::rv_depart(r, lane);
+    return out;
+}
+template <class T>
+static inline T __reduce_add_sync(unsigned mask, T v) {
+    int lane;
+    emu::Rendezvous &r = emu::rv_arrive(mask, emu::OP_REDUCE, emu::to_bits(v), &lane);
+    T out = 0;
+    for (int i = 0; i < 32; i++)
+        if ((r.arrived >> i) & 1u) out += emu::from_bits<T>(r.val[i]);
+    emu::rv_depart(r, lane);
+    return out;
+}
+
+// ---- atomics (one OS thread executes kernels at a time; other host threads only read results after a launch) ----
+template <class T, class U>
+static inline T atomicAdd(T *p, U v) { return __atomic_fetch_add(p, (T)v, __ATOMIC_SEQ_CST); }
+template <class T, class U>
+static inline T atomicOr(T *p, U v) { return __atomic_fetch_or(p, (T)v, __ATOMIC_SEQ_CST); }
+template <class T, class U>
+static inline T atomicAnd(T *p, U v) { return __atomic_fetch_and(p, (T)v, __ATOMIC_SEQ_CST); }
+template <class T, class U>
+static inline T atomicExch(T *p, U v) { return __atomic_exchange_n(p, (T)v, __ATOMIC_SEQ_CST); }
+template <class T, class U>
+static inline T atomicMin(T *p, U v) {
+    T old = *p;
+    if ((T)v < old) *p = (T)v;
+    return old;
+}
+template <class T, class U>
+static inline T atomicMax(T *p, U v) {
+    T old = *p;
+    if ((T)v > old) *p = (T)v;
+    return old;
+}
+template <class T, class U, class V>
+static inline T atomicCAS(T *p, U cmp, V v) {
+    T expected = (T)cmp;
+    __atomic_compare_exchange_n(p, &expected, (T)v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+    return expected;
+}
+
+// ---- integer intrinsics -----------------------------------------------------------------------------------------
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
+static inline int __ffs(int x) { return __builtin_ffs(x); }
+static inline int __ffsll(long long x) { return __builtin_ffsll(x); }
+static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
+static inline int __clzll(long long x) { return x ? __builtin_clzll((unsigned long long)x) : 64; }
+static inline unsigned __brev(unsigned x) {
+    unsigned r = 0;
+    for (int i = 0; i < 32; i++) r |= ((x >> i) & 1u) << (31 - i);
+    return r;
+}
+static inline unsigned long long __brevll(unsigned long long x) {
+    unsigned long long r = 0;
+    for (int i = 0; i < 64; i++) r |= ((x >> i) & 1ull) << (63 - i);
+    return r;
+}
+static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift) {
+    const unsigned long long v = ((unsigned long long)hi << 32) | lo;
+    return (unsigned)(v >> (shift & 31));
+}
+static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned shift) {
+    const unsigned long long v = ((unsigned long long)hi << 32) | lo;
+    return (unsigned)((v << (shift & 31)) >> 32);
+}
+static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel) {
+    const unsigned long long v = ((unsigned long long)b << 32) | a;
+    unsigned r = 0;
+    for (int i = 0; i < 4; i++) r |= (unsigned)((v >> (8 * ((sel >> (4 * i)) & 7))) & 0xFF) << (8 * i);
+    return r;
+}
+static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
+template <class T>
+static inline T __ldg(const T *p) { return *p; }
+template <class T>
+static inline T __ldcg(const T *p) { return *reinterpret_cast<const volatile T *>(p); }
+template <>
+inline uint4 __ldcg<uint4>(const uint4 *p) { return *p; }
+template <>
+inline uint2 __ldcg<uint2>(const uint2 *p) { return *p; }
+template <>
+inline ulonglong2 __ldcg<ulonglong2>(const ulonglong2 *p) { return *p; }
+template <>
+inline longlong2 __ldcg<longlong2>(const longlong2 *p) { return *p; }
+template <class T>
+static inline T __ldcs(const T *p) { return *p; }
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline long long clock64() { return (long long)(emu::st().clock += (1ull << 24)); }  // spin loops time out fast
+static inline size_t __cvta_generic_to_shared(const void *p) {
+    return (size_t)(reinterpret_cast<const uint8_t *>(p) - emu::smem_base());
+}
+static inline void __nanosleep(unsigned) { emu::yield(); }
+
+// ---- the runtime API (host memory stands in for device memory; everything is synchronous) -----------------------
+typedef int cudaError_t;
+enum {
+    cudaSuccess = 0,
+    cudaErrorInvalidValue = 1,
+    cudaErrorMemoryAllocation = 2,
+    cudaErrorNotReady = 600,
+    cudaErrorPeerAccessAlreadyEnabled = 704,
+    cudaErrorNotSupported = 801
+};
+enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
+typedef struct emu_stream *cudaStream_t;
+struct emu_event {
+    std::chrono::steady_clock::time_point t;
+};
+typedef emu_event *cudaEvent_t;
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaEventDefault = 0 };
+enum { cudaHostAllocDefault = 0, cudaHostAllocPortable = 1, cudaHostAllocMapped = 2, cudaHostRegisterDefault = 0 };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum { cudaEnableDefault = 0 };
+enum cudaDriverEntryPointQueryResult { cudaDriverEntryPointSuccess = 0, cudaDriverEntryPointSymbolNotFound = 1 };
+enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2, cudaMemoryTypeManaged = 3 };
+struct cudaPointerAttributes {
+    cudaMemoryType type;
+    int device;
+    void *devicePointer;
+    void *hostPointer;
+};
+struct cudaDeviceProp {
+    char name[256];
+    int multiProcessorCount;
+    int major, minor;
+    size_t totalGlobalMem;
+    size_t sharedMemPerBlockOptin;
+    int l2CacheSize;
+};
+struct cudaIpcMemHandle_t {
+    char reserved[64];
+};
+enum { cudaIpcMemLazyEnablePeerAccess = 1 };
+
+namespace emu {
+struct HostRanges {  // what cudaHostAlloc / cudaMallocHost handed out (cudaPointerGetAttributes)
+    std::mutex mu;
+    std::vector<std::pair<uintptr_t, size_t>> v;
+};
+inline HostRanges &host_ranges() {
+    static HostRanges h;
+    return h;
+}
+inline int sm_count() {
+    const char *e = getenv("FZB_EMU_SMS");
+    const int n = e ? atoi(e) : 0;
+    return n > 0 ? n : 4;
+}
+inline void *alloc_bytes(size_t n, int fill) {
+    void *p = nullptr;
+    if (posix_memalign(&p, 1024, n ? n : 1)) return nullptr;
+    memset(p, fill, n);
+    return p;
+}
+}  // namespace emu
+
+static inline const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated CUDA error"; }
+static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+static inline cudaError_t cudaGetDeviceCount(int *n) {
+    *n = getenv("FZB_EMU_NO_DEVICE") ? 0 : 1;
+    return cudaSuccess;
+}
+static inline cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : cudaErrorInvalidValue; }
+static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
+    memset(p, 0, sizeof(*p));
+    snprintf(p->name, sizeof(p->name), "cuda-emu (CPU)");
+    p->multiProcessorCount = emu::sm_count();
+    p->major = 10;
+    p->minor = 0;
+    p->totalGlobalMem = (size_t)8 << 30;
+    p->sharedMemPerBlockOptin = emu::kDynSmemBytes;
+    p->l2CacheSize = 126 << 20;
+    return cudaSuccess;
+}
+template <class T>
+static inline cudaError_t cudaMalloc(T **p, size_t n) {
+    *p = (T *)emu::alloc_bytes(n, 0xCD);
+    return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
+static inline cudaError_t cudaFree(void *p) {
+    free(p);
+    return cudaSuccess;
+}
+template <class T>
+static inline cudaError_t cudaHostAlloc(T **p, size_t n, unsigned) {
+    *p = (T *)emu::alloc_bytes(n, 0xCD);
+    if (!*p) return cudaErrorMemoryAllocation;
+    emu::HostRanges &h = emu::host_ranges();
+    std::lock_guard<std::mutex> l(h.mu);
+    h.v.push_back(std::make_pair((uintptr_t)*p, n));
+    return cudaSuccess;
+}
+template <class T>
+static inline cudaError_t cudaMallocHost(T **p, size_t n) { return cudaHostAlloc(p, n, 0); }
+static inline cudaError_t cudaFreeHost(void *p) {
+    emu::HostRanges &h = emu::host_ranges();
+    {
+        std::lock_guard<std::mutex> l(h.mu);
+        for (size_t i = 0; i < h.v.size(); i++)
+            if (h.v[i].first == (uintptr_t)p) {
+                h.v.erase(h.v.begin() + i);
+                break;
+            }
+    }
+    free(p);
+    return cudaSuccess;
+}
+static inline cudaError_t cudaHostRegister(void *, size_t, unsigned) { return cudaSuccess; }
+static inline cudaError_t cudaHostUnregister(void *) { return cudaSuccess; }
+static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *p) {
+    emu::HostRanges &h = emu::host_ranges();
+    std::lock_guard<std::mutex> l(h.mu);
+    a->type = cudaMemoryTypeUnregistered;
+    a->device = 0;
+    a->devicePointer = a->hostPointer = const_cast<void *>(p);
+    for (size_t i = 0; i < h.v.size(); i++)
+        if ((uintptr_t)p >= h.v[i].first && (uintptr_t)p < h.v[i].first + h.v[i].second) a->type = cudaMemoryTypeHost;
+    return cudaSuccess;
+}
+static inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) {
+    std::lock_guard<std::recursive_mutex> lock(emu::launch_mutex());
+    memmove(d, s, n);
+    return cudaSuccess;
+}
+static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind k, cudaStream_t = nullptr) {
+    return cudaMemcpy(d, s, n, k);
+}
+static inline cudaError_t cudaMemset(void *d, int v, size_t n) {
+    std::lock_guard<std::recursive_mutex> lock(emu::launch_mutex());
+    memset(d, v, n);
+    return cudaSuccess;
+}
+static inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t = nullptr) { return cudaMemset(d, v, n); }
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) {
+    *s = (cudaStream_t)malloc(8);
+    return cudaSuccess;
+}
+static inline cudaError_t cudaStreamDestroy(cudaStream_t s) {
+    free(s);
+    return cudaSuccess;
+}
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaStreamQuery(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+static inline cudaError_t cudaEventCreate(cudaEvent_t *e) {
+    *e = new emu_event();
+    return cudaSuccess;
+}
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { return cudaEventCreate(e); }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t e) {
+    delete e;
+    return cudaSuccess;
+}
+static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) {
+    e->t = std::chrono::steady_clock::now();
+    return cudaSuccess;
+}
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventQuery(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) {
+    *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count();
+    return cudaSuccess;
+}
+template <class F>
+static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+template <class F>
+static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, F, int, size_t) {
+    *n = 2;
+    return cudaSuccess;
+}
+static inline cudaError_t cudaDeviceCanAccessPeer(int *can, int, int) {
+    *can = 0;
+    return cudaSuccess;
+}
+static inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaErrorNotSupported; }
+static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return cudaErrorNotSupported; }
+static inline cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
+static inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaErrorNotSupported; }
+cudaError_t cudaGetDriverEntryPoint(const char *name, void **fn, unsigned long long flags,
+                                    cudaDriverEntryPointQueryResult *q);  // cuda.h
