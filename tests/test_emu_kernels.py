@@ -1,0 +1,139 @@
+"""The product's CUDA sources replayed on the CPU: `pytest -m "not gpu"` coverage of the KERNELS and of api.cu.
+
+tests/emu compiles fuzzysearch_b200/csrc (api.cu and every *.cuh, the code that ships) against a small CUDA
+execution-model emulator -- fibers for threads, rendezvous for the warp collectives, TMA / mbarrier restated -- into
+tests/emu/_build/libfuzzb200_emu.so with the same C-ABI.  The tests below bind it in place of libfuzzb200.so and run
+the bodies of the `-m gpu` parity tests (same functions, same oracle, same fixtures) at the sizes a CPU can do in
+seconds.  It proves kernel LOGIC and host logic -- filters lose no match, work lists and overflow paths, bit-parallel
+expansions, consolidation, batches, wide symbols, file loops, locking -- not timing, memory-model behaviour or the
+multi-GPU worlds (those need the B200: tests/test_gpu_global.py, bench.py).  The emulated library is test
+infrastructure: nothing in the product can load it.
+
+`FZB_TEST_BACKEND=emu python -m pytest tests -m gpu` replays the whole GPU suite this way (minutes), and
+`python tests/emu/fuzz_emu.py` runs a randomised campaign far beyond what fits a GPU budget.
+"""
+import gc
+import inspect
+
+import pytest
+
+import conftest
+import test_gpu_batch
+import test_gpu_expand
+import test_gpu_file
+import test_gpu_fuzz
+import test_gpu_golden
+import test_gpu_oracle
+import test_gpu_python_api
+import test_gpu_symbols
+from fuzzysearch_b200 import _native, search
+
+
+@pytest.fixture(scope="module")
+def emu_lib():
+    return conftest.load_emulated_library()
+
+
+@pytest.fixture()
+def emu_device(emu_lib, monkeypatch):
+    monkeypatch.setattr(_native, "_lib", emu_lib)
+    saved = dict(search._WORKSPACE)
+    search._WORKSPACE.clear()
+    yield 0
+    search.release_workspace()
+    gc.collect()  # every handle of the emulated library dies while it is still the bound one
+    search._WORKSPACE.update(saved)
+
+
+def _cases(func):
+    """Expand the @pytest.mark.parametrize marks of a gpu test function into keyword dicts."""
+    out = [{}]
+    for mark in getattr(func, "pytestmark", []):
+        if mark.name != "parametrize":
+            continue
+        names = [a.strip() for a in mark.args[0].split(",")]
+        new = []
+        for base in out:
+            for values in mark.args[1]:
+                if len(names) == 1:
+                    values = (values,)
+                d = dict(base)
+                d.update(zip(names, values))
+                new.append(d)
+        out = new
+    return out
+
+
+def _run(func, device, **extra):
+    for kw in _cases(func):
+        kw.update(extra)
+        func(device, **kw)
+
+
+def test_emulator_is_the_product_source(emu_lib):
+    """Same exported C-ABI as the header declares, and it says it is an emulator only through the device name."""
+    for name in _native.SYMBOLS:
+        assert hasattr(emu_lib, name), name
+    assert emu_lib.fzb_device_count() == 1
+
+
+def test_emu_ngram_route_vs_oracle(emu_device):
+    _run(test_gpu_oracle.test_levenshtein_ngrams_matches_oracle, emu_device)
+
+
+def test_emu_hamming_lp_generic_vs_oracle(emu_device):
+    _run(test_gpu_oracle.test_hamming_matches_oracle, emu_device)
+    _run(test_gpu_oracle.test_levenshtein_lp_matches_oracle, emu_device)
+    _run(test_gpu_oracle.test_generic_matches_oracle, emu_device)
+
+
+def test_emu_shards_edge_cases_python_surface(emu_device):
+    _run(test_gpu_oracle.test_sharded_union_equals_whole, emu_device)
+    test_gpu_oracle.test_edge_cases(emu_device)
+    test_gpu_oracle.test_python_surface_variants(emu_device)
+
+
+def test_emu_random_sweeps(emu_device):
+    test_gpu_fuzz.test_levenshtein_random_sweep(emu_device)
+    test_gpu_fuzz.test_hamming_random_sweep(emu_device)
+    test_gpu_fuzz.test_generic_random_sweep(emu_device)
+
+
+def test_emu_expansion_kernels(emu_device):
+    test_gpu_expand.test_expand_golden_records(emu_device)
+    test_gpu_expand.test_expand_quirk_vectors(emu_device)
+    test_gpu_expand.test_expand_fuzz_vs_oracle(emu_device)
+
+
+def test_emu_reference_suite_calls(emu_device):
+    test_gpu_golden.test_gpu_replays_reference_suite_calls(emu_device)
+
+
+def test_emu_batches(emu_device):
+    test_gpu_batch.test_batch_matches_oracle(emu_device)
+    test_gpu_batch.test_batch_shared_scan_edge_cases(emu_device)
+
+
+def test_emu_file_search(emu_device, tmp_path):
+    for i, kw in enumerate(_cases(test_gpu_file.test_match_split_between_chunks)):
+        d = tmp_path / ("c%d" % i)
+        d.mkdir()
+        test_gpu_file.test_match_split_between_chunks(emu_device, tmp_path=d, **kw)
+    test_gpu_file.test_file_random_corpus(emu_device, tmp_path)
+
+
+def test_emu_threads_and_has_near_match(emu_device):
+    test_gpu_python_api.test_find_near_matches_is_thread_safe(emu_device)
+    test_gpu_python_api.test_threads_share_one_resident_sequence(emu_device)
+    test_gpu_python_api.test_has_near_match_all_routes_vs_oracle(emu_device)
+
+
+def test_emu_wide_symbols(emu_device, tmp_path):
+    for kw in _cases(test_gpu_symbols.test_device_reduction_of_code_units):
+        if kw["n"] <= 1 << 16:
+            test_gpu_symbols.test_device_reduction_of_code_units(emu_device, **kw)
+    test_gpu_symbols.test_resident_wide_sequence_and_batches(emu_device)
+    test_gpu_symbols.test_items_resident_and_mixed_types(emu_device)
+    sig = inspect.signature(test_gpu_symbols.test_wide_cases_of_the_reference_suite)
+    assert list(sig.parameters) == ["cuda_device", "tmp_path"]
+    test_gpu_symbols.test_wide_cases_of_the_reference_suite(emu_device, tmp_path)
