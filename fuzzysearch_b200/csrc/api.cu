@@ -1769,6 +1769,14 @@ static int search_lev_lp(fzb_haystack *h, const uint8_t *pattern, uint32_t m, ui
 static int search_generic(fzb_haystack *h, const uint8_t *pattern, uint32_t m, uint32_t max_subs, uint32_t max_ins,
                           uint32_t max_dels, uint32_t max_l, bool ngrams, uint32_t flags, fzb_result *res,
                           int post_mode) {
+    // LP route: every substitution and every deletion consumes a pattern character (so does the "insertion +
+    // deletion" pair the reference books when the substitutions are used up, generic_search.py:111-128), hence a
+    // live candidate at pattern index j has spent l <= j + n_ins < m + max_ins: a total limit above m + max_ins
+    // never binds -- not in `l_dist < max_l_dist` (:101-102), not in the deletion loop's bound (:141), not in the
+    // final loop (:172-177) -- and can be lowered to it without changing the raw stream.  (Not so on the n-gram
+    // route, where max_l_dist also sets the n-gram length and the windows.)  E.g. max_substitutions=100,
+    // max_insertions=1, max_deletions=1 on 20 symbols: 102 -> 21.
+    if (!ngrams) max_l = (uint32_t)std::min<uint64_t>(max_l, (uint64_t)m + std::min(max_ins, max_l));
     // the packed candidate of sim_generic keeps 6 bits per counter
     if (max_l > 63) return fail(FZB_E_UNSUPPORTED, "max_l_dist > 63 is not supported by the generic search");
     // no counter can exceed max_l (every operation that increments one costs >= 1), so clamping the

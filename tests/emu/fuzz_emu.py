@@ -276,10 +276,13 @@ def batch_trial(rng):
         return
     for i, (p, k, res) in enumerate(zip(pats, ks, results)):
         cpu = oracle.levenshtein_raw(p, hay, k)
-        want = tup(oracle.consolidate(cpu)) if k > 0 else sorted(tup(cpu))
+        want = tup(oracle.consolidate(cpu))
         got = res.triples(F.FINAL)
         if got != want:
             fail("batch", ctx + (i, len(p), k, len(got), len(want)))
+        # k == 0: find_near_matches_batch() hands out the RAW stream (ExactSearch does not consolidate)
+        if k == 0 and sorted(res.triples(F.RAW)) != sorted(tup(cpu)):
+            fail("batch-raw-k0", ctx + (i, len(p)))
         res.close()
     hs.close()
 

@@ -96,6 +96,10 @@ def test_levenshtein_lp_matches_oracle(cuda_device, alphabet, n, m, k):
     (DNA, 1 << 12, 12, (1, 1, 0, 2), 0),
     (ASCII, 1 << 14, 8, (1, 2, 1, 3), F.F_FORCE_LP),
     (DNA, 1 << 11, 6, (2, 0, 2, 3), F.F_FORCE_LP),
+    # limits far above what 20 symbols can spend (max_l_dist=None -> the sum, common.py:86-104): the LP route lowers
+    # the total to m + max_insertions, which cannot change the raw stream (search_generic, api.cu)
+    (ASCII, 1 << 12, 20, (100, 1, 1, 102), F.F_FORCE_LP),
+    (b"abcd", 1 << 9, 12, (50, 2, 50, 102), F.F_FORCE_LP),
 ])
 def test_generic_matches_oracle(cuda_device, alphabet, n, m, limits, flags):
     pat, hay, _ = make_corpus(9, n, alphabet, m, 32, limits[3] + 1)
