@@ -47,7 +47,7 @@ struct PostArgs {
 
 __device__ __forceinline__ uint32_t gtimer_lo() {
 #ifdef FZB_EMU
-    return (uint32_t)clock64();
+    return (uint32_t)emu::cycles();
 #else
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));

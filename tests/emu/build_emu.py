@@ -1,10 +1,11 @@
 """Build tests/emu/_build/libfuzzb200_emu.so: the PRODUCT sources compiled for the CPU emulator.  Test infrastructure.
 
-The sources under fuzzysearch_b200/csrc are copied into tests/emu/_build/src with TWO textual rewrites -- g++ cannot
+The sources under fuzzysearch_b200/csrc are copied into tests/emu/_build/src with THREE textual rewrites -- g++ cannot
 parse them otherwise -- and compiled with -DFZB_EMU against tests/emu/include (cuda_runtime.h / cuda.h stand-ins):
 
   kernel<<<grid, block, smem, stream>>>(args);   ->  emu::launch(dim3(grid), dim3(block), smem, [..]{ kernel(args); });
   extern __shared__ __align__(N) T name[];       ->  T *name = emu::dyn_smem<T>();
+  __shared__ T a[N], b;                          ->  static T a[N], b; static emu::SharedReg ...(&a, sizeof(a)), ...;
 
 (the argument expressions are evaluated once, into a tuple, before the CTAs run).  Everything else -- the kernels, the
 host logic of api.cu, the C-ABI -- is the code that ships; the handful of inline-PTX helpers carry an `#ifdef FZB_EMU`
@@ -71,18 +72,34 @@ def rewrite_launches(src):
         b = _match_paren(src, a)
         args = src[a + 1:b]
         smem = cfg[2] if len(cfg) > 2 else "0"
-        call = ("do { auto emu_args_ = std::make_tuple(%s); emu::launch(dim3(%s), dim3(%s), (size_t)(%s), [&]() { "
-                "std::apply([](auto &...emu_a_) { %s(emu_a_...); }, emu_args_); }); } while (0)"
-                % (args, cfg[0], cfg[1], smem, m.group(1)))
+        stream = cfg[3] if len(cfg) > 3 else "nullptr"
+        call = ("do { auto emu_args_ = std::make_tuple(%s); emu::launch(dim3(%s), dim3(%s), (size_t)(%s), %s, "
+                "[emu_args_]() { std::apply([](const auto &...emu_a_) { %s(emu_a_...); }, emu_args_); }); } while (0)"
+                % (args, cfg[0], cfg[1], smem, stream, m.group(1)))
         out += src[pos:m.start(1)] + call
         pos = b + 1
 
 
 _DYN_RE = re.compile(r"extern\s+__shared__\s+__align__\(\d+\)\s+(\w+)\s+(\w+)\[\];")
+_SHARED_RE = re.compile(r"^(\s*)__shared__\s+((?:__align__\(\d+\)\s+)?)([^;]+);", re.M)
+
+
+def _rewrite_shared(m):
+    """`__shared__ T a[N], b;` -> a function-local static plus its registration with the emulator (which saves and
+    restores the __shared__ variables of a CTA that has to wait for another one)."""
+    indent, align, body = m.group(1), m.group(2), m.group(3)
+    decls = _split_top(body)
+    first = re.match(r"(.*?)(\w+)\s*((?:\[[^\]]*\])*)$", decls[0].strip())
+    assert first, body
+    names = [first.group(2)] + [re.match(r"(\w+)", d.strip()).group(1) for d in decls[1:]]
+    regs = ", ".join("emu_reg_%s(&%s, sizeof(%s))" % (n, n, n) for n in names)
+    return "%sstatic %s%s; static emu::SharedReg %s;" % (indent, align, body, regs)
 
 
 def rewrite(src):
     src = _DYN_RE.sub(lambda m: "%s *%s = emu::dyn_smem<%s>();" % (m.group(1), m.group(2), m.group(1)), src)
+    src = _SHARED_RE.sub(_rewrite_shared, src)
+    assert not re.search(r"^\s*(extern\s+)?__shared__", src, re.M), "unhandled __shared__ declaration"
     return rewrite_launches(src)
 
 

@@ -1,6 +1,6 @@
 """Randomised parity campaign on the CPU emulator: product kernels (tests/emu) vs the CPU oracle.  Developer tool.
 
-    python tests/emu/fuzz_emu.py --seed 1 --trials 400 [--routes lev,ham,generic,exact,shard,batch,has]
+    python tests/emu/fuzz_emu.py --seed 1 --trials 400 [--routes world,lev,ham,generic,exact,shard,batch,has]
 
 Far more geometry than the `-m gpu` suite can afford on a B200 budget: tiny and empty sequences, every pattern
 length, forced filters, capped work lists (overflow paths), shards with arbitrary seams, grid sizes (FZB_EMU_SMS),
@@ -25,6 +25,8 @@ from fuzzysearch_b200 import _native as F  # noqa: E402
 from parity import tup  # noqa: E402
 
 ALPHABETS = [b"a", b"ab", DNA, b"abcdefgh", ASCII, bytes(range(256))]
+if os.environ.get("FZB_FUZZ_ZEROS"):  # the buffers are zero-padded: patterns and text made of zero bytes
+    ALPHABETS = [b"\x00", b"\x00\x01", b"\x00\xff\x00\x00", bytes(range(4))]
 FAILS = []
 
 
@@ -323,7 +325,58 @@ def has_trial(rng):
     hs.close()
 
 
-TRIALS = {"lev": lev_trial, "ham": ham_trial, "generic": generic_trial, "exact": exact_trial, "shard": shard_trial,
+def world_trial(rng):
+    """In-process world (one host thread per shard): the k_push / k_merge reduction vs the oracle's global list."""
+    from fuzzysearch_b200.sharding import init_local_world, search_all, shard_bounds
+    alphabet = ALPHABETS[int(rng.integers(2, len(ALPHABETS)))]
+    world = int(rng.integers(1, 9))
+    m = int(rng.choice([3, 5, 8, 12, 20, 33, 64]))
+    k = int(rng.integers(0, min(m - 1, 4) + 1))
+    n = int(rng.choice([64, 300, 4096, 4097, 70000]))
+    if k > 0 and m // (k + 1) < 3:
+        k = min(k, 2)
+        n = min(n, 4096)
+    if len(alphabet) <= 4:
+        n = min(n, 4096)
+    n = max(n, world * 32)
+    seed = int(rng.integers(1 << 30))
+    pat, hay, _ = make_corpus(seed, n, alphabet, m, int(rng.integers(1, 12)), k + 1, clusters=int(rng.integers(0, 4)))
+    halo = m + max(k, 3)
+    for r in range(1, world):  # something straddling every seam
+        seam = shard_bounds(n, world, r, halo)[2]
+        pos = seam - int(rng.integers(0, m + 1))
+        if 0 <= pos and pos + m <= n:
+            hay[pos:pos + m] = np.frombuffer(pat, dtype=np.uint8)
+    shards = []
+    for r in range(world):
+        blo, bhi, lo, hi = shard_bounds(n, world, r, halo)
+        shards.append(F.Haystack.from_host(hay[blo:bhi], buf_lo=blo, global_len=n, own_lo=lo, own_hi=hi))
+    ctx = ("world", seed, len(alphabet), world, m, k, n)
+    try:
+        init_local_world(shards)
+        want = {"lev": oracle.find_near_matches(pat, hay, max_l_dist=k),
+                "ham": tup(oracle.substitutions(pat, hay, min(k, 3))),
+                "exact": [(int(i), int(i) + m, 0) for i in oracle.search_exact(pat, bytes(hay))]}
+        calls = {"lev": lambda h: h.search_levenshtein(pat, k, F.F_GLOBAL).triples(F.FINAL),
+                 "ham": lambda h: h.search_hamming(pat, min(k, 3), F.F_GLOBAL).triples(F.FINAL),
+                 "exact": lambda h: h.search_exact(pat, F.F_GLOBAL).triples(F.FINAL)}
+        for name in ("lev", "ham", "exact", "lev"):
+            try:
+                got = search_all(shards, calls[name])
+            except F.UnsupportedError:
+                continue  # more groups than a peer slot holds: the in-process world has no staged path
+            for r in range(world):
+                if got[r] != want[name]:
+                    fail("world-" + name, ctx + (r, len(got[r]), len(want[name])))
+                    break
+    except Exception as e:  # noqa: BLE001
+        fail("world-exception %r" % (e,), ctx)
+    finally:
+        for h in shards:
+            h.close()
+
+
+TRIALS = {"world": world_trial, "lev": lev_trial, "ham": ham_trial, "generic": generic_trial, "exact": exact_trial, "shard": shard_trial,
           "batch": batch_trial, "has": has_trial}
 
 

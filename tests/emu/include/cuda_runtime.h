@@ -4,14 +4,20 @@
 // (fuzzysearch_b200/csrc/api.cu + *.cuh, textually unchanged except for the launch syntax, see the script) with g++
 // against this header instead of the CUDA toolkit's, into tests/emu/_build/libfuzzb200_emu.so.  The library exports
 // the same C-ABI, so the `-m gpu` parity tests can be replayed here, without a GPU, against the kernels' real source:
-// host logic (api.cu), kernel logic, work lists, overflow paths, the post-processing kernel -- everything except
-// timing, memory-system behaviour and the multi-GPU worlds.
+// host logic (api.cu), kernel logic, work lists, overflow paths, the post-processing kernel, the in-process
+// multi-shard worlds -- everything except timing, memory-model behaviour, CUDA IPC and NCCL.
 //
-// Model: one launch at a time (global mutex); CTAs of a grid run one after another; the threads of a CTA are
-// fibers (own stacks, hand-written x86-64 context switch) scheduled round-robin; a fiber runs until it blocks in
-// __syncthreads(), a warp collective (*_sync: rendezvous of the lanes named in the mask) or an explicit spin-wait.
-// __shared__ variables are function-local statics (CTAs are sequential), dynamic shared memory is one static
-// buffer.  Device memory is host memory filled with 0xCD on allocation (an uninitialised read shows).
+// Model: one host thread inside the emulator at a time (global mutex); the CTAs of a grid run one after another;
+// the threads of a CTA are fibers (own stacks, hand-written x86-64 context switch) scheduled round-robin; a fiber
+// runs until it blocks in __syncthreads(), a warp collective (*_sync: rendezvous of the lanes named in the mask) or
+// a spin-wait.  A CTA in which every runnable thread merely spins (a grid-wide barrier, a flag a peer GPU raises)
+// is SET ASIDE -- its __shared__ variables (function-local statics, registered by build_emu.py) and its dynamic
+// shared memory saved -- and the next CTA starts; a launch whose remaining CTAs all wait is left pending on its
+// stream and the call returns to the host, like an asynchronous launch; any later runtime call (cudaStreamQuery from
+// the product's completion poll, a launch by another host thread) advances it.  That is enough for the multi-GPU
+// reduction kernels (k_push / k_merge) of an in-process world with one host thread per shard.
+// Device memory is host memory filled with 0xCD on allocation (an uninitialised read shows); shared memory
+// starts as 0xA5.
 #pragma once
 #if !defined(__x86_64__)
 #error "the CUDA emulator's context switch is written for x86-64"
@@ -21,6 +27,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <sys/mman.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <chrono>
@@ -106,9 +113,10 @@ fzb_emu_switch:
 namespace emu {
 
 constexpr unsigned kMaxThreads = 1024;
-constexpr size_t kStackBytes = 256 * 1024;
+constexpr size_t kStackBytes = 128 * 1024;
 constexpr size_t kDynSmemBytes = 232448;  // 227 KiB
 constexpr int kRendezvous = 4;            // concurrent collectives per warp (disjoint masks)
+constexpr size_t kMaxLiveCtas = 32;       // co-resident CTAs of one launch that wait for something
 
 enum Op { OP_SYNCWARP, OP_SHFL, OP_SHFL_UP, OP_SHFL_DOWN, OP_SHFL_XOR, OP_BALLOT, OP_ANY, OP_ALL, OP_MATCH, OP_REDUCE };
 
@@ -130,34 +138,69 @@ struct Warp {
 struct Fiber {
     void *sp = nullptr;
     bool done = true;
+    bool spun = false;                             // left the CPU through yield(): a spin-wait, no progress
     const volatile uint32_t *wait_word = nullptr;  // runnable iff !wait_word || *wait_word != wait_val
     uint32_t wait_val = 0;
     uint3 tid{0, 0, 0};
     unsigned lin = 0;
 };
 
-struct State {
+// One CTA: resumable.  A CTA whose runnable threads all spin (a grid barrier, a flag another GPU raises) is set
+// aside -- its __shared__ variables and dynamic shared memory saved -- while other CTAs / launches / host threads run.
+struct Cta {
     Fiber fib[kMaxThreads];
     Warp warp[kMaxThreads / 32];
     unsigned nthreads = 0, alive = 0;
     unsigned bar_arrived = 0;
     uint32_t bar_gen = 0;
-    void *sched_sp = nullptr;
-    Fiber *cur = nullptr;
     uint3 bid{0, 0, 0};
-    dim3 bdim, gdim;
-    const std::function<void()> *body = nullptr;
     char *stacks = nullptr;
-    unsigned long long clock = 0;
+    size_t stack_bytes = 0;
+    bool progressed = false;
+    size_t dyn_bytes = 0;
+    size_t saved_vars = 0;  // how many registry entries the snapshot holds
+    bool has_snapshot = false;
+    std::vector<uint8_t> snap_static, snap_dyn;
 };
 
-inline State &st() {
-    static State s;
-    return s;
-}
-inline std::recursive_mutex &launch_mutex() {
-    static std::recursive_mutex m;
-    return m;
+struct Launch {
+    dim3 grid, block;
+    size_t smem = 0;
+    std::function<void()> body;
+    unsigned long long next = 0, total = 0;
+    std::vector<Cta *> live;
+};
+
+struct SharedVar {
+    void *p;
+    size_t n;
+};
+
+}  // namespace emu
+
+struct emu_stream {
+    emu::Launch *pending = nullptr;  // at most one suspended launch (every stream-ordered call drains the stream first)
+};
+typedef emu_stream *cudaStream_t;
+
+namespace emu {
+
+struct Global {
+    std::mutex mu;  // ONE host thread inside the emulator at a time
+    Launch *cur_launch = nullptr;
+    Cta *cur_cta = nullptr;
+    Fiber *cur = nullptr;
+    void *sched_sp = nullptr;
+    Cta *owner = nullptr;  // whose data the __shared__ statics / the dynamic buffer hold right now
+    std::vector<SharedVar> registry;
+    std::vector<emu_stream *> pending;
+    std::vector<Cta *> free_ctas;
+    std::vector<std::pair<char *, size_t>> free_stacks;
+    emu_stream default_stream;
+};
+inline Global &g() {
+    static Global *G = new Global();  // never destroyed: host threads may still be inside at exit
+    return *G;
 }
 alignas(1024) static uint8_t g_dyn_smem[kDynSmemBytes];
 inline uint8_t *smem_base() { return g_dyn_smem; }
@@ -166,25 +209,33 @@ inline T *dyn_smem() {
     return reinterpret_cast<T *>(g_dyn_smem);
 }
 
+// every `__shared__` declaration registers its storage the first time control passes it (build_emu.py adds the
+// registration next to the declaration)
+struct SharedReg {
+    SharedReg(void *p, size_t n) { g().registry.push_back(SharedVar{p, n}); }
+};
+
 [[noreturn]] inline void die(const char *what) {
-    State &s = st();
-    fprintf(stderr, "cuda-emu: %s (block %u,%u,%u thread %u)\n", what, s.bid.x, s.bid.y, s.bid.z, s.cur ? s.cur->lin : 0u);
+    Global &G = g();
+    fprintf(stderr, "cuda-emu: %s (block %u,%u,%u thread %u)\n", what, G.cur_cta ? G.cur_cta->bid.x : 0u,
+            G.cur_cta ? G.cur_cta->bid.y : 0u, G.cur_cta ? G.cur_cta->bid.z : 0u, G.cur ? G.cur->lin : 0u);
     abort();
 }
 
-inline void yield() {  // still runnable: spin-wait on memory some other fiber (or OS thread) writes
-    State &s = st();
-    Fiber *f = s.cur;
+inline void yield() {  // still runnable: spin-wait on memory some other CTA, launch or host thread writes
+    Global &G = g();
+    Fiber *f = G.cur;
     f->wait_word = nullptr;
-    fzb_emu_switch(&f->sp, s.sched_sp);
+    f->spun = true;
+    fzb_emu_switch(&f->sp, G.sched_sp);
 }
 inline void block_on(const volatile uint32_t *word, uint32_t val) {
-    State &s = st();
-    Fiber *f = s.cur;
+    Global &G = g();
+    Fiber *f = G.cur;
     while (*word == val) {
         f->wait_word = word;
         f->wait_val = val;
-        fzb_emu_switch(&f->sp, s.sched_sp);
+        fzb_emu_switch(&f->sp, G.sched_sp);
     }
     f->wait_word = nullptr;
 }
@@ -198,100 +249,250 @@ inline void rv_check_complete(Warp &w, Rendezvous &r) {
 }
 
 inline void fiber_exit() {
-    State &s = st();
-    Fiber *f = s.cur;
+    Global &G = g();
+    Cta &c = *G.cur_cta;
+    Fiber *f = G.cur;
     f->done = true;
-    s.alive--;
-    Warp &w = s.warp[f->lin >> 5];
+    c.alive--;
+    Warp &w = c.warp[f->lin >> 5];
     w.alive &= ~(1u << (f->lin & 31));
     for (int i = 0; i < kRendezvous; i++) rv_check_complete(w, w.rv[i]);  // a lane others were waiting for has left
-    if (s.bar_arrived && s.bar_arrived == s.alive) {                       // ... or the CTA barrier was waiting for it
-        s.bar_arrived = 0;
-        s.bar_gen++;
+    if (c.bar_arrived && c.bar_arrived == c.alive) {                       // ... or the CTA barrier was waiting for it
+        c.bar_arrived = 0;
+        c.bar_gen++;
     }
     void *dummy;
-    fzb_emu_switch(&dummy, s.sched_sp);
+    fzb_emu_switch(&dummy, G.sched_sp);
     die("resumed a finished fiber");
 }
 
 extern "C" inline void fzb_emu_trampoline() {
-    (*st().body)();
+    g().cur_launch->body();
     fiber_exit();
 }
 
-inline void run_block() {
-    State &s = st();
-    const unsigned n = s.bdim.x * s.bdim.y * s.bdim.z;
-    if (n == 0 || n > kMaxThreads) die("bad block size");
-    if (!s.stacks) {
-        s.stacks = (char *)mmap(nullptr, kStackBytes * kMaxThreads, PROT_READ | PROT_WRITE,
-                                MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
-        if (s.stacks == (char *)MAP_FAILED) die("cannot map fiber stacks");
+inline void save_owner() {
+    Global &G = g();
+    Cta *o = G.owner;
+    if (!o) return;
+    size_t total = 0;
+    for (const SharedVar &v : G.registry) total += v.n;
+    o->snap_static.resize(total);
+    size_t off = 0;
+    for (const SharedVar &v : G.registry) {
+        memcpy(o->snap_static.data() + off, v.p, v.n);
+        off += v.n;
     }
-    s.nthreads = s.alive = n;
-    s.bar_arrived = 0;
+    o->saved_vars = G.registry.size();
+    o->snap_dyn.assign(g_dyn_smem, g_dyn_smem + o->dyn_bytes);
+    o->has_snapshot = true;
+}
+inline void make_owner(Cta *c) {  // before c runs: its shared memory must be the one in place
+    Global &G = g();
+    if (G.owner == c) return;
+    save_owner();
+    if (c->has_snapshot) {
+        size_t off = 0;
+        for (size_t i = 0; i < c->saved_vars; i++) {
+            memcpy(G.registry[i].p, c->snap_static.data() + off, G.registry[i].n);
+            off += G.registry[i].n;
+        }
+        memcpy(g_dyn_smem, c->snap_dyn.data(), c->snap_dyn.size());
+    } else {
+        memset(g_dyn_smem, 0xA5, c->dyn_bytes);  // shared memory starts as garbage, like on the device
+    }
+    G.owner = c;
+}
+
+inline Cta *cta_start(Launch *L, unsigned long long index) {
+    Global &G = g();
+    Cta *c;
+    if (!G.free_ctas.empty()) {
+        c = G.free_ctas.back();
+        G.free_ctas.pop_back();
+    } else {
+        c = new Cta();
+    }
+    const unsigned n = L->block.x * L->block.y * L->block.z;
+    if (n == 0 || n > kMaxThreads) die("bad block size");
+    const size_t need = (size_t)n * kStackBytes;
+    c->stacks = nullptr;
+    for (size_t i = 0; i < G.free_stacks.size(); i++)
+        if (G.free_stacks[i].second >= need) {
+            c->stacks = G.free_stacks[i].first;
+            c->stack_bytes = G.free_stacks[i].second;
+            G.free_stacks.erase(G.free_stacks.begin() + i);
+            break;
+        }
+    if (!c->stacks) {
+        c->stack_bytes = std::max(need, (size_t)256 * kStackBytes);
+        c->stacks = (char *)mmap(nullptr, c->stack_bytes, PROT_READ | PROT_WRITE,
+                                 MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+        if (c->stacks == (char *)MAP_FAILED) die("cannot map fiber stacks");
+    }
+    c->bid.x = (unsigned)(index % L->grid.x);
+    c->bid.y = (unsigned)((index / L->grid.x) % L->grid.y);
+    c->bid.z = (unsigned)(index / ((unsigned long long)L->grid.x * L->grid.y));
+    c->nthreads = c->alive = n;
+    c->bar_arrived = 0;
+    c->dyn_bytes = L->smem;
+    c->has_snapshot = false;
+    c->progressed = false;
     for (unsigned w = 0; w < (n + 31) / 32; w++) {
-        s.warp[w] = Warp();
+        c->warp[w] = Warp();
         const unsigned cnt = std::min(32u, n - 32 * w);
-        s.warp[w].alive = cnt == 32 ? 0xFFFFFFFFu : ((1u << cnt) - 1u);
+        c->warp[w].alive = cnt == 32 ? 0xFFFFFFFFu : ((1u << cnt) - 1u);
     }
     for (unsigned i = 0; i < n; i++) {
-        Fiber &f = s.fib[i];
+        Fiber &f = c->fib[i];
         f.done = false;
+        f.spun = false;
         f.wait_word = nullptr;
         f.lin = i;
-        f.tid.x = i % s.bdim.x;
-        f.tid.y = (i / s.bdim.x) % s.bdim.y;
-        f.tid.z = i / (s.bdim.x * s.bdim.y);
-        uint64_t *top = reinterpret_cast<uint64_t *>(s.stacks + (size_t)(i + 1) * kStackBytes);  // 16-byte aligned
-        top[-1] = 0;                                                                            // fake return address
+        f.tid.x = i % L->block.x;
+        f.tid.y = (i / L->block.x) % L->block.y;
+        f.tid.z = i / (L->block.x * L->block.y);
+        uint64_t *top = reinterpret_cast<uint64_t *>(c->stacks + (size_t)(i + 1) * kStackBytes);  // 16-byte aligned
+        top[-1] = 0;                                                                             // fake return address
         top[-2] = reinterpret_cast<uint64_t>(&fzb_emu_trampoline);
         for (int r = 3; r <= 8; r++) top[-r] = 0;  // rbp rbx r12 r13 r14 r15
         f.sp = top - 8;
     }
-    while (s.alive) {
-        bool ran = false;
-        for (unsigned i = 0; i < n; i++) {
-            Fiber &f = s.fib[i];
-            if (f.done) continue;
-            if (f.wait_word && *f.wait_word == f.wait_val) continue;
-            s.cur = &f;
-            ran = true;
-            fzb_emu_switch(&s.sched_sp, f.sp);
-        }
-        if (!ran) die("deadlock: every live thread of the CTA is blocked (divergent barrier or collective?)");
-    }
-    s.cur = nullptr;
+    return c;
+}
+inline void cta_release(Cta *c) {
+    Global &G = g();
+    if (G.owner == c) G.owner = nullptr;
+    G.free_stacks.push_back(std::make_pair(c->stacks, c->stack_bytes));
+    c->stacks = nullptr;
+    G.free_ctas.push_back(c);
 }
 
-// one kernel launch: CTAs in order, arguments evaluated once (by the caller's lambda capture)
-template <class Body>
-inline void launch(dim3 grid, dim3 block, size_t smem, Body &&body) {
-    std::lock_guard<std::recursive_mutex> lock(launch_mutex());
-    if (smem > kDynSmemBytes) die("dynamic shared memory request too large");
-    State &s = st();
-    if (s.cur) die("nested launch");
-    const std::function<void()> fn = std::forward<Body>(body);
-    s.body = &fn;
-    s.gdim = grid;
-    s.bdim = block;
-    for (unsigned z = 0; z < grid.z; z++)
-        for (unsigned y = 0; y < grid.y; y++)
-            for (unsigned x = 0; x < grid.x; x++) {
-                s.bid = uint3{x, y, z};
-                memset(g_dyn_smem, 0xA5, smem);  // shared memory starts as garbage, like on the device
-                run_block();
+// run the CTA until it has finished (true) or every thread that can run merely spins (false)
+inline bool cta_run(Launch *L, Cta *c) {
+    Global &G = g();
+    make_owner(c);
+    G.cur_launch = L;
+    G.cur_cta = c;
+    c->progressed = false;
+    bool finished = true;
+    while (c->alive) {
+        bool ran = false, progress = false;
+        for (unsigned i = 0; i < c->nthreads; i++) {
+            Fiber &f = c->fib[i];
+            if (f.done) continue;
+            if (f.wait_word && *f.wait_word == f.wait_val) continue;
+            G.cur = &f;
+            ran = true;
+            f.spun = false;
+            fzb_emu_switch(&G.sched_sp, f.sp);
+            if (!f.spun) progress = true;
+        }
+        if (!ran) die("deadlock: every live thread of the CTA is blocked (divergent barrier or collective?)");
+        if (!progress) {
+            finished = false;
+            break;
+        }
+        c->progressed = true;
+    }
+    G.cur = nullptr;
+    G.cur_cta = nullptr;
+    G.cur_launch = nullptr;
+    return finished;
+}
+
+// advance a launch: true = every CTA has finished; false = what is left of it waits for somebody else
+inline bool launch_run(Launch *L) {
+    for (;;) {
+        bool any = false;
+        for (size_t i = 0; i < L->live.size();) {
+            Cta *c = L->live[i];
+            const bool fin = cta_run(L, c);
+            any |= c->progressed;
+            if (fin) {
+                cta_release(c);
+                L->live.erase(L->live.begin() + i);
+            } else {
+                i++;
             }
-    s.body = nullptr;
+        }
+        while (L->next < L->total && L->live.size() < kMaxLiveCtas) {
+            Cta *c = cta_start(L, L->next++);
+            any = true;
+            if (cta_run(L, c))
+                cta_release(c);
+            else
+                L->live.push_back(c);
+        }
+        if (L->live.empty() && L->next == L->total) return true;
+        if (!any) return false;
+    }
+}
+
+// give every suspended launch another go (any host thread that enters the emulator does this)
+inline void pump_locked() {
+    Global &G = g();
+    for (size_t i = 0; i < G.pending.size();) {
+        emu_stream *S = G.pending[i];
+        if (launch_run(S->pending)) {
+            delete S->pending;
+            S->pending = nullptr;
+            G.pending.erase(G.pending.begin() + i);
+        } else {
+            i++;
+        }
+    }
+}
+// stream order: whatever comes next on S waits for the launch S still has in flight
+inline void drain_locked(std::unique_lock<std::mutex> &lk, emu_stream *S) {
+    for (;;) {
+        pump_locked();
+        if (!S->pending) return;
+        lk.unlock();
+        usleep(50);  // let the host thread whose kernels are being waited for take the lock
+        lk.lock();
+    }
+}
+inline void drain_all_locked(std::unique_lock<std::mutex> &lk) {
+    for (;;) {
+        pump_locked();
+        if (g().pending.empty()) return;
+        lk.unlock();
+        usleep(50);
+        lk.lock();
+    }
+}
+
+// one kernel launch: CTAs in order (a CTA that waits is set aside), arguments evaluated once by the caller
+template <class Body>
+inline void launch(dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Body &&body) {
+    Global &G = g();
+    std::unique_lock<std::mutex> lk(G.mu);
+    if (G.cur) die("nested launch");
+    if (smem > kDynSmemBytes) die("dynamic shared memory request too large");
+    emu_stream *S = stream ? stream : &G.default_stream;
+    drain_locked(lk, S);
+    Launch *L = new Launch();
+    L->grid = grid;
+    L->block = block;
+    L->smem = smem;
+    L->body = std::forward<Body>(body);
+    L->total = (unsigned long long)grid.x * grid.y * grid.z;
+    if (launch_run(L)) {
+        delete L;
+    } else {
+        S->pending = L;
+        G.pending.push_back(S);
+    }
 }
 
 // ---- warp collectives ---------------------------------------------------------------------------------------
 inline Rendezvous &rv_arrive(uint32_t mask, int op, uint64_t v, int *lane_out) {
-    State &s = st();
-    Fiber *f = s.cur;
+    Global &G = g();
+    Fiber *f = G.cur;
     const int lane = f->lin & 31;
     *lane_out = lane;
-    Warp &w = s.warp[f->lin >> 5];
+    Warp &w = G.cur_cta->warp[f->lin >> 5];
     if (!(mask & (1u << lane))) die("collective: the calling lane is not in its own mask");
     Rendezvous *r = nullptr;
     for (int i = 0; i < kRendezvous && !r; i++)
@@ -307,9 +508,9 @@ inline Rendezvous &rv_arrive(uint32_t mask, int op, uint64_t v, int *lane_out) {
     if (r->op != op) die("collective: lanes of one mask met in different operations (divergence bug)");
     r->val[lane] = v;
     r->arrived |= 1u << lane;
-    const uint32_t g = r->gen;
+    const uint32_t gen = r->gen;
     rv_check_complete(w, *r);
-    if (!r->complete) block_on(&r->gen, g);
+    if (!r->complete) block_on(&r->gen, gen);
     return *r;
 }
 inline void rv_depart(Rendezvous &r, int lane) {
@@ -358,21 +559,21 @@ inline T shfl_generic(uint32_t mask, T v, int op, int arg, int width) {
 
 }  // namespace emu
 
-#define threadIdx (emu::st().cur->tid)
-#define blockIdx (emu::st().bid)
-#define blockDim (emu::st().bdim)
-#define gridDim (emu::st().gdim)
+#define threadIdx (emu::g().cur->tid)
+#define blockIdx (emu::g().cur_cta->bid)
+#define blockDim (emu::g().cur_launch->block)
+#define gridDim (emu::g().cur_launch->grid)
 #define warpSize 32
 
 static inline void __syncthreads() {
-    emu::State &s = emu::st();
-    const uint32_t g = s.bar_gen;
-    if (++s.bar_arrived == s.alive) {
-        s.bar_arrived = 0;
-        s.bar_gen++;
+    emu::Cta &c = *emu::g().cur_cta;
+    const uint32_t gen = c.bar_gen;
+    if (++c.bar_arrived == c.alive) {
+        c.bar_arrived = 0;
+        c.bar_gen++;
         return;
     }
-    emu::block_on(&s.bar_gen, g);
+    emu::block_on(&c.bar_gen, gen);
 }
 static inline void __syncwarp(unsigned mask = 0xFFFFFFFFu) {
     int lane;
@@ -513,7 +714,19 @@ static inline T __ldcs(const T *p) { return *p; }
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
-static inline long long clock64() { return (long long)(emu::st().clock += (1ull << 24)); }  // spin loops time out fast
+namespace emu {
+inline long long cycles() {  // a slow clock (0.2 "GHz" of wall time): the kernels' bounded spin-waits for a peer allow for
+                             // host threads that take turns inside the emulator on a busy box
+    return (long long)(std::chrono::duration_cast<std::chrono::nanoseconds>(
+                           std::chrono::steady_clock::now().time_since_epoch()).count() / 5);
+}
+}  // namespace emu
+// the kernels read the clock in their bounded spin-waits (a flag another CTA / GPU raises): the natural place to
+// hand the CPU to whoever is being waited for
+static inline long long clock64() {
+    if (emu::g().cur) emu::yield();
+    return emu::cycles();
+}
 static inline size_t __cvta_generic_to_shared(const void *p) {
     return (size_t)(reinterpret_cast<const uint8_t *>(p) - emu::smem_base());
 }
@@ -530,7 +743,6 @@ enum {
     cudaErrorNotSupported = 801
 };
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
-typedef struct emu_stream *cudaStream_t;
 struct emu_event {
     std::chrono::steady_clock::time_point t;
 };
@@ -605,7 +817,9 @@ static inline cudaError_t cudaMalloc(T **p, size_t n) {
     *p = (T *)emu::alloc_bytes(n, 0xCD);
     return *p ? cudaSuccess : cudaErrorMemoryAllocation;
 }
+static inline cudaError_t cudaDeviceSynchronize();
 static inline cudaError_t cudaFree(void *p) {
+    cudaDeviceSynchronize();  // as on the device: no kernel may still be using it
     free(p);
     return cudaSuccess;
 }
@@ -645,31 +859,58 @@ static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, con
         if ((uintptr_t)p >= h.v[i].first && (uintptr_t)p < h.v[i].first + h.v[i].second) a->type = cudaMemoryTypeHost;
     return cudaSuccess;
 }
+namespace emu {
+inline void stream_op(cudaStream_t stream, const std::function<void()> &fn) {  // stream-ordered host-side operation
+    Global &G = g();
+    std::unique_lock<std::mutex> lk(G.mu);
+    drain_locked(lk, stream ? stream : &G.default_stream);
+    fn();
+}
+}  // namespace emu
 static inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) {
-    std::lock_guard<std::recursive_mutex> lock(emu::launch_mutex());
-    memmove(d, s, n);
+    emu::stream_op(nullptr, [&]() { memmove(d, s, n); });
     return cudaSuccess;
 }
-static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind k, cudaStream_t = nullptr) {
-    return cudaMemcpy(d, s, n, k);
+static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t st = nullptr) {
+    emu::stream_op(st, [&]() { memmove(d, s, n); });
+    return cudaSuccess;
 }
 static inline cudaError_t cudaMemset(void *d, int v, size_t n) {
-    std::lock_guard<std::recursive_mutex> lock(emu::launch_mutex());
-    memset(d, v, n);
+    emu::stream_op(nullptr, [&]() { memset(d, v, n); });
     return cudaSuccess;
 }
-static inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t = nullptr) { return cudaMemset(d, v, n); }
+static inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t st = nullptr) {
+    emu::stream_op(st, [&]() { memset(d, v, n); });
+    return cudaSuccess;
+}
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) {
-    *s = (cudaStream_t)malloc(8);
+    *s = new emu_stream();
+    return cudaSuccess;
+}
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t st) {
+    emu::stream_op(st, []() {});
     return cudaSuccess;
 }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t s) {
-    free(s);
+    cudaStreamSynchronize(s);
+    delete s;
     return cudaSuccess;
 }
-static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
-static inline cudaError_t cudaStreamQuery(cudaStream_t) { return cudaSuccess; }
-static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+static inline cudaError_t cudaStreamQuery(cudaStream_t st) {  // also the host's chance to advance suspended launches
+    emu::Global &G = emu::g();
+    std::unique_lock<std::mutex> lk(G.mu);
+    emu::pump_locked();
+    if (!(st ? st : &G.default_stream)->pending) return cudaSuccess;
+    lk.unlock();
+    usleep(20);  // the caller polls: give the peers' host threads room
+    return cudaErrorNotReady;
+}
+static inline cudaError_t cudaDeviceSynchronize() {
+    emu::Global &G = emu::g();
+    std::unique_lock<std::mutex> lk(G.mu);
+    emu::drain_all_locked(lk);
+    return cudaSuccess;
+}
 static inline cudaError_t cudaEventCreate(cudaEvent_t *e) {
     *e = new emu_event();
     return cudaSuccess;
@@ -679,8 +920,8 @@ static inline cudaError_t cudaEventDestroy(cudaEvent_t e) {
     delete e;
     return cudaSuccess;
 }
-static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) {
-    e->t = std::chrono::steady_clock::now();
+static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t st = nullptr) {
+    emu::stream_op(st, [&]() { e->t = std::chrono::steady_clock::now(); });
     return cudaSuccess;
 }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }

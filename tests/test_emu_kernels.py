@@ -5,8 +5,9 @@ execution-model emulator -- fibers for threads, rendezvous for the warp collecti
 tests/emu/_build/libfuzzb200_emu.so with the same C-ABI.  The tests below bind it in place of libfuzzb200.so and run
 the bodies of the `-m gpu` parity tests (same functions, same oracle, same fixtures) at the sizes a CPU can do in
 seconds.  It proves kernel LOGIC and host logic -- filters lose no match, work lists and overflow paths, bit-parallel
-expansions, consolidation, batches, wide symbols, file loops, locking -- not timing, memory-model behaviour or the
-multi-GPU worlds (those need the B200: tests/test_gpu_global.py, bench.py).  The emulated library is test
+expansions, consolidation, batches, wide symbols, file loops, locking, the peer-memory reduction of in-process
+multi-shard worlds -- not timing, memory-model behaviour, CUDA IPC or NCCL (those need the B200:
+tests/test_gpu_global.py, bench.py).  The emulated library is test
 infrastructure: nothing in the product can load it.
 
 `FZB_TEST_BACKEND=emu python -m pytest tests -m gpu` replays the whole GPU suite this way (minutes), and
@@ -22,6 +23,7 @@ import test_gpu_batch
 import test_gpu_expand
 import test_gpu_file
 import test_gpu_fuzz
+import test_gpu_global
 import test_gpu_golden
 import test_gpu_oracle
 import test_gpu_python_api
@@ -126,6 +128,15 @@ def test_emu_threads_and_has_near_match(emu_device):
     test_gpu_python_api.test_find_near_matches_is_thread_safe(emu_device)
     test_gpu_python_api.test_threads_share_one_resident_sequence(emu_device)
     test_gpu_python_api.test_has_near_match_all_routes_vs_oracle(emu_device)
+
+
+def test_emu_multi_shard_worlds(emu_device):
+    """The multi-GPU reduction (k_push -> k_merge over the peers' receive areas, grid-wide barrier included) in
+    in-process worlds of 2, 3, 4 and 8 shards, one host thread per shard: every rank must hold the oracle's
+    global list.  (CUDA IPC / NCCL bootstrap and the staged path need real devices: tests/test_gpu_global.py.)"""
+    _run(test_gpu_global.test_multi_rank_world_on_one_gpu, emu_device)
+    test_gpu_global.test_multi_rank_lp_and_dna_routes(emu_device)
+    test_gpu_global.test_local_world_refuses_what_needs_the_staged_path(emu_device)
 
 
 def test_emu_wide_symbols(emu_device, tmp_path):

@@ -23,6 +23,25 @@ def test_product_never_imports_the_oracle():
     assert "oracle" not in header
 
 
+def test_emulator_never_reaches_the_product_build():
+    """tests/emu compiles the product sources with -DFZB_EMU for the CPU suite.  The shipped library must never be
+    built that way, and nothing in the package may load the emulated one."""
+    mk = open(os.path.join(ROOT, "fuzzysearch_b200", "csrc", "Makefile")).read()
+    assert "FZB_EMU" not in mk
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "fuzzysearch_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "emu" not in text.lower().replace("enumerate", ""), os.path.join(dirpath, f)
+    for f in ("bench.py", "__graft_entry__.py"):
+        assert "libfuzzb200_emu" not in open(os.path.join(ROOT, f)).read() and \
+            "FZB_TEST_BACKEND" not in open(os.path.join(ROOT, f)).read(), f
+    so = os.path.join(ROOT, "fuzzysearch_b200", "libfuzzb200.so")
+    if os.path.exists(so):
+        blob = open(so, "rb").read()
+        assert b"cuda-emu" not in blob and b"fzb_emu_switch" not in blob
+
+
 def test_reference_arm_prints_the_contract_line():
     if not os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "fuzzysearch")):
         import pytest
