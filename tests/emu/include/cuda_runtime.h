@@ -368,6 +368,19 @@ inline void cta_release(Cta *c) {
     G.free_ctas.push_back(c);
 }
 
+inline int sched_order() {
+    const char *e = getenv("FZB_EMU_SCHED");
+    if (!e) return 0;
+    return strcmp(e, "reverse") == 0 ? 1 : (strcmp(e, "random") == 0 ? 2 : 0);
+}
+inline uint64_t sched_rand() {
+    static uint64_t x = 0x9E3779B97F4A7C15ull;
+    x ^= x << 13;
+    x ^= x >> 7;
+    x ^= x << 17;
+    return x;
+}
+
 // run the CTA until it has finished (true) or every thread that can run merely spins (false)
 inline bool cta_run(Launch *L, Cta *c) {
     Global &G = g();
@@ -376,9 +389,16 @@ inline bool cta_run(Launch *L, Cta *c) {
     G.cur_cta = c;
     c->progressed = false;
     bool finished = true;
+    const int order = sched_order();
     while (c->alive) {
         bool ran = false, progress = false;
-        for (unsigned i = 0; i < c->nthreads; i++) {
+        const unsigned rot = order == 2 ? (unsigned)(sched_rand() % c->nthreads) : 0u;
+        for (unsigned j = 0; j < c->nthreads; j++) {
+            // thread order of a sweep: ascending (default), descending, or rotated by a random amount per sweep with a
+            // random direction -- FZB_EMU_SCHED=reverse|random: results must not depend on it (a missing barrier does)
+            unsigned i = j;
+            if (order == 1) i = c->nthreads - 1 - j;
+            if (order == 2) i = ((rot & 1u) ? c->nthreads - 1 - j : j), i = (i + rot) % c->nthreads;
             Fiber &f = c->fib[i];
             if (f.done) continue;
             if (f.wait_word && *f.wait_word == f.wait_val) continue;
