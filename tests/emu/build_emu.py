@@ -113,6 +113,7 @@ def build(force=False, verbose=False):
         t = rewrite(open(os.path.join(CSRC, n)).read())
         texts[n] = t
         digest.update(n.encode() + b"\0" + t.encode())
+    digest.update(os.environ.get("FZB_EMU_COVERAGE", "").encode())
     for extra in (os.path.join(HERE, "include", "cuda_runtime.h"), os.path.join(HERE, "include", "cuda.h"),
                   os.path.join(ROOT, "include", "fuzzb200.h"), os.path.abspath(__file__)):
         digest.update(open(extra, "rb").read())
@@ -124,7 +125,10 @@ def build(force=False, verbose=False):
         with open(os.path.join(srcdir, n), "w") as f:
             f.write(t)
     cxx = os.environ.get("CXX", "g++")
-    cmd = [cxx, "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-DFZB_EMU",
+    opt = ["-O1"]
+    if os.environ.get("FZB_EMU_COVERAGE"):  # gcov line coverage of the product sources under the test-suite
+        opt = ["-O0", "--coverage"]
+    cmd = [cxx] + opt + ["-g", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-DFZB_EMU",
            "-fno-omit-frame-pointer", "-Wno-unknown-pragmas", "-Wno-attributes",
            "-I", os.path.join(HERE, "include"), "-I", os.path.join(ROOT, "include"), "-I", srcdir,
            "-x", "c++", os.path.join(srcdir, "api.cu"), "-o", OUT, "-lpthread", "-ldl"]

@@ -114,6 +114,7 @@ def test_emu_reference_suite_calls(emu_device):
 def test_emu_batches(emu_device):
     test_gpu_batch.test_batch_matches_oracle(emu_device)
     test_gpu_batch.test_batch_shared_scan_edge_cases(emu_device)
+    test_gpu_batch.test_batch_lp_pass_with_large_budgets(emu_device)
 
 
 def test_emu_file_search(emu_device, tmp_path):
@@ -136,6 +137,7 @@ def test_emu_multi_shard_worlds(emu_device):
     global list.  (CUDA IPC / NCCL bootstrap and the staged path need real devices: tests/test_gpu_global.py.)"""
     _run(test_gpu_global.test_multi_rank_world_on_one_gpu, emu_device)
     test_gpu_global.test_multi_rank_lp_and_dna_routes(emu_device)
+    _run(test_gpu_global.test_seam_rows_interleave_between_runs, emu_device)
     test_gpu_global.test_local_world_refuses_what_needs_the_staged_path(emu_device)
 
 

@@ -102,3 +102,32 @@ def test_batch_shared_scan_edge_cases(cuda_device):
         res.close()
     assert shared >= 100
     hs.close()
+
+
+def test_batch_lp_pass_with_large_budgets(cuda_device):
+    """LP-route patterns with max_l_dist 5..8 share a pass too (`k_lp_verify_multi<8>`: nine automaton masks per
+    lane); some end inside the sequence's last bytes (end-of-sequence acceptance, levenshtein.py:145-148)."""
+    rng = np.random.default_rng(58)
+    for alphabet, n in ((ASCII, 20000), (b"abcdefgh", 3000)):
+        alpha = np.frombuffer(alphabet, dtype=np.uint8)
+        hay = alpha[rng.integers(0, len(alpha), size=n)].copy()
+        pats, ks = [], []
+        for k in (5, 6, 7, 8, 5, 8, 2, 3):
+            m = int(rng.integers(k + 1, min(3 * (k + 1) - 1, 31 - k) + 1))  # m // (k + 1) < 3 and m + k <= 31
+            pat = bytes(alpha[rng.integers(0, len(alpha), size=m)])
+            for _ in range(3):
+                pos = int(rng.integers(50, n - 100))
+                v = mutate(rng, pat, alphabet, int(rng.integers(0, k + 1)))
+                hay[pos:pos + len(v)] = np.frombuffer(v, dtype=np.uint8)
+            pats.append(pat)
+            ks.append(k)
+        hay[n - 7:] = np.frombuffer(pats[0][:7], dtype=np.uint8)  # a prefix of pattern 0 runs into the end
+        hs = F.Haystack.from_host(hay)
+        results, _ = hs.search_levenshtein_batch(pats, ks)
+        for pat, k, res in zip(pats, ks, results):
+            raw = oracle.levenshtein_raw(pat, hay, k)
+            assert res.stats()["route"] == "lp"
+            assert sorted(res.triples(F.RAW)) == sorted(tup(raw)), (pat, k)
+            assert res.triples(F.FINAL) == tup(oracle.consolidate(raw)), (pat, k)
+            res.close()
+        hs.close()

@@ -195,3 +195,37 @@ def test_global_multi_process_world(cuda_device):
         p.join(timeout=120)
         assert p.exitcode == 0
     assert all(ok for _, ok, _, _ in results), results
+
+
+@pytest.mark.parametrize("world", [2, 3, 5])
+def test_seam_rows_interleave_between_runs(cuda_device, world):
+    """k_merge's binary search: a row of rank q whose hull starts INSIDE the range of hull starts of another rank's
+    run.  Ranks own matches by ANCHOR, so it takes an occurrence that starts before the seam but is found only
+    through its last n-gram (anchored after the seam: rank q) and a second, later-starting occurrence whose first
+    n-gram is anchored before the seam (rank q - 1), plus an unrelated earlier group on rank q - 1.  A pattern of
+    period 10 lets the two occurrences overlap."""
+    m, k, n = 20, 2, 1 << 14
+    pat = b"abcdefghij" * 2
+    rng = np.random.default_rng(3)
+    hay = rng.integers(48, 58, size=n, dtype=np.uint8)  # digits: no accidental hits
+    for r in range(1, world):
+        seam = shard_bounds(n, world, r, m + k)[2]
+        hay[seam - 300:seam - 280] = np.frombuffer(pat, dtype=np.uint8)      # an earlier, isolated group of rank r - 1
+        run = bytearray(b"abcdefghij" * 3)                                   # occurrences at seam - 12 and seam - 2
+        run[2] = ord("X")                                                    # ... the first one keeps only its third
+        run[8] = ord("Y")                                                    #     n-gram, anchored at `seam`
+        hay[seam - 12:seam + 18] = np.frombuffer(bytes(run), dtype=np.uint8)
+    shards = _make_world(hay, world, m + k)
+    try:
+        exp = oracle.find_near_matches(pat, hay, max_l_dist=k)
+        assert len(exp) == 2 * (world - 1)
+        got = search_all(shards, lambda h: h.search_levenshtein(pat, k, F.F_GLOBAL).triples(F.FINAL))
+        for r in range(world):
+            assert got[r] == exp, r
+        # the rows really interleave: rank r's own list ends with a group starting after rank r + 1's first one
+        own = search_all(shards, lambda h: h.search_levenshtein(pat, k).group_rows())
+        for r in range(world - 1):
+            assert own[r][-1][3] > own[r + 1][0][3] > own[r][0][3], (r, own[r][:, 3], own[r + 1][:, 3])
+    finally:
+        for h in shards:
+            h.close()
