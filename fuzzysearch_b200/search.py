@@ -14,6 +14,20 @@ import numpy as np
 from . import _native
 from .common import FuzzySearchBase, Match, consolidate_overlapping_matches
 
+try:  # optional, exactly like the reference (search_exact.py:14-19): Bio.Seq.Seq sequences are text
+    from Bio.Seq import Seq as _BioSeq
+except ImportError:
+    _BioSeq = None
+
+
+def _text(seq):
+    """Bio.Seq.Seq -> its str (the reference walks a Seq with Seq.find / item access, i.e. as text); anything
+    else unchanged.  ``Match.matched`` is still sliced from the ORIGINAL object."""
+    if _BioSeq is not None and isinstance(seq, _BioSeq):
+        return str(seq)
+    return seq
+
+
 __all__ = ["DeviceSequence", "ExactSearch", "SubstitutionsOnlySearch", "LevenshteinSearch",
            "GenericSearch", "RawMatches", "search_exact"]
 
@@ -35,9 +49,12 @@ class DeviceSequence(object):
         self._alphabet = None    # ... and the pattern alphabet the resident bytes were reduced with
         self._is_str = False
         self._kind = "bytes"
+        self._orig = None        # a Bio.Seq.Seq: `matched` is sliced from it
         if _haystack is not None:
             self.haystack, self._host = _haystack, _host
             return
+        if _text(data) is not data:
+            self._orig, data = data, _text(data)
         self._kind = _kind(data)
         self._is_str = self._kind == "str"
         host = _narrow(data, self._kind)
@@ -50,6 +67,8 @@ class DeviceSequence(object):
             self.haystack = _native.Haystack.alloc(max(len(data), 1), device=device)
 
     def __len__(self):
+        if self._orig is not None:
+            return len(self._orig)
         return len(self._wide) if self._wide is not None else len(self.haystack)
 
     def _bind(self, subsequence):
@@ -57,6 +76,7 @@ class DeviceSequence(object):
         return self._bind_many([subsequence])[0]
 
     def _bind_many(self, subsequences):
+        subsequences = [_text(p) for p in subsequences]
         kinds = set(_kind(p) for p in subsequences)
         if kinds != {self._kind}:
             raise TypeError("subsequence and sequence must both be str or both be byte-like")
@@ -74,6 +94,8 @@ class DeviceSequence(object):
         return [_rename(p, self._kind, alphabet) for p in subsequences]
 
     def slice(self, start, end):
+        if self._orig is not None:
+            return self._orig[start:end]
         if self._wide is not None:
             return self._wide[start:end]
         if self._host is not None:
@@ -229,6 +251,8 @@ def _prepare_many(subsequences, sequence):
     """-> (patterns as u8 arrays, haystack handle holding the sequence, slicer)"""
     if isinstance(sequence, DeviceSequence):
         return sequence._bind_many(subsequences), sequence.haystack, sequence.slice
+    original, sequence = sequence, _text(sequence)
+    subsequences = [_text(p) for p in subsequences]
     kind = _kind(sequence)
     if any(_kind(p) != kind for p in subsequences):
         raise TypeError("subsequence and sequence must both be str or both be byte-like")
@@ -244,7 +268,7 @@ def _prepare_many(subsequences, sequence):
         _upload_reduced(hay, sequence, kind, alphabet)
     if kind != "bytes" or isinstance(sequence, (bytes, bytearray)):
         def slicer(s, e):
-            return sequence[s:e]
+            return original[s:e]
     else:
         mv = memoryview(host)
 
@@ -309,6 +333,7 @@ def search_exact(subsequence, sequence, start_index=0, end_index=None):
     ``DeviceSequence`` is searched through a view of its resident buffer (fzb_search_exact_window)."""
     if len(subsequence) == 0:
         raise ValueError("subsequence must not be empty")
+    sequence = _text(sequence)  # a Bio.Seq.Seq is searched as its text; the result is positions only
     n = len(sequence)
     if end_index is None:
         end_index = n

@@ -150,3 +150,56 @@ def test_threads_share_workspace_and_resident_sequences(fake_device):  # noqa: F
     for th in threads:
         th.join()
     assert not errors, errors
+
+
+class FakeSeq(object):
+    """Stand-in for Bio.Seq.Seq (BioPython is not in this image): text with Seq's slicing / str / find protocol."""
+
+    def __init__(self, data):
+        self._data = str(data)
+
+    def __str__(self):
+        return self._data
+
+    def __len__(self):
+        return len(self._data)
+
+    def __getitem__(self, i):
+        return FakeSeq(self._data[i]) if isinstance(i, slice) else self._data[i]
+
+    def __eq__(self, other):
+        return str(self) == str(other)
+
+    __hash__ = None
+
+    def find(self, sub, start=0, end=None):
+        return self._data.find(str(sub), start, len(self._data) if end is None else end)
+
+
+def test_bio_seq_objects_are_searched_as_text(fake_device, monkeypatch):  # noqa: F811
+    """The reference treats Bio.Seq.Seq as a text class (search_exact.py:14-19): same matches as for the str,
+    `matched` a slice of the ORIGINAL Seq.  Sequence, subsequence, resident sequence and search_exact."""
+    from fuzzysearch_b200 import DeviceSequence, find_near_matches, has_near_match, search
+    monkeypatch.setattr(search, "_BioSeq", FakeSeq)
+    text = "GATTACA" * 3 + "TGCACTGTAGGGATAACAAT" + "ACGT" * 5 + "TGCACTGTAGGATAACAAT" + "CC"
+    pat = "TGCACTGTAGGGATAACAAT"
+    expected = find_near_matches(pat, text, max_l_dist=2)
+    assert [(m.start, m.end, m.dist) for m in expected] == oracle.find_near_matches(
+        pat.encode(), text.encode(), max_l_dist=2)
+    for p, t in ((pat, FakeSeq(text)), (FakeSeq(pat), FakeSeq(text)), (FakeSeq(pat), text)):
+        got = find_near_matches(p, t, max_l_dist=2)
+        assert got == expected
+        for m in got:
+            assert type(m.matched) is type(t) and str(m.matched) == text[m.start:m.end]
+        assert has_near_match(p, t, max_l_dist=2) is True
+        assert find_near_matches(p, t, max_substitutions=1, max_insertions=0, max_deletions=0) == \
+            find_near_matches(pat, text, max_substitutions=1, max_insertions=0, max_deletions=0)
+    resident = DeviceSequence(FakeSeq(text))
+    assert len(resident) == len(text)
+    got = find_near_matches(FakeSeq(pat), resident, max_l_dist=2)
+    assert got == expected and all(isinstance(m.matched, FakeSeq) for m in got)
+    assert search.search_exact("ACGT", FakeSeq(text), 3, 60) == search.search_exact("ACGT", text, 3, 60)
+    assert search.search_exact(FakeSeq("ACGT"), resident) == search.search_exact("ACGT", text)
+    resident.close()
+    with pytest.raises(TypeError):
+        find_near_matches(FakeSeq(pat), text.encode(), max_l_dist=2)  # text against bytes, as for a str
