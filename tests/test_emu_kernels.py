@@ -93,6 +93,7 @@ def test_emu_shards_edge_cases_python_surface(emu_device):
     _run(test_gpu_oracle.test_sharded_union_equals_whole, emu_device)
     test_gpu_oracle.test_edge_cases(emu_device)
     test_gpu_oracle.test_python_surface_variants(emu_device)
+    test_gpu_oracle.test_positions_are_64_bit_everywhere(emu_device)
 
 
 def test_emu_random_sweeps(emu_device):

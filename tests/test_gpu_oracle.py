@@ -211,3 +211,35 @@ def test_python_surface_variants(cuda_device):
     dev.close()
     with pytest.raises(TypeError):
         find_near_matches(pat, raw.decode("latin-1"), max_l_dist=1)   # bytes pattern vs str sequence
+
+
+def test_positions_are_64_bit_everywhere(cuda_device):
+    """A shard far inside a huge global sequence (offsets up to 2^44) must report what the same bytes report at
+    offset 0, shifted: every route, raw and final, also through the work-list overflow path.  (BASELINE configs[3]
+    reaches 2^35; the full-size bench checks that one offset, this checks the arithmetic.)"""
+    rng = np.random.default_rng(4)
+    for trial in range(12):
+        alphabet = [ASCII, DNA, b"abcdefgh"][trial % 3]
+        m = int(rng.choice([5, 8, 12, 20, 33, 64, 100]))
+        k = int(rng.integers(0, min(m // 3, 4) + 1))
+        n = 4096 if len(alphabet) <= 4 else int(rng.choice([4096, 70000]))
+        pat, hay, _ = make_corpus(100 + trial, n, alphabet, m, 10, k + 1, clusters=2)
+        shift = int(rng.choice([1 << 32, (1 << 35) - 4096, (1 << 40) + 16 * 12345, 1 << 44]))
+        lo, hi = 256, n - 256  # interior anchors, halo on both sides, no global end in sight
+        a = F.Haystack.from_host(hay, buf_lo=0, global_len=n + (1 << 20), own_lo=lo, own_hi=hi)
+        b = F.Haystack.from_host(hay, buf_lo=shift, global_len=shift + n + (1 << 20), own_lo=shift + lo,
+                                 own_hi=shift + hi)
+        calls = [lambda h: h.search_levenshtein(pat, k), lambda h: h.search_hamming(pat, min(k, 3)),
+                 lambda h: h.search_exact(pat), lambda h: h.search_levenshtein(pat, k, F.F_FORCE_DENSE),
+                 lambda h: h.search_levenshtein(pat, k, F.F_TINY_LIST)]
+        if k >= 1:
+            calls.append(lambda h: h.search_generic(pat, k, 1, 1, k))
+        for ci, call in enumerate(calls):
+            ra, rb = call(a), call(b)
+            for which in (F.RAW, F.FINAL):
+                ta, tb = sorted(ra.triples(which)), sorted(rb.triples(which))
+                assert [(s + shift, e + shift, d) for s, e, d in ta] == tb, (trial, ci, which, m, k, hex(shift))
+            ra.close()
+            rb.close()
+        a.close()
+        b.close()
