@@ -2733,6 +2733,8 @@ extern "C" int fzb_has_near_match(fzb_haystack *h, const uint8_t *pattern, uint3
     if (h->buf_len) sample_collision_prob(h);  // byte statistics of the WHOLE buffer (the views reuse them)
     const uint64_t halo = round_up((uint64_t)m + std::min<uint64_t>(max_l, m), 128) + 128;
     uint64_t chunk = 64ull << 20, lo = saved.own_lo;
+    if (const char *e = getenv("FZB_HAS_CHUNK_BYTES"))  // testing: chunk seams on small sequences
+        chunk = std::max<uint64_t>(128, round_up(strtoull(e, nullptr, 10), 128));
     rc = FZB_OK;
     do {  // (at least one pass: an empty sequence still has its k >= m matches)
         uint64_t hi = std::min(saved.own_hi, round_up(lo + chunk, 128));

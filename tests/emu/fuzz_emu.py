@@ -314,14 +314,20 @@ def has_trial(rng):
         lim = (subs, ins, dels, l)
         want = len(oracle.find_near_matches(pat, hay, subs, ins, dels, l)) > 0
     hs = F.Haystack.from_host(hay)
+    chunk = int(rng.choice([0, 128, 512, 4096]))  # chunked early termination: seams at small sizes
+    if chunk:
+        os.environ["FZB_HAS_CHUNK_BYTES"] = str(chunk)
+    else:
+        os.environ.pop("FZB_HAS_CHUNK_BYTES", None)
     try:
         got = hs.has_near_match(pat, *lim)
         if bool(got) != want:
-            fail("has", ("has", seed, len(alphabet), m, len(hay), lim, got, want))
+            fail("has", ("has", seed, len(alphabet), m, len(hay), lim, got, want, chunk))
     except F.UnsupportedError:
         pass
     except Exception as e:  # noqa: BLE001
         fail("has-exception %r" % (e,), ("has", seed, m, len(hay), lim))
+    os.environ.pop("FZB_HAS_CHUNK_BYTES", None)
     hs.close()
 
 

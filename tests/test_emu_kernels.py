@@ -126,6 +126,10 @@ def test_emu_file_search(emu_device, tmp_path):
     test_gpu_file.test_file_random_corpus(emu_device, tmp_path)
 
 
+def test_emu_has_near_match_chunk_seams(emu_device, monkeypatch):
+    test_gpu_python_api.test_has_near_match_chunk_seams_at_small_scale(emu_device, monkeypatch)
+
+
 def test_emu_threads_and_has_near_match(emu_device):
     test_gpu_python_api.test_find_near_matches_is_thread_safe(emu_device)
     test_gpu_python_api.test_threads_share_one_resident_sequence(emu_device)

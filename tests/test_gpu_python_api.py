@@ -173,3 +173,32 @@ def test_has_near_match_stops_early_on_a_long_sequence(cuda_device):
     t_early = (time.perf_counter() - t0) / 5
     assert t_early < t_none, (t_early, t_none)  # the first chunk answers: the other 236 MiB are never read
     seq.close()
+
+
+def test_has_near_match_chunk_seams_at_small_scale(cuda_device, monkeypatch):
+    """The chunked early termination with the chunk size shrunk by the test hook (FZB_HAS_CHUNK_BYTES): chunks of
+    256, 1024, 4096, ... bytes, the ONLY near-match planted at every delta around several chunk seams, every
+    search class -- each chunk is a view of the resident buffer with its own halo, so nothing may be lost or
+    invented at a seam."""
+    monkeypatch.setenv("FZB_HAS_CHUNK_BYTES", "256")
+    rng = np.random.default_rng(77)
+    m = 12
+    pat = b"needle-hay-x"
+    cases = [dict(max_l_dist=0), dict(max_l_dist=2), dict(max_substitutions=2, max_insertions=0, max_deletions=0),
+             dict(max_substitutions=1, max_insertions=1, max_deletions=1), dict(max_l_dist=4)]
+    n = 9000
+    base = rng.integers(48, 58, size=n, dtype=np.uint8)  # digits: no accidental matches
+    for kw in cases:
+        assert has_near_match(pat, base.tobytes(), **kw) is (kw.get("max_l_dist", 0) >= m)
+    seams = [256, 256 + 1024, 256 + 1024 + 4096]
+    for seam in seams:
+        for delta in range(-m - 4, 5):
+            hay = base.copy()
+            v = bytearray(pat)
+            v[5] = ord("#")  # one substitution: found by every class but the exact one
+            hay[seam + delta:seam + delta + m] = np.frombuffer(bytes(v), dtype=np.uint8)
+            for kw in cases:
+                exp = len(oracle.find_near_matches(pat, hay, **kw)) > 0
+                assert has_near_match(pat, hay.tobytes(), **kw) is exp, (seam, delta, kw)
+            hay[seam + delta + 5] = pat[5]
+            assert has_near_match(pat, hay.tobytes(), max_l_dist=0), (seam, delta)
