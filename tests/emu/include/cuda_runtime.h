@@ -33,6 +33,7 @@
 #include <chrono>
 #include <functional>
 #include <mutex>
+#include <string>
 #include <tuple>
 #include <type_traits>
 #include <utility>
@@ -806,10 +807,30 @@ inline int sm_count() {
     const int n = e ? atoi(e) : 0;
     return n > 0 ? n : 4;
 }
+// fault injection for the host error paths: FZB_EMU_FAIL_ALLOC=N makes the N-th allocation from now on fail
+// (device or pinned), once; the counter re-arms whenever the variable's value changes
+inline bool alloc_should_fail() {
+    static std::mutex mu;
+    static std::string armed;
+    static long left = 0;
+    const char *e = getenv("FZB_EMU_FAIL_ALLOC");
+    std::lock_guard<std::mutex> l(mu);
+    if (!e || !*e) {
+        armed.clear();
+        return false;
+    }
+    if (armed != e) {
+        armed = e;
+        left = atol(e);
+    }
+    if (left <= 0) return false;
+    return --left == 0;
+}
 inline void *alloc_bytes(size_t n, int fill) {
+    if (alloc_should_fail()) return nullptr;
     void *p = nullptr;
     if (posix_memalign(&p, 1024, n ? n : 1)) return nullptr;
-    memset(p, fill, n);
+    memset(p, fill, std::min(n, (size_t)8 << 20));  // (the tail of a huge buffer stays untouched: lazily mapped pages)
     return p;
 }
 }  // namespace emu

@@ -155,3 +155,53 @@ def test_emu_wide_symbols(emu_device, tmp_path):
     sig = inspect.signature(test_gpu_symbols.test_wide_cases_of_the_reference_suite)
     assert list(sig.parameters) == ["cuda_device", "tmp_path"]
     test_gpu_symbols.test_wide_cases_of_the_reference_suite(emu_device, tmp_path)
+
+
+def test_emu_allocation_failures_surface_cleanly(emu_device, monkeypatch):
+    """Fault injection (FZB_EMU_FAIL_ALLOC=N: the N-th device / pinned allocation fails once): every failure must
+    come back as CudaError through the C-ABI -- no crash, no wrong answer -- and the library must be sane afterwards
+    (an out-of-memory search on a shared box is not allowed to poison the process)."""
+    import os
+
+    import numpy as np  # noqa: F401
+
+    import oracle
+    from corpus import ASCII, DNA, make_corpus
+    from parity import tup
+    F = _native
+    pat, hay, _ = make_corpus(5, 1 << 13, ASCII, 20, 8, 3)
+    patd, hayd, _ = make_corpus(6, 1 << 11, DNA, 20, 8, 3)
+
+    def searches():
+        hs = F.Haystack.from_host(hay)
+        out = [hs.search_levenshtein(pat, 2).triples(F.FINAL), hs.search_hamming(pat, 3).triples(F.FINAL),
+               hs.search_levenshtein(pat[:8], 3).triples(F.FINAL), hs.search_generic(pat, 1, 2, 1, 2).triples(F.FINAL)]
+        hs2 = F.Haystack.from_host(hayd)
+        out.append(hs2.search_levenshtein(patd, 2).triples(F.FINAL))
+        out.append(hs.has_near_match(pat, 1 << 29, 1 << 29, 1 << 29, 2))
+        hs2.close()
+        hs.close()
+        return out
+
+    def batch():
+        hs = F.Haystack.from_host(hay)
+        res, _ = hs.search_levenshtein_batch([pat, pat[:30], pat[2:12], pat[:9], pat[1:9]], [2, 1, 1, 3, 3])
+        out = [r.triples(F.FINAL) for r in res]
+        hs.close()
+        return out
+
+    assert searches()[0] == tup(oracle.consolidate(oracle.levenshtein_raw(pat, hay, 2)))
+    for scenario, upto, at_least in ((searches, 80, 20), (batch, 60, 15)):
+        good = scenario()
+        raised = 0
+        for nth in range(1, upto):
+            monkeypatch.setenv("FZB_EMU_FAIL_ALLOC", str(nth))
+            try:
+                assert scenario() == good, nth   # no such allocation, or an optional buffer
+            except F.CudaError:
+                raised += 1
+                monkeypatch.setenv("FZB_EMU_FAIL_ALLOC", "")
+                assert scenario() == good, ("library state after a failed allocation", nth)
+            monkeypatch.setenv("FZB_EMU_FAIL_ALLOC", "")
+        assert raised >= at_least, (scenario.__name__, raised)
+    assert "FZB_EMU_FAIL_ALLOC" in os.environ
