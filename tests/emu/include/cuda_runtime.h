@@ -826,10 +826,15 @@ inline bool alloc_should_fail() {
     if (left <= 0) return false;
     return --left == 0;
 }
+inline long &live_allocations() {  // device + pinned allocations not yet freed (leak checks of the error paths)
+    static long n = 0;
+    return n;
+}
 inline void *alloc_bytes(size_t n, int fill) {
     if (alloc_should_fail()) return nullptr;
     void *p = nullptr;
     if (posix_memalign(&p, 1024, n ? n : 1)) return nullptr;
+    __atomic_add_fetch(&live_allocations(), 1, __ATOMIC_SEQ_CST);
     memset(p, fill, std::min(n, (size_t)8 << 20));  // (the tail of a huge buffer stays untouched: lazily mapped pages)
     return p;
 }
@@ -861,6 +866,7 @@ static inline cudaError_t cudaMalloc(T **p, size_t n) {
 static inline cudaError_t cudaDeviceSynchronize();
 static inline cudaError_t cudaFree(void *p) {
     cudaDeviceSynchronize();  // as on the device: no kernel may still be using it
+    if (p) __atomic_sub_fetch(&emu::live_allocations(), 1, __ATOMIC_SEQ_CST);
     free(p);
     return cudaSuccess;
 }
@@ -885,6 +891,7 @@ static inline cudaError_t cudaFreeHost(void *p) {
                 break;
             }
     }
+    if (p) __atomic_sub_fetch(&emu::live_allocations(), 1, __ATOMIC_SEQ_CST);
     free(p);
     return cudaSuccess;
 }
@@ -988,3 +995,6 @@ static inline cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsi
 static inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaErrorNotSupported; }
 cudaError_t cudaGetDriverEntryPoint(const char *name, void **fn, unsigned long long flags,
                                     cudaDriverEntryPointQueryResult *q);  // cuda.h
+
+// emulator-only export (not part of include/fuzzb200.h): live device + pinned allocations
+extern "C" __attribute__((visibility("default"), used)) long fzb_emu_live_allocations() { return emu::live_allocations(); }

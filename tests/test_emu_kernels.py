@@ -13,6 +13,7 @@ infrastructure: nothing in the product can load it.
 `FZB_TEST_BACKEND=emu python -m pytest tests -m gpu` replays the whole GPU suite this way (minutes), and
 `python tests/emu/fuzz_emu.py` runs a randomised campaign far beyond what fits a GPU budget.
 """
+import ctypes
 import gc
 import inspect
 
@@ -160,7 +161,7 @@ def test_emu_wide_symbols(emu_device, tmp_path):
 def test_emu_allocation_failures_surface_cleanly(emu_device, monkeypatch):
     """Fault injection (FZB_EMU_FAIL_ALLOC=N: the N-th device / pinned allocation fails once): every failure must
     come back as CudaError through the C-ABI -- no crash, no wrong answer -- and the library must be sane afterwards
-    (an out-of-memory search on a shared box is not allowed to poison the process)."""
+    (an out-of-memory search on a shared box is not allowed to poison the process), with nothing leaked."""
     import os
 
     import numpy as np  # noqa: F401
@@ -191,8 +192,12 @@ def test_emu_allocation_failures_surface_cleanly(emu_device, monkeypatch):
         return out
 
     assert searches()[0] == tup(oracle.consolidate(oracle.levenshtein_raw(pat, hay, 2)))
+    live = _native.lib().fzb_emu_live_allocations  # emulator-only export: device + pinned allocations not yet freed
+    live.restype = ctypes.c_long
     for scenario, upto, at_least in ((searches, 80, 20), (batch, 60, 15)):
         good = scenario()
+        gc.collect()
+        baseline = live()
         raised = 0
         for nth in range(1, upto):
             monkeypatch.setenv("FZB_EMU_FAIL_ALLOC", str(nth))
@@ -201,6 +206,8 @@ def test_emu_allocation_failures_surface_cleanly(emu_device, monkeypatch):
             except F.CudaError:
                 raised += 1
                 monkeypatch.setenv("FZB_EMU_FAIL_ALLOC", "")
+                gc.collect()  # the handles of the failed scenario are gone: whatever it allocated must be, too
+                assert live() == baseline, ("leak on the error path of allocation", nth)
                 assert scenario() == good, ("library state after a failed allocation", nth)
             monkeypatch.setenv("FZB_EMU_FAIL_ALLOC", "")
         assert raised >= at_least, (scenario.__name__, raised)
