@@ -201,14 +201,16 @@ def test_emu_allocation_failures_surface_cleanly(emu_device, monkeypatch):
         raised = 0
         for nth in range(1, upto):
             monkeypatch.setenv("FZB_EMU_FAIL_ALLOC", str(nth))
+            failed = False
             try:
                 assert scenario() == good, nth   # no such allocation, or an optional buffer
             except F.CudaError:
+                failed = True  # (the traceback keeps the scenario's handles alive until the handler is left)
+            monkeypatch.setenv("FZB_EMU_FAIL_ALLOC", "")
+            if failed:
                 raised += 1
-                monkeypatch.setenv("FZB_EMU_FAIL_ALLOC", "")
                 gc.collect()  # the handles of the failed scenario are gone: whatever it allocated must be, too
                 assert live() == baseline, ("leak on the error path of allocation", nth)
                 assert scenario() == good, ("library state after a failed allocation", nth)
-            monkeypatch.setenv("FZB_EMU_FAIL_ALLOC", "")
         assert raised >= at_least, (scenario.__name__, raised)
     assert "FZB_EMU_FAIL_ALLOC" in os.environ
