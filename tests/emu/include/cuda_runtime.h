@@ -27,6 +27,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <sys/mman.h>
+#if defined(__SANITIZE_ADDRESS__)
+#include <sanitizer/asan_interface.h>
+#endif
 #include <unistd.h>
 
 #include <algorithm>
@@ -331,6 +334,11 @@ inline Cta *cta_start(Launch *L, unsigned long long index) {
                                  MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
         if (c->stacks == (char *)MAP_FAILED) die("cannot map fiber stacks");
     }
+#if defined(__SANITIZE_ADDRESS__)
+    // FZB_EMU_ASAN build: fibers of the previous CTA never return (they switch away for good), so the red zones of
+    // their frames are still poisoned in the shadow of this stack region
+    __asan_unpoison_memory_region(c->stacks, need);
+#endif
     c->bid.x = (unsigned)(index % L->grid.x);
     c->bid.y = (unsigned)((index / L->grid.x) % L->grid.y);
     c->bid.z = (unsigned)(index / ((unsigned long long)L->grid.x * L->grid.y));
