@@ -113,7 +113,7 @@ def build(force=False, verbose=False):
         t = rewrite(open(os.path.join(CSRC, n)).read())
         texts[n] = t
         digest.update(n.encode() + b"\0" + t.encode())
-    digest.update((os.environ.get("FZB_EMU_COVERAGE", "") + "/" + os.environ.get("FZB_EMU_ASAN", "")).encode())
+    digest.update((os.environ.get("FZB_EMU_COVERAGE", "") + "/" + os.environ.get("FZB_EMU_ASAN", "") + "/" + os.environ.get("FZB_EMU_UBSAN", "")).encode())
     for extra in (os.path.join(HERE, "include", "cuda_runtime.h"), os.path.join(HERE, "include", "cuda.h"),
                   os.path.join(ROOT, "include", "fuzzb200.h"), os.path.abspath(__file__)):
         digest.update(open(extra, "rb").read())
@@ -130,6 +130,8 @@ def build(force=False, verbose=False):
         opt = ["-O0", "--coverage"]
     if os.environ.get("FZB_EMU_ASAN"):  # AddressSanitizer: out-of-bounds accesses of kernels and host code
         opt = ["-O1", "-fsanitize=address"]  # (run python with LD_PRELOAD=$(gcc -print-file-name=libasan.so))
+    if os.environ.get("FZB_EMU_UBSAN"):  # shifts past the width, signed overflow, misaligned accesses, ...
+        opt = ["-O1", "-fsanitize=undefined", "-fno-sanitize=vptr,pointer-overflow", "-fno-sanitize-recover=undefined"]  # (W = H - buf_lo: virtual base pointers wrap by design)
     cmd = [cxx] + opt + ["-g", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-DFZB_EMU",
            "-fno-omit-frame-pointer", "-Wno-unknown-pragmas", "-Wno-attributes",
            "-I", os.path.join(HERE, "include"), "-I", os.path.join(ROOT, "include"), "-I", srcdir,

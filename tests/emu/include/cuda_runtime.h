@@ -301,7 +301,7 @@ inline void make_owner(Cta *c) {  // before c runs: its shared memory must be th
             memcpy(G.registry[i].p, c->snap_static.data() + off, G.registry[i].n);
             off += G.registry[i].n;
         }
-        memcpy(g_dyn_smem, c->snap_dyn.data(), c->snap_dyn.size());
+        if (!c->snap_dyn.empty()) memcpy(g_dyn_smem, c->snap_dyn.data(), c->snap_dyn.size());
     } else {
         memset(g_dyn_smem, 0xA5, c->dyn_bytes);  // shared memory starts as garbage, like on the device
     }
