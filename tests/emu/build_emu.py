@@ -103,7 +103,16 @@ def rewrite(src):
     return rewrite_launches(src)
 
 
+def _flavour():
+    for name in ("COVERAGE", "ASAN", "UBSAN", "TSAN"):
+        if os.environ.get("FZB_EMU_" + name):
+            return name.lower()
+    return ""
+
+
 def build(force=False, verbose=False):
+    flavour = _flavour()  # the instrumented builds live next to the plain one
+    out = OUT if not flavour else OUT.replace(".so", "-%s.so" % flavour)
     srcdir = os.path.join(BUILD, "src")
     os.makedirs(srcdir, exist_ok=True)
     digest = hashlib.sha256()
@@ -113,14 +122,14 @@ def build(force=False, verbose=False):
         t = rewrite(open(os.path.join(CSRC, n)).read())
         texts[n] = t
         digest.update(n.encode() + b"\0" + t.encode())
-    digest.update((os.environ.get("FZB_EMU_COVERAGE", "") + "/" + os.environ.get("FZB_EMU_ASAN", "") + "/" + os.environ.get("FZB_EMU_UBSAN", "")).encode())
+    digest.update((os.environ.get("FZB_EMU_COVERAGE", "") + "/" + os.environ.get("FZB_EMU_ASAN", "") + "/" + os.environ.get("FZB_EMU_UBSAN", "") + "/" + os.environ.get("FZB_EMU_TSAN", "")).encode())
     for extra in (os.path.join(HERE, "include", "cuda_runtime.h"), os.path.join(HERE, "include", "cuda.h"),
                   os.path.join(ROOT, "include", "fuzzb200.h"), os.path.abspath(__file__)):
         digest.update(open(extra, "rb").read())
-    stamp = os.path.join(BUILD, "stamp")
-    if (not force and os.path.exists(OUT) and os.path.exists(stamp)
+    stamp = os.path.join(BUILD, "stamp" + ("-" + flavour if flavour else ""))
+    if (not force and os.path.exists(out) and os.path.exists(stamp)
             and open(stamp).read() == digest.hexdigest()):
-        return OUT
+        return out
     for n, t in texts.items():
         with open(os.path.join(srcdir, n), "w") as f:
             f.write(t)
@@ -130,18 +139,20 @@ def build(force=False, verbose=False):
         opt = ["-O0", "--coverage"]
     if os.environ.get("FZB_EMU_ASAN"):  # AddressSanitizer: out-of-bounds accesses of kernels and host code
         opt = ["-O1", "-fsanitize=address"]  # (run python with LD_PRELOAD=$(gcc -print-file-name=libasan.so))
+    if os.environ.get("FZB_EMU_TSAN"):  # ThreadSanitizer as a racecheck of the kernels (cuda_runtime.h explains the edges)
+        opt = ["-O1", "-fsanitize=thread"]
     if os.environ.get("FZB_EMU_UBSAN"):  # shifts past the width, signed overflow, misaligned accesses, ...
         opt = ["-O1", "-fsanitize=undefined", "-fno-sanitize=vptr,pointer-overflow", "-fno-sanitize-recover=undefined"]  # (W = H - buf_lo: virtual base pointers wrap by design)
     cmd = [cxx] + opt + ["-g", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-DFZB_EMU",
            "-fno-omit-frame-pointer", "-Wno-unknown-pragmas", "-Wno-attributes",
            "-I", os.path.join(HERE, "include"), "-I", os.path.join(ROOT, "include"), "-I", srcdir,
-           "-x", "c++", os.path.join(srcdir, "api.cu"), "-o", OUT, "-lpthread", "-ldl"]
+           "-x", "c++", os.path.join(srcdir, "api.cu"), "-o", out, "-lpthread", "-ldl"]
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)
     with open(stamp, "w") as f:
         f.write(digest.hexdigest())
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

@@ -41,17 +41,21 @@ inline CUresult encode_tiled(CUtensorMap *map, CUtensorMapDataType dt, cuuint32_
 }
 
 // mbarrier word: low half = completed phases, high half = transaction bytes still expected in the current phase
-inline void mbar_init(uint64_t *bar, uint32_t) { *bar = 0; }
-inline void mbar_tx(uint64_t *bar, int64_t delta, bool arrive) {
+EMU_NOTSAN inline void mbar_init(uint64_t *bar, uint32_t) { *bar = 0; }
+EMU_NOTSAN inline void mbar_tx(uint64_t *bar, int64_t delta, bool arrive) {
     int64_t pending = (int64_t)(int32_t)(*bar >> 32) + delta;
     uint32_t phases = (uint32_t)*bar;
     (void)arrive;
-    if (pending == 0) phases++;  // the single expected arrival has happened and every byte has landed
+    if (pending == 0) {  // the single expected arrival has happened and every byte has landed
+        phases++;
+        EMU_TSAN(__tsan_release(bar);)  // phase completion publishes the tile to whoever waits on the barrier
+    }
     *bar = ((uint64_t)(uint32_t)(int32_t)pending << 32) | phases;
 }
 inline void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { mbar_tx(bar, (int64_t)bytes, true); }
-inline void mbar_wait(uint64_t *bar, uint32_t parity) {
+EMU_NOTSAN inline void mbar_wait(uint64_t *bar, uint32_t parity) {
     while ((((uint32_t)*reinterpret_cast<volatile uint64_t *>(bar)) & 1u) == parity) yield();
+    EMU_TSAN(__tsan_acquire(bar);)
 }
 // cp.async.bulk.tensor.2d: box (box0 x box1) at element coordinates (c0, c1); out-of-bounds elements read as zero;
 // SWIZZLE_128B: within each 128-byte row of the destination, 16-byte chunk j lands at chunk j ^ (row % 8), rows

@@ -90,6 +90,23 @@ static inline typename std::common_type<A, B>::type max(A a, B b) {
     return (T)a > (T)b ? (T)a : (T)b;
 }
 
+// ---- ThreadSanitizer (FZB_EMU_TSAN build): fibers are TSan fibers, the only happens-before edges are the ones CUDA
+// gives -- launch -> threads, __syncthreads(), the *_sync warp primitives, fences, mbarrier phases, thread exit ->
+// end of the launch -- so two
+// conflicting accesses of different CUDA threads that nothing orders are REPORTED (a racecheck over shared AND
+// global memory).  The emulator's own bookkeeping is not instrumented.
+#if defined(__SANITIZE_THREAD__)
+#include <sanitizer/tsan_interface.h>
+extern "C" void AnnotateNewMemory(const char *file, int line, const volatile void *mem, long size);
+#define EMU_NOTSAN __attribute__((no_sanitize("thread")))
+#define EMU_TSAN(...) __VA_ARGS__
+#define EMU_ATOMIC_ORDER __ATOMIC_RELAXED  // device atomics order nothing by themselves
+#else
+#define EMU_NOTSAN
+#define EMU_TSAN(...)
+#define EMU_ATOMIC_ORDER __ATOMIC_SEQ_CST
+#endif
+
 // ---- the fiber scheduler ----------------------------------------------------------------------------------------
 extern "C" void fzb_emu_switch(void **save_sp, void *load_sp);
 asm(R"(
@@ -147,6 +164,7 @@ struct Fiber {
     uint32_t wait_val = 0;
     uint3 tid{0, 0, 0};
     unsigned lin = 0;
+    void *tsan = nullptr;  // TSan fiber context (FZB_EMU_TSAN build)
 };
 
 // One CTA: resumable.  A CTA whose runnable threads all spin (a grid barrier, a flag another GPU raises) is set
@@ -157,6 +175,7 @@ struct Cta {
     unsigned nthreads = 0, alive = 0;
     unsigned bar_arrived = 0;
     uint32_t bar_gen = 0;
+    char bar_token = 0;
     uint3 bid{0, 0, 0};
     char *stacks = nullptr;
     size_t stack_bytes = 0;
@@ -201,8 +220,10 @@ struct Global {
     std::vector<Cta *> free_ctas;
     std::vector<std::pair<char *, size_t>> free_stacks;
     emu_stream default_stream;
+    void *sched_tsan = nullptr;
+    char launch_token = 0, done_token = 0, fence_token = 0;  // addresses TSan hangs happens-before edges on
 };
-inline Global &g() {
+EMU_NOTSAN inline Global &g() {
     static Global *G = new Global();  // never destroyed: host threads may still be inside at exit
     return *G;
 }
@@ -216,7 +237,7 @@ inline T *dyn_smem() {
 // every `__shared__` declaration registers its storage the first time control passes it (build_emu.py adds the
 // registration next to the declaration)
 struct SharedReg {
-    SharedReg(void *p, size_t n) { g().registry.push_back(SharedVar{p, n}); }
+    EMU_NOTSAN SharedReg(void *p, size_t n) { g().registry.push_back(SharedVar{p, n}); }
 };
 
 [[noreturn]] inline void die(const char *what) {
@@ -226,25 +247,27 @@ struct SharedReg {
     abort();
 }
 
-inline void yield() {  // still runnable: spin-wait on memory some other CTA, launch or host thread writes
+EMU_NOTSAN inline void yield() {  // still runnable: spin-wait on memory some other CTA, launch or host thread writes
     Global &G = g();
     Fiber *f = G.cur;
     f->wait_word = nullptr;
     f->spun = true;
+    EMU_TSAN(__tsan_switch_to_fiber(G.sched_tsan, __tsan_switch_to_fiber_no_sync);)
     fzb_emu_switch(&f->sp, G.sched_sp);
 }
-inline void block_on(const volatile uint32_t *word, uint32_t val) {
+EMU_NOTSAN inline void block_on(const volatile uint32_t *word, uint32_t val) {
     Global &G = g();
     Fiber *f = G.cur;
     while (*word == val) {
         f->wait_word = word;
         f->wait_val = val;
+        EMU_TSAN(__tsan_switch_to_fiber(G.sched_tsan, __tsan_switch_to_fiber_no_sync);)
         fzb_emu_switch(&f->sp, G.sched_sp);
     }
     f->wait_word = nullptr;
 }
 
-inline void rv_check_complete(Warp &w, Rendezvous &r) {
+EMU_NOTSAN inline void rv_check_complete(Warp &w, Rendezvous &r) {
     const uint32_t need = r.mask & w.alive;
     if (!r.complete && r.mask && (r.arrived & need) == need) {
         r.complete = 1;
@@ -252,7 +275,7 @@ inline void rv_check_complete(Warp &w, Rendezvous &r) {
     }
 }
 
-inline void fiber_exit() {
+EMU_NOTSAN inline void fiber_exit() {
     Global &G = g();
     Cta &c = *G.cur_cta;
     Fiber *f = G.cur;
@@ -266,16 +289,19 @@ inline void fiber_exit() {
         c.bar_gen++;
     }
     void *dummy;
+    EMU_TSAN(__tsan_release(&G.done_token);)  // ... and what this thread did is visible to the host after the launch
+    EMU_TSAN(__tsan_switch_to_fiber(G.sched_tsan, __tsan_switch_to_fiber_no_sync);)
     fzb_emu_switch(&dummy, G.sched_sp);
     die("resumed a finished fiber");
 }
 
-extern "C" inline void fzb_emu_trampoline() {
+extern "C" EMU_NOTSAN inline void fzb_emu_trampoline() {
+    EMU_TSAN(__tsan_acquire(&g().launch_token);)  // what the host did before the launch is visible to every thread
     g().cur_launch->body();
     fiber_exit();
 }
 
-inline void save_owner() {
+EMU_NOTSAN inline void save_owner() {
     Global &G = g();
     Cta *o = G.owner;
     if (!o) return;
@@ -291,7 +317,7 @@ inline void save_owner() {
     o->snap_dyn.assign(g_dyn_smem, g_dyn_smem + o->dyn_bytes);
     o->has_snapshot = true;
 }
-inline void make_owner(Cta *c) {  // before c runs: its shared memory must be the one in place
+EMU_NOTSAN inline void make_owner(Cta *c) {  // before c runs: its shared memory must be the one in place
     Global &G = g();
     if (G.owner == c) return;
     save_owner();
@@ -308,7 +334,7 @@ inline void make_owner(Cta *c) {  // before c runs: its shared memory must be th
     G.owner = c;
 }
 
-inline Cta *cta_start(Launch *L, unsigned long long index) {
+EMU_NOTSAN inline Cta *cta_start(Launch *L, unsigned long long index) {
     Global &G = g();
     Cta *c;
     if (!G.free_ctas.empty()) {
@@ -366,12 +392,21 @@ inline Cta *cta_start(Launch *L, unsigned long long index) {
         top[-2] = reinterpret_cast<uint64_t>(&fzb_emu_trampoline);
         for (int r = 3; r <= 8; r++) top[-r] = 0;  // rbp rbx r12 r13 r14 r15
         f.sp = top - 8;
+        EMU_TSAN(f.tsan = __tsan_create_fiber(0);)
     }
+#if defined(__SANITIZE_THREAD__)
+    // The emulator reuses its stacks and its shared-memory storage from CTA to CTA, so under TSan each CTA is ordered
+    // after the previous one (scope of the check = compute-sanitizer racecheck's: the threads of ONE CTA, but over
+    // shared AND global memory; races between CTAs are not looked for)
+    __tsan_acquire(&G.done_token);
+    __tsan_release(&G.launch_token);
+#endif
     return c;
 }
-inline void cta_release(Cta *c) {
+EMU_NOTSAN inline void cta_release(Cta *c) {
     Global &G = g();
     if (G.owner == c) G.owner = nullptr;
+    EMU_TSAN(for (unsigned i = 0; i < c->nthreads; i++) __tsan_destroy_fiber(c->fib[i].tsan);)
     G.free_stacks.push_back(std::make_pair(c->stacks, c->stack_bytes));
     c->stacks = nullptr;
     G.free_ctas.push_back(c);
@@ -391,11 +426,12 @@ inline uint64_t sched_rand() {
 }
 
 // run the CTA until it has finished (true) or every thread that can run merely spins (false)
-inline bool cta_run(Launch *L, Cta *c) {
+EMU_NOTSAN inline bool cta_run(Launch *L, Cta *c) {
     Global &G = g();
     make_owner(c);
     G.cur_launch = L;
     G.cur_cta = c;
+    EMU_TSAN(G.sched_tsan = __tsan_get_current_fiber();)
     c->progressed = false;
     bool finished = true;
     const int order = sched_order();
@@ -414,6 +450,7 @@ inline bool cta_run(Launch *L, Cta *c) {
             G.cur = &f;
             ran = true;
             f.spun = false;
+            EMU_TSAN(__tsan_switch_to_fiber(f.tsan, __tsan_switch_to_fiber_no_sync);)
             fzb_emu_switch(&G.sched_sp, f.sp);
             if (!f.spun) progress = true;
         }
@@ -431,7 +468,7 @@ inline bool cta_run(Launch *L, Cta *c) {
 }
 
 // advance a launch: true = every CTA has finished; false = what is left of it waits for somebody else
-inline bool launch_run(Launch *L) {
+EMU_NOTSAN inline bool launch_run(Launch *L) {
     for (;;) {
         bool any = false;
         for (size_t i = 0; i < L->live.size();) {
@@ -459,11 +496,12 @@ inline bool launch_run(Launch *L) {
 }
 
 // give every suspended launch another go (any host thread that enters the emulator does this)
-inline void pump_locked() {
+EMU_NOTSAN inline void pump_locked() {
     Global &G = g();
     for (size_t i = 0; i < G.pending.size();) {
         emu_stream *S = G.pending[i];
         if (launch_run(S->pending)) {
+            EMU_TSAN(__tsan_acquire(&G.done_token); __tsan_release(&G.done_token);)
             delete S->pending;
             S->pending = nullptr;
             G.pending.erase(G.pending.begin() + i);
@@ -494,7 +532,7 @@ inline void drain_all_locked(std::unique_lock<std::mutex> &lk) {
 
 // one kernel launch: CTAs in order (a CTA that waits is set aside), arguments evaluated once by the caller
 template <class Body>
-inline void launch(dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Body &&body) {
+EMU_NOTSAN inline void launch(dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Body &&body) {
     Global &G = g();
     std::unique_lock<std::mutex> lk(G.mu);
     if (G.cur) die("nested launch");
@@ -507,7 +545,9 @@ inline void launch(dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Body
     L->smem = smem;
     L->body = std::forward<Body>(body);
     L->total = (unsigned long long)grid.x * grid.y * grid.z;
+    EMU_TSAN(__tsan_release(&G.launch_token);)
     if (launch_run(L)) {
+        EMU_TSAN(__tsan_acquire(&G.done_token);)
         delete L;
     } else {
         S->pending = L;
@@ -516,7 +556,7 @@ inline void launch(dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Body
 }
 
 // ---- warp collectives ---------------------------------------------------------------------------------------
-inline Rendezvous &rv_arrive(uint32_t mask, int op, uint64_t v, int *lane_out) {
+EMU_NOTSAN inline Rendezvous &rv_arrive(uint32_t mask, int op, uint64_t v, int *lane_out) {
     Global &G = g();
     Fiber *f = G.cur;
     const int lane = f->lin & 31;
@@ -538,11 +578,15 @@ inline Rendezvous &rv_arrive(uint32_t mask, int op, uint64_t v, int *lane_out) {
     r->val[lane] = v;
     r->arrived |= 1u << lane;
     const uint32_t gen = r->gen;
+    // every *_sync primitive is a convergence point: no named lane leaves before all have arrived, so what a lane
+    // did before it cannot collide with what another does after it (TSan: release on arrival, acquire on leaving)
+    EMU_TSAN(__tsan_release(&w.alive);)
     rv_check_complete(w, *r);
     if (!r->complete) block_on(&r->gen, gen);
+    EMU_TSAN(__tsan_acquire(&w.alive);)
     return *r;
 }
-inline void rv_depart(Rendezvous &r, int lane) {
+EMU_NOTSAN inline void rv_depart(Rendezvous &r, int lane) {
     r.departed |= 1u << lane;
     if (r.departed == r.arrived) r.mask = 0;  // free
 }
@@ -561,7 +605,7 @@ inline T from_bits(uint64_t b) {
     return v;
 }
 template <class T>
-inline T shfl_generic(uint32_t mask, T v, int op, int arg, int width) {
+EMU_NOTSAN inline T shfl_generic(uint32_t mask, T v, int op, int arg, int width) {
     int lane;
     Rendezvous &r = rv_arrive(mask, op, to_bits(v), &lane);
     const int seg = lane & ~(width - 1);
@@ -594,17 +638,20 @@ inline T shfl_generic(uint32_t mask, T v, int op, int arg, int width) {
 #define gridDim (emu::g().cur_launch->grid)
 #define warpSize 32
 
-static inline void __syncthreads() {
+EMU_NOTSAN static inline void __syncthreads() {
     emu::Cta &c = *emu::g().cur_cta;
     const uint32_t gen = c.bar_gen;
+    EMU_TSAN(__tsan_release(&c.bar_token);)
     if (++c.bar_arrived == c.alive) {
         c.bar_arrived = 0;
         c.bar_gen++;
+        EMU_TSAN(__tsan_acquire(&c.bar_token);)
         return;
     }
     emu::block_on(&c.bar_gen, gen);
+    EMU_TSAN(__tsan_acquire(&c.bar_token);)
 }
-static inline void __syncwarp(unsigned mask = 0xFFFFFFFFu) {
+EMU_NOTSAN static inline void __syncwarp(unsigned mask = 0xFFFFFFFFu) {
     int lane;
     emu::Rendezvous &r = emu::rv_arrive(mask, emu::OP_SYNCWARP, 0, &lane);
     emu::rv_depart(r, lane);
@@ -625,7 +672,7 @@ template <class T>
 static inline T __shfl_xor_sync(unsigned mask, T v, int lanemask, int width = 32) {
     return emu::shfl_generic(mask, v, emu::OP_SHFL_XOR, lanemask, width);
 }
-static inline unsigned __ballot_sync(unsigned mask, int pred) {
+EMU_NOTSAN static inline unsigned __ballot_sync(unsigned mask, int pred) {
     int lane;
     emu::Rendezvous &r = emu::rv_arrive(mask, emu::OP_BALLOT, pred ? 1 : 0, &lane);
     unsigned out = 0;
@@ -635,7 +682,7 @@ static inline unsigned __ballot_sync(unsigned mask, int pred) {
     return out;
 }
 static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
-static inline int __all_sync(unsigned mask, int pred) {
+EMU_NOTSAN static inline int __all_sync(unsigned mask, int pred) {
     int lane;
     emu::Rendezvous &r = emu::rv_arrive(mask, emu::OP_ALL, pred ? 1 : 0, &lane);
     int out = 1;
@@ -645,7 +692,7 @@ static inline int __all_sync(unsigned mask, int pred) {
     return out;
 }
 template <class T>
-static inline unsigned __match_any_sync(unsigned mask, T v) {
+EMU_NOTSAN static inline unsigned __match_any_sync(unsigned mask, T v) {
     int lane;
     const uint64_t mine = emu::to_bits(v);
     emu::Rendezvous &r = emu::rv_arrive(mask, emu::OP_MATCH, mine, &lane);
@@ -656,7 +703,7 @@ static inline unsigned __match_any_sync(unsigned mask, T v) {
     return out;
 }
 template <class T>
-static inline T __reduce_add_sync(unsigned mask, T v) {
+EMU_NOTSAN static inline T __reduce_add_sync(unsigned mask, T v) {
     int lane;
     emu::Rendezvous &r = emu::rv_arrive(mask, emu::OP_REDUCE, emu::to_bits(v), &lane);
     T out = 0;
@@ -668,29 +715,29 @@ static inline T __reduce_add_sync(unsigned mask, T v) {
 
 // ---- atomics (one OS thread executes kernels at a time; other host threads only read results after a launch) ----
 template <class T, class U>
-static inline T atomicAdd(T *p, U v) { return __atomic_fetch_add(p, (T)v, __ATOMIC_SEQ_CST); }
+static inline T atomicAdd(T *p, U v) { return __atomic_fetch_add(p, (T)v, EMU_ATOMIC_ORDER); }
 template <class T, class U>
-static inline T atomicOr(T *p, U v) { return __atomic_fetch_or(p, (T)v, __ATOMIC_SEQ_CST); }
+static inline T atomicOr(T *p, U v) { return __atomic_fetch_or(p, (T)v, EMU_ATOMIC_ORDER); }
 template <class T, class U>
-static inline T atomicAnd(T *p, U v) { return __atomic_fetch_and(p, (T)v, __ATOMIC_SEQ_CST); }
+static inline T atomicAnd(T *p, U v) { return __atomic_fetch_and(p, (T)v, EMU_ATOMIC_ORDER); }
 template <class T, class U>
-static inline T atomicExch(T *p, U v) { return __atomic_exchange_n(p, (T)v, __ATOMIC_SEQ_CST); }
+static inline T atomicExch(T *p, U v) { return __atomic_exchange_n(p, (T)v, EMU_ATOMIC_ORDER); }
 template <class T, class U>
 static inline T atomicMin(T *p, U v) {
-    T old = *p;
-    if ((T)v < old) *p = (T)v;
+    T old = __atomic_load_n(p, EMU_ATOMIC_ORDER);
+    if ((T)v < old) __atomic_store_n(p, (T)v, EMU_ATOMIC_ORDER);  // (one host thread runs kernels at a time)
     return old;
 }
 template <class T, class U>
 static inline T atomicMax(T *p, U v) {
-    T old = *p;
-    if ((T)v > old) *p = (T)v;
+    T old = __atomic_load_n(p, EMU_ATOMIC_ORDER);
+    if ((T)v > old) __atomic_store_n(p, (T)v, EMU_ATOMIC_ORDER);
     return old;
 }
 template <class T, class U, class V>
 static inline T atomicCAS(T *p, U cmp, V v) {
     T expected = (T)cmp;
-    __atomic_compare_exchange_n(p, &expected, (T)v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+    __atomic_compare_exchange_n(p, &expected, (T)v, false, EMU_ATOMIC_ORDER, EMU_ATOMIC_ORDER);
     return expected;
 }
 
@@ -740,9 +787,20 @@ template <>
 inline longlong2 __ldcg<longlong2>(const longlong2 *p) { return *p; }
 template <class T>
 static inline T __ldcs(const T *p) { return *p; }
+#if defined(__SANITIZE_THREAD__)
+// (TSan does not model atomic_thread_fence: a fence publishes everything before it to whoever fences later)
+EMU_NOTSAN static inline void emu_fence() {
+    __tsan_release(&emu::g().fence_token);
+    __tsan_acquire(&emu::g().fence_token);
+}
+static inline void __threadfence() { emu_fence(); }
+static inline void __threadfence_block() { emu_fence(); }
+static inline void __threadfence_system() { emu_fence(); }
+#else
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+#endif
 namespace emu {
 inline long long cycles() {  // a slow clock (0.2 "GHz" of wall time): the kernels' bounded spin-waits for a peer allow for
                              // host threads that take turns inside the emulator on a busy box
