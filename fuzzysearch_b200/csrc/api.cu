@@ -514,7 +514,12 @@ extern "C" int fzb_haystack_read(fzb_haystack *h, uint64_t global_offset, uint8_
     return FZB_OK;
 }
 
-extern "C" uint64_t fzb_haystack_len(const fzb_haystack *h) { return h ? h->global_len : 0; }
+extern "C" uint64_t fzb_haystack_len(const fzb_haystack *h) {
+    // under the handle's lock like every other call: a windowed exact search / has_near_match on another thread
+    // swaps the geometry (global_len included) for the duration of its view
+    HandleLock handle_lock(const_cast<fzb_haystack *>(h));
+    return h ? h->global_len : 0;
+}
 
 // ------------------------------------------------------------------------------------------------
 // Upload of PAGEABLE host memory (what a Python bytes object is).  cudaMemcpy from pageable memory stages through

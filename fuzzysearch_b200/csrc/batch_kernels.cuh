@@ -185,7 +185,8 @@ struct MdenseParams {
     uint32_t hits_cap;
 };
 
-__device__ __forceinline__ void mdense_append(const MdenseParams &p, unsigned long long *sBuf, uint32_t *sN,
+// -> true when this append brought the CTA buffer to its flush threshold
+__device__ __forceinline__ bool mdense_append(const MdenseParams &p, unsigned long long *sBuf, uint32_t *sN,
                                               unsigned long long hit) {
     const uint32_t slot = atomicAdd(sN, 1u);
     if (slot < (uint32_t)kMdBuf) {
@@ -194,16 +195,19 @@ __device__ __forceinline__ void mdense_append(const MdenseParams &p, unsigned lo
         const uint32_t g = atomicAdd(&p.mp.counters[CNT_MHITS], 1u);
         if (g < p.hits_cap) p.hits[g] = hit;
     }
+    return slot + 1u >= (uint32_t)kMdFlush;
 }
 
 // position `g` (global) starts with the 3-byte prefix `pre`: walk its postings, compare the rest of each n-gram
-__device__ __noinline__ void mdense_confirm(const MdenseParams &p, unsigned long long *sBuf, uint32_t *sN, uint32_t pre,
+// (-> true when one of its appends brought the CTA buffer to the flush threshold)
+__device__ __noinline__ bool mdense_confirm(const MdenseParams &p, unsigned long long *sBuf, uint32_t *sN, uint32_t pre,
                                             int64_t g) {
-    if (g < p.mp.own_lo || g >= p.mp.own_hi) return;
+    if (g < p.mp.own_lo || g >= p.mp.own_hi) return false;
+    bool full = false;
     uint32_t slot = (pre * kGramMul) & p.mp.gtab_mask;
     for (;;) {
         const uint2 e = __ldg(p.mp.gtab + slot);
-        if (e.y == 0u) return;
+        if (e.y == 0u) return full;
         if (e.x == pre) {
             const uint32_t first = e.y & 0xFFFFFFu, cnt = e.y >> 24;
             for (uint32_t i = 0; i < cnt; i++) {
@@ -219,7 +223,7 @@ __device__ __noinline__ void mdense_confirm(const MdenseParams &p, unsigned long
                         eq = false;
                         break;
                     }
-                if (eq) mdense_append(p, sBuf, sN, (unsigned long long)g | ((unsigned long long)j << 40) | ((unsigned long long)pid << 48));
+                if (eq) full |= mdense_append(p, sBuf, sN, (unsigned long long)g | ((unsigned long long)j << 40) | ((unsigned long long)pid << 48));
             }
         }
         slot = (slot + 1) & p.mp.gtab_mask;
@@ -239,6 +243,7 @@ k_filter_mdense(const __grid_constant__ MdenseParams p, int64_t nvec, int64_t nt
     const int lane = threadIdx.x & 31;
     const uint4 *base = reinterpret_cast<const uint4 *>(p.mp.H);
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        bool full = false;
 #pragma unroll 1
         for (int u = 0; u < kMultiUnroll; u++) {
             const int64_t v = t * kMultiTileVecs + (int64_t)u * kMultiThreads + threadIdx.x;
@@ -261,13 +266,14 @@ k_filter_mdense(const __grid_constant__ MdenseParams p, int64_t nvec, int64_t nt
                     const int b = 15 - bit;
                     if (off + b + 3 > p.mp.buf_len) continue;
                     const uint32_t w = __funnelshift_r(ws[b >> 2], ws[(b >> 2) + 1], 8 * (b & 3)) & 0xFFFFFFu;
-                    mdense_confirm(p, sBuf, sN, w, p.mp.buf_lo + off + b);
+                    full |= mdense_confirm(p, sBuf, sN, w, p.mp.buf_lo + off + b);
                 }
             }
         }
-        __syncthreads();
-        const uint32_t n = min(*sN, (uint32_t)kMdBuf);
-        if (n >= (uint32_t)kMdFlush) {
+        // flush decision reduced inside the barrier from what happened before it (see k_lp_scan): warps that are a
+        // tile ahead may already be appending again when a slower warp would read the count
+        if (__syncthreads_or(full)) {
+            const uint32_t n = min(*sN, (uint32_t)kMdBuf);
             if (threadIdx.x == 0) sBase = atomicAdd(&p.mp.counters[CNT_MHITS], n);
             __syncthreads();
             for (uint32_t i = threadIdx.x; i < n; i += kMultiThreads)

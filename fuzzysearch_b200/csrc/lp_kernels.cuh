@@ -258,16 +258,24 @@ k_lp_scan(const ScanParams p, unsigned long long *list, uint32_t list_cap) {
         const unsigned long long look = (unsigned long long)A | ((unsigned long long)n1 << 16) |
                                         ((unsigned long long)n2 << 32) | ((unsigned long long)n3 << 48);
         if (lane >= 29) Fm = 0;  // look-ahead lanes: the next warp / iteration owns these starts
+        bool full = false;
         while (Fm) {
             const int i = __ffs(Fm) - 1;
             Fm &= Fm - 1;
             const int64_t s0 = g0 + i;
             if (s0 < p.own_lo || s0 >= hi) continue;
-            if (__popcll((look >> i) & wmask) >= need) sBuf[atomicAdd(&sN, 1u)] = (unsigned long long)s0;
+            if (__popcll((look >> i) & wmask) >= need) {
+                const uint32_t slot = atomicAdd(&sN, 1u);
+                sBuf[slot] = (unsigned long long)s0;
+                full |= slot + 1u >= (uint32_t)kLpsFlush;
+            }
         }
-        __syncthreads();
-        const uint32_t n = sN;
-        if (n >= (uint32_t)kLpsFlush) {
+        // Flush once the buffer has reached the threshold.  The decision is reduced INSIDE the barrier from what
+        // each thread saw before it: a count read after the barrier could already include appends of warps that are
+        // an iteration ahead, and the warps of the CTA must agree both on taking this branch (it contains barriers)
+        // and on n.  Inside the branch nobody appends, so sN is stable.
+        if (__syncthreads_or(full)) {
+            const uint32_t n = sN;
             if (threadIdx.x == 0) sBase = atomicAdd(&p.counters[CNT_LPLIST], n);
             __syncthreads();
             const uint32_t b0 = sBase;

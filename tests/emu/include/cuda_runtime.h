@@ -176,6 +176,7 @@ struct Cta {
     unsigned bar_arrived = 0;
     uint32_t bar_gen = 0;
     char bar_token = 0;
+    int bar_or_acc = 0, bar_or_res[2] = {0, 0};  // __syncthreads_or
     uint3 bid{0, 0, 0};
     char *stacks = nullptr;
     size_t stack_bytes = 0;
@@ -285,6 +286,8 @@ EMU_NOTSAN inline void fiber_exit() {
     w.alive &= ~(1u << (f->lin & 31));
     for (int i = 0; i < kRendezvous; i++) rv_check_complete(w, w.rv[i]);  // a lane others were waiting for has left
     if (c.bar_arrived && c.bar_arrived == c.alive) {                       // ... or the CTA barrier was waiting for it
+        c.bar_or_res[c.bar_gen & 1u] = c.bar_or_acc;
+        c.bar_or_acc = 0;
         c.bar_arrived = 0;
         c.bar_gen++;
     }
@@ -370,6 +373,7 @@ EMU_NOTSAN inline Cta *cta_start(Launch *L, unsigned long long index) {
     c->bid.z = (unsigned)(index / ((unsigned long long)L->grid.x * L->grid.y));
     c->nthreads = c->alive = n;
     c->bar_arrived = 0;
+    c->bar_or_acc = 0;
     c->dyn_bytes = L->smem;
     c->has_snapshot = false;
     c->progressed = false;
@@ -651,7 +655,23 @@ EMU_NOTSAN static inline void __syncthreads() {
     emu::block_on(&c.bar_gen, gen);
     EMU_TSAN(__tsan_acquire(&c.bar_token);)
 }
-EMU_NOTSAN static inline void __syncwarp(unsigned mask = 0xFFFFFFFFu) {
+EMU_NOTSAN EMU_NOTSAN static inline int __syncthreads_or(int pred) {  // barrier + OR-reduction of the predicate (BAR.RED.OR)
+    emu::Cta &c = *emu::g().cur_cta;
+    const uint32_t gen = c.bar_gen;
+    if (pred) c.bar_or_acc = 1;
+    EMU_TSAN(__tsan_release(&c.bar_token);)
+    if (++c.bar_arrived == c.alive) {
+        c.bar_or_res[gen & 1u] = c.bar_or_acc;
+        c.bar_or_acc = 0;
+        c.bar_arrived = 0;
+        c.bar_gen++;
+    } else {
+        emu::block_on(&c.bar_gen, gen);
+    }
+    EMU_TSAN(__tsan_acquire(&c.bar_token);)
+    return c.bar_or_res[gen & 1u];
+}
+static inline void __syncwarp(unsigned mask = 0xFFFFFFFFu) {
     int lane;
     emu::Rendezvous &r = emu::rv_arrive(mask, emu::OP_SYNCWARP, 0, &lane);
     emu::rv_depart(r, lane);

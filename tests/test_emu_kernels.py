@@ -117,6 +117,7 @@ def test_emu_batches(emu_device):
     test_gpu_batch.test_batch_matches_oracle(emu_device)
     test_gpu_batch.test_batch_shared_scan_edge_cases(emu_device)
     test_gpu_batch.test_batch_lp_pass_with_large_budgets(emu_device)
+    test_gpu_batch.test_batch_dense_pass_flushes_and_overflows_its_cta_buffer(emu_device)
 
 
 def test_emu_file_search(emu_device, tmp_path):
@@ -214,3 +215,22 @@ def test_emu_allocation_failures_surface_cleanly(emu_device, monkeypatch):
                 assert scenario() == good, ("library state after a failed allocation", nth)
         assert raised >= at_least, (scenario.__name__, raised)
     assert "FZB_EMU_FAIL_ALLOC" in os.environ
+
+
+def test_emulator_racecheck_sees_a_missing_barrier():
+    """tests/emu/selftest: under the emulator's ThreadSanitizer mode a kernel without its __syncthreads() and one
+    whose threads all store to one global word are reported; the correct twins (__syncthreads, __syncwarp within a
+    warp) are not.  (The product kernels run clean in that mode: tests/emu/README.md.)"""
+    import importlib.util
+    import os
+    import subprocess
+    if not os.path.exists(subprocess.run(["/usr/bin/gcc", "-print-file-name=libtsan.so"], capture_output=True,
+                                         text=True).stdout.strip() or "/nonexistent"):
+        pytest.skip("libtsan not installed")
+    spec = importlib.util.spec_from_file_location("fzb_emu_selftest", os.path.join(conftest.ROOT, "tests", "emu",
+                                                                                    "selftest.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    reports = mod.run()
+    assert reports[0] == 0 and reports[2] == 0, reports
+    assert reports[1] > 0 and reports[3] > 0, reports

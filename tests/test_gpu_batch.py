@@ -131,3 +131,34 @@ def test_batch_lp_pass_with_large_budgets(cuda_device):
             assert res.triples(F.FINAL) == tup(oracle.consolidate(raw)), (pat, k)
             res.close()
         hs.close()
+
+
+def test_batch_dense_pass_flushes_and_overflows_its_cta_buffer(cuda_device):
+    """k_filter_mdense buffers hits per CTA (3 072 entries, flushed at 1 024, straight to the global list when full).
+    Thousands of occurrences packed into ONE 64 KiB tile drive one CTA through all three paths; the lists must still
+    equal the single-pattern searches and the oracle."""
+    rng = np.random.default_rng(91)
+    n = 1 << 20
+    alpha = np.frombuffer(ASCII, dtype=np.uint8)
+    hay = alpha[rng.integers(0, len(alpha), size=n)].copy()
+    pats = [b"QWERTYUIOPAS", b"zxcvbnmlkjhg", b"0192837465ab"]   # m = 12, k = 3: L = 3, the lemma does not hold
+    ks = [3, 3, 3]
+    hay[100:100 + 12 * 1500] = np.frombuffer(pats[0] * 1500, dtype=np.uint8)            # 6 000 n-gram hits in tile 0
+    off = 3 * (1 << 16) + 40
+    hay[off:off + 13 * 600] = np.frombuffer((pats[1] + b"-") * 600, dtype=np.uint8)     # 2 400 in another tile
+    for i in range(50):
+        pos = int(rng.integers(1 << 18, n - 100))
+        hay[pos:pos + 12] = np.frombuffer(mutate(rng, pats[2], ASCII, int(rng.integers(0, 4)))[:12].ljust(12, b"#"),
+                                          dtype=np.uint8)
+    hs = F.Haystack.from_host(hay)
+    results, _ = hs.search_levenshtein_batch(pats, ks)
+    for pat, k, res in zip(pats, ks, results):
+        assert res.stats()["route"] == "ngrams/dense-filter"
+        one = hs.search_levenshtein(pat, k)
+        assert res.triples(F.RAW) == one.triples(F.RAW), pat
+        raw = oracle.levenshtein_raw(pat, hay, k)
+        assert res.triples(F.RAW) == tup(raw), pat
+        assert res.triples(F.FINAL) == tup(oracle.consolidate(raw)), pat
+        one.close()
+        res.close()
+    hs.close()
