@@ -46,6 +46,13 @@ def _cuda_available():
         return False
 
 
+def needs_real_gpu(what):
+    """For the handful of gpu tests the CPU emulator cannot stand in for (FZB_TEST_BACKEND=emu replays): NCCL,
+    CUDA IPC between processes, 4 GiB inputs."""
+    if os.environ.get("FZB_TEST_BACKEND") == "emu":
+        pytest.skip("needs a real B200: " + what)
+
+
 @pytest.fixture(scope="session")
 def cuda_device():
     if not _cuda_available():

@@ -11,6 +11,7 @@ import pytest
 
 import oracle
 from fuzzysearch_b200 import _native as F
+from conftest import needs_real_gpu
 from parity import tup
 
 pytestmark = pytest.mark.gpu
@@ -61,6 +62,7 @@ def _raw_with_anchor(res):
 
 
 def test_levenshtein_4gib_ascii(cuda_device):
+    needs_real_gpu("4 GiB input")
     n, m, k = 4 * GiB, 20, 2
     hs = F.Haystack.alloc(n)
     hs.fill_synthetic(ASCII, 20260923)
@@ -132,6 +134,7 @@ def test_levenshtein_4gib_ascii(cuda_device):
 
 
 def test_hamming_4gib_dna(cuda_device):
+    needs_real_gpu("4 GiB input")
     n, m, k = 4 * GiB, 32, 3
     hs = F.Haystack.alloc(n)
     hs.fill_synthetic(DNA, 7)

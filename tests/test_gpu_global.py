@@ -11,6 +11,7 @@ import oracle
 from corpus import ASCII, DNA, make_corpus
 from fuzzysearch_b200 import _native as F
 from fuzzysearch_b200.sharding import init_local_world, init_shard_comm, search_all, shard_bounds
+from conftest import needs_real_gpu
 from parity import tup
 
 pytestmark = pytest.mark.gpu
@@ -18,6 +19,7 @@ pytestmark = pytest.mark.gpu
 
 def test_global_flag_world_of_one(cuda_device):
     """A world of one rank: through NCCL bootstrap (peer-memory path with itself) and as a local world."""
+    needs_real_gpu("NCCL bootstrap")
     pat, hay, _ = make_corpus(4, 1 << 20, ASCII, 20, 64, 3)
     hs = F.Haystack.from_host(hay)
     with pytest.raises(ValueError):
@@ -183,6 +185,7 @@ def test_global_multi_process_world(cuda_device):
     NCCL-bootstrapped world.  With ONE GPU: both processes on device 0 through the NCCL-free world (CUDA IPC between
     processes sharing a GPU) -- so this test never skips."""
     import multiprocessing as mp
+    needs_real_gpu("CUDA IPC / NCCL between processes")
     devices = [0, 1] if F.device_count() >= 2 else [0, 0]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
