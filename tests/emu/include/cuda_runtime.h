@@ -97,7 +97,8 @@ static inline typename std::common_type<A, B>::type max(A a, B b) {
 // global memory).  The emulator's own bookkeeping is not instrumented.
 #if defined(__SANITIZE_THREAD__)
 #include <sanitizer/tsan_interface.h>
-extern "C" void AnnotateNewMemory(const char *file, int line, const volatile void *mem, long size);
+extern "C" void AnnotateBenignRaceSized(const char *file, int line, const volatile void *mem, long size,
+                                        const char *description);
 #define EMU_NOTSAN __attribute__((no_sanitize("thread")))
 #define EMU_TSAN(...) __VA_ARGS__
 #define EMU_ATOMIC_ORDER __ATOMIC_RELAXED  // device atomics order nothing by themselves
@@ -235,10 +236,23 @@ inline T *dyn_smem() {
     return reinterpret_cast<T *>(g_dyn_smem);
 }
 
+inline bool tsan_grid_mode() {
+    static const bool on = [] {
+        const char *e = getenv("FZB_EMU_TSAN_GRID");
+        const bool v = e && *e && *e != '0';
+        EMU_TSAN(if (v) AnnotateBenignRaceSized(__FILE__, __LINE__, g_dyn_smem, (long)kDynSmemBytes, "emulated dynamic smem");)
+        return v;
+    }();
+    return on;
+}
+
 // every `__shared__` declaration registers its storage the first time control passes it (build_emu.py adds the
 // registration next to the declaration)
 struct SharedReg {
-    EMU_NOTSAN SharedReg(void *p, size_t n) { g().registry.push_back(SharedVar{p, n}); }
+    EMU_NOTSAN SharedReg(void *p, size_t n) {
+        g().registry.push_back(SharedVar{p, n});
+        EMU_TSAN(if (tsan_grid_mode()) AnnotateBenignRaceSized(__FILE__, __LINE__, p, (long)n, "emulated __shared__");)
+    }
 };
 
 [[noreturn]] inline void die(const char *what) {
@@ -362,6 +376,8 @@ EMU_NOTSAN inline Cta *cta_start(Launch *L, unsigned long long index) {
         c->stacks = (char *)mmap(nullptr, c->stack_bytes, PROT_READ | PROT_WRITE,
                                  MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
         if (c->stacks == (char *)MAP_FAILED) die("cannot map fiber stacks");
+        EMU_TSAN(if (tsan_grid_mode())
+                     AnnotateBenignRaceSized(__FILE__, __LINE__, c->stacks, (long)c->stack_bytes, "fiber stacks");)
     }
 #if defined(__SANITIZE_ADDRESS__)
     // FZB_EMU_ASAN build: fibers of the previous CTA never return (they switch away for good), so the red zones of
@@ -399,11 +415,15 @@ EMU_NOTSAN inline Cta *cta_start(Launch *L, unsigned long long index) {
         EMU_TSAN(f.tsan = __tsan_create_fiber(0);)
     }
 #if defined(__SANITIZE_THREAD__)
-    // The emulator reuses its stacks and its shared-memory storage from CTA to CTA, so under TSan each CTA is ordered
-    // after the previous one (scope of the check = compute-sanitizer racecheck's: the threads of ONE CTA, but over
-    // shared AND global memory; races between CTAs are not looked for)
-    __tsan_acquire(&G.done_token);
-    __tsan_release(&G.launch_token);
+    // The emulator reuses its stacks and its shared-memory storage from CTA to CTA.  Default mode: each CTA is ordered
+    // after the previous one (scope = compute-sanitizer racecheck's: the threads of ONE CTA, but over shared AND
+    // global memory).  FZB_EMU_TSAN_GRID=1: the CTAs of a grid stay UNORDERED, as on the device, and the reused
+    // storage is declared race-free instead -- that pass looks for races BETWEEN CTAs in global memory (and is blind
+    // to shared memory).
+    if (!tsan_grid_mode()) {
+        __tsan_acquire(&G.done_token);
+        __tsan_release(&G.launch_token);
+    }
 #endif
     return c;
 }

@@ -1,5 +1,5 @@
 """Self-test of the emulator's ThreadSanitizer mode: a kernel with a missing __syncthreads() MUST be reported, its
-correct twins must not.  Test infrastructure (run by tests/test_emu_kernels.py when libtsan is present)."""
+correct twins must not; a race between two CTAs is seen in grid mode (FZB_EMU_TSAN_GRID=1) only.  Test infrastructure (run by tests/test_emu_kernels.py when libtsan is present)."""
 import os
 import subprocess
 import sys
@@ -21,17 +21,18 @@ def run():
                            "-Wno-attributes", "-I", os.path.join(HERE, "include"), "-x", "c++", src, "-o", exe,
                            "-lpthread"])
     results = {}
-    for which in range(4):
+    for which, grid in ((0, "0"), (1, "0"), (2, "0"), (3, "0"), (4, "0"), (4, "1"), (0, "1")):
         p = subprocess.run([exe, str(which)], capture_output=True, text=True, timeout=300,
-                           env=dict(os.environ, TSAN_OPTIONS="halt_on_error=0 exitcode=0"))
+                           env=dict(os.environ, TSAN_OPTIONS="halt_on_error=0 exitcode=0", FZB_EMU_TSAN_GRID=grid))
         assert "done %d" % which in p.stdout, (which, p.stdout, p.stderr[-2000:])
-        results[which] = p.stderr.count("WARNING: ThreadSanitizer: data race")
+        results[(which, grid == "1")] = p.stderr.count("WARNING: ThreadSanitizer: data race")
     return results
 
 
 if __name__ == "__main__":
     r = run()
     print(r)
-    ok = r[0] == 0 and r[1] > 0 and r[2] == 0 and r[3] > 0
+    ok = (r[(0, False)] == 0 and r[(1, False)] > 0 and r[(2, False)] == 0 and r[(3, False)] > 0
+          and r[(4, False)] == 0 and r[(4, True)] > 0 and r[(0, True)] == 0)
     print("selftest", "OK" if ok else "FAILED")
     sys.exit(0 if ok else 1)
