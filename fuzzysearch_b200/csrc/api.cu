@@ -2517,13 +2517,17 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static int make_row_maps(fzb_haystack *h, CUtensorMap *map256, CUtensorMap *map8) {
-    static EncodeTiledFn encode = nullptr;
-    if (!encode) {
+    // resolved once per process; a function-local static's initialisation is thread-safe (handles of different
+    // threads get here concurrently)
+    static const EncodeTiledFn encode = []() -> EncodeTiledFn {
         void *fn = nullptr;
         cudaDriverEntryPointQueryResult q;
-        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
-        if (!fn || q != cudaDriverEntryPointSuccess) return fail(FZB_E_CUDA, "cuTensorMapEncodeTiled not available");
-        encode = (EncodeTiledFn)fn;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+        return (fn && q == cudaDriverEntryPointSuccess) ? (EncodeTiledFn)fn : nullptr;
+    }();
+    if (!encode) {
+        cudaGetLastError();
+        return fail(FZB_E_CUDA, "cuTensorMapEncodeTiled not available");
     }
     const cuuint64_t rows = h->padded_len / kHcRowBytes;  // whole rows inside the allocation
     const cuuint64_t dims[2] = {(cuuint64_t)kHcRowBytes, rows};

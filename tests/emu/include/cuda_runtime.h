@@ -267,8 +267,10 @@ EMU_NOTSAN inline void yield() {  // still runnable: spin-wait on memory some ot
     Fiber *f = G.cur;
     f->wait_word = nullptr;
     f->spun = true;
+    EMU_TSAN(__tsan_release(&G.done_token);)  // (only the scheduler acquires it, at CTA boundaries)
     EMU_TSAN(__tsan_switch_to_fiber(G.sched_tsan, __tsan_switch_to_fiber_no_sync);)
     fzb_emu_switch(&f->sp, G.sched_sp);
+    EMU_TSAN(__tsan_acquire(&g().launch_token);)
 }
 EMU_NOTSAN inline void block_on(const volatile uint32_t *word, uint32_t val) {
     Global &G = g();
@@ -276,8 +278,10 @@ EMU_NOTSAN inline void block_on(const volatile uint32_t *word, uint32_t val) {
     while (*word == val) {
         f->wait_word = word;
         f->wait_val = val;
+        EMU_TSAN(__tsan_release(&G.done_token);)
         EMU_TSAN(__tsan_switch_to_fiber(G.sched_tsan, __tsan_switch_to_fiber_no_sync);)
         fzb_emu_switch(&f->sp, G.sched_sp);
+        EMU_TSAN(__tsan_acquire(&g().launch_token);)
     }
     f->wait_word = nullptr;
 }
@@ -318,6 +322,14 @@ extern "C" EMU_NOTSAN inline void fzb_emu_trampoline() {
     fiber_exit();
 }
 
+// (a plain loop: under the sanitizers memcpy is an intercepted call, and these copies are the emulator's own business)
+EMU_NOTSAN inline void raw_copy(void *dst, const void *src, size_t n) {
+    uint8_t *d = static_cast<uint8_t *>(dst);
+    const uint8_t *s = static_cast<const uint8_t *>(src);
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) *reinterpret_cast<uint64_t *>(d + i) = *reinterpret_cast<const uint64_t *>(s + i);
+    for (; i < n; i++) d[i] = s[i];
+}
 EMU_NOTSAN inline void save_owner() {
     Global &G = g();
     Cta *o = G.owner;
@@ -327,11 +339,12 @@ EMU_NOTSAN inline void save_owner() {
     o->snap_static.resize(total);
     size_t off = 0;
     for (const SharedVar &v : G.registry) {
-        memcpy(o->snap_static.data() + off, v.p, v.n);
+        raw_copy(o->snap_static.data() + off, v.p, v.n);
         off += v.n;
     }
     o->saved_vars = G.registry.size();
-    o->snap_dyn.assign(g_dyn_smem, g_dyn_smem + o->dyn_bytes);
+    o->snap_dyn.resize(o->dyn_bytes);
+    raw_copy(o->snap_dyn.data(), g_dyn_smem, o->dyn_bytes);
     o->has_snapshot = true;
 }
 EMU_NOTSAN inline void make_owner(Cta *c) {  // before c runs: its shared memory must be the one in place
@@ -341,10 +354,10 @@ EMU_NOTSAN inline void make_owner(Cta *c) {  // before c runs: its shared memory
     if (c->has_snapshot) {
         size_t off = 0;
         for (size_t i = 0; i < c->saved_vars; i++) {
-            memcpy(G.registry[i].p, c->snap_static.data() + off, G.registry[i].n);
+            raw_copy(G.registry[i].p, c->snap_static.data() + off, G.registry[i].n);
             off += G.registry[i].n;
         }
-        if (!c->snap_dyn.empty()) memcpy(g_dyn_smem, c->snap_dyn.data(), c->snap_dyn.size());
+        if (!c->snap_dyn.empty()) raw_copy(g_dyn_smem, c->snap_dyn.data(), c->snap_dyn.size());
     } else {
         memset(g_dyn_smem, 0xA5, c->dyn_bytes);  // shared memory starts as garbage, like on the device
     }
@@ -414,17 +427,6 @@ EMU_NOTSAN inline Cta *cta_start(Launch *L, unsigned long long index) {
         f.sp = top - 8;
         EMU_TSAN(f.tsan = __tsan_create_fiber(0);)
     }
-#if defined(__SANITIZE_THREAD__)
-    // The emulator reuses its stacks and its shared-memory storage from CTA to CTA.  Default mode: each CTA is ordered
-    // after the previous one (scope = compute-sanitizer racecheck's: the threads of ONE CTA, but over shared AND
-    // global memory).  FZB_EMU_TSAN_GRID=1: the CTAs of a grid stay UNORDERED, as on the device, and the reused
-    // storage is declared race-free instead -- that pass looks for races BETWEEN CTAs in global memory (and is blind
-    // to shared memory).
-    if (!tsan_grid_mode()) {
-        __tsan_acquire(&G.done_token);
-        __tsan_release(&G.launch_token);
-    }
-#endif
     return c;
 }
 EMU_NOTSAN inline void cta_release(Cta *c) {
@@ -456,6 +458,19 @@ EMU_NOTSAN inline bool cta_run(Launch *L, Cta *c) {
     G.cur_launch = L;
     G.cur_cta = c;
     EMU_TSAN(G.sched_tsan = __tsan_get_current_fiber();)
+#if defined(__SANITIZE_THREAD__)
+    // The emulator reuses its stacks and its shared-memory storage from CTA to CTA.  Default mode: each CTA is ordered
+    // after the previous one (scope = compute-sanitizer racecheck's: the threads of ONE CTA, but over shared AND
+    // global memory).  FZB_EMU_TSAN_GRID=1: the CTAs of a grid stay UNORDERED, as on the device, and the reused
+    // storage is declared race-free instead -- that pass looks for races BETWEEN CTAs in global memory (and is blind
+    // to shared memory).
+    // (A CTA that was set aside and is resumed here gets the same treatment: whatever ran meanwhile is ordered before
+    // the rest of it; the fibers pick the edge up when they are switched in again.)
+    if (!tsan_grid_mode()) {
+        __tsan_acquire(&G.done_token);
+        __tsan_release(&G.launch_token);
+    }
+#endif
     c->progressed = false;
     bool finished = true;
     const int order = sched_order();
