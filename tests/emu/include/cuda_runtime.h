@@ -217,7 +217,8 @@ struct Global {
     Fiber *cur = nullptr;
     void *sched_sp = nullptr;
     Cta *owner = nullptr;  // whose data the __shared__ statics / the dynamic buffer hold right now
-    std::vector<SharedVar> registry;
+    SharedVar registry[4096];  // (a plain array: the sanitizer builds must not see the emulator's own bookkeeping)
+    size_t nregistry = 0;
     std::vector<emu_stream *> pending;
     std::vector<Cta *> free_ctas;
     std::vector<std::pair<char *, size_t>> free_stacks;
@@ -250,7 +251,9 @@ inline bool tsan_grid_mode() {
 // registration next to the declaration)
 struct SharedReg {
     EMU_NOTSAN SharedReg(void *p, size_t n) {
-        g().registry.push_back(SharedVar{p, n});
+        Global &G = g();
+        if (G.nregistry == 4096) abort();  // too many __shared__ declarations
+        G.registry[G.nregistry++] = SharedVar{p, n};
         EMU_TSAN(if (tsan_grid_mode()) AnnotateBenignRaceSized(__FILE__, __LINE__, p, (long)n, "emulated __shared__");)
     }
 };
@@ -335,14 +338,14 @@ EMU_NOTSAN inline void save_owner() {
     Cta *o = G.owner;
     if (!o) return;
     size_t total = 0;
-    for (const SharedVar &v : G.registry) total += v.n;
+    for (size_t i = 0; i < G.nregistry; i++) total += G.registry[i].n;
     o->snap_static.resize(total);
     size_t off = 0;
-    for (const SharedVar &v : G.registry) {
-        raw_copy(o->snap_static.data() + off, v.p, v.n);
-        off += v.n;
+    for (size_t i = 0; i < G.nregistry; i++) {
+        raw_copy(o->snap_static.data() + off, G.registry[i].p, G.registry[i].n);
+        off += G.registry[i].n;
     }
-    o->saved_vars = G.registry.size();
+    o->saved_vars = G.nregistry;
     o->snap_dyn.resize(o->dyn_bytes);
     raw_copy(o->snap_dyn.data(), g_dyn_smem, o->dyn_bytes);
     o->has_snapshot = true;
@@ -857,10 +860,16 @@ static inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CS
 static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 #endif
 namespace emu {
-inline long long cycles() {  // a slow clock (0.2 "GHz" of wall time): the kernels' bounded spin-waits for a peer allow for
-                             // host threads that take turns inside the emulator on a busy box
+inline long long cycles() {  // a slow clock (0.2 "GHz" of wall time by default): the kernels' bounded spin-waits for a
+                             // peer allow for host threads that take turns inside the emulator on a busy box
+                             // (FZB_EMU_CLOCK_DIV: ns per tick, e.g. 200 for the sanitizer builds)
+    static const long long div = [] {
+        const char *e = getenv("FZB_EMU_CLOCK_DIV");
+        const long long v = e ? atoll(e) : 0;
+        return v > 0 ? v : 5ll;
+    }();
     return (long long)(std::chrono::duration_cast<std::chrono::nanoseconds>(
-                           std::chrono::steady_clock::now().time_since_epoch()).count() / 5);
+                           std::chrono::steady_clock::now().time_since_epoch()).count() / div);
 }
 }  // namespace emu
 // the kernels read the clock in their bounded spin-waits (a flag another CTA / GPU raises): the natural place to
