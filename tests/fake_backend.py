@@ -93,7 +93,14 @@ class FakeHaystack(object):
         return p
 
     def search_levenshtein(self, p, k, flags=0):
-        raw = oracle.levenshtein_raw(self._pat(p), self.data, k)
+        if flags & F.F_FORCE_NGRAMS:
+            if len(self._pat(p)) // (k + 1) == 0:
+                raise ValueError("the subsequence length must be greater than max_l_dist")
+            raw = oracle.levenshtein_ngrams_raw(self._pat(p), self.data, k)
+        elif flags & F.F_FORCE_LP:
+            raw = oracle.levenshtein_lp_raw(self._pat(p), self.data, k)
+        else:
+            raw = oracle.levenshtein_raw(self._pat(p), self.data, k)
         return FakeResult(raw, oracle.consolidate(raw))
 
     def search_hamming(self, p, k, flags=0):
@@ -101,7 +108,12 @@ class FakeHaystack(object):
         return FakeResult(raw, raw)
 
     def search_generic(self, p, subs, ins, dels, l, flags=0):
-        raw = oracle.generic_raw(self._pat(p), self.data, subs, ins, dels, l)
+        if flags & F.F_FORCE_NGRAMS:
+            raw = oracle.generic_ngrams_raw(self._pat(p), self.data, subs, ins, dels, l)
+        elif flags & F.F_FORCE_LP:
+            raw = oracle.generic_lp_raw(self._pat(p), self.data, subs, ins, dels, l)
+        else:
+            raw = oracle.generic_raw(self._pat(p), self.data, subs, ins, dels, l)
         return FakeResult(raw, oracle.consolidate(raw))
 
     def search_exact(self, p, flags=0, start=None, end=None):

@@ -112,6 +112,7 @@ def test_emu_expansion_kernels(emu_device):
 
 def test_emu_reference_suite_calls(emu_device):
     test_gpu_golden.test_gpu_replays_reference_suite_calls(emu_device)
+    test_gpu_golden.test_gpu_module_level_route_functions(emu_device)
 
 
 def test_emu_batches(emu_device):

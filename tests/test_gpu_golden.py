@@ -105,3 +105,55 @@ def test_gpu_replays_reference_suite_calls(cuda_device):
 def test_gpu_replays_reference_fuzz(cuda_device):
     counts = _replay(load_golden("ref_fuzz.json"), cuda_device)
     assert sum(counts.values()) > 3000
+
+
+def replay_route_functions(records):
+    """The reference's module-level route functions, under their own names (fuzzysearch_b200.levenshtein,
+    .levenshtein_ngram, .substitutions_only, .generic_search): every golden record of a route function is replayed
+    through the public Python function and must give the reference's raw stream."""
+    from fuzzysearch_b200 import LevenshteinSearchParams
+    from fuzzysearch_b200.generic_search import (find_near_matches_generic_linear_programming,
+                                                 find_near_matches_generic_ngrams)
+    from fuzzysearch_b200.levenshtein import find_near_matches_levenshtein_linear_programming
+    from fuzzysearch_b200.levenshtein_ngram import find_near_matches_levenshtein_ngrams
+    from fuzzysearch_b200.substitutions_only import (find_near_matches_substitutions_lp,
+                                                     find_near_matches_substitutions_ngrams)
+    t = lambda ms: [(m.start, m.end, m.dist) for m in ms]  # noqa: E731
+    n = 0
+    for rec in records:
+        fn, a = rec["fn"], rec["args"]
+        if "exc" in rec or fn not in ("lev_ngrams_raw", "lev_lp_raw", "generic_lp_raw", "generic_ngrams_raw", "subs_lp",
+                                      "subs_ngrams"):
+            continue
+        pat, hay = _b(a[0]), _b(a[1])
+        if len(pat) == 0 or len(pat) > F.FZB_MAX_PATTERN:
+            continue
+        exp, ctx = tup(rec["result"]), "%s%r" % (fn, a)
+        if fn == "lev_ngrams_raw":
+            ms = find_near_matches_levenshtein_ngrams(pat, hay, a[2])
+            assert t(ms) == exp, ctx  # generation order
+            assert all(m.matched == hay[m.start:m.end] for m in ms), ctx
+        elif fn == "lev_lp_raw":
+            assert sorted(t(find_near_matches_levenshtein_linear_programming(pat, hay, a[2]))) == sorted(exp), ctx
+        elif fn in ("generic_lp_raw", "generic_ngrams_raw"):
+            if a[5] > 63:
+                continue
+            params = LevenshteinSearchParams(a[2], a[3], a[4], a[5])
+            if params.unpacked != (a[2], a[3], a[4], a[5]):
+                continue  # recorded with limits the public parameter object would normalise differently
+            call = find_near_matches_generic_linear_programming if fn == "generic_lp_raw" else \
+                find_near_matches_generic_ngrams
+            assert sorted(t(call(pat, hay, params))) == sorted(exp), ctx
+        else:
+            call = find_near_matches_substitutions_lp if fn == "subs_lp" else find_near_matches_substitutions_ngrams
+            if fn == "subs_ngrams" and len(pat) // (a[2] + 1) == 0:
+                continue
+            assert t(call(pat, hay, a[2])) == exp, ctx
+        n += 1
+    return n
+
+
+def test_gpu_module_level_route_functions(cuda_device):
+    n = replay_route_functions(load_golden("ref_suite_calls.json")) + \
+        replay_route_functions(load_golden("ref_fuzz.json")[::7])
+    assert n > 400

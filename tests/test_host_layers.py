@@ -203,3 +203,41 @@ def test_bio_seq_objects_are_searched_as_text(fake_device, monkeypatch):  # noqa
     resident.close()
     with pytest.raises(TypeError):
         find_near_matches(FakeSeq(pat), text.encode(), max_l_dist=2)  # text against bytes, as for a str
+
+
+def test_module_level_route_functions_on_the_fake_backend(fake_device):  # noqa: F811
+    """fuzzysearch_b200.levenshtein / .levenshtein_ngram / .substitutions_only / .generic_search mirror the
+    reference's module-level functions (names, arguments, errors); here their Python side, the kernels behind them in
+    tests/test_gpu_golden.py (and on the emulator)."""
+    from fuzzysearch_b200 import LevenshteinSearchParams
+    from fuzzysearch_b200.generic_search import find_near_matches_generic, has_near_match_generic_ngrams
+    from fuzzysearch_b200.levenshtein import find_near_matches_levenshtein
+    from fuzzysearch_b200.levenshtein_ngram import find_near_matches_levenshtein_ngrams
+    from fuzzysearch_b200.search_exact import search_exact as se
+    from fuzzysearch_b200.substitutions_only import (find_near_matches_substitutions,
+                                                     find_near_matches_substitutions_ngrams,
+                                                     has_near_match_substitutions)
+    from test_gpu_golden import replay_route_functions
+    assert replay_route_functions(load_golden("ref_suite_calls.json")) > 300
+    t = lambda ms: [(m.start, m.end, m.dist) for m in ms]  # noqa: E731
+    # SURVEY 8c known answers
+    assert t(find_near_matches_levenshtein_ngrams(b"PATTERN", b"----------PATT-ERN---------", 2)) == [(10, 18, 1)] * 3
+    assert sorted(t(find_near_matches_levenshtein(b"PATTERN", b"----------PATT-ERN---------", 2))) == \
+        [(10, 18, 1), (10, 18, 2), (11, 18, 2)]  # 7 // 3 < 3: the router takes the LP route
+    assert t(find_near_matches_levenshtein_ngrams(b"def", b"abcddefg", 1)) == [(3, 7, 1), (4, 7, 0), (4, 7, 0), (4, 7, 0)]
+    assert t(find_near_matches_levenshtein("def", "abcddefg", 0)) == [(4, 7, 0)]
+    assert t(find_near_matches_substitutions(b"abc", b"xbz", 5)) == [(0, 3, 2)]
+    assert has_near_match_substitutions(b"abc", b"xbz", 1) is False
+    assert se(b"ab", b"abab") == [0, 2]
+    params = LevenshteinSearchParams(1, 1, 1, 2)
+    assert t(find_near_matches_generic(b"PATTERN", b"---PATERN---", params)) == \
+        tup(oracle.generic_raw(b"PATTERN", b"---PATERN---", 1, 1, 1, 2))
+    assert has_near_match_generic_ngrams(b"PATTERN", b"---PATERN---", LevenshteinSearchParams(1, 1, 1, 1)) is True
+    for bad in (lambda: find_near_matches_levenshtein(b"", b"abc", 1), lambda: find_near_matches_levenshtein(b"a", b"abc", -1),
+                lambda: find_near_matches_levenshtein_ngrams(b"ab", b"abc", 2),
+                lambda: find_near_matches_substitutions(b"", b"abc", 1),
+                lambda: find_near_matches_substitutions(b"ab", b"abc", -1),
+                lambda: find_near_matches_substitutions_ngrams(b"ab", b"abc", 2),
+                lambda: find_near_matches_generic(b"", b"abc", params)):
+        with pytest.raises(ValueError):
+            bad()
