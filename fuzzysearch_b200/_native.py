@@ -454,8 +454,9 @@ def debug_expand(cases, device=0):
     """Test hook: cases = [(sub, seq, max_l, variant)], variant 0 auto / 1 short / 2 long ->
     int32 array [n, 8] (see fzb_debug_expand in include/fuzzb200.h)."""
     n = len(cases)
-    subs = np.frombuffer(b"".join(bytes(c[0]) for c in cases), dtype=np.uint8)
-    seqs = np.frombuffer(b"".join(bytes(c[1]) for c in cases), dtype=np.uint8)
+    # (one spare byte each: a batch made of empty sequences only must still hand the library a non-NULL pointer)
+    subs = np.frombuffer(b"".join(bytes(c[0]) for c in cases) + b"\0", dtype=np.uint8)
+    seqs = np.frombuffer(b"".join(bytes(c[1]) for c in cases) + b"\0", dtype=np.uint8)
     so = np.zeros(n + 1, dtype=np.uint32)
     qo = np.zeros(n + 1, dtype=np.uint32)
     so[1:] = np.cumsum([len(c[0]) for c in cases])

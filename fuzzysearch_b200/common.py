@@ -5,7 +5,8 @@
 ``LevenshteinSearchParams`` mirrors common.py:35-116 (validation + normalisation).
 """
 
-__all__ = ["Match", "LevenshteinSearchParams", "FuzzySearchBase", "consolidate_overlapping_matches"]
+__all__ = ["Match", "LevenshteinSearchParams", "FuzzySearchBase", "consolidate_overlapping_matches", "group_matches",
+           "GroupOfMatches", "get_best_match_in_group", "count_differences_with_maximum"]
 
 
 def _check_match_fields(start, end, dist, matched):  # common.py:21-32
@@ -223,3 +224,50 @@ def consolidate_overlapping_matches(matches):
     for m in matches:
         by_key.setdefault((m.start, m.end, m.dist), m)
     return [by_key[(int(s), int(e), int(d))] for s, e, d in zip(os_, oe, od)]
+
+
+# ---- small host-side helpers of fuzzysearch.common that callers (and the reference's tests) import by name ----------
+def count_differences_with_maximum(sequence1, sequence2, max_differences):
+    """common.py:119-126: the number of positions at which the two sequences differ, counting no further than
+    `max_differences` (a limit that is never REACHED -- zero or negative -- stops nothing, as in the reference)."""
+    total = sum(1 for a, b in zip(sequence1, sequence2) if a != b)
+    return min(total, max_differences) if max_differences > 0 else total
+
+
+class GroupOfMatches(object):
+    """common.py:145-158: a set of matches and the hull [start, end) they span."""
+
+    def __init__(self, match):
+        assert match.start <= match.end
+        self.start, self.end, self.matches = match.start, match.end, {match}
+
+    def is_match_in_group(self, match):
+        return match.end > self.start and match.start < self.end
+
+    def add_match(self, match):
+        self.matches.add(match)
+        self.start, self.end = min(self.start, match.start), max(self.end, match.end)
+
+
+def group_matches(matches):
+    """common.py:161-177: the groups (sets) of transitively overlapping matches, in order of first appearance.
+    Same incremental definition as the reference -- a match joins the groups whose CURRENT hull it overlaps and
+    fuses them -- which is what consolidate_overlapping_matches's native sweep computes for whole lists."""
+    groups = []
+    for match in matches:
+        touched = [g for g in groups if g.is_match_in_group(match)]
+        if len(touched) == 1:
+            touched[0].add_match(match)
+            continue
+        fused = GroupOfMatches(match)  # a group of its own, or the union of every group it bridges
+        for g in touched:
+            for m in g.matches:
+                fused.add_match(m)
+        groups = [g for g in groups if all(g is not t for t in touched)]
+        groups.append(fused)
+    return [g.matches for g in groups]
+
+
+def get_best_match_in_group(group):
+    """common.py:180-182: smallest distance, then longest; further ties go to the smallest (start, end) here."""
+    return min(group, key=lambda m: (m.dist, -(m.end - m.start), m.start, m.end))

@@ -26,6 +26,9 @@ def find_near_matches_generic_linear_programming(subsequence, sequence, search_p
     return list(_run(subsequence, sequence, lambda h, p: h.search_generic(p, subs, ins, dels, l, flags), False))
 
 
+_find_near_matches_generic_linear_programming = find_near_matches_generic_linear_programming  # generic_search.py:57,180-185
+
+
 def find_near_matches_generic_ngrams(subsequence, sequence, search_params):
     """generic_search.py:198-237; ValueError when len(subsequence) // (max_l_dist + 1) == 0 (:213-215)."""
     subs, ins, dels, l = _limits(subsequence, search_params)
